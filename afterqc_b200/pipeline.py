@@ -1,0 +1,368 @@
+"""Per-file pipeline driver: the host side of seqFilter.run() (preprocesser.py:234-783).
+
+Everything per-read runs in the engine (afterqc_b200.engine.Engine -> libafterqc_b200.so,
+hand-written sm_100a kernels).  This module keeps only what the reference does once per file:
+prefilter sampling window (qualitycontrol.py:331-357), autoTrim wiring (:260-280), output
+directory layout and naming (:285-371, getMainName :14-17), bad-flag renaming (:206-232),
+counter -> JSON assembly (:660-778).
+
+`backend_factory(params)` must return an object with the Engine interface; the default is the
+CUDA engine and there is NO CPU fallback (the import fails loudly without the built library).
+Tests inject the CPU oracle through the same hook to pin the host logic.
+"""
+import json
+import os
+
+import numpy as np
+
+from . import _abi, fastq_io
+from .qc import QualityControl
+
+READ_TO_SKIP = 1000          # qualitycontrol.py:333
+HEAD_ORDER_BASE = 1 << 40    # k-mer order index of the re-stat'd head reads (after the window)
+
+
+def getMainName(filename):
+    """preprocesser.py:14-17"""
+    baseName = os.path.basename(filename)
+    return baseName.replace(".fastq", "").replace(".fq", "").replace(".gz", "")
+
+
+def makeDict(opt):
+    """the `command` echo of the JSON (preprocesser.py:86-123)"""
+    keys = ['index2_flag', 'draw', 'barcode', 'index1_flag', 'seq_len_req', 'index1_file',
+            'overlap_output_folder', 'trim_tail', 'trim_pair_same', 'poly_size_limit',
+            'good_output_folder', 'debubble_dir', 'index2_file', 'qualified_quality_phred',
+            'barcode_flag', 'trim_front', 'barcode_verify', 'read2_file', 'n_base_limit',
+            'barcode_length', 'trim_tail2', 'unqualified_base_limit', 'allow_mismatch_in_poly',
+            'input_dir', 'read1_file', 'read2_flag', 'store_overlap', 'debubble', 'read1_flag',
+            'trim_front2', 'bad_output_folder', 'qc_only', 'qc_sample', 'qc_kmer']
+    return {k: getattr(opt, k) for k in keys}
+
+
+def params_from_options(opt, paired):
+    return _abi.Params.defaults(
+        paired=1 if paired else 0,
+        trim_front=max(opt.trim_front, 0), trim_tail=max(opt.trim_tail, 0),
+        trim_front2=max(opt.trim_front2, 0), trim_tail2=max(opt.trim_tail2, 0),
+        seq_len_req=opt.seq_len_req, poly_size_limit=opt.poly_size_limit,
+        allow_mismatch_in_poly=opt.allow_mismatch_in_poly,
+        qualified_quality_phred=opt.qualified_quality_phred,
+        unqualified_base_limit=opt.unqualified_base_limit, n_base_limit=opt.n_base_limit,
+        no_overlap=1 if opt.no_overlap else 0, no_correction=1 if opt.no_correction else 0,
+        mask_mismatch=1 if opt.mask_mismatch else 0, qc_sample=opt.qc_sample, qc_kmer=opt.qc_kmer)
+
+
+def default_backend(params):
+    from .engine import Engine   # fails loudly when the CUDA library is missing
+    return Engine(params)
+
+
+def prefilter_stat(backend, rec, slot, sample_limit, batch_records, mate_of=None, paired_batches=None):
+    """QualityControl.statFile (qualitycontrol.py:331-357) for one file already parsed into `rec`.
+
+    Window = records [999, 999+limit) (all if limit <= 0); if fewer than 1000 reads were counted in
+    the window loop, the first 999 are stat'd afterwards."""
+    n = rec.n
+    lo = READ_TO_SKIP - 1
+    if sample_limit > 0:
+        hi = min(n, lo + sample_limit)
+        stat_reads_num = min(max(n - lo, 0), sample_limit + 1)
+    else:
+        hi = n
+        stat_reads_num = max(n - lo, 0)
+    for a in range(lo, hi, batch_records):
+        b = min(hi, a + batch_records)
+        batch = fastq_io.to_batch(rec, None, a, b)
+        backend.stat_reads(batch, slot, -1, stat_lo=lo, stat_hi=hi, order_base=0)
+    if stat_reads_num < READ_TO_SKIP:
+        head = min(n, READ_TO_SKIP - 1)
+        if head > 0:
+            batch = fastq_io.to_batch(rec, None, 0, head)
+            backend.stat_reads(batch, slot, -1, stat_lo=0, stat_hi=head, order_base=HEAD_ORDER_BASE)
+
+
+def _emit(out, name, seq, plus, qual):
+    out.append(name); out.append(b"\n"); out.append(seq); out.append(b"\n")
+    out.append(plus); out.append(b"\n"); out.append(qual); out.append(b"\n")
+
+
+def apply_result(r, s1, q1, s2, q2):
+    """Return the final (seq1, qual1, seq2, qual2) bytes of one pair given its aqc_result."""
+    n_edits = int(r["n_edits"])
+    if n_edits:
+        s1 = bytearray(s1); q1 = bytearray(q1)
+        if s2 is not None:
+            s2 = bytearray(s2); q2 = bytearray(q2)
+        for e in r["edits"][:n_edits]:
+            f = _abi.edit_fields(e)
+            if f["kind"] == 0:
+                s1[f["pos"]] = f["base"]; q1[f["pos"]] = f["qual"]
+            elif f["kind"] == 1:
+                s2[f["pos"]] = f["base"]; q2[f["pos"]] = f["qual"]
+            elif f["kind"] == 2:
+                q1[f["pos"]] = 0x21; q2[f["pos2"]] = 0x21
+    a1, l1 = int(r["start1"]), int(r["len1"])
+    o1, p1 = bytes(s1[a1:a1 + l1]), bytes(q1[a1:a1 + l1])
+    if s2 is None:
+        return o1, p1, None, None
+    a2, l2 = int(r["start2"]), int(r["len2"])
+    return o1, p1, bytes(s2[a2:a2 + l2]), bytes(q2[a2:a2 + l2])
+
+
+class seqFilter:
+    """Drop-in for preprocesser.seqFilter: seqFilter(options).run()."""
+
+    def __init__(self, opt, backend_factory=None, batch_records=1 << 18):
+        self.options = opt
+        self.backend_factory = backend_factory or default_backend
+        self.batch_records = batch_records
+        self.paired = opt.read2_file is not None
+        self.stat = None
+
+    def run(self):
+        opt = self.options
+        if getattr(opt, "debubble", False):
+            raise NotImplementedError("--debubble is outside the B200 hot-path scope (SURVEY.md section 2, #12)")
+        if getattr(opt, "barcode", False):
+            raise NotImplementedError("barcode (UMI) processing is outside the B200 hot-path scope (SURVEY.md section 2, #11)")
+        if opt.index1_file is not None or opt.index2_file is not None:
+            raise NotImplementedError("index files (-7/-5) are a 'next' row (SURVEY.md section 8(f) #4)")
+
+        rec1 = fastq_io.read_all(opt.read1_file)
+        rec2 = fastq_io.read_all(opt.read2_file) if self.paired else None
+
+        params = params_from_options(opt, self.paired)
+        be = self.backend_factory(params)
+        self.backend = be
+
+        # ---- prefilter QC (preprocesser.py:247-251) ----
+        prefilter_stat(be, rec1, _abi.QC_R1_PRE, opt.qc_sample, self.batch_records)
+        if self.paired:
+            prefilter_stat(be, rec2, _abi.QC_R2_PRE, opt.qc_sample, self.batch_records)
+        self.r1qc_prefilter = QualityControl(opt.qc_sample, opt.qc_kmer).load(be.qc(_abi.QC_R1_PRE), be.kmers(_abi.QC_R1_PRE))
+        self.r1qc_prefilter.qc()
+        self.r2qc_prefilter = QualityControl(opt.qc_sample, opt.qc_kmer)
+        if self.paired:
+            self.r2qc_prefilter.load(be.qc(_abi.QC_R2_PRE), be.kmers(_abi.QC_R2_PRE))
+            self.r2qc_prefilter.qc()
+
+        readLen = self.r1qc_prefilter.readLen
+
+        # ---- auto trim (preprocesser.py:260-280) ----
+        if opt.trim_front == -1 or opt.trim_tail == -1:
+            trimFront, trimTail = self.r1qc_prefilter.autoTrim()
+            if opt.trim_front == -1:
+                opt.trim_front = trimFront
+            if opt.trim_tail == -1:
+                opt.trim_tail = trimTail
+            if self.paired:
+                if opt.trim_pair_same:
+                    opt.trim_front2 = opt.trim_front
+                    opt.trim_tail2 = opt.trim_tail
+                else:
+                    trimFront2, trimTail2 = self.r2qc_prefilter.autoTrim()
+                    if opt.trim_front2 == -1:
+                        opt.trim_front2 = trimFront2
+                    if opt.trim_tail2 == -1:
+                        opt.trim_tail2 = trimTail2
+        for k in ("trim_front", "trim_tail", "trim_front2", "trim_tail2"):
+            if getattr(opt, k) < 0:
+                raise ValueError("%s=%d is outside the supported domain" % (k, getattr(opt, k)))
+
+        print(opt.read1_file + " options:")
+        print(opt)
+
+        # ---- output layout (preprocesser.py:285-371) ----
+        good_dir = opt.good_output_folder
+        if good_dir is None:
+            good_dir = os.path.dirname(opt.read1_file)
+        bad_dir = opt.bad_output_folder
+        if bad_dir is None:
+            bad_dir = os.path.join(os.path.dirname(os.path.dirname(good_dir + "/")), "bad")
+        overlap_dir = opt.overlap_output_folder
+        if overlap_dir is None:
+            overlap_dir = os.path.join(os.path.dirname(os.path.dirname(good_dir + "/")), "overlap")
+        qc_dir = opt.report_output_folder
+        if qc_dir is None:
+            qc_dir = os.path.join(os.path.dirname(os.path.dirname(good_dir + "/")), "QC")
+        for d in (qc_dir, good_dir, bad_dir):
+            if not os.path.exists(d):
+                os.makedirs(d)
+        if opt.store_overlap and self.paired and not os.path.exists(overlap_dir):
+            os.makedirs(overlap_dir)
+        gzip_out = opt.gzip or opt.read1_file.endswith(".gz")
+        comp = opt.compression
+
+        writers = {}
+        if not opt.qc_only:
+            def mk(d, f, suffix):
+                return fastq_io.Writer(os.path.join(d, getMainName(f) + suffix), gzip_out, comp)
+            writers["good1"] = mk(good_dir, opt.read1_file, ".good.fq")
+            writers["bad1"] = mk(bad_dir, opt.read1_file, ".bad.fq")
+            if opt.store_overlap:
+                writers["ov1"] = mk(overlap_dir, opt.read1_file, ".overlap.fq")
+            if self.paired:
+                writers["good2"] = mk(good_dir, opt.read2_file, ".good.fq")
+                writers["bad2"] = mk(bad_dir, opt.read2_file, ".bad.fq")
+                if opt.store_overlap:
+                    writers["ov2"] = mk(overlap_dir, opt.read2_file, ".overlap.fq")
+
+        # ---- the per-read loop, in batches (preprocesser.py:411-631) ----
+        params = params_from_options(opt, self.paired)
+        be.set_params(params)
+        n = min(rec1.n, rec2.n) if self.paired else rec1.n
+        stop = n
+        if opt.qc_only:
+            stop = self._qc_only_stop(be, rec1, rec2, n)
+            be.reset_filter_counters()
+        for a in range(0, stop, self.batch_records):
+            b = min(stop, a + self.batch_records)
+            batch = fastq_io.to_batch(rec1, rec2, a, b)
+            res = be.filter_pairs(batch)
+            if not opt.qc_only:
+                self._write(writers, rec1, rec2, a, res)
+        for w in writers.values():
+            w.close()
+
+        cnt = be.counters()
+        self.counters = cnt
+        hist_len = readLen + 1
+        if cnt[_abi.C_OVERLAP_HIST + hist_len:_abi.C_OVERLAP_HIST + _abi.MAX_LEN + 1].any() or \
+           cnt[_abi.C_DISTANCE_HIST + hist_len:_abi.C_DISTANCE_HIST + _abi.MAX_LEN + 1].any():
+            raise IndexError("list index out of range")   # overlap_histgram is readLen+1 long (preprocesser.py:257,517)
+
+        self.r1qc_postfilter = QualityControl(opt.qc_sample, opt.qc_kmer).load(be.qc(_abi.QC_R1_POST), be.kmers(_abi.QC_R1_POST))
+        self.r1qc_postfilter.qc()
+        self.r2qc_postfilter = QualityControl(opt.qc_sample, opt.qc_kmer)
+        if self.paired:
+            self.r2qc_postfilter.load(be.qc(_abi.QC_R2_POST), be.kmers(_abi.QC_R2_POST))
+            self.r2qc_postfilter.qc()
+
+        # quirk Q1: the reference only adds R2's bases when an index2 file is present, and the R1
+        # record read just before a shorter R2 ran out is still counted (preprocesser.py:416-431)
+        extra = int(rec1.lengths()[n]) if (self.paired and rec1.n > n and not opt.qc_only) else 0
+        stat = self._build_stat(cnt, readLen, extra)
+        self.stat = stat
+        with open(os.path.join(qc_dir, os.path.basename(opt.read1_file) + ".json"), "w") as f:
+            f.write(json.dumps(stat, sort_keys=True, indent=4, separators=(',', ': ')))
+        be.close()
+        return stat
+
+    # ------------------------------------------------------------------------------------------
+    def _qc_only_stop(self, be, rec1, rec2, n):
+        """--qc_only stops after the first GOOD pair whose TOTAL_READS >= qc_sample
+        (preprocesser.py:630-631); find that index with a counter-free dry run."""
+        qs = self.options.qc_sample
+        for a in range(0, n, self.batch_records):
+            b = min(n, a + self.batch_records)
+            if b < qs:
+                continue
+            batch = fastq_io.to_batch(rec1, rec2, a, b)
+            res = be.filter_pairs(batch)
+            idx = np.arange(a, b) + 1
+            hit = np.flatnonzero((res["cls"] == _abi.GOOD) & (idx >= qs))
+            if len(hit):
+                return a + int(hit[0]) + 1
+        return n
+
+    def _write(self, writers, rec1, rec2, base, res):
+        good1, bad1, good2, bad2, ov1, ov2 = [], [], [], [], [], []
+        store_ov = "ov1" in writers
+        for j in range(len(res)):
+            r = res[j]
+            i = base + j
+            s2 = q2 = None
+            if rec2 is not None:
+                s2 = rec2.seqs.get(i); q2 = rec2.quals.get(i)
+            o1, p1, o2, p2 = apply_result(r, rec1.seqs.get(i), rec1.quals.get(i), s2, q2)
+            cls = int(r["cls"])
+            n1 = rec1.names.get(i)
+            if cls == _abi.GOOD:
+                _emit(good1, n1, o1, rec1.plus.get(i), p1)
+                if rec2 is not None:
+                    n2 = rec2.names.get(i)
+                    _emit(good2, n2, o2, rec2.plus.get(i), p2)
+                    if store_ov and int(r["ov_len"]) > 30:
+                        ne = int(r["n_edits"])
+                        corrected = sum(1 for e in r["edits"][:ne] if ((int(e) >> 10) & 3) < 2)
+                        d = int(r["ov_diff"])
+                        if d == 0 or d == corrected:          # preprocesser.py:615-617
+                            ol = int(r["ov_len"])
+                            _emit(ov1, n1, o1[len(o1) - ol:], rec1.plus.get(i), p1[len(p1) - ol:])
+                            _emit(ov2, n2, o2[len(o2) - ol:], rec2.plus.get(i), p2[len(p2) - ol:])
+            else:
+                flag = _abi.CLASS_FLAGS[cls].encode()
+                _emit(bad1, b"@" + flag + n1[1:], o1, rec1.plus.get(i), p1)     # preprocesser.py:212-213
+                if rec2 is not None:
+                    n2 = rec2.names.get(i)
+                    _emit(bad2, b"@" + flag + n2[1:], o2, rec2.plus.get(i), p2)
+        writers["good1"].write(b"".join(good1)); writers["bad1"].write(b"".join(bad1))
+        if rec2 is not None:
+            writers["good2"].write(b"".join(good2)); writers["bad2"].write(b"".join(bad2))
+        if store_ov:
+            writers["ov1"].write(b"".join(ov1))
+            if rec2 is not None:
+                writers["ov2"].write(b"".join(ov2))
+
+    def _build_stat(self, cnt, readLen, extra_total_bases):
+        """preprocesser.py:660-778"""
+        opt = self.options
+        c = lambda name: int(cnt[_abi.CIDX[name]])
+        result = {
+            'total_bases': c("TOTAL_BASES_R1") + extra_total_bases,
+            'good_bases': c("GOOD_BASES_R1"),
+            'total_reads': c("TOTAL_READS"),
+            'good_reads': c("GOOD_READS"),
+            'bad_reads': c("TOTAL_READS") - c("GOOD_READS"),
+            'bad_reads_with_bad_barcode': 0,
+            'bad_reads_with_reads_in_bubble': 0,
+            'bad_reads_with_bad_read_length': c("BADLEN") + c("BADTRIM1") + c("BADTRIM2"),
+            'bad_reads_with_polyX': c("BADPOL"),
+            'bad_reads_with_low_quality': c("BADLQC"),
+            'bad_reads_with_too_many_N': c("BADNCT"),
+            'bad_reads_with_bad_overlap': c("BADMISMATCH") + c("BADDIFF"),
+            'readlen': readLen,
+        }
+        qcs = [("read1_prefilter", self.r1qc_prefilter), ("read1_postfilter", self.r1qc_postfilter)]
+        if self.paired:
+            qcs += [("read2_prefilter", self.r2qc_prefilter), ("read2_postfilter", self.r2qc_postfilter)]
+        for _, q in qcs:
+            q.squeeze()
+        stat = {"afterqc_main_summary": result, "command": makeDict(opt),
+                "kmer_content": {}, "base_quality": {}, "mean_quality": {}, "base_content": {}, "gc_content": {}}
+        for name, q in qcs:
+            stat["kmer_content"][name] = [list(t) for t in q.topKmerCount[0:10]]
+            stat["base_quality"][name] = q.baseMeanQual
+            stat["mean_quality"][name] = q.meanQual
+            stat["base_content"][name] = q.percents
+            stat["gc_content"][name] = q.gcPercents
+        if self.paired:
+            ov = {}
+            overlapped = c("OVERLAPPED")
+            ov['overlapped_pairs'] = overlapped
+            ov['average_overlap_length'] = float(c("OVERLAP_LEN_SUM") // overlapped) if overlapped > 0 else 0.0
+            ov['bad_mismatch_reads'] = c("BADMISMATCH")
+            ov['bad_diff'] = c("BADDIFF")
+            ov['bad_indel_reads'] = 0
+            ov['corrected_reads'] = c("READ_CORRECTED")
+            ov['corrected_bases'] = c("BASE_CORRECTED")
+            ov['skipped_correction_bases'] = c("BASE_SKIPPED_CORRECTION")
+            ov['zero_qual_masked'] = c("BASE_ZERO_QUAL_MASKED")
+            ov['zero_qual_skipped'] = c("BASE_ZERO_QUAL_MASKED")
+            ov['trimmed_adapter_bases'] = c("TRIMMED_ADAPTER_BASE")
+            ov['trimmed_adapter_reads'] = c("TRIMMED_ADAPTER_READ")
+            base_sum = c("OVERLAP_BASE_SUM")
+            ov['error_rate'] = float(c("OVERLAP_BASE_ERR")) / float(base_sum) if base_sum > 0 else 0.0
+            em = {}
+            for i, cb in enumerate(_abi.ALL_BASES):
+                em[cb] = {}
+                for j, eb in enumerate(_abi.ALL_BASES):
+                    if cb != eb:
+                        em[cb][eb] = int(cnt[_abi.C_ERR_MATRIX + i * 4 + j])
+            ov['error_matrix'] = em
+            dh = cnt[_abi.C_DISTANCE_HIST:_abi.C_DISTANCE_HIST + readLen + 1].tolist()
+            ov['edit_distance_histogram'] = dh[0:10]
+            stat["afterqc_overlap"] = ov
+            self.overlap_histgram = cnt[_abi.C_OVERLAP_HIST:_abi.C_OVERLAP_HIST + readLen + 1].tolist()
+        return stat

@@ -1,0 +1,247 @@
+/*
+ * afterqc_b200.h -- C-ABI of the B200-native AfterQC per-read hot path.
+ *
+ * This is the drop-in boundary.  The reference has exactly one FFI precedent:
+ * util.py:4-24 loads editdistance/libed.so with ctypes and calls two extern "C" symbols with
+ * caller-owned buffers, POD arguments and sentinel/int returns (_editdistance.h:16,23).  This
+ * header keeps those conventions (extern "C", plain pointers and sizes, int return codes, no
+ * exceptions, no allocation ownership crossing the boundary except the explicit pinned-host
+ * helpers) and replaces the *Python* per-read loop instead of only seek_overlap:
+ *
+ *   aqc_stat_reads     replaces QualityControl.statFile/statRead      qualitycontrol.py:73-122,331-357
+ *   aqc_filter_pairs   replaces the seqFilter.run() loop body          preprocesser.py:411-631
+ *                      (trim :455-466, length :476-479, hasPolyX :30-51/:482-490,
+ *                       lowQualityNum :61-68/:493-501, nNumber :70-76/:504-512,
+ *                       util.overlap -> overlap_hm util.py:88-89,158-212,
+ *                       adapter trim + rescan :516-541, correction walk :542-617,
+ *                       postfilter statRead :624-627, counters :378-409)
+ *   aqc_ops_pairs      the bare per-read operators (hasPolyX / lowQualityNum / nNumber /
+ *                      util.overlap) for operator-level parity tests
+ *   aqc_get_*          fetch the integer counter blocks the JSON writer (preprocesser.py:660-778)
+ *                      and QualityControl.qc() (qualitycontrol.py:124-156) consume
+ *
+ * The same structs and enums are used by the CPU oracle (oracle/aqc_oracle.c, symbols aqo_*),
+ * which is test infrastructure and never linked into the product.
+ *
+ * Reads are passed as packed SoA batches: one byte column for bases, one for qualities and an
+ * n+1 offsets column per mate (variable length).  Qualities share the offsets of the bases
+ * (a FASTQ record whose quality line length differs from its sequence length is rejected by
+ * the host parser; the reference tolerates it only inside statRead, qualitycontrol.py:81-87).
+ */
+#ifndef AFTERQC_B200_H
+#define AFTERQC_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AQC_ABI_VERSION 1
+#define AQC_MAX_LEN 1000      /* qualitycontrol.py:23  MAX_LEN; longer reads raise IndexError there */
+#define AQC_MAX_KMER 8        /* dense 4^k table + 64-bit raw-byte keys for non-ACGT k-mers; --qc_kmer outside 1..8 is rejected */
+#define AQC_NUM_QC 4          /* r1 prefilter, r2 prefilter, r1 postfilter, r2 postfilter */
+
+/* error codes (0 = ok); aqc_last_error() gives text */
+enum {
+    AQC_OK = 0,
+    AQC_ERR_INVALID = 1,        /* bad argument / parameter out of the supported domain */
+    AQC_ERR_CUDA = 2,           /* CUDA runtime failure */
+    AQC_ERR_TOO_LONG = 3,       /* a read longer than AQC_MAX_LEN (reference: IndexError) */
+    AQC_ERR_KMER_TABLE_FULL = 4,/* non-ACGT k-mer side table overflow; raise kmer_side_log2 */
+    AQC_ERR_NOMEM = 5,
+    AQC_ERR_TOO_SHORT_STAT = 6  /* a read of 1..4 bases reached statRead (reference: IndexError,
+                                   qualitycontrol.py:97-108 indexes seq[j+1] up to 4) */
+};
+
+/* where the batch columns and the result array live */
+enum { AQC_MEM_HOST = 0, AQC_MEM_DEVICE = 1 };
+
+/* pair classes in the reference's priority order (preprocesser.py:436-614); the numeric
+ * value is what aqc_result.cls holds.  BADBCD1/2 and BADBBL are out of scope (barcode, debubble). */
+enum {
+    AQC_GOOD = 0,
+    AQC_BADTRIM1 = 1,     /* :457-460 */
+    AQC_BADTRIM2 = 2,     /* :463-466 */
+    AQC_BADLEN = 3,       /* :476-479 and :529-532 */
+    AQC_BADPOL = 4,       /* :487-490 */
+    AQC_BADLQC = 5,       /* :498-501 */
+    AQC_BADNCT = 6,       /* :509-512 */
+    AQC_BADDIFF = 7,      /* :538-541 */
+    AQC_BADMISMATCH = 8,  /* :611-614 */
+    AQC_NUM_CLASSES = 9
+};
+
+/* Filter parameters = the resolved option values the loop reads (after.py:14-93; trim values
+ * already resolved by autoTrim, preprocesser.py:260-280, so they are >= 0 here). */
+typedef struct aqc_params {
+    int32_t paired;                  /* read2_file != None */
+    int32_t trim_front, trim_tail;   /* -f / -t (R1) */
+    int32_t trim_front2, trim_tail2; /* R2 values (trim_pair_same copies R1's) */
+    int32_t seq_len_req;             /* -s 35 */
+    int32_t poly_size_limit;         /* -p 35 */
+    int32_t allow_mismatch_in_poly;  /* -a 2 */
+    int32_t qualified_quality_phred; /* -q 15 */
+    int32_t unqualified_base_limit;  /* -u 60 */
+    int32_t n_base_limit;            /* -n 5 */
+    int32_t no_overlap;              /* --no_overlap */
+    int32_t no_correction;           /* --no_correction */
+    int32_t mask_mismatch;           /* --mask_mismatch */
+    int32_t qc_sample;               /* --qc_sample 200000 (postfilter gate, preprocesser.py:624) */
+    int32_t qc_kmer;                 /* --qc_kmer 8 */
+    int32_t kmer_side_log2;          /* log2 capacity of the non-ACGT k-mer side table (0 = default 20) */
+    int32_t reserved[7];
+} aqc_params;
+
+/* One packed batch.  off*[i]..off*[i+1] delimit record i in seq* and qual*.  seq2/qual2/off2
+ * are NULL for single-end input.  first_index is the 0-based global record index of record 0
+ * (the reference's TOTAL_READS for record i is first_index + i + 1).  Device-side columns need
+ * 16 readable bytes of slack after the last base (bulk copies are 16-byte granular). */
+typedef struct aqc_batch {
+    uint64_t first_index;
+    uint32_t n;
+    uint32_t flags;             /* reserved, 0 */
+    const uint8_t *seq1, *qual1;
+    const uint32_t *off1;
+    const uint8_t *seq2, *qual2;
+    const uint32_t *off2;
+} aqc_batch;
+
+/* Per-pair outcome, 32 bytes.  start/len are the final coordinates into the ORIGINAL read after
+ * front/tail trim and adapter cut (what the good/bad writer must emit).  edits are the byte
+ * changes of the correction walk (preprocesser.py:563-598), applied in order:
+ *   bits 0-9 pos (index into the ORIGINAL read), bits 10-11 kind, bits 16-23 base, bits 24-31 qual
+ *   kind 0: r1[pos] := base, r1q[pos] := qual     (:583-584)
+ *   kind 1: r2[pos] := base, r2q[pos] := qual     (:575-576)
+ *   kind 2: mask_mismatch -- r1q[pos] := '!' and the mate position r2q[pos2] := '!' where pos2 is
+ *           carried in bits 16-25 instead of base/qual                     (:590-592)
+ *   kind 3: mismatch skipped (no byte change; kept so the host can count)  (:595)
+ * ov_* is the result of the last util.overlap call for the pair (after the adapter rescan). */
+typedef struct aqc_result {
+    uint8_t cls;
+    uint8_t n_edits;
+    uint16_t start1, len1, start2, len2;
+    int16_t ov_offset;
+    uint16_t ov_len, ov_diff;
+    uint32_t edits[4];
+} aqc_result;
+
+#define AQC_EDIT_POS(e) ((e) & 0x3FFu)
+#define AQC_EDIT_KIND(e) (((e) >> 10) & 3u)
+#define AQC_EDIT_BASE(e) (((e) >> 16) & 0xFFu)
+#define AQC_EDIT_QUAL(e) (((e) >> 24) & 0xFFu)
+#define AQC_EDIT_POS2(e) (((e) >> 16) & 0x3FFu)
+
+/* Bare operator outputs on the (front/tail-trimmed) mates, 32 bytes; no classification. */
+typedef struct aqc_ops {
+    uint8_t poly1, poly2;       /* hasPolyX return char, 0 = None            preprocesser.py:30-51 */
+    uint16_t lowq1, lowq2;      /* lowQualityNum                             :61-68 */
+    uint16_t n1, n2;            /* nNumber                                   :70-76 */
+    uint16_t len1, len2;        /* trimmed lengths                           :19-28 */
+    int16_t ov_offset;          /* util.overlap(r1, r2) first call           util.py:158-212 */
+    uint16_t ov_len, ov_diff;
+    uint8_t pad[12];
+} aqc_ops;
+
+/* Scalar counter block (int64), indices; names follow preprocesser.py:378-409. */
+enum {
+    AQC_C_TOTAL_READS = 0,
+    AQC_C_TOTAL_BASES_R1, AQC_C_TOTAL_BASES_R2,   /* raw lengths; host applies quirk Q1 (:416,:431) */
+    AQC_C_GOOD_READS,
+    AQC_C_GOOD_BASES_R1, AQC_C_GOOD_BASES_R2,     /* final lengths of good pairs (:621-623) */
+    AQC_C_BADTRIM1, AQC_C_BADTRIM2, AQC_C_BADLEN, AQC_C_BADPOL, AQC_C_BADLQC, AQC_C_BADNCT,
+    AQC_C_BADDIFF, AQC_C_BADMISMATCH,
+    AQC_C_READ_CORRECTED, AQC_C_BASE_CORRECTED, AQC_C_BASE_SKIPPED_CORRECTION, AQC_C_BASE_ZERO_QUAL_MASKED,
+    AQC_C_OVERLAPPED, AQC_C_OVERLAP_LEN_SUM, AQC_C_OVERLAP_BASE_SUM, AQC_C_OVERLAP_BASE_ERR,
+    AQC_C_TRIMMED_ADAPTER_BASE, AQC_C_TRIMMED_ADAPTER_READ,
+    AQC_C_ERR_MATRIX = 32,      /* 16 cells [correct][error], base order A,T,C,G (ALL_BASES, qualitycontrol.py:24) */
+    AQC_C_SCALARS = 64,
+    AQC_C_OVERLAP_HIST = 64,                          /* [AQC_MAX_LEN+1]  overlap_histgram  :517 */
+    AQC_C_DISTANCE_HIST = 64 + AQC_MAX_LEN + 1,       /* [AQC_MAX_LEN+1]  distance_histgram :536 */
+    AQC_C_TOTAL = 64 + 2 * (AQC_MAX_LEN + 1)
+};
+
+/* QC slots */
+enum { AQC_QC_R1_PRE = 0, AQC_QC_R2_PRE = 1, AQC_QC_R1_POST = 2, AQC_QC_R2_POST = 3 };
+
+/* Per-cycle integer counters of one QualityControl object (qualitycontrol.py:33-57), each
+ * AQC_MAX_LEN long, base order A,T,C,G. */
+typedef struct aqc_qc_counters {
+    int64_t totalNum[AQC_MAX_LEN];
+    int64_t totalQual[AQC_MAX_LEN];
+    int64_t baseCounts[4][AQC_MAX_LEN];
+    int64_t baseTotalQual[4][AQC_MAX_LEN];
+    int64_t totalDiscontinuity[AQC_MAX_LEN];
+    int64_t gcHistogram[AQC_MAX_LEN + 1];
+    int64_t totalKmer;
+    int64_t reads;              /* number of reads stat'd into this object */
+} aqc_qc_counters;
+
+/* K-mer first-seen key: (order_index << 11) | (pos << 1) | seeded_by_revcomp.  Sorting the
+ * entries that have first != AQC_KMER_NEVER by (count desc, first asc) reproduces
+ * sorted(kmerCount.items(), key=count, reverse=True) over an insertion-ordered dict
+ * (qualitycontrol.py:113-122,155-156; quirk Q12). */
+#define AQC_KMER_NEVER 0xFFFFFFFFFFFFFFFFull
+
+typedef struct aqc_ctx aqc_ctx;
+
+/* ---- lifecycle ---- */
+int aqc_abi_version(void);
+/* device < 0: the current CUDA device. */
+int aqc_create(int device, const aqc_params *params, aqc_ctx **out);
+void aqc_destroy(aqc_ctx *ctx);
+int aqc_set_params(aqc_ctx *ctx, const aqc_params *params);
+int aqc_reset(aqc_ctx *ctx);                       /* zero all counters / QC objects */
+int aqc_reset_filter(aqc_ctx *ctx);                /* zero the scalar block, both histograms and the two
+                                                      postfilter QC slots; prefilter slots are kept */
+const char *aqc_last_error(const aqc_ctx *ctx);    /* ctx may be NULL: last create error */
+
+/* pinned host memory for async copies (optional; pageable host buffers also work) */
+int aqc_host_alloc(size_t bytes, void **out);
+void aqc_host_free(void *p);
+/* plain device buffers (so callers can keep batches resident in HBM) */
+int aqc_device_alloc(aqc_ctx *ctx, size_t bytes, void **out);
+void aqc_device_free(aqc_ctx *ctx, void *p);
+int aqc_memcpy_h2d(aqc_ctx *ctx, void *dst, const void *src, size_t bytes);
+int aqc_memcpy_d2h(aqc_ctx *ctx, void *dst, const void *src, size_t bytes);
+
+/* ---- the hot path ---- */
+/* Prefilter statistics: statRead for every record i with stat_lo <= first_index+i < stat_hi;
+ * mate 1 goes to QC slot qc1, mate 2 (if present) to qc2 (pass -1 to skip a mate).  The k-mer
+ * order index of record i is order_base + (first_index + i - stat_lo). */
+int aqc_stat_reads(aqc_ctx *ctx, const aqc_batch *batch, int mem, int qc1, int qc2,
+                   uint64_t stat_lo, uint64_t stat_hi, uint64_t order_base);
+
+/* The fused per-pair loop body.  results: n entries in the same memory space as the batch.
+ * Accumulates the scalar counters, both histograms, the error matrix and the postfilter QC
+ * slots (gated by qc_sample exactly as preprocesser.py:624). */
+int aqc_filter_pairs(aqc_ctx *ctx, const aqc_batch *batch, int mem, aqc_result *results);
+
+/* Operator-level outputs (no counters touched). */
+int aqc_ops_pairs(aqc_ctx *ctx, const aqc_batch *batch, int mem, aqc_ops *out);
+
+/* Wait for all queued work of this context. */
+int aqc_sync(aqc_ctx *ctx);
+
+/* ---- fetch (host pointers; these synchronise) ---- */
+int aqc_get_counters(aqc_ctx *ctx, int64_t *out /* AQC_C_TOTAL */);
+int aqc_add_counters(aqc_ctx *ctx, const int64_t *in /* AQC_C_TOTAL */);   /* merge another shard's block */
+int aqc_get_qc(aqc_ctx *ctx, int slot, aqc_qc_counters *out);
+/* dense table: 4^k entries, index = sum code(base_j) << 2*(k-1-j), code A=0 C=1 G=2 T=3 */
+int aqc_get_kmer_dense(aqc_ctx *ctx, int slot, uint64_t *counts, uint64_t *first);
+/* side table of k-mers with a non-ACGT byte: keys are the k raw bytes, first byte in the
+ * most-significant position of a k-byte big-endian integer. *n_out receives the entry count
+ * (AQC_ERR_INVALID if cap is too small; call with cap = 0 to query). */
+int aqc_get_kmer_side(aqc_ctx *ctx, int slot, uint64_t *keys, uint64_t *counts, uint64_t *first,
+                      uint32_t cap, uint32_t *n_out);
+
+/* instrumentation for bench.py: kernels launched by this context so far, and the device
+ * time in ms of the last filter/stat call's kernels (CUDA events on the launching stream) */
+uint64_t aqc_launch_count(const aqc_ctx *ctx);
+float aqc_last_kernel_ms(const aqc_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFTERQC_B200_H */
