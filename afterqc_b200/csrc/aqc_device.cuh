@@ -1,0 +1,424 @@
+// aqc_device.cuh -- device-side building blocks of the B200 AfterQC engine (sm_100a).
+//
+// Execution model: one WARP per read pair.  A persistent CTA (8 warps) walks tiles of <= 32
+// pairs; the four byte columns of a tile (bases/quals of both mates) are contiguous in HBM and
+// are staged into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier), double
+// buffered.  Inside a warp the bases of a mate are turned into BIT-PLANES with warp ballots
+// (lane j holds bits 32j..32j+31 of each plane), so that
+//   * the sliding-offset Hamming scan of util.overlap_hm (util.py:158-212) becomes: each lane
+//     scores ONE candidate offset with funnel-shift + XOR + popc on the first 32 positions,
+//     a ballot picks the survivors in scan order, and a warp-wide popc/redux evaluates the
+//     reference's acceptance rule exactly (closed form of the leaked loop variable, quirk Q6);
+//   * hasPolyX (preprocesser.py:30-51) is screened by a bit-parallel run-length test and only
+//     candidate reads take the exact sliding-window path;
+//   * N / low-quality counts are ballots + popc.
+// All arithmetic is integer/byte work; there is no tensor-core use by design.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/afterqc_b200.h"
+
+namespace aqc {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int WARPS = 8;
+constexpr int THREADS = WARPS * 32;
+constexpr int NSTAGES = 2;
+constexpr int MAX_TILE_PAIRS = 32;
+constexpr int QC_CLASSES = 5;              // A, T, C, G, other  (ALL_BASES order, qualitycontrol.py:24)
+constexpr uint32_t QC_FLUSH_READS = 4000;  // packed smem word = count(12 bit) << 20 | byte sum (20 bit)
+
+enum Mode { MODE_FILTER = 0, MODE_STAT = 1, MODE_OPS = 2 };
+
+// lut1[b]: low nibble = comparison code of b as an R1 byte, high nibble = code of COMP[b] (rc side)
+//   codes: A0 C1 G2 T3 N4 a8 c9 g10 t11 '\n'12, any other R1 byte 15 (never equal to an rc code)
+// lut2[b]: bits0-2 QC class (A0 T1 C2 G3 other4), bit3 = G|C, bits4-5 k-mer code (A0 C1 G2 T3),
+//          bit6 = uppercase ACGT, bit7 = member of hasPolyX's polyArray (preprocesser.py:35)
+// lut3[b]: COMP[b] as a byte, unknown -> 'N' (util.py:27,47-50)
+struct Luts { uint8_t lut1[256], lut2[256], lut3[256]; };
+
+// global accumulators of one QualityControl object
+struct QcDev {
+    unsigned long long *cls_cnt;    // [5][AQC_MAX_LEN]
+    unsigned long long *cls_qsum;   // [5][AQC_MAX_LEN] raw quality-byte sums (33 not subtracted)
+    unsigned long long *disc;       // [AQC_MAX_LEN]
+    unsigned long long *gchist;     // [AQC_MAX_LEN+1]
+    unsigned long long *scal;       // [0] totalKmer, [1] reads
+    unsigned long long *kcnt;       // dense 4^k, internal index (plane1bits << k) | plane0bits
+    unsigned long long *kfirst;
+    unsigned long long *skeys, *scnt, *sfirst;   // side table (non-ACGT k-mers)
+    uint32_t smask;
+    uint32_t valid;                 // 0 = this mate is not stat'd in this launch
+};
+
+struct KArgs {
+    // batch
+    const uint8_t *seq1, *qual1, *seq2, *qual2;
+    const uint32_t *off1, *off2;
+    uint32_t n;
+    uint32_t num_tiles;
+    uint64_t first_index;
+    // tiling
+    int tile_pairs;       // pairs per tile (<= 32)
+    int col_cap;          // bytes reserved per column per stage
+    int max_len;          // longest read in the batch (smem accumulator extent)
+    int mode;
+    // parameters
+    aqc_params p;
+    // stat gating (MODE_STAT): records with stat_lo <= global < stat_hi; order = order_base + g - stat_lo
+    uint64_t stat_lo, stat_hi, order_base;
+    // outputs
+    aqc_result *results;          // MODE_FILTER
+    aqc_ops *ops;                 // MODE_OPS
+    unsigned long long *counters; // AQC_C_TOTAL
+    QcDev qc[2];                  // [0] mate 1, [1] mate 2 for this launch
+    int *error_flag;
+    const Luts *luts;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + 1-D bulk async copy (TMA) + proxy fence
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) { }
+}
+// global -> shared bulk copy; dst, src and bytes are multiples of 16
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// bit-plane helpers.  A "plane set" is uint32_t P[4]; lane j holds positions 32j..32j+31.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lowmask(int nbits) {   // nbits may be <= 0 or >= 32
+    return nbits >= 32 ? 0xffffffffu : (nbits <= 0 ? 0u : ((1u << nbits) - 1u));
+}
+
+// 32 bits of plane word array `p` starting at bit (32*word + sh), word may exceed 31 (-> zeros)
+__device__ __forceinline__ uint32_t plane_window(uint32_t p, int word, int sh) {
+    uint32_t a = __shfl_sync(FULL, p, word & 31);
+    uint32_t b = __shfl_sync(FULL, p, (word + 1) & 31);
+    if (word > 31) a = 0;
+    if (word + 1 > 31) b = 0;
+    return __funnelshift_r(a, b, sh);
+}
+
+// Build the planes of a read from shared-memory bytes.  rev: position i takes byte len-1-i and the
+// rc-side code (this yields the planes of reverseComplement(read), util.py:42-51).
+// Also returns the exact count of 'N' bytes (nNumber, preprocesser.py:70-76) and whether any
+// position has a code >= 4 (then planes 2,3 are needed by the comparisons).
+__device__ __forceinline__ void build_planes(const uint8_t *s, int len, bool rev, const uint8_t *lut1, int lane,
+                                             uint32_t (&P)[4], int &n_count, bool &exotic) {
+    P[0] = P[1] = P[2] = P[3] = 0;
+    n_count = 0;
+    uint32_t anyx = 0;
+    const int nchunks = (len + 31) >> 5;
+    for (int c = 0; c < nchunks; c++) {
+        int pos = (c << 5) + lane;
+        bool valid = pos < len;
+        uint32_t byte = valid ? s[rev ? (len - 1 - pos) : pos] : 0u;
+        uint32_t l = lut1[byte];
+        uint32_t code = valid ? (rev ? (l >> 4) : (l & 15u)) : 0u;
+        uint32_t b0 = __ballot_sync(FULL, code & 1u);
+        uint32_t b1 = __ballot_sync(FULL, code & 2u);
+        uint32_t bx = __ballot_sync(FULL, code & 12u);
+        uint32_t bn = __ballot_sync(FULL, valid && byte == 'N');
+        n_count += __popc(bn);
+        uint32_t b2 = 0, b3 = 0;
+        if (bx) {   // warp-uniform
+            b2 = __ballot_sync(FULL, code & 4u);
+            b3 = __ballot_sync(FULL, code & 8u);
+            anyx |= bx;
+        }
+        if (lane == c) { P[0] = b0; P[1] = b1; P[2] = b2; P[3] = b3; }
+    }
+    exotic = anyx != 0;
+}
+
+// lowQualityNum (preprocesser.py:61-68): number of quality bytes < qual + 33
+__device__ __forceinline__ int count_lowq(const uint8_t *q, int len, int thr, int lane) {
+    int n = 0;
+    for (int base = 0; base < len; base += 32) {
+        int pos = base + lane;
+        bool hit = pos < len && (int)q[pos] < thr;
+        n += __popc(__ballot_sync(FULL, hit));
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// util.overlap_hm (util.py:158-212) on planes.
+// scan_dir scans offsets o = 0 .. lenS-31 of the "shifted" read S against the "fixed" read F:
+//   compare S[o+i] with F[i], i < ol = min(lenS-o, lenF)
+// forward pass: S = r1, F = rc(r2);  reverse pass: S = rc(r2), F = r1 (offset = -o).
+// Acceptance (closed form of the leaked loop variable, validated against the reference):
+//   mm50 = mismatches among i < min(50, ol);  mm = mismatches among all i < ol
+//   accept  <=>  mm50 < 3  and  (mm < 3  or  ol >= 52);   returned diff = mm
+// ------------------------------------------------------------------------------------------
+template <int NP>
+__device__ __forceinline__ int scan_dir(const uint32_t (&S)[4], const uint32_t (&F)[4], int lenS, int lenF, int lane,
+                                        int &ol_out, int &mm_out) {
+    const int nOff = lenS - 30;     // overlap_require = 30 (util.py:164)
+    if (nOff <= 0) return -1;
+    uint32_t f0[NP];
+#pragma unroll
+    for (int k = 0; k < NP; k++) f0[k] = __shfl_sync(FULL, F[k], 0);
+    for (int base = 0; base < nOff; base += 32) {
+        const int r = base >> 5;
+        const int o = base + lane;
+        uint32_t x = 0;
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            uint32_t a = __shfl_sync(FULL, S[k], r);
+            uint32_t b = (r + 1 < 32) ? __shfl_sync(FULL, S[k], (r + 1) & 31) : 0u;
+            x |= __funnelshift_r(a, b, lane) ^ f0[k];
+        }
+        int ol = min(lenS - o, lenF);
+        bool surv = (o < nOff) && (__popc(x & lowmask(ol)) < 3);   // first min(32, ol) positions
+        uint32_t sv = __ballot_sync(FULL, surv);
+        while (sv) {   // warp-uniform loop over survivors in scan order
+            int l = __ffs(sv) - 1;
+            sv &= sv - 1;
+            int oc = base + l;
+            int olc = min(lenS - oc, lenF);
+            int q = oc >> 5, sh = oc & 31;
+            uint32_t xx = 0;
+#pragma unroll
+            for (int k = 0; k < NP; k++) xx |= plane_window(S[k], lane + q, sh) ^ F[k];
+            int lo = lane << 5;
+            xx &= lowmask(olc - lo);
+            int mm = __reduce_add_sync(FULL, (unsigned)__popc(xx));
+            int mm50 = __reduce_add_sync(FULL, (unsigned)__popc(xx & lowmask(min(50, olc) - lo)));
+            if (mm50 < 3 && (mm < 3 || olc >= 52)) { ol_out = olc; mm_out = mm; return oc; }
+        }
+    }
+    return -1;
+}
+
+template <int NP>
+__device__ __forceinline__ void overlap_hm(const uint32_t (&P1)[4], const uint32_t (&RC)[4], int len1, int len2, int lane,
+                                           int &offset, int &ol, int &diff) {
+    int o = scan_dir<NP>(P1, RC, len1, len2, lane, ol, diff);      // forward  util.py:172-186
+    if (o >= 0) { offset = o; return; }
+    o = scan_dir<NP>(RC, P1, len2, len1, lane, ol, diff);          // reverse  util.py:194-209
+    if (o >= 0) { offset = -o; return; }
+    offset = 0; ol = 0; diff = 0;                                   // util.py:212
+}
+
+__device__ __forceinline__ void overlap_any(bool exotic, const uint32_t (&P1)[4], const uint32_t (&RC)[4], int len1, int len2,
+                                            int lane, int &offset, int &ol, int &diff) {
+    if (exotic) overlap_hm<4>(P1, RC, len1, len2, lane, offset, ol, diff);
+    else overlap_hm<2>(P1, RC, len1, len2, lane, offset, ol, diff);
+}
+
+// ------------------------------------------------------------------------------------------
+// hasPolyX (preprocesser.py:30-51)
+// ------------------------------------------------------------------------------------------
+// Shift a plane word array left by `s` positions (new[x] = old[x - s]).
+__device__ __forceinline__ uint32_t plane_shl(uint32_t y, int s, int lane) {
+    int q = s >> 5, r = s & 31;
+    int src_hi = lane - q, src_lo = lane - q - 1;
+    uint32_t hi = __shfl_sync(FULL, y, src_hi & 31);
+    uint32_t lo = __shfl_sync(FULL, y, src_lo & 31);
+    if (src_hi < 0) hi = 0;
+    if (src_lo < 0) lo = 0;
+    return __funnelshift_l(lo, hi, r);
+}
+
+// Necessary condition for hasPolyX != None: the read contains a run of >= R identical codes,
+// R = ceil(T / (mismatch + 1)), T = maxPoly - mismatch  (<= mismatch interruptions split the >= T
+// equal bases of a flagged window into <= mismatch + 1 runs).  Works on either orientation.
+__device__ __forceinline__ bool polyx_screen(const uint32_t (&P)[4], bool exotic, int len, int maxPoly, int mismatch, int lane) {
+    if (len < maxPoly) return false;               // :31-32
+    if (mismatch < 0) return false;                // count <= maxPoly < threshold: never flagged
+    int T = maxPoly - mismatch;
+    if (T <= 1) return true;
+    int R = (T + mismatch) / (mismatch + 1);
+    int m = R - 1;                                 // need m consecutive "same as previous" bits
+    if (m <= 0) return true;
+    uint32_t d = 0;
+    {
+        uint32_t prev;
+        prev = plane_shl(P[0], 1, lane); d |= P[0] ^ prev;
+        prev = plane_shl(P[1], 1, lane); d |= P[1] ^ prev;
+        if (exotic) {
+            prev = plane_shl(P[2], 1, lane); d |= P[2] ^ prev;
+            prev = plane_shl(P[3], 1, lane); d |= P[3] ^ prev;
+        }
+    }
+    uint32_t y = ~d & lowmask(len - (lane << 5));
+    if (lane == 0) y &= ~1u;                       // position 0 has no predecessor
+    int t = 1;
+    while (t < m) {                                // y_t[x] = AND_{i<t} same[x-i]
+        int step = min(t, m - t);
+        y &= plane_shl(y, step, lane);
+        t += step;
+    }
+    return __ballot_sync(FULL, y != 0) != 0;
+}
+
+// Exact hasPolyX on the raw bytes (taken only by screened candidates).  Returns the char or 0.
+__device__ __forceinline__ int polyx_exact(const uint8_t *s, int len, int maxPoly, int mismatch, const uint8_t *lut2, int lane) {
+    if (len < maxPoly) return 0;
+    const int T = maxPoly - mismatch;
+    // first byte outside polyArray aborts the scan (:41-42)
+    int limit = len;
+    for (int base = 0; base < len; base += 32) {
+        int pos = base + lane;
+        bool foreign = pos < len && !(lut2[s[pos]] & 0x80);
+        uint32_t fb = __ballot_sync(FULL, foreign);
+        if (fb) { limit = base + __ffs(fb) - 1; break; }
+    }
+    for (int base = 0; base < limit; base += 32) {
+        int x = base + lane;
+        bool flag = false;
+        if (x < limit) {
+            uint8_t c = s[x];
+            int lo = max(0, x - maxPoly + 1);
+            int cnt = 0;
+            for (int y = x; y >= lo; y--) cnt += (s[y] == c);
+            flag = cnt >= T;
+        }
+        uint32_t fb = __ballot_sync(FULL, flag);
+        if (fb) return s[base + __ffs(fb) - 1];
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory QC accumulators of one CTA (flushed to QcDev with 64-bit atomics)
+// ------------------------------------------------------------------------------------------
+struct QcSmem {
+    uint32_t *acc;    // [2 mates][5 classes][max_len]  count << 20 | byte sum
+    uint32_t *disc;   // [2 mates][max_len]
+    int max_len;
+};
+
+__device__ __forceinline__ unsigned long long side_hash(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return k;
+}
+
+// insert-or-find `key` in the side table; returns slot or -1 on overflow
+__device__ __forceinline__ int side_slot(const QcDev &q, unsigned long long key) {
+    uint32_t h = (uint32_t)side_hash(key) & q.smask;
+    for (uint32_t probe = 0; probe <= q.smask; probe++) {
+        unsigned long long prev = atomicCAS(&q.skeys[h], AQC_KMER_NEVER, key);
+        if (prev == AQC_KMER_NEVER || prev == key) return (int)h;
+        h = (h + 1) & q.smask;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ void first_min(unsigned long long *addr, unsigned long long key) {
+    if (*((volatile unsigned long long *)addr) > key) atomicMin(addr, key);
+}
+
+// QualityControl.statRead (qualitycontrol.py:73-122) for one read, warp-cooperative.
+// s/qv: shared-memory bytes of the (trimmed, corrected) read; mate selects the accumulator half.
+__device__ __forceinline__ void stat_read(const uint8_t *s, const uint8_t *qv, int len, int mate, uint64_t order,
+                                          const QcSmem &sm, const QcDev &qd, const Luts *lutp, const uint8_t *lut2, const uint8_t *lut3,
+                                          int K, int lane, int *error_flag) {
+    if (len <= 0) return;
+    if (len < 5) { if (lane == 0) atomicExch(error_flag, AQC_ERR_TOO_SHORT_STAT); return; }
+    uint32_t *acc = sm.acc + (size_t)mate * QC_CLASSES * sm.max_len;
+    uint32_t *dsc = sm.disc + (size_t)mate * sm.max_len;
+    int gc = 0;
+    const int nk = len - K;                         // k-mers start at i < len - K (quirk Q11)
+    // k-mer plane words of the previous chunk (positions base-32 .. base-1)
+    uint32_t pk0 = 0, pk1 = 0, pkv = 0;
+    const int nchunks = (len + 31) >> 5;
+    for (int c = 0; c <= nchunks; c++) {            // one extra iteration drains the k-mer pipeline
+        const int base = c << 5;
+        const int pos = base + lane;
+        uint32_t k0 = 0, k1 = 0, kv = 0;
+        if (c < nchunks) {
+            bool valid = pos < len;
+            uint32_t b = valid ? s[pos] : 0u;
+            uint32_t l2 = valid ? lut2[b] : 4u;
+            if (valid) {
+                uint32_t q = qv[pos];
+                // discontinuity window (:97-108)
+                int left = pos - 2;
+                if (left < 0) left = 0;
+                else if (pos + 3 >= len) left = len - 5;
+                uint32_t c0 = s[left], c1 = s[left + 1], c2 = s[left + 2], c3 = s[left + 3], c4 = s[left + 4];
+                uint32_t d = (c0 != c1) + (c1 != c2) + (c2 != c3) + (c3 != c4);
+                atomicAdd(&acc[(l2 & 7u) * sm.max_len + pos], (1u << 20) | q);
+                if (d) atomicAdd(&dsc[pos], d);
+            }
+            gc += __popc(__ballot_sync(FULL, valid && (l2 & 8u)));
+            k0 = __ballot_sync(FULL, valid && (l2 & 0x10u));
+            k1 = __ballot_sync(FULL, valid && (l2 & 0x20u));
+            kv = __ballot_sync(FULL, valid && (l2 & 0x40u));
+        }
+        if (c > 0) {
+            // k-mers starting in the previous chunk: i = base - 32 + lane
+            const int i = base - 32 + lane;
+            if (i < nk) {
+                const uint32_t km = (K >= 32) ? 0xffffffffu : ((1u << K) - 1u);
+                uint32_t w0 = __funnelshift_r(pk0, k0, lane) & km;
+                uint32_t w1 = __funnelshift_r(pk1, k1, lane) & km;
+                uint32_t wv = __funnelshift_r(pkv, kv, lane) & km;
+                unsigned long long when = (order << 11) | ((unsigned long long)i << 1);
+                if (wv == km) {
+                    uint32_t idx = (w1 << K) | w0;
+                    // reverse complement: reverse the K positions, complement = invert both bits
+                    uint32_t r0 = (__brev(~w0) >> (32 - K)) & km;
+                    uint32_t r1 = (__brev(~w1) >> (32 - K)) & km;
+                    uint32_t ridx = (r1 << K) | r0;
+                    atomicAdd(&qd.kcnt[idx], 1ULL);
+                    first_min(&qd.kfirst[idx], when);
+                    first_min(&qd.kfirst[ridx], when | 1ULL);
+                } else {
+                    unsigned long long key = 0, rkey = 0;
+                    for (int j = 0; j < K; j++) {
+                        unsigned long long bj = s[i + j];
+                        key = (key << 8) | bj;
+                        rkey |= (unsigned long long)lut3[bj] << (8 * j);
+                    }
+                    if (key == AQC_KMER_NEVER || rkey == AQC_KMER_NEVER) atomicExch(error_flag, AQC_ERR_INVALID);
+                    else {
+                        int h = side_slot(qd, key);
+                        int hr = side_slot(qd, rkey);
+                        if (h < 0 || hr < 0) atomicExch(error_flag, AQC_ERR_KMER_TABLE_FULL);
+                        else {
+                            atomicAdd(&qd.scnt[h], 1ULL);
+                            first_min(&qd.sfirst[h], when);
+                            first_min(&qd.sfirst[hr], when | 1ULL);
+                        }
+                    }
+                }
+            }
+        }
+        pk0 = k0; pk1 = k1; pkv = kv;
+    }
+    if (lane == 0) {
+        atomicAdd(&qd.gchist[gc], 1ULL);            // :112
+        if (nk > 0) atomicAdd(&qd.scal[0], (unsigned long long)nk);   // totalKmer :114
+        atomicAdd(&qd.scal[1], 1ULL);
+    }
+    (void)lutp;
+}
+
+}  // namespace aqc

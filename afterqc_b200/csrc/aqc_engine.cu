@@ -1,0 +1,610 @@
+// aqc_engine.cu -- C-ABI of libafterqc_b200.so (include/afterqc_b200.h) on top of pair_kernel.
+//
+// Host responsibilities only: context + device buffers, tile sizing, the chunked
+// H2D -> kernel -> D2H pipeline for host-resident batches, counter fetch/convert.
+// There is NO CPU implementation of the hot path in this library.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include "aqc_kernel.cuh"
+
+using namespace aqc;
+
+namespace {
+
+thread_local char g_create_err[256] = "";
+
+struct QcHost {      // owning handles of one QC slot's device arrays
+    QcDev d;
+    size_t dense_n;
+    uint32_t side_cap;
+};
+
+struct Staging {     // device staging of one host chunk
+    uint8_t *col[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t *off[2] = {nullptr, nullptr};
+    void *res = nullptr;
+    size_t col_cap = 0, off_cap = 0, res_cap = 0;
+    cudaEvent_t h2d_done = nullptr, k_done = nullptr, d2h_done = nullptr;
+};
+
+}  // namespace
+
+struct aqc_ctx {
+    int device = 0;
+    aqc_params p;
+    int sm_count = 148;
+    cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
+    unsigned long long *d_counters = nullptr;
+    QcHost qc[AQC_NUM_QC];
+    Luts *d_luts = nullptr;
+    int *d_error = nullptr;
+    uint32_t *d_maxlen = nullptr;
+    Staging stg[2];
+    uint32_t chunk_pairs = 1u << 18;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    size_t ev_used = 0;
+    uint64_t launches = 0;
+    int sticky_err = 0;
+    char err[256] = "";
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            snprintf(ctx->err, sizeof ctx->err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return AQC_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+int fail(aqc_ctx *ctx, int code, const char *msg) {
+    snprintf(ctx->err, sizeof ctx->err, "%s", msg);
+    return code;
+}
+
+void fill_luts(Luts &L) {
+    for (int b = 0; b < 256; b++) {
+        uint8_t c1 = 15, crc = 4, comp = 'N';
+        switch (b) {
+            case 'A': c1 = 0; crc = 3; comp = 'T'; break;
+            case 'C': c1 = 1; crc = 2; comp = 'G'; break;
+            case 'G': c1 = 2; crc = 1; comp = 'C'; break;
+            case 'T': c1 = 3; crc = 0; comp = 'A'; break;
+            case 'N': c1 = 4; crc = 4; comp = 'N'; break;
+            case 'a': c1 = 8; crc = 11; comp = 't'; break;
+            case 'c': c1 = 9; crc = 10; comp = 'g'; break;
+            case 'g': c1 = 10; crc = 9; comp = 'c'; break;
+            case 't': c1 = 11; crc = 8; comp = 'a'; break;
+            case '\n': c1 = 12; crc = 12; comp = '\n'; break;
+            default: break;
+        }
+        L.lut1[b] = (uint8_t)(c1 | (crc << 4));
+        L.lut3[b] = comp;
+        uint8_t l2 = 4;   // class "other"
+        switch (b) {
+            case 'A': l2 = 0 | (0 << 4) | 0x40; break;
+            case 'T': l2 = 1 | (3 << 4) | 0x40; break;
+            case 'C': l2 = 2 | 8 | (1 << 4) | 0x40; break;
+            case 'G': l2 = 3 | 8 | (2 << 4) | 0x40; break;
+            default: break;
+        }
+        if (b == 'A' || b == 'T' || b == 'C' || b == 'G' || b == 'a' || b == 't' || b == 'c' || b == 'g' || b == 'N') l2 |= 0x80;
+        L.lut2[b] = l2;
+    }
+}
+
+int check_params(const aqc_params *p, char *err, size_t errn) {
+    if (p->qc_kmer < 1 || p->qc_kmer > AQC_MAX_KMER) { snprintf(err, errn, "qc_kmer %d outside 1..%d", p->qc_kmer, AQC_MAX_KMER); return AQC_ERR_INVALID; }
+    if (p->trim_front < 0 || p->trim_tail < 0 || p->trim_front2 < 0 || p->trim_tail2 < 0) { snprintf(err, errn, "negative trim value (resolve auto-trim on the host first)"); return AQC_ERR_INVALID; }
+    return 0;
+}
+
+size_t smem_bytes_for(int P, int col_cap, int max_len) {
+    int off_cap = ((P + 8) * 4 + 15) & ~15;
+    size_t stage = ((size_t)4 * col_cap + 2 * off_cap + 127) & ~(size_t)127;
+    size_t acc = (size_t)(2 * QC_CLASSES * max_len + 2 * max_len + 2 * (max_len + 1)) * 4;
+    return NSTAGES * stage + 768 + acc + 64;
+}
+
+int alloc_qc(aqc_ctx *ctx, QcHost &q) {
+    q.dense_n = (size_t)1 << (2 * ctx->p.qc_kmer);
+    int lg = ctx->p.kmer_side_log2 > 0 ? ctx->p.kmer_side_log2 : 20;
+    if (lg < 4 || lg > 30) return fail(ctx, AQC_ERR_INVALID, "kmer_side_log2 out of range");
+    q.side_cap = 1u << lg;
+    q.d.smask = q.side_cap - 1;
+    q.d.valid = 1;
+    CK(cudaMalloc(&q.d.cls_cnt, sizeof(unsigned long long) * QC_CLASSES * AQC_MAX_LEN));
+    CK(cudaMalloc(&q.d.cls_qsum, sizeof(unsigned long long) * QC_CLASSES * AQC_MAX_LEN));
+    CK(cudaMalloc(&q.d.disc, sizeof(unsigned long long) * AQC_MAX_LEN));
+    CK(cudaMalloc(&q.d.gchist, sizeof(unsigned long long) * (AQC_MAX_LEN + 1)));
+    CK(cudaMalloc(&q.d.scal, sizeof(unsigned long long) * 2));
+    CK(cudaMalloc(&q.d.kcnt, sizeof(unsigned long long) * q.dense_n));
+    CK(cudaMalloc(&q.d.kfirst, sizeof(unsigned long long) * q.dense_n));
+    CK(cudaMalloc(&q.d.skeys, sizeof(unsigned long long) * q.side_cap));
+    CK(cudaMalloc(&q.d.scnt, sizeof(unsigned long long) * q.side_cap));
+    CK(cudaMalloc(&q.d.sfirst, sizeof(unsigned long long) * q.side_cap));
+    return 0;
+}
+
+int zero_qc(aqc_ctx *ctx, QcHost &q) {
+    cudaStream_t s = ctx->compute;
+    CK(cudaMemsetAsync(q.d.cls_cnt, 0, sizeof(unsigned long long) * QC_CLASSES * AQC_MAX_LEN, s));
+    CK(cudaMemsetAsync(q.d.cls_qsum, 0, sizeof(unsigned long long) * QC_CLASSES * AQC_MAX_LEN, s));
+    CK(cudaMemsetAsync(q.d.disc, 0, sizeof(unsigned long long) * AQC_MAX_LEN, s));
+    CK(cudaMemsetAsync(q.d.gchist, 0, sizeof(unsigned long long) * (AQC_MAX_LEN + 1), s));
+    CK(cudaMemsetAsync(q.d.scal, 0, sizeof(unsigned long long) * 2, s));
+    CK(cudaMemsetAsync(q.d.kcnt, 0, sizeof(unsigned long long) * q.dense_n, s));
+    CK(cudaMemsetAsync(q.d.kfirst, 0xFF, sizeof(unsigned long long) * q.dense_n, s));
+    CK(cudaMemsetAsync(q.d.skeys, 0xFF, sizeof(unsigned long long) * q.side_cap, s));
+    CK(cudaMemsetAsync(q.d.scnt, 0, sizeof(unsigned long long) * q.side_cap, s));
+    CK(cudaMemsetAsync(q.d.sfirst, 0xFF, sizeof(unsigned long long) * q.side_cap, s));
+    return 0;
+}
+
+void free_qc(QcHost &q) {
+    cudaFree(q.d.cls_cnt); cudaFree(q.d.cls_qsum); cudaFree(q.d.disc); cudaFree(q.d.gchist); cudaFree(q.d.scal);
+    cudaFree(q.d.kcnt); cudaFree(q.d.kfirst); cudaFree(q.d.skeys); cudaFree(q.d.scnt); cudaFree(q.d.sfirst);
+}
+
+int poll_error(aqc_ctx *ctx) {   // requires the compute stream to be idle
+    int e = 0;
+    CK(cudaMemcpy(&e, ctx->d_error, sizeof e, cudaMemcpyDeviceToHost));
+    if (e && !ctx->sticky_err) {
+        ctx->sticky_err = e;
+        const char *m = e == AQC_ERR_TOO_LONG ? "a read is longer than AQC_MAX_LEN" :
+                        e == AQC_ERR_KMER_TABLE_FULL ? "non-ACGT k-mer side table full (raise kmer_side_log2)" :
+                        e == AQC_ERR_TOO_SHORT_STAT ? "a read of 1..4 bases reached statRead (the reference raises IndexError)" :
+                        "device-side domain error";
+        snprintf(ctx->err, sizeof ctx->err, "%s", m);
+    }
+    return ctx->sticky_err;
+}
+
+struct DevBatch {    // device-visible view of a (chunk of a) batch
+    const uint8_t *seq1, *qual1, *seq2, *qual2;
+    const uint32_t *off1, *off2;
+    uint32_t n;
+    uint64_t first_index;
+    int max_len;
+};
+
+struct LaunchExtra {
+    int mode;
+    int qc1, qc2;                 // slots (or -1)
+    uint64_t stat_lo, stat_hi, order_base;
+    void *out;                    // results / ops (device)
+};
+
+int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t stream, bool timed) {
+    if (b.n == 0) return 0;
+    if (b.max_len > AQC_MAX_LEN) { ctx->sticky_err = AQC_ERR_TOO_LONG; return fail(ctx, AQC_ERR_TOO_LONG, "a read is longer than AQC_MAX_LEN"); }
+    KArgs A;
+    memset(&A, 0, sizeof A);
+    A.seq1 = b.seq1; A.qual1 = b.qual1; A.seq2 = b.seq2; A.qual2 = b.qual2; A.off1 = b.off1; A.off2 = b.off2;
+    A.n = b.n; A.first_index = b.first_index;
+    int maxl = std::max(b.max_len, 8);
+    // tile: <= 32 pairs and <= ~24 KB of column bytes per mate column group
+    int P = std::min(MAX_TILE_PAIRS, std::max(1, (24 * 1024) / (4 * maxl)));
+    // small batches: shrink tiles so that every SM gets work
+    while (P > 8 && (b.n + P - 1) / P < (uint32_t)ctx->sm_count * 2) P >>= 1;
+    A.tile_pairs = P;
+    A.col_cap = (P * maxl + 32 + 15) & ~15;
+    A.max_len = maxl;
+    A.num_tiles = (b.n + P - 1) / P;
+    A.mode = x.mode;
+    A.p = ctx->p;
+    A.stat_lo = x.stat_lo; A.stat_hi = x.stat_hi; A.order_base = x.order_base;
+    A.results = x.mode == MODE_FILTER ? (aqc_result *)x.out : nullptr;
+    A.ops = x.mode == MODE_OPS ? (aqc_ops *)x.out : nullptr;
+    A.counters = ctx->d_counters;
+    A.error_flag = ctx->d_error;
+    A.luts = ctx->d_luts;
+    for (int m = 0; m < 2; m++) {
+        int slot = m == 0 ? x.qc1 : x.qc2;
+        if (slot >= 0) { A.qc[m] = ctx->qc[slot].d; A.qc[m].valid = 1; }
+        else { A.qc[m] = ctx->qc[0].d; A.qc[m].valid = 0; }
+    }
+    size_t smem = smem_bytes_for(P, A.col_cap, maxl);
+    if (smem > 227 * 1024) return fail(ctx, AQC_ERR_INVALID, "tile does not fit shared memory");
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_kernel, THREADS, smem));
+    if (occ < 1) occ = 1;
+    uint32_t grid = std::min<uint32_t>(A.num_tiles, (uint32_t)(ctx->sm_count * occ));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (timed) {
+        if (ctx->ev_used == ctx->ev_pool.size()) {
+            cudaEvent_t a, c;
+            CK(cudaEventCreate(&a)); CK(cudaEventCreate(&c));
+            ctx->ev_pool.push_back({a, c});
+        }
+        e0 = ctx->ev_pool[ctx->ev_used].first; e1 = ctx->ev_pool[ctx->ev_used].second;
+        ctx->ev_used++;
+        CK(cudaEventRecord(e0, stream));
+    }
+    pair_kernel<<<grid, THREADS, smem, stream>>>(A);
+    CK(cudaGetLastError());
+    if (timed) CK(cudaEventRecord(e1, stream));
+    ctx->launches++;
+    return 0;
+}
+
+int ensure_staging(aqc_ctx *ctx, Staging &s, size_t col_bytes, size_t off_entries, size_t res_bytes) {
+    if (!s.h2d_done) {
+        CK(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
+    }
+    if (col_bytes > s.col_cap) {
+        for (int k = 0; k < 4; k++) { cudaFree(s.col[k]); s.col[k] = nullptr; }
+        size_t cap = col_bytes + col_bytes / 4 + 256;
+        for (int k = 0; k < 4; k++) CK(cudaMalloc(&s.col[k], cap));
+        s.col_cap = cap;
+    }
+    if (off_entries > s.off_cap) {
+        for (int k = 0; k < 2; k++) { cudaFree(s.off[k]); s.off[k] = nullptr; }
+        size_t cap = off_entries + 64;
+        for (int k = 0; k < 2; k++) CK(cudaMalloc(&s.off[k], cap * 4));
+        s.off_cap = cap;
+    }
+    if (res_bytes > s.res_cap) {
+        cudaFree(s.res); s.res = nullptr;
+        CK(cudaMalloc(&s.res, res_bytes + 256));
+        s.res_cap = res_bytes;
+    }
+    return 0;
+}
+
+// host-resident batch: chunked, double-buffered H2D -> kernel -> D2H
+int run_host(aqc_ctx *ctx, const aqc_batch *b, const LaunchExtra &x0, void *out_host, size_t out_elem) {
+    const bool paired = b->seq2 != nullptr;
+    ctx->ev_used = 0;
+    uint32_t done = 0;
+    int slot = 0;
+    bool used[2] = {false, false};
+    while (done < b->n) {
+        uint32_t lo = done, hi = std::min(b->n, lo + ctx->chunk_pairs);
+        uint32_t cn = hi - lo;
+        uint32_t a1 = b->off1[lo], e1 = b->off1[hi], g1 = a1 & ~15u;
+        uint32_t a2 = 0, e2 = 0, g2 = 0;
+        if (paired) { a2 = b->off2[lo]; e2 = b->off2[hi]; g2 = a2 & ~15u; }
+        int maxl = 0;
+        for (uint32_t i = lo; i < hi; i++) {
+            maxl = std::max<int>(maxl, (int)(b->off1[i + 1] - b->off1[i]));
+            if (paired) maxl = std::max<int>(maxl, (int)(b->off2[i + 1] - b->off2[i]));
+        }
+        Staging &s = ctx->stg[slot];
+        if (used[slot]) CK(cudaEventSynchronize(s.d2h_done));    // slot free again
+        size_t cb = std::max<size_t>(e1 - g1, paired ? (size_t)(e2 - g2) : 0) + 64;
+        int rc = ensure_staging(ctx, s, cb, (size_t)cn + 8, out_host ? (size_t)cn * out_elem : 0);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(s.col[0], b->seq1 + g1, e1 - g1, cudaMemcpyHostToDevice, ctx->copy_in));
+        CK(cudaMemcpyAsync(s.col[1], b->qual1 + g1, e1 - g1, cudaMemcpyHostToDevice, ctx->copy_in));
+        CK(cudaMemcpyAsync(s.off[0], b->off1 + lo, (size_t)(cn + 1) * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+        if (paired) {
+            CK(cudaMemcpyAsync(s.col[2], b->seq2 + g2, e2 - g2, cudaMemcpyHostToDevice, ctx->copy_in));
+            CK(cudaMemcpyAsync(s.col[3], b->qual2 + g2, e2 - g2, cudaMemcpyHostToDevice, ctx->copy_in));
+            CK(cudaMemcpyAsync(s.off[1], b->off2 + lo, (size_t)(cn + 1) * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+        }
+        CK(cudaEventRecord(s.h2d_done, ctx->copy_in));
+        CK(cudaStreamWaitEvent(ctx->compute, s.h2d_done, 0));
+        DevBatch d;
+        // virtual column bases so that the absolute offsets of the chunk index the staged bytes
+        d.seq1 = s.col[0] - g1; d.qual1 = s.col[1] - g1;
+        d.seq2 = paired ? s.col[2] - g2 : nullptr; d.qual2 = paired ? s.col[3] - g2 : nullptr;
+        d.off1 = s.off[0]; d.off2 = paired ? s.off[1] : nullptr;
+        d.n = cn; d.first_index = b->first_index + lo; d.max_len = maxl;
+        LaunchExtra x = x0;
+        x.out = s.res;
+        rc = launch(ctx, d, x, ctx->compute, true);
+        if (rc) return rc;
+        CK(cudaEventRecord(s.k_done, ctx->compute));
+        CK(cudaStreamWaitEvent(ctx->copy_out, s.k_done, 0));
+        if (out_host)
+            CK(cudaMemcpyAsync((uint8_t *)out_host + (size_t)lo * out_elem, s.res, (size_t)cn * out_elem, cudaMemcpyDeviceToHost, ctx->copy_out));
+        CK(cudaEventRecord(s.d2h_done, ctx->copy_out));
+        used[slot] = true;
+        slot ^= 1;
+        done = hi;
+    }
+    CK(cudaStreamSynchronize(ctx->copy_out));
+    CK(cudaStreamSynchronize(ctx->compute));
+    int e = poll_error(ctx);
+    return e;
+}
+
+int run_device(aqc_ctx *ctx, const aqc_batch *b, const LaunchExtra &x) {
+    ctx->ev_used = 0;
+    DevBatch d;
+    d.seq1 = b->seq1; d.qual1 = b->qual1; d.seq2 = b->seq2; d.qual2 = b->qual2; d.off1 = b->off1; d.off2 = b->off2;
+    d.n = b->n; d.first_index = b->first_index;
+    int hint = (int)(b->flags & 0xFFFFu);
+    if (hint > 0) d.max_len = hint;
+    else {
+        uint32_t m = 0;
+        CK(cudaMemsetAsync(ctx->d_maxlen, 0, 4, ctx->compute));
+        if (b->n) {
+            maxlen_kernel<<<std::min<uint32_t>((b->n + 255) / 256, 1024u), 256, 0, ctx->compute>>>(b->off1, b->off2, b->n, ctx->d_maxlen);
+            ctx->launches++;
+        }
+        CK(cudaMemcpyAsync(&m, ctx->d_maxlen, 4, cudaMemcpyDeviceToHost, ctx->compute));
+        CK(cudaStreamSynchronize(ctx->compute));
+        d.max_len = (int)m;
+    }
+    return launch(ctx, d, x, ctx->compute, true);
+}
+
+int check_batch(aqc_ctx *ctx, const aqc_batch *b, int mem) {
+    if (!ctx || !b) return AQC_ERR_INVALID;
+    if (mem != AQC_MEM_HOST && mem != AQC_MEM_DEVICE) return fail(ctx, AQC_ERR_INVALID, "bad memory space");
+    if (b->n && (!b->seq1 || !b->qual1 || !b->off1)) return fail(ctx, AQC_ERR_INVALID, "null mate-1 column");
+    if (b->seq2 && (!b->qual2 || !b->off2)) return fail(ctx, AQC_ERR_INVALID, "incomplete mate-2 columns");
+    if (ctx->sticky_err) return ctx->sticky_err;
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int aqc_abi_version(void) { return AQC_ABI_VERSION; }
+
+const char *aqc_last_error(const aqc_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
+    if (!params || !out) { snprintf(g_create_err, sizeof g_create_err, "null argument"); return AQC_ERR_INVALID; }
+    int rc = check_params(params, g_create_err, sizeof g_create_err);
+    if (rc) return rc;
+    aqc_ctx *ctx = new aqc_ctx();
+    ctx->p = *params;
+    auto bail = [&](int code) { snprintf(g_create_err, sizeof g_create_err, "%s", ctx->err); aqc_destroy(ctx); return code; };
+    cudaError_t e;
+    if (device < 0) { e = cudaGetDevice(&device); if (e != cudaSuccess) { snprintf(ctx->err, sizeof ctx->err, "cudaGetDevice: %s", cudaGetErrorString(e)); return bail(AQC_ERR_CUDA); } }
+    ctx->device = device;
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { snprintf(ctx->err, sizeof ctx->err, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e)); return bail(AQC_ERR_CUDA); }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { snprintf(ctx->err, sizeof ctx->err, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return bail(AQC_ERR_CUDA); }
+    ctx->sm_count = prop.multiProcessorCount;
+    auto init = [&]() -> int {
+        CK(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        CK(cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * AQC_C_TOTAL));
+        CK(cudaMalloc(&ctx->d_luts, sizeof(Luts)));
+        CK(cudaMalloc(&ctx->d_error, sizeof(int)));
+        CK(cudaMalloc(&ctx->d_maxlen, sizeof(uint32_t)));
+        Luts L; fill_luts(L);
+        CK(cudaMemcpy(ctx->d_luts, &L, sizeof L, cudaMemcpyHostToDevice));
+        CK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        for (int s = 0; s < AQC_NUM_QC; s++) { int r = alloc_qc(ctx, ctx->qc[s]); if (r) return r; }
+        return aqc_reset(ctx);
+    };
+    rc = init();
+    if (rc) return bail(rc);
+    *out = ctx;
+    return 0;
+}
+
+void aqc_destroy(aqc_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->compute) cudaStreamSynchronize(ctx->compute);
+    for (int s = 0; s < AQC_NUM_QC; s++) free_qc(ctx->qc[s]);
+    for (auto &st : ctx->stg) {
+        for (int k = 0; k < 4; k++) cudaFree(st.col[k]);
+        for (int k = 0; k < 2; k++) cudaFree(st.off[k]);
+        cudaFree(st.res);
+        if (st.h2d_done) { cudaEventDestroy(st.h2d_done); cudaEventDestroy(st.k_done); cudaEventDestroy(st.d2h_done); }
+    }
+    for (auto &ev : ctx->ev_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    cudaFree(ctx->d_counters); cudaFree(ctx->d_luts); cudaFree(ctx->d_error); cudaFree(ctx->d_maxlen);
+    if (ctx->compute) cudaStreamDestroy(ctx->compute);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    delete ctx;
+}
+
+int aqc_set_params(aqc_ctx *ctx, const aqc_params *params) {
+    if (!ctx || !params) return AQC_ERR_INVALID;
+    int rc = check_params(params, ctx->err, sizeof ctx->err);
+    if (rc) return rc;
+    if (params->qc_kmer != ctx->p.qc_kmer) return fail(ctx, AQC_ERR_INVALID, "qc_kmer cannot change after create");
+    int keep = ctx->p.kmer_side_log2;
+    ctx->p = *params;
+    ctx->p.kmer_side_log2 = keep;
+    return 0;
+}
+
+int aqc_reset(aqc_ctx *ctx) {
+    if (!ctx) return AQC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * AQC_C_TOTAL, ctx->compute));
+    CK(cudaMemsetAsync(ctx->d_error, 0, sizeof(int), ctx->compute));
+    for (int s = 0; s < AQC_NUM_QC; s++) { int r = zero_qc(ctx, ctx->qc[s]); if (r) return r; }
+    CK(cudaStreamSynchronize(ctx->compute));
+    ctx->sticky_err = 0; ctx->err[0] = 0;
+    return 0;
+}
+
+int aqc_reset_filter(aqc_ctx *ctx) {
+    if (!ctx) return AQC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * AQC_C_TOTAL, ctx->compute));
+    for (int s = AQC_QC_R1_POST; s < AQC_NUM_QC; s++) { int r = zero_qc(ctx, ctx->qc[s]); if (r) return r; }
+    CK(cudaStreamSynchronize(ctx->compute));
+    return 0;
+}
+
+int aqc_host_alloc(size_t bytes, void **out) {
+    if (!out) return AQC_ERR_INVALID;
+    return cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? 0 : AQC_ERR_NOMEM;
+}
+void aqc_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int aqc_device_alloc(aqc_ctx *ctx, size_t bytes, void **out) {
+    if (!ctx || !out) return AQC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMalloc(out, bytes ? bytes : 16));
+    return 0;
+}
+void aqc_device_free(aqc_ctx *ctx, void *p) { if (ctx && p) { cudaSetDevice(ctx->device); cudaFree(p); } }
+int aqc_memcpy_h2d(aqc_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx) return AQC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+int aqc_memcpy_d2h(aqc_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx) return AQC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->compute));
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int aqc_stat_reads(aqc_ctx *ctx, const aqc_batch *batch, int mem, int qc1, int qc2, uint64_t stat_lo, uint64_t stat_hi, uint64_t order_base) {
+    int rc = check_batch(ctx, batch, mem);
+    if (rc) return rc;
+    if (qc1 >= AQC_NUM_QC || qc2 >= AQC_NUM_QC) return fail(ctx, AQC_ERR_INVALID, "bad QC slot");
+    CK(cudaSetDevice(ctx->device));
+    LaunchExtra x; x.mode = MODE_STAT; x.qc1 = qc1; x.qc2 = batch->seq2 ? qc2 : -1;
+    x.stat_lo = stat_lo; x.stat_hi = stat_hi; x.order_base = order_base; x.out = nullptr;
+    return mem == AQC_MEM_HOST ? run_host(ctx, batch, x, nullptr, 0) : run_device(ctx, batch, x);
+}
+
+int aqc_filter_pairs(aqc_ctx *ctx, const aqc_batch *batch, int mem, aqc_result *results) {
+    int rc = check_batch(ctx, batch, mem);
+    if (rc) return rc;
+    if (!results && batch->n) return fail(ctx, AQC_ERR_INVALID, "null results");
+    CK(cudaSetDevice(ctx->device));
+    LaunchExtra x; x.mode = MODE_FILTER; x.qc1 = AQC_QC_R1_POST; x.qc2 = batch->seq2 ? AQC_QC_R2_POST : -1;
+    x.stat_lo = 0; x.stat_hi = 0; x.order_base = 0; x.out = results;
+    return mem == AQC_MEM_HOST ? run_host(ctx, batch, x, results, sizeof(aqc_result)) : run_device(ctx, batch, x);
+}
+
+int aqc_ops_pairs(aqc_ctx *ctx, const aqc_batch *batch, int mem, aqc_ops *out) {
+    int rc = check_batch(ctx, batch, mem);
+    if (rc) return rc;
+    if (!out && batch->n) return fail(ctx, AQC_ERR_INVALID, "null output");
+    CK(cudaSetDevice(ctx->device));
+    LaunchExtra x; x.mode = MODE_OPS; x.qc1 = -1; x.qc2 = -1;
+    x.stat_lo = 0; x.stat_hi = 0; x.order_base = 0; x.out = out;
+    return mem == AQC_MEM_HOST ? run_host(ctx, batch, x, out, sizeof(aqc_ops)) : run_device(ctx, batch, x);
+}
+
+int aqc_sync(aqc_ctx *ctx) {
+    if (!ctx) return AQC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->compute));
+    return poll_error(ctx);
+}
+
+int aqc_get_counters(aqc_ctx *ctx, int64_t *out) {
+    if (!ctx || !out) return AQC_ERR_INVALID;
+    int rc = aqc_sync(ctx);
+    CK(cudaMemcpy(out, ctx->d_counters, sizeof(int64_t) * AQC_C_TOTAL, cudaMemcpyDeviceToHost));
+    return rc;
+}
+
+int aqc_add_counters(aqc_ctx *ctx, const int64_t *in) {
+    if (!ctx || !in) return AQC_ERR_INVALID;
+    std::vector<int64_t> cur(AQC_C_TOTAL);
+    int rc = aqc_get_counters(ctx, cur.data());
+    if (rc) return rc;
+    for (int i = 0; i < AQC_C_TOTAL; i++) cur[i] += in[i];
+    CK(cudaMemcpy(ctx->d_counters, cur.data(), sizeof(int64_t) * AQC_C_TOTAL, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int aqc_get_qc(aqc_ctx *ctx, int slot, aqc_qc_counters *out) {
+    if (!ctx || !out || slot < 0 || slot >= AQC_NUM_QC) return AQC_ERR_INVALID;
+    int rc = aqc_sync(ctx);
+    QcHost &q = ctx->qc[slot];
+    std::vector<unsigned long long> cnt(QC_CLASSES * AQC_MAX_LEN), qs(QC_CLASSES * AQC_MAX_LEN), disc(AQC_MAX_LEN), gch(AQC_MAX_LEN + 1);
+    unsigned long long scal[2];
+    CK(cudaMemcpy(cnt.data(), q.d.cls_cnt, cnt.size() * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(qs.data(), q.d.cls_qsum, qs.size() * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(disc.data(), q.d.disc, disc.size() * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(gch.data(), q.d.gchist, gch.size() * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(scal, q.d.scal, sizeof scal, cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof *out);
+    for (int i = 0; i < AQC_MAX_LEN; i++) {
+        int64_t tn = 0, tq = 0;
+        for (int c = 0; c < QC_CLASSES; c++) { tn += (int64_t)cnt[c * AQC_MAX_LEN + i]; tq += (int64_t)qs[c * AQC_MAX_LEN + i]; }
+        out->totalNum[i] = tn;
+        out->totalQual[i] = tq - 33 * tn;                       // util.qualNum: ord(q) - 33
+        for (int c = 0; c < 4; c++) {
+            out->baseCounts[c][i] = (int64_t)cnt[c * AQC_MAX_LEN + i];
+            out->baseTotalQual[c][i] = (int64_t)qs[c * AQC_MAX_LEN + i] - 33 * (int64_t)cnt[c * AQC_MAX_LEN + i];
+        }
+        out->totalDiscontinuity[i] = (int64_t)disc[i];
+    }
+    for (int i = 0; i <= AQC_MAX_LEN; i++) out->gcHistogram[i] = (int64_t)gch[i];
+    out->totalKmer = (int64_t)scal[0];
+    out->reads = (int64_t)scal[1];
+    return rc;
+}
+
+int aqc_get_kmer_dense(aqc_ctx *ctx, int slot, uint64_t *counts, uint64_t *first) {
+    if (!ctx || !counts || !first || slot < 0 || slot >= AQC_NUM_QC) return AQC_ERR_INVALID;
+    int rc = aqc_sync(ctx);
+    QcHost &q = ctx->qc[slot];
+    const int K = ctx->p.qc_kmer;
+    std::vector<unsigned long long> c(q.dense_n), f(q.dense_n);
+    CK(cudaMemcpy(c.data(), q.d.kcnt, q.dense_n * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(f.data(), q.d.kfirst, q.dense_n * 8, cudaMemcpyDeviceToHost));
+    // internal index (plane1 bits << K) | plane0 bits, bit t = base t  ->  natural index, base 0 most significant
+    for (size_t in = 0; in < q.dense_n; in++) {
+        uint32_t w0 = (uint32_t)in & ((1u << K) - 1u), w1 = (uint32_t)(in >> K);
+        size_t nat = 0;
+        for (int t = 0; t < K; t++) {
+            uint32_t code = ((w0 >> t) & 1u) | (((w1 >> t) & 1u) << 1);
+            nat |= (size_t)code << (2 * (K - 1 - t));
+        }
+        counts[nat] = c[in];
+        first[nat] = f[in];
+    }
+    return rc;
+}
+
+int aqc_get_kmer_side(aqc_ctx *ctx, int slot, uint64_t *keys, uint64_t *counts, uint64_t *first, uint32_t cap, uint32_t *n_out) {
+    if (!ctx || !n_out || slot < 0 || slot >= AQC_NUM_QC) return AQC_ERR_INVALID;
+    int rc = aqc_sync(ctx);
+    QcHost &q = ctx->qc[slot];
+    std::vector<unsigned long long> k(q.side_cap);
+    CK(cudaMemcpy(k.data(), q.d.skeys, (size_t)q.side_cap * 8, cudaMemcpyDeviceToHost));
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < q.side_cap; i++) if (k[i] != AQC_KMER_NEVER) n++;
+    *n_out = n;
+    if (cap == 0 && !keys) return rc;
+    if (cap < n || !keys || !counts || !first) return fail(ctx, AQC_ERR_INVALID, "side-table output too small");
+    std::vector<unsigned long long> c(q.side_cap), f(q.side_cap);
+    CK(cudaMemcpy(c.data(), q.d.scnt, (size_t)q.side_cap * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(f.data(), q.d.sfirst, (size_t)q.side_cap * 8, cudaMemcpyDeviceToHost));
+    uint32_t j = 0;
+    for (uint32_t i = 0; i < q.side_cap; i++)
+        if (k[i] != AQC_KMER_NEVER) { keys[j] = k[i]; counts[j] = c[i]; first[j] = f[i]; j++; }
+    return rc;
+}
+
+uint64_t aqc_launch_count(const aqc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+float aqc_last_kernel_ms(const aqc_ctx *ctx) {
+    if (!ctx) return 0.f;
+    float total = 0.f;
+    for (size_t i = 0; i < ctx->ev_used; i++) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ctx->ev_pool[i].second) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, ctx->ev_pool[i].first, ctx->ev_pool[i].second) == cudaSuccess) total += ms;
+    }
+    return total;
+}
+
+}  // extern "C"

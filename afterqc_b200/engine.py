@@ -1,0 +1,190 @@
+"""Engine: python face of the C-ABI (include/afterqc_b200.h).
+
+Mirrors the reference's operator interface for the hot path: the batch methods are what the
+pipeline uses; overlap()/hasPolyX()/lowQualityNum()/nNumber() are the per-read operators of
+util.py:88 and preprocesser.py:30,61,70 routed through the GPU (for operator-level parity tests).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi, _native
+from .batch import PackedBatch
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__("afterqc_b200 engine error %d (%s): %s" % (code, _abi.ERR_NAMES.get(code, "?"), msg))
+        self.code = code
+
+
+class DeviceBatch:
+    """A batch resident in HBM (columns uploaded once)."""
+
+    def __init__(self, engine, host):
+        self.engine = engine
+        self.n = host.n
+        self.first_index = host.first_index
+        self.paired = host.paired
+        self.max_len = host.max_len()
+        self._ptrs = []
+        L = engine._L
+
+        def up(arr, extra=64):
+            p = C.c_void_p()
+            nbytes = arr.nbytes
+            engine._check(L.aqc_device_alloc(engine._h, nbytes + extra, C.byref(p)))
+            engine._check(L.aqc_memcpy_h2d(engine._h, p, arr.ctypes.data, nbytes))
+            self._ptrs.append(p)
+            return p
+
+        self.seq1, self.qual1, self.off1 = up(host.seq1), up(host.qual1), up(host.off1)
+        if host.paired:
+            self.seq2, self.qual2, self.off2 = up(host.seq2), up(host.qual2), up(host.off2)
+        else:
+            self.seq2 = self.qual2 = self.off2 = None
+        self.results = C.c_void_p()
+        engine._check(L.aqc_device_alloc(engine._h, max(1, self.n) * 32, C.byref(self.results)))
+        self._ptrs.append(self.results)
+
+    def as_struct(self):
+        b = _abi.Batch()
+        b.first_index = self.first_index
+        b.n = self.n
+        b.flags = self.max_len
+        b.seq1, b.qual1, b.off1 = self.seq1, self.qual1, self.off1
+        b.seq2, b.qual2, b.off2 = self.seq2, self.qual2, self.off2
+        return b
+
+    def free(self):
+        for p in self._ptrs:
+            self.engine._L.aqc_device_free(self.engine._h, p)
+        self._ptrs = []
+
+
+class Engine:
+    def __init__(self, params, device=-1):
+        self._L = _native.lib()
+        self.params = params
+        self._h = C.c_void_p()
+        rc = self._L.aqc_create(device, C.byref(params), C.byref(self._h))
+        if rc:
+            raise EngineError(rc, self._L.aqc_last_error(None).decode())
+
+    # ---- lifecycle -----------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.aqc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise EngineError(rc, self._L.aqc_last_error(self._h).decode())
+
+    def set_params(self, params):
+        self.params = params
+        self._check(self._L.aqc_set_params(self._h, C.byref(params)))
+
+    def reset(self):
+        self._check(self._L.aqc_reset(self._h))
+
+    def reset_filter_counters(self):
+        self._check(self._L.aqc_reset_filter(self._h))
+
+    def sync(self):
+        self._check(self._L.aqc_sync(self._h))
+
+    def upload(self, host_batch):
+        return DeviceBatch(self, host_batch)
+
+    # ---- hot path --------------------------------------------------------------------------
+    def stat_reads(self, batch, qc1, qc2, stat_lo=0, stat_hi=(1 << 63), order_base=0):
+        mem = _abi.MEM_DEVICE if isinstance(batch, DeviceBatch) else _abi.MEM_HOST
+        b = batch.as_struct()
+        self._check(self._L.aqc_stat_reads(self._h, C.byref(b), mem, qc1, qc2, stat_lo, stat_hi, order_base))
+
+    def filter_pairs(self, batch, out=None):
+        """Host batch: returns the result records (copies inside).  DeviceBatch: asynchronous, results stay in HBM."""
+        if isinstance(batch, DeviceBatch):
+            b = batch.as_struct()
+            self._check(self._L.aqc_filter_pairs(self._h, C.byref(b), _abi.MEM_DEVICE, batch.results))
+            return None
+        res = out if out is not None else np.zeros(batch.n, dtype=_abi.RESULT_DTYPE)
+        b = batch.as_struct()
+        self._check(self._L.aqc_filter_pairs(self._h, C.byref(b), _abi.MEM_HOST, res.ctypes.data))
+        return res
+
+    def fetch_results(self, dbatch):
+        res = np.zeros(dbatch.n, dtype=_abi.RESULT_DTYPE)
+        if dbatch.n:
+            self._check(self._L.aqc_memcpy_d2h(self._h, res.ctypes.data, dbatch.results, res.nbytes))
+        return res
+
+    def ops_pairs(self, batch):
+        res = np.zeros(batch.n, dtype=_abi.OPS_DTYPE)
+        b = batch.as_struct()
+        self._check(self._L.aqc_ops_pairs(self._h, C.byref(b), _abi.MEM_HOST, res.ctypes.data))
+        return res
+
+    # ---- fetch ---------------------------------------------------------------------------
+    def counters(self):
+        out = np.zeros(_abi.C_TOTAL, dtype=np.int64)
+        self._check(self._L.aqc_get_counters(self._h, out.ctypes.data))
+        return out
+
+    def add_counters(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.int64)
+        self._check(self._L.aqc_add_counters(self._h, arr.ctypes.data))
+
+    def qc(self, slot):
+        out = np.zeros(1, dtype=_abi.QC_DTYPE)
+        self._check(self._L.aqc_get_qc(self._h, slot, out.ctypes.data))
+        return out[0]
+
+    def kmers(self, slot):
+        nk = 1 << (2 * self.params.qc_kmer)
+        cnt = np.zeros(nk, dtype=np.uint64)
+        first = np.zeros(nk, dtype=np.uint64)
+        self._check(self._L.aqc_get_kmer_dense(self._h, slot, cnt.ctypes.data, first.ctypes.data))
+        n = C.c_uint32(0)
+        self._check(self._L.aqc_get_kmer_side(self._h, slot, None, None, None, 0, C.byref(n)))
+        keys = np.zeros(n.value, dtype=np.uint64)
+        sc = np.zeros(n.value, dtype=np.uint64)
+        sf = np.zeros(n.value, dtype=np.uint64)
+        if n.value:
+            self._check(self._L.aqc_get_kmer_side(self._h, slot, keys.ctypes.data, sc.ctypes.data, sf.ctypes.data, n.value, C.byref(n)))
+        order = np.argsort(keys, kind="stable")
+        return cnt, first, keys[order], sc[order], sf[order]
+
+    def launch_count(self):
+        return int(self._L.aqc_launch_count(self._h))
+
+    def last_kernel_ms(self):
+        return float(self._L.aqc_last_kernel_ms(self._h))
+
+    # ---- reference operator interface (single reads; util.py:88, preprocesser.py:30,61,70) ----
+    def _ops1(self, r1, q1, r2=None, q2=None):
+        b = PackedBatch.from_reads([(r1, q1)], [(r2, q2)] if r2 is not None else None)
+        return self.ops_pairs(b)[0]
+
+    def overlap(self, r1, r2):
+        """util.overlap(r1, r2) -> (offset, overlap_len, distance)"""
+        o = self._ops1(r1, "I" * len(r1), r2, "I" * len(r2))
+        return (int(o["ov_offset"]), int(o["ov_len"]), int(o["ov_diff"]))
+
+    def hasPolyX(self, seq):
+        """hasPolyX(seq, maxPoly, mismatch) with the engine's -p/-a parameters; returns base or None"""
+        o = self._ops1(seq, "I" * len(seq))
+        return chr(int(o["poly1"])) if o["poly1"] else None
+
+    def lowQualityNum(self, read):
+        return int(self._ops1(read[1], read[3])["lowq1"])
+
+    def nNumber(self, read):
+        return int(self._ops1(read[1], read[3])["n1"])

@@ -166,7 +166,7 @@ class seqFilter:
                         opt.trim_front2 = trimFront2
                     if opt.trim_tail2 == -1:
                         opt.trim_tail2 = trimTail2
-        for k in ("trim_front", "trim_tail", "trim_front2", "trim_tail2"):
+        for k in ("trim_front", "trim_tail") + (("trim_front2", "trim_tail2") if self.paired else ()):
             if getattr(opt, k) < 0:
                 raise ValueError("%s=%d is outside the supported domain" % (k, getattr(opt, k)))
 

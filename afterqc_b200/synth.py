@@ -169,3 +169,27 @@ def generate(config, n, seed=None, first_index=0, len_jitter=0):
         return PackedBatch(np8(t["seq1"]), np8(t["qual1"]), npo(t["off1"]), np8(t["seq2"]), np8(t["qual2"]), npo(t["off2"]),
                            first_index=first_index)
     return PackedBatch(np8(t["seq1"]), np8(t["qual1"]), npo(t["off1"]), first_index=first_index)
+
+
+def write_fastq(batch, path1, path2=None, name_prefix="SYN:1:FC:1:1101"):
+    """Write a PackedBatch as plain FASTQ (Illumina-style names)."""
+    import gzip
+
+    def op(p):
+        return gzip.open(p, "wb", compresslevel=1) if p.endswith(".gz") else open(p, "wb")
+
+    def dump(path, mate, seq, qual, off):
+        with op(path) as f:
+            out = []
+            for i in range(batch.n):
+                g = batch.first_index + i
+                a, b = int(off[i]), int(off[i + 1])
+                out.append(b"@%s:%d:%d %d:N:0:A\n" % (name_prefix.encode(), g, g, mate))
+                out.append(seq[a:b].tobytes()); out.append(b"\n+\n"); out.append(qual[a:b].tobytes()); out.append(b"\n")
+                if len(out) > 40000:
+                    f.write(b"".join(out)); out = []
+            f.write(b"".join(out))
+
+    dump(path1, 1, batch.seq1, batch.qual1, batch.off1)
+    if path2 is not None and batch.paired:
+        dump(path2, 2, batch.seq2, batch.qual2, batch.off2)
