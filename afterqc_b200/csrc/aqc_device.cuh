@@ -46,7 +46,8 @@ struct QcDev {
     unsigned long long *scal;       // [0] totalKmer, [1] reads
     unsigned long long *kcnt;       // dense 4^k, internal index (plane1bits << k) | plane0bits
     unsigned long long *kfirst;
-    unsigned long long *skeys, *scnt, *sfirst;   // side table (non-ACGT k-mers)
+    unsigned long long *skeys, *scnt, *sfirst;   // side table (non-ACGT k-mers): key, count, first DIRECT sighting
+    unsigned long long *sseed;                   // first seeding by a k-mer holding a byte outside util.COMP (see below)
     uint32_t smask;
     uint32_t valid;                 // 0 = this mate is not stat'd in this launch
 };
@@ -336,8 +337,17 @@ __device__ __forceinline__ void first_min(unsigned long long *addr, unsigned lon
 
 // QualityControl.statRead (qualitycontrol.py:73-122) for one read, warp-cooperative.
 // s/qv: shared-memory bytes of the (trimmed, corrected) read; mate selects the accumulator half.
+//
+// k-mer insertion order (quirk Q12).  The reference inserts a k-mer X at its first direct sighting and, only at
+// that NEW insertion, seeds reverseComplement(X) with 0.  For k-mers over util.COMP's alphabet revcomp is an
+// involution and "first = min(direct sightings of X, sightings of rc(X) | 1)" is exact; the dense table stores
+// exactly that.  A k-mer holding a byte outside COMP maps that byte to 'N' (util.py:47-50), so revcomp is not
+// invertible there: such a k-mer has no pre-image (it is always newly inserted by its first sighting and always
+// seeds), while a k-mer X over COMP's alphabet seeds rc(X) only if X itself was not seeded earlier.  The side
+// table therefore keeps the first direct sighting (sfirst) and the first seeding by a foreign-byte k-mer (sseed)
+// apart, guarantees a slot for rc(X), and aqc_get_kmer_side resolves the partner rule on the host.
 __device__ __forceinline__ void stat_read(const uint8_t *s, const uint8_t *qv, int len, int mate, uint64_t order,
-                                          const QcSmem &sm, const QcDev &qd, const Luts *lutp, const uint8_t *lut2, const uint8_t *lut3,
+                                          const QcSmem &sm, const QcDev &qd, const uint8_t *lut1, const uint8_t *lut2, const uint8_t *lut3,
                                           int K, int lane, int *error_flag) {
     if (len <= 0) return;
     if (len < 5) { if (lane == 0) atomicExch(error_flag, AQC_ERR_TOO_SHORT_STAT); return; }
@@ -392,10 +402,12 @@ __device__ __forceinline__ void stat_read(const uint8_t *s, const uint8_t *qv, i
                     first_min(&qd.kfirst[ridx], when | 1ULL);
                 } else {
                     unsigned long long key = 0, rkey = 0;
+                    bool foreign = false;
                     for (int j = 0; j < K; j++) {
                         unsigned long long bj = s[i + j];
                         key = (key << 8) | bj;
                         rkey |= (unsigned long long)lut3[bj] << (8 * j);
+                        foreign |= (lut1[bj] & 15u) == 15u;
                     }
                     if (key == AQC_KMER_NEVER || rkey == AQC_KMER_NEVER) atomicExch(error_flag, AQC_ERR_INVALID);
                     else {
@@ -405,7 +417,7 @@ __device__ __forceinline__ void stat_read(const uint8_t *s, const uint8_t *qv, i
                         else {
                             atomicAdd(&qd.scnt[h], 1ULL);
                             first_min(&qd.sfirst[h], when);
-                            first_min(&qd.sfirst[hr], when | 1ULL);
+                            if (foreign) first_min(&qd.sseed[hr], when | 1ULL);
                         }
                     }
                 }
@@ -418,7 +430,6 @@ __device__ __forceinline__ void stat_read(const uint8_t *s, const uint8_t *qv, i
         if (nk > 0) atomicAdd(&qd.scal[0], (unsigned long long)nk);   // totalKmer :114
         atomicAdd(&qd.scal[1], 1ULL);
     }
-    (void)lutp;
 }
 
 }  // namespace aqc

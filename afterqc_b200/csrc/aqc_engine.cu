@@ -36,6 +36,7 @@ struct aqc_ctx {
     int device = 0;
     aqc_params p;
     int sm_count = 148;
+    size_t max_dyn_smem = 200 * 1024;
     cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
     unsigned long long *d_counters = nullptr;
     QcHost qc[AQC_NUM_QC];
@@ -98,6 +99,11 @@ void fill_luts(Luts &L) {
     }
 }
 
+unsigned long long host_side_hash(unsigned long long k) {   // must match aqc::side_hash
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return k;
+}
+
 int check_params(const aqc_params *p, char *err, size_t errn) {
     if (p->qc_kmer < 1 || p->qc_kmer > AQC_MAX_KMER) { snprintf(err, errn, "qc_kmer %d outside 1..%d", p->qc_kmer, AQC_MAX_KMER); return AQC_ERR_INVALID; }
     if (p->trim_front < 0 || p->trim_tail < 0 || p->trim_front2 < 0 || p->trim_tail2 < 0) { snprintf(err, errn, "negative trim value (resolve auto-trim on the host first)"); return AQC_ERR_INVALID; }
@@ -128,6 +134,7 @@ int alloc_qc(aqc_ctx *ctx, QcHost &q) {
     CK(cudaMalloc(&q.d.skeys, sizeof(unsigned long long) * q.side_cap));
     CK(cudaMalloc(&q.d.scnt, sizeof(unsigned long long) * q.side_cap));
     CK(cudaMalloc(&q.d.sfirst, sizeof(unsigned long long) * q.side_cap));
+    CK(cudaMalloc(&q.d.sseed, sizeof(unsigned long long) * q.side_cap));
     return 0;
 }
 
@@ -143,12 +150,13 @@ int zero_qc(aqc_ctx *ctx, QcHost &q) {
     CK(cudaMemsetAsync(q.d.skeys, 0xFF, sizeof(unsigned long long) * q.side_cap, s));
     CK(cudaMemsetAsync(q.d.scnt, 0, sizeof(unsigned long long) * q.side_cap, s));
     CK(cudaMemsetAsync(q.d.sfirst, 0xFF, sizeof(unsigned long long) * q.side_cap, s));
+    CK(cudaMemsetAsync(q.d.sseed, 0xFF, sizeof(unsigned long long) * q.side_cap, s));
     return 0;
 }
 
 void free_qc(QcHost &q) {
     cudaFree(q.d.cls_cnt); cudaFree(q.d.cls_qsum); cudaFree(q.d.disc); cudaFree(q.d.gchist); cudaFree(q.d.scal);
-    cudaFree(q.d.kcnt); cudaFree(q.d.kfirst); cudaFree(q.d.skeys); cudaFree(q.d.scnt); cudaFree(q.d.sfirst);
+    cudaFree(q.d.kcnt); cudaFree(q.d.kfirst); cudaFree(q.d.skeys); cudaFree(q.d.scnt); cudaFree(q.d.sfirst); cudaFree(q.d.sseed);
 }
 
 int poll_error(aqc_ctx *ctx) {   // requires the compute stream to be idle
@@ -210,7 +218,12 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         else { A.qc[m] = ctx->qc[0].d; A.qc[m].valid = 0; }
     }
     size_t smem = smem_bytes_for(P, A.col_cap, maxl);
-    if (smem > 227 * 1024) return fail(ctx, AQC_ERR_INVALID, "tile does not fit shared memory");
+    while (smem > ctx->max_dyn_smem && P > 1) {
+        P >>= 1;
+        A.tile_pairs = P; A.col_cap = (P * maxl + 32 + 15) & ~15; A.num_tiles = (b.n + P - 1) / P;
+        smem = smem_bytes_for(P, A.col_cap, maxl);
+    }
+    if (smem > ctx->max_dyn_smem) return fail(ctx, AQC_ERR_INVALID, "tile does not fit shared memory");
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_kernel, THREADS, smem));
     if (occ < 1) occ = 1;
@@ -382,7 +395,12 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
         CK(cudaMalloc(&ctx->d_maxlen, sizeof(uint32_t)));
         Luts L; fill_luts(L);
         CK(cudaMemcpy(ctx->d_luts, &L, sizeof L, cudaMemcpyHostToDevice));
-        CK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        int optin = 0;
+        CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, pair_kernel));
+        ctx->max_dyn_smem = (size_t)optin - fa.sharedSizeBytes;
+        CK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->max_dyn_smem));
         for (int s = 0; s < AQC_NUM_QC; s++) { int r = alloc_qc(ctx, ctx->qc[s]); if (r) return r; }
         return aqc_reset(ctx);
     };
@@ -578,19 +596,55 @@ int aqc_get_kmer_side(aqc_ctx *ctx, int slot, uint64_t *keys, uint64_t *counts, 
     if (!ctx || !n_out || slot < 0 || slot >= AQC_NUM_QC) return AQC_ERR_INVALID;
     int rc = aqc_sync(ctx);
     QcHost &q = ctx->qc[slot];
-    std::vector<unsigned long long> k(q.side_cap);
+    const int K = ctx->p.qc_kmer;
+    std::vector<unsigned long long> k(q.side_cap), c(q.side_cap), d(q.side_cap), sf(q.side_cap);
     CK(cudaMemcpy(k.data(), q.d.skeys, (size_t)q.side_cap * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(c.data(), q.d.scnt, (size_t)q.side_cap * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(d.data(), q.d.sfirst, (size_t)q.side_cap * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(sf.data(), q.d.sseed, (size_t)q.side_cap * 8, cudaMemcpyDeviceToHost));
+    Luts L; fill_luts(L);
+    auto find = [&](unsigned long long key) -> long {
+        uint32_t h = (uint32_t)host_side_hash(key) & q.d.smask;
+        for (uint32_t probe = 0; probe <= q.d.smask; probe++) {
+            if (k[h] == key) return (long)h;
+            if (k[h] == AQC_KMER_NEVER) return -1;
+            h = (h + 1) & q.d.smask;
+        }
+        return -1;
+    };
+    // resolve the insertion stamp of every slot (see the comment above stat_read in aqc_device.cuh)
+    std::vector<unsigned long long> stamp(q.side_cap, AQC_KMER_NEVER);
     uint32_t n = 0;
-    for (uint32_t i = 0; i < q.side_cap; i++) if (k[i] != AQC_KMER_NEVER) n++;
+    for (uint32_t i = 0; i < q.side_cap; i++) {
+        if (k[i] == AQC_KMER_NEVER) continue;
+        unsigned long long key = k[i], rkey = 0;
+        bool foreign = false;
+        for (int j = 0; j < K; j++) {
+            uint8_t bj = (uint8_t)(key >> (8 * (K - 1 - j)));
+            rkey |= (unsigned long long)L.lut3[bj] << (8 * j);
+            foreign |= (L.lut1[bj] & 15u) == 15u;
+        }
+        unsigned long long p;
+        if (foreign) p = d[i];                                  // no pre-image: present from its first sighting
+        else {
+            p = std::min(d[i], sf[i]);
+            if (rkey != key) {
+                long j = find(rkey);
+                if (j >= 0 && d[j] < d[i]) {                    // partner sighted first: it seeds us iff it was newly inserted
+                    bool partner_new = d[j] < sf[j];
+                    if (partner_new) p = std::min(p, d[j] | 1ULL);
+                }
+            }
+        }
+        stamp[i] = p;
+        if (p != AQC_KMER_NEVER) n++;
+    }
     *n_out = n;
     if (cap == 0 && !keys) return rc;
     if (cap < n || !keys || !counts || !first) return fail(ctx, AQC_ERR_INVALID, "side-table output too small");
-    std::vector<unsigned long long> c(q.side_cap), f(q.side_cap);
-    CK(cudaMemcpy(c.data(), q.d.scnt, (size_t)q.side_cap * 8, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(f.data(), q.d.sfirst, (size_t)q.side_cap * 8, cudaMemcpyDeviceToHost));
-    uint32_t j = 0;
+    uint32_t o = 0;
     for (uint32_t i = 0; i < q.side_cap; i++)
-        if (k[i] != AQC_KMER_NEVER) { keys[j] = k[i]; counts[j] = c[i]; first[j] = f[i]; j++; }
+        if (stamp[i] != AQC_KMER_NEVER) { keys[o] = k[i]; counts[o] = c[i]; first[o] = stamp[i]; o++; }
     return rc;
 }
 

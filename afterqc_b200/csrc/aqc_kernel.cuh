@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(THREADS, 2) pair_kernel(const __grid_constant_
             if (A.mode == MODE_STAT) {
                 if (gidx >= A.stat_lo && gidx < A.stat_hi) {
                     uint64_t order = A.order_base + (gidx - A.stat_lo);
-                    if (A.qc[0].valid) stat_read(S1, Q1, olen1, 0, order, qsm, A.qc[0], A.luts, lut2, lut3, A.p.qc_kmer, lane, A.error_flag);
-                    if (paired && A.qc[1].valid) stat_read(S2, Q2, olen2, 1, order, qsm, A.qc[1], A.luts, lut2, lut3, A.p.qc_kmer, lane, A.error_flag);
+                    if (A.qc[0].valid) stat_read(S1, Q1, olen1, 0, order, qsm, A.qc[0], lut1, lut2, lut3, A.p.qc_kmer, lane, A.error_flag);
+                    if (paired && A.qc[1].valid) stat_read(S2, Q2, olen2, 1, order, qsm, A.qc[1], lut1, lut2, lut3, A.p.qc_kmer, lane, A.error_flag);
                 }
                 continue;
             }
@@ -360,8 +360,8 @@ __global__ void __launch_bounds__(THREADS, 2) pair_kernel(const __grid_constant_
                 bump(AQC_C_GOOD_BASES_R2, (unsigned long long)len2);
                 const uint64_t total_reads = gidx + 1;
                 if (A.p.qc_sample <= 0 || total_reads < (uint64_t)A.p.qc_sample) {       // :624
-                    stat_read(S1 + start1, Q1 + start1, len1, 0, gidx, qsm, A.qc[0], A.luts, lut2, lut3, A.p.qc_kmer, lane, A.error_flag);
-                    if (paired) stat_read(S2 + start2, Q2 + start2, len2, 1, gidx, qsm, A.qc[1], A.luts, lut2, lut3, A.p.qc_kmer, lane, A.error_flag);
+                    stat_read(S1 + start1, Q1 + start1, len1, 0, gidx, qsm, A.qc[0], lut1, lut2, lut3, A.p.qc_kmer, lane, A.error_flag);
+                    if (paired) stat_read(S2 + start2, Q2 + start2, len2, 1, gidx, qsm, A.qc[1], lut1, lut2, lut3, A.p.qc_kmer, lane, A.error_flag);
                 }
             } else {
                 bump(AQC_C_BADTRIM1 + (cls - AQC_BADTRIM1), 1);
