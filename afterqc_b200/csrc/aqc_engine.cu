@@ -38,6 +38,7 @@ struct aqc_ctx {
     int sm_count = 148;
     size_t max_dyn_smem = 200 * 1024;
     cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
+    cudaStream_t own_compute = nullptr;
     unsigned long long *d_counters = nullptr;
     QcHost qc[AQC_NUM_QC];
     Luts *d_luts = nullptr;
@@ -387,6 +388,7 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     auto init = [&]() -> int {
         CK(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+        ctx->own_compute = ctx->compute;
         CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
         CK(cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * AQC_C_TOTAL));
@@ -423,7 +425,7 @@ void aqc_destroy(aqc_ctx *ctx) {
     }
     for (auto &ev : ctx->ev_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     cudaFree(ctx->d_counters); cudaFree(ctx->d_luts); cudaFree(ctx->d_error); cudaFree(ctx->d_maxlen);
-    if (ctx->compute) cudaStreamDestroy(ctx->compute);
+    if (ctx->own_compute) cudaStreamDestroy(ctx->own_compute);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     delete ctx;
@@ -515,6 +517,36 @@ int aqc_ops_pairs(aqc_ctx *ctx, const aqc_batch *batch, int mem, aqc_ops *out) {
     LaunchExtra x; x.mode = MODE_OPS; x.qc1 = -1; x.qc2 = -1;
     x.stat_lo = 0; x.stat_hi = 0; x.order_base = 0; x.out = out;
     return mem == AQC_MEM_HOST ? run_host(ctx, batch, x, out, sizeof(aqc_ops)) : run_device(ctx, batch, x);
+}
+
+int aqc_set_stream(aqc_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return AQC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->compute));
+    ctx->compute = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_compute;
+    return 0;
+}
+
+int aqc_device_ptr(aqc_ctx *ctx, int what, int slot, void **ptr_out, uint64_t *n_out) {
+    if (!ctx || !ptr_out || !n_out) return AQC_ERR_INVALID;
+    if (what == 0) { *ptr_out = ctx->d_counters; *n_out = AQC_C_TOTAL; return 0; }
+    if (slot < 0 || slot >= AQC_NUM_QC) return AQC_ERR_INVALID;
+    QcHost &q = ctx->qc[slot];
+    switch (what) {
+        case 1: *ptr_out = q.d.cls_cnt; *n_out = QC_CLASSES * AQC_MAX_LEN; break;
+        case 2: *ptr_out = q.d.cls_qsum; *n_out = QC_CLASSES * AQC_MAX_LEN; break;
+        case 3: *ptr_out = q.d.disc; *n_out = AQC_MAX_LEN; break;
+        case 4: *ptr_out = q.d.gchist; *n_out = AQC_MAX_LEN + 1; break;
+        case 5: *ptr_out = q.d.scal; *n_out = 2; break;
+        case 6: *ptr_out = q.d.kcnt; *n_out = q.dense_n; break;
+        case 7: *ptr_out = q.d.kfirst; *n_out = q.dense_n; break;
+        case 8: *ptr_out = q.d.skeys; *n_out = q.side_cap; break;
+        case 9: *ptr_out = q.d.scnt; *n_out = q.side_cap; break;
+        case 10: *ptr_out = q.d.sfirst; *n_out = q.side_cap; break;
+        case 11: *ptr_out = q.d.sseed; *n_out = q.side_cap; break;
+        default: return AQC_ERR_INVALID;
+    }
+    return 0;
 }
 
 int aqc_sync(aqc_ctx *ctx) {

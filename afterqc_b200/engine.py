@@ -100,6 +100,16 @@ class Engine:
     def sync(self):
         self._check(self._L.aqc_sync(self._h))
 
+    def set_stream(self, cuda_stream_handle):
+        """Run this engine's kernels on an external CUDA stream (int handle, e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._check(self._L.aqc_set_stream(self._h, C.c_void_p(cuda_stream_handle) if cuda_stream_handle else None))
+
+    def device_ptr(self, what, slot=0):
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self._L.aqc_device_ptr(self._h, what, slot, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
+
     def upload(self, host_batch):
         return DeviceBatch(self, host_batch)
 

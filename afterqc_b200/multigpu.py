@@ -1,0 +1,142 @@
+"""Read-sharded multi-GPU execution.
+
+Pairs are independent, so rank r filters the contiguous record range [n*r/W, n*(r+1)/W) with its own
+engine and NO data-path collective.  The only exchange is the reduction of the accumulator blocks
+(scalar counters, histograms, error matrix, per-cycle QC counters, dense k-mer tables) -- SUM, and MIN for
+the k-mer first-seen stamps -- done once per phase over torch.distributed (NCCL over NVLink on GPUs,
+gloo in the CPU tests).  Rank 0 then writes the JSON; good/bad outputs are written per rank and
+concatenated in rank order, which reproduces the single-process files byte for byte.
+"""
+import os
+import shutil
+import tempfile
+
+import numpy as np
+
+from . import _abi
+
+
+class DistBackend:
+    """Wraps a local backend (Engine or, in tests, the oracle); fetches return GLOBAL (all-reduced) values."""
+
+    def __init__(self, local, group=None, device=None):
+        import torch.distributed as dist
+        self.local = local
+        self.dist = dist
+        self.group = group
+        self.device = device          # torch device for the collective buffers ("cuda:N" for NCCL, None/cpu for gloo)
+        self.params = local.params
+
+    # ---- pass-through of the per-shard work ----
+    def set_params(self, p):
+        self.params = p
+        self.local.set_params(p)
+
+    def stat_reads(self, *a, **k):
+        return self.local.stat_reads(*a, **k)
+
+    def filter_pairs(self, *a, **k):
+        return self.local.filter_pairs(*a, **k)
+
+    def reset_filter_counters(self):
+        self.local.reset_filter_counters()
+
+    def close(self):
+        self.local.close()
+
+    # ---- reductions ----
+    def _allreduce(self, arr, op):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.int64).copy())
+        if self.device is not None:
+            t = t.to(self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM if op == "sum" else self.dist.ReduceOp.MIN, group=self.group)
+        return t.cpu().numpy()
+
+    def counters(self):
+        return self._allreduce(self.local.counters(), "sum")
+
+    def qc(self, slot):
+        rec = self.local.qc(slot)
+        flat = np.frombuffer(rec.tobytes(), dtype=np.int64)
+        out = self._allreduce(flat, "sum")
+        return np.frombuffer(out.tobytes(), dtype=_abi.QC_DTYPE)[0]
+
+    def kmers(self, slot):
+        cnt, first, skeys, scnt, sfirst = self.local.kmers(slot)
+        cnt = self._allreduce(cnt, "sum").view(np.uint64)
+        # stamps are unsigned; MIN over int64 views is order-preserving only below 2^63, NEVER (all ones) is -1:
+        # shift into the signed range first
+        bias = np.uint64(1) << np.uint64(63)
+        f = self._allreduce((first ^ bias), "min").view(np.uint64) ^ bias
+        # side tables (non-ACGT k-mers): gather and merge by key (sum counts, min stamps)
+        world = self.dist.get_world_size(group=self.group)
+        gathered = [None] * world
+        self.dist.all_gather_object(gathered, (skeys, scnt, sfirst), group=self.group)
+        keys = np.concatenate([g[0] for g in gathered])
+        if len(keys):
+            cs = np.concatenate([g[1] for g in gathered]); fs = np.concatenate([g[2] for g in gathered])
+            uk, inv = np.unique(keys, return_inverse=True)
+            c2 = np.zeros(len(uk), dtype=np.uint64); np.add.at(c2, inv, cs)
+            f2 = np.full(len(uk), np.iinfo(np.uint64).max, dtype=np.uint64); np.minimum.at(f2, inv, fs)
+            return cnt, f, uk, c2, f2
+        return cnt, f, skeys, scnt, sfirst
+
+
+def shard_range(n, rank, world):
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def concat_outputs(paths, dest):
+    """Concatenate per-rank output files (plain or gzip members) in rank order."""
+    with open(dest, "wb") as out:
+        for p in paths:
+            with open(p, "rb") as f:
+                shutil.copyfileobj(f, out)
+
+
+def _resolve(spec):
+    mod, attr = spec.split(":")
+    import importlib
+    return getattr(importlib.import_module(mod), attr)
+
+
+def _worker(rank, world, options, port, backend_name, result_q, local_factory=None):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if backend_name == "nccl":
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    from .pipeline import seqFilter, default_backend
+
+    def factory(params):
+        if backend_name == "nccl":
+            from .engine import Engine
+            return DistBackend(Engine(params, device=rank), device="cuda:%d" % rank)
+        if local_factory is not None:        # tests: "module:callable" building the per-rank backend
+            return DistBackend(_resolve(local_factory)(params))
+        return DistBackend(default_backend(params))
+    sf = seqFilter(options, backend_factory=factory, shard=(rank, world))
+    sf.run()
+    dist.barrier()
+    dist.destroy_process_group()
+    if result_q is not None and rank == 0:
+        result_q.put(True)
+
+
+def run_sharded(options, gpus, port=None):
+    """after.py --gpus N: one process per GPU of this box."""
+    import torch.multiprocessing as mp
+    port = port or (29500 + os.getpid() % 2000)
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_worker, args=(r, gpus, options, port, "nccl", None)) for r in range(gpus)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join()
+    if any(p.exitcode != 0 for p in procs):
+        raise RuntimeError("a shard process failed")

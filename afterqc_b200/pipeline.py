@@ -58,12 +58,13 @@ def default_backend(params):
     return Engine(params)
 
 
-def prefilter_stat(backend, rec, slot, sample_limit, batch_records, mate_of=None, paired_batches=None):
+def prefilter_stat(backend, rec, slot, sample_limit, batch_records, shard=(0, 1)):
     """QualityControl.statFile (qualitycontrol.py:331-357) for one file already parsed into `rec`.
 
     Window = records [999, 999+limit) (all if limit <= 0); if fewer than 1000 reads were counted in
     the window loop, the first 999 are stat'd afterwards."""
     n = rec.n
+    s_lo, s_hi = (n * shard[0]) // shard[1], (n * (shard[0] + 1)) // shard[1]   # this rank's records
     lo = READ_TO_SKIP - 1
     if sample_limit > 0:
         hi = min(n, lo + sample_limit)
@@ -71,14 +72,15 @@ def prefilter_stat(backend, rec, slot, sample_limit, batch_records, mate_of=None
     else:
         hi = n
         stat_reads_num = max(n - lo, 0)
-    for a in range(lo, hi, batch_records):
-        b = min(hi, a + batch_records)
+    for a in range(max(lo, s_lo), min(hi, s_hi), batch_records):
+        b = min(hi, s_hi, a + batch_records)
         batch = fastq_io.to_batch(rec, None, a, b)
         backend.stat_reads(batch, slot, -1, stat_lo=lo, stat_hi=hi, order_base=0)
     if stat_reads_num < READ_TO_SKIP:
         head = min(n, READ_TO_SKIP - 1)
-        if head > 0:
-            batch = fastq_io.to_batch(rec, None, 0, head)
+        a, b = max(0, s_lo), min(head, s_hi)
+        if b > a:
+            batch = fastq_io.to_batch(rec, None, a, b)
             backend.stat_reads(batch, slot, -1, stat_lo=0, stat_hi=head, order_base=HEAD_ORDER_BASE)
 
 
@@ -113,8 +115,9 @@ def apply_result(r, s1, q1, s2, q2):
 class seqFilter:
     """Drop-in for preprocesser.seqFilter: seqFilter(options).run()."""
 
-    def __init__(self, opt, backend_factory=None, batch_records=1 << 18):
+    def __init__(self, opt, backend_factory=None, batch_records=1 << 18, shard=(0, 1)):
         self.options = opt
+        self.shard = shard            # (rank, world): this process filters records [n*rank/world, n*(rank+1)/world)
         self.backend_factory = backend_factory or default_backend
         self.batch_records = batch_records
         self.paired = opt.read2_file is not None
@@ -137,9 +140,9 @@ class seqFilter:
         self.backend = be
 
         # ---- prefilter QC (preprocesser.py:247-251) ----
-        prefilter_stat(be, rec1, _abi.QC_R1_PRE, opt.qc_sample, self.batch_records)
+        prefilter_stat(be, rec1, _abi.QC_R1_PRE, opt.qc_sample, self.batch_records, self.shard)
         if self.paired:
-            prefilter_stat(be, rec2, _abi.QC_R2_PRE, opt.qc_sample, self.batch_records)
+            prefilter_stat(be, rec2, _abi.QC_R2_PRE, opt.qc_sample, self.batch_records, self.shard)
         self.r1qc_prefilter = QualityControl(opt.qc_sample, opt.qc_kmer).load(be.qc(_abi.QC_R1_PRE), be.kmers(_abi.QC_R1_PRE))
         self.r1qc_prefilter.qc()
         self.r2qc_prefilter = QualityControl(opt.qc_sample, opt.qc_kmer)
@@ -170,8 +173,10 @@ class seqFilter:
             if getattr(opt, k) < 0:
                 raise ValueError("%s=%d is outside the supported domain" % (k, getattr(opt, k)))
 
-        print(opt.read1_file + " options:")
-        print(opt)
+        rank, world = self.shard
+        if rank == 0:
+            print(opt.read1_file + " options:")
+            print(opt)
 
         # ---- output layout (preprocesser.py:285-371) ----
         good_dir = opt.good_output_folder
@@ -187,17 +192,19 @@ class seqFilter:
         if qc_dir is None:
             qc_dir = os.path.join(os.path.dirname(os.path.dirname(good_dir + "/")), "QC")
         for d in (qc_dir, good_dir, bad_dir):
-            if not os.path.exists(d):
-                os.makedirs(d)
-        if opt.store_overlap and self.paired and not os.path.exists(overlap_dir):
-            os.makedirs(overlap_dir)
+            os.makedirs(d, exist_ok=True)
+        if opt.store_overlap and self.paired:
+            os.makedirs(overlap_dir, exist_ok=True)
         gzip_out = opt.gzip or opt.read1_file.endswith(".gz")
         comp = opt.compression
 
         writers = {}
         if not opt.qc_only:
+            part = "" if world == 1 else ".part%04d" % rank   # per-rank pieces, concatenated by rank 0 below
+
             def mk(d, f, suffix):
-                return fastq_io.Writer(os.path.join(d, getMainName(f) + suffix), gzip_out, comp)
+                w = fastq_io.Writer(os.path.join(d, getMainName(f) + suffix + part), gzip_out, comp)
+                return w
             writers["good1"] = mk(good_dir, opt.read1_file, ".good.fq")
             writers["bad1"] = mk(bad_dir, opt.read1_file, ".bad.fq")
             if opt.store_overlap:
@@ -214,16 +221,35 @@ class seqFilter:
         n = min(rec1.n, rec2.n) if self.paired else rec1.n
         stop = n
         if opt.qc_only:
+            if world > 1:
+                raise NotImplementedError("--qc_only stops at a data-dependent record; run it on one GPU")
             stop = self._qc_only_stop(be, rec1, rec2, n)
             be.reset_filter_counters()
-        for a in range(0, stop, self.batch_records):
-            b = min(stop, a + self.batch_records)
+        s_lo, s_hi = (stop * rank) // world, (stop * (rank + 1)) // world
+        for a in range(s_lo, s_hi, self.batch_records):
+            b = min(s_hi, a + self.batch_records)
             batch = fastq_io.to_batch(rec1, rec2, a, b)
             res = be.filter_pairs(batch)
             if not opt.qc_only:
                 self._write(writers, rec1, rec2, a, res)
         for w in writers.values():
             w.close()
+        if world > 1 and not opt.qc_only:
+            import torch.distributed as dist
+            dist.barrier()
+            if rank == 0:
+                from .multigpu import concat_outputs
+                for w in writers.values():
+                    base = w.filename[:-len(".part0000")]
+                    final = base
+                    # Writer appended ".gz" after the part suffix when gzip is forced: normalise the final name
+                    if w.filename.endswith(".gz") and not base.endswith(".gz"):
+                        base = w.filename[:-len(".part0000.gz")]
+                        final = base + ".gz"
+                    pieces = [w.filename.replace(".part0000", ".part%04d" % r) for r in range(world)]
+                    concat_outputs(pieces, final)
+                    for pth in pieces:
+                        os.unlink(pth)
 
         cnt = be.counters()
         self.counters = cnt
@@ -244,8 +270,9 @@ class seqFilter:
         extra = int(rec1.lengths()[n]) if (self.paired and rec1.n > n and not opt.qc_only) else 0
         stat = self._build_stat(cnt, readLen, extra)
         self.stat = stat
-        with open(os.path.join(qc_dir, os.path.basename(opt.read1_file) + ".json"), "w") as f:
-            f.write(json.dumps(stat, sort_keys=True, indent=4, separators=(',', ': ')))
+        if rank == 0:
+            with open(os.path.join(qc_dir, os.path.basename(opt.read1_file) + ".json"), "w") as f:
+                f.write(json.dumps(stat, sort_keys=True, indent=4, separators=(',', ': ')))
         be.close()
         return stat
 

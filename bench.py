@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 AfterQC hot path (BASELINE.json metric).
+
+Workload (config.workload): BASELINE.json configs[2] = synthetic PE150, 10 M read pairs per GPU,
+reference defaults + `-f 0 -t 0` (so qc_sample = 200000: prefilter statistics over records
+999..200998 of both mates, postfilter statistics over the good pairs with index < 200000, and
+filter + overlap scan + adapter trim + correction over every pair).  One "step" = one full pass
+of that path over the batch:  aqc_stat_reads(window) + aqc_filter_pairs(all pairs).
+
+  value      whole-job M read-pairs/s with the batch resident in HBM (CUDA events on the launching stream)
+  e2e        the same pass through the host-buffer C-ABI entry (pinned host columns -> H2D -> kernels -> D2H of
+             the 32-byte records), copies inside the timed region
+  roofline   algorithmic bytes of the dominant kernel launch (pair_kernel, filter mode) / its event-timed
+             duration vs the measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle (C restatement of the reference algorithm, kind "port") on a bounded sample
+             of the same workload with all host threads
+
+N > 1 (torchrun): weak scaling, one process per GPU, each rank filters its own contiguous shard of
+10 M pairs (global record indices rank*n ..), no data-path collective; every step ends with the NCCL
+all-reduce of the counter blocks (the only exchange the path has).
+`--impl reference` times the CPU arm alone (rank 0 only).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+PAIRS_PER_GPU = 10_000_000
+READ_LEN = 150
+QC_SAMPLE = 200_000
+STAT_LO = 999
+ALGO_BYTES_PER_PAIR = 4 * READ_LEN + 32 + 8          # 2 mates x (bases + quals) + result record + 2 offsets
+WORKLOAD = "synthetic PE150 10M pairs/GPU, overlap correction + adapter trim, defaults -f 0 -t 0 (BASELINE configs[2])"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU (default = BASELINE config)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU sample (0 = auto)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (test infrastructure) timed on host cores -- the only place bench.py runs oracle/
+# ------------------------------------------------------------------------------------------------
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_arm(sample_pairs, threads, steps=1, warmup=0):
+    """Oracle throughput on `sample_pairs` pairs of the workload, split over `threads` host threads.
+    The sample keeps the workload's mix: the QC window is scaled to the same 2 % of the pairs."""
+    from afterqc_b200 import _abi, synth
+    from oracle import oracle as orc_mod
+    orc_mod.build()
+    batch = synth.generate("pe150", sample_pairs)
+    qs = max(1000, sample_pairs * QC_SAMPLE // PAIRS_PER_GPU)
+    params = _abi.Params.defaults(qc_sample=qs)
+    per = (sample_pairs + threads - 1) // threads
+    parts = [batch.slice(i * per, min(sample_pairs, (i + 1) * per)) for i in range(threads) if i * per < sample_pairs]
+
+    def work(part, out, k):
+        o = orc_mod.Oracle(params)
+        lo = min(STAT_LO, max(0, part.n - 1))
+        o.stat_reads(part, _abi.QC_R1_PRE, _abi.QC_R2_PRE, stat_lo=lo, stat_hi=lo + qs)
+        res = o.filter_pairs(part)
+        out[k] = int((res["cls"] == 0).sum())
+        o.close()
+
+    times = []
+    for it in range(warmup + steps):
+        out = [0] * len(parts)
+        ths = [threading.Thread(target=work, args=(p, out, k)) for k, p in enumerate(parts)]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"pairs_per_s": sample_pairs * len(times) / total, "seconds": total, "threads": len(parts),
+            "sample_pairs": sample_pairs, "qc_sample_scaled": qs, "ms_per_step": 1e3 * total / len(times)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    sample = args.cpu_sample or min(args.pairs, 100_000 * threads)
+    r = cpu_arm(sample, threads, steps=args.steps, warmup=min(args.warmup, 1))
+    mps = r["pairs_per_s"] / 1e6
+    line = {
+        "impl": "reference",
+        "metric": "read-pairs/s PE150 (filter + overlap correction + adapter trim + per-cycle QC)",
+        "value": mps, "unit": "M read-pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_pairs_per_step": sample},
+        "cpu_baseline": {"value": mps, "unit": "M read-pairs/s", "cores": r["threads"], "kind": "port",
+                         "sample": "%d pairs of the PE150 workload per step, QC window scaled to %d reads (same 2%% mix); "
+                                   "C oracle (oracle/aqc_oracle.c), one context per host thread; the reference itself is "
+                                   "Python 2 and cannot run on the GPU box" % (sample, r["qc_sample_scaled"])},
+        "e2e": {"value": mps, "unit": "M read-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = "/tmp/aqc_clocks_%d_%d.csv" % (os.getpid(), gpu_index)
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, smax, reasons = [], [], set()
+        with open(self.path) as f:
+            for line in f:
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); smax.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class TorchBatch:
+    """HBM-resident batch backed by torch tensors (plumbing only: memory + RNG)."""
+
+    def __init__(self, t, first_index, n, max_len):
+        import torch
+        self.t = t
+        self.n = n
+        self.first_index = first_index
+        self.max_len = max_len
+        self.results = torch.empty(max(1, n) * 32, dtype=torch.uint8, device=t["seq1"].device)
+
+    def struct(self, lo=0, hi=None):
+        """aqc_batch over records [lo, hi); lo must be a multiple of 4 (16-byte aligned offsets for the bulk copies)."""
+        from afterqc_b200 import _abi
+        hi = self.n if hi is None else hi
+        assert lo % 4 == 0
+        b = _abi.Batch()
+        b.first_index = self.first_index + lo
+        b.n = hi - lo
+        b.flags = self.max_len
+        b.seq1 = self.t["seq1"].data_ptr(); b.qual1 = self.t["qual1"].data_ptr(); b.off1 = self.t["off1"].data_ptr() + 4 * lo
+        b.seq2 = self.t["seq2"].data_ptr(); b.qual2 = self.t["qual2"].data_ptr(); b.off2 = self.t["off2"].data_ptr() + 4 * lo
+        return b
+
+
+def make_device_workload(device, n, seed, first_index):
+    import torch
+    from afterqc_b200 import synth
+    t = synth.generate_device("pe150", n, device=device, seed=seed)
+    for k in ("off1", "off2"):
+        last = t[k][-1:].to(torch.int32)
+        t[k] = torch.cat([t[k].to(torch.int32), last.expand(8)])   # slack entries for the 16-byte granular copies
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return TorchBatch(t, first_index, n, READ_LEN)
+
+
+def cuda_tensor_view(ptr, n, torch_dtype, device):
+    """torch tensor aliasing `n` 64-bit elements at device address `ptr` (for in-place NCCL reductions)."""
+    import torch
+
+    class _Shim:
+        pass
+    s = _Shim()
+    s.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
+    return torch.as_tensor(s, device=device)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from afterqc_b200 import _abi
+    from afterqc_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    n = args.pairs
+    params = _abi.Params.defaults(qc_sample=QC_SAMPLE)
+    eng = Engine(params, device=local_rank)
+    stream = torch.cuda.Stream(device)          # the launching stream of every kernel below (torch events time it)
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    L = eng._L
+
+    first_index = rank * n
+    wb = make_device_workload(device, n, seed=20260927 + rank, first_index=first_index)
+
+    # records of this shard inside the prefilter window [999, 999 + qc_sample) (global indices)
+    w_lo_g, w_hi_g = STAT_LO, STAT_LO + QC_SAMPLE
+    s_lo = max(w_lo_g, first_index) - first_index
+    s_hi = min(w_hi_g, first_index + n) - first_index
+    has_window = s_hi > s_lo
+    s_lo_al = (s_lo // 4) * 4
+
+    reduce_views = []
+    if world > 1:
+        p, cnt = eng.device_ptr(0)
+        reduce_views.append(("sum", cuda_tensor_view(p, cnt, torch.int64, device)))
+        for slot in range(4):
+            for what in (1, 2, 3, 4, 5, 6):
+                p, cnt = eng.device_ptr(what, slot)
+                reduce_views.append(("sum", cuda_tensor_view(p, cnt, torch.int64, device)))
+            p, cnt = eng.device_ptr(7, slot)
+            reduce_views.append(("min", cuda_tensor_view(p, cnt, torch.int64, device)))
+
+    def step_resident():
+        if has_window:
+            b = wb.struct(s_lo_al, s_hi)
+            eng._check(L.aqc_stat_reads(eng._h, C.byref(b), _abi.MEM_DEVICE, _abi.QC_R1_PRE, _abi.QC_R2_PRE, w_lo_g, w_hi_g, 0))
+        b = wb.struct()
+        eng._check(L.aqc_filter_pairs(eng._h, C.byref(b), _abi.MEM_DEVICE, wb.results.data_ptr()))
+        if world > 1:   # the path's only exchange: reduce (copies of) the counter blocks over NVLink
+            for op, v in reduce_views:
+                c = v.clone()
+                dist.all_reduce(c, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MIN)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- resident (kernel-side) number ----------------
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    barrier()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    filter_ms = []
+    for _ in range(args.steps):
+        step_resident()
+        filter_ms.append(None)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = eng.launch_count() - launches0
+    # duration of the dominant kernel (filter-mode pair_kernel): events on its launching stream, one more launch
+    kms = []
+    for _ in range(3):
+        b = wb.struct()
+        eng._check(L.aqc_filter_pairs(eng._h, C.byref(b), _abi.MEM_DEVICE, wb.results.data_ptr()))
+        kms.append(eng.last_kernel_ms())
+    kernel_ms = float(np.mean(kms))
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e6
+
+    # ---------------- end-to-end through the host-buffer C-ABI ----------------
+    e2e = None
+    if not args.no_e2e:
+        host = {}
+        for k in ("seq1", "qual1", "seq2", "qual2", "off1", "off2"):
+            h = torch.empty(wb.t[k].shape, dtype=wb.t[k].dtype, pin_memory=True)
+            h.copy_(wb.t[k])
+            host[k] = h
+        res_host = torch.empty(n * 32, dtype=torch.uint8, pin_memory=True)
+        torch.cuda.synchronize()
+
+        def hstruct(lo, hi):
+            b = _abi.Batch()
+            b.first_index = first_index + lo
+            b.n = hi - lo
+            b.flags = 0
+            b.seq1 = host["seq1"].data_ptr(); b.qual1 = host["qual1"].data_ptr(); b.off1 = host["off1"].data_ptr() + 4 * lo
+            b.seq2 = host["seq2"].data_ptr(); b.qual2 = host["qual2"].data_ptr(); b.off2 = host["off2"].data_ptr() + 4 * lo
+            return b
+
+        off1 = host["off1"].numpy(); off2 = host["off2"].numpy()
+        h2d = 2 * int(off1[n] - off1[0]) + 2 * int(off2[n] - off2[0]) + 8 * (n + 1)
+        if has_window:
+            h2d += 2 * int(off1[s_hi] - off1[s_lo]) + 2 * int(off2[s_hi] - off2[s_lo]) + 8 * (s_hi - s_lo + 1)
+        d2h = 32 * n
+
+        def step_e2e():
+            if has_window:
+                b = hstruct(s_lo, s_hi)
+                eng._check(L.aqc_stat_reads(eng._h, C.byref(b), _abi.MEM_HOST, _abi.QC_R1_PRE, _abi.QC_R2_PRE, w_lo_g, w_hi_g, 0))
+            b = hstruct(0, n)
+            eng._check(L.aqc_filter_pairs(eng._h, C.byref(b), _abi.MEM_HOST, res_host.data_ptr()))
+
+        e_steps = max(1, min(args.steps, 5))
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(e_steps):
+            step_e2e()
+        a1.record(stream)
+        barrier()
+        t = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item()) / e_steps
+        e2e = {"value": world * n / (ms_e2e * 1e-3) / 1e6, "unit": "M read-pairs/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e_steps,
+               "note": "aqc_stat_reads + aqc_filter_pairs with AQC_MEM_HOST on pinned host columns; chunked H2D/kernels/D2H pipeline inside"}
+        del host, res_host
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            peak = float(json.load(f)["hbm_gbs"])
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    off1 = wb.t["off1"]; off2 = wb.t["off2"]
+    col_bytes = 2 * int(off1[n].item() - off1[0].item()) + 2 * int(off2[n].item() - off2[0].item())
+    algo_bytes = col_bytes + 32 * n + 8 * n
+    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_filter_kernel_dram_bytes.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_per_pair"] * n     # ncu capture was taken on a smaller launch; per-pair traffic x pairs/launch
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "aqc::pair_kernel (MODE_FILTER, %d pairs/launch)" % n, "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
+                "note": "integer ALU-bound kernel: see DESIGN.md (instruction budget per pair vs HBM budget)"}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu:
+            threads = host_threads()
+            sample = args.cpu_sample or min(n, 100_000 * threads)
+            r = cpu_arm(sample, threads)
+            cpu = {"value": r["pairs_per_s"] / 1e6, "unit": "M read-pairs/s", "cores": r["threads"], "kind": "port",
+                   "sample": "%d pairs of the same PE150 workload (QC window scaled to %d reads, the same 2%% mix), %.1f s of wall time on %d threads; "
+                             "C oracle oracle/aqc_oracle.c" % (sample, r["qc_sample_scaled"], r["seconds"], r["threads"])}
+        line = {
+            "metric": "read-pairs/s PE150 (filter + overlap correction + adapter trim + per-cycle QC)",
+            "value": value, "unit": "M read-pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu": n, "read_len": READ_LEN, "qc_sample": QC_SAMPLE,
+                       "l2": "inputs (%.1f GB/GPU) exceed the 126 MB L2; no explicit flush" % (col_bytes / 1e9),
+                       "parallelism": "read-sharded x%d, NCCL all-reduce of the counter blocks per step" % world if world > 1 else "1 GPU"},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

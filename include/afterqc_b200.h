@@ -221,6 +221,19 @@ int aqc_filter_pairs(aqc_ctx *ctx, const aqc_batch *batch, int mem, aqc_result *
 /* Operator-level outputs (no counters touched). */
 int aqc_ops_pairs(aqc_ctx *ctx, const aqc_batch *batch, int mem, aqc_ops *out);
 
+/* Use an externally owned CUDA stream (cudaStream_t passed as void*) for all kernels and device-side
+ * work of this context (e.g. the caller's current stream, so that the caller's events time it).
+ * NULL restores the context's own stream. */
+int aqc_set_stream(aqc_ctx *ctx, void *cuda_stream);
+
+/* Device addresses of the accumulator blocks, for in-place collectives (NCCL) across shards.
+ * what: 0 = scalar/histogram counter block (int64[AQC_C_TOTAL]);
+ *       1..10 = arrays of QC slot `slot`: 1 cls_cnt[5][MAX_LEN], 2 cls_qsum[5][MAX_LEN] (raw byte sums),
+ *       3 disc[MAX_LEN], 4 gchist[MAX_LEN+1], 5 scal[2], 6 dense k-mer counts[4^k], 7 dense k-mer first[4^k] (MIN-reduce),
+ *       8 side keys, 9 side counts, 10 side first-direct, 11 side first-seed   (side tables are not reducible in place)
+ * *n_out receives the number of 64-bit elements. */
+int aqc_device_ptr(aqc_ctx *ctx, int what, int slot, void **ptr_out, uint64_t *n_out);
+
 /* Wait for all queued work of this context. */
 int aqc_sync(aqc_ctx *ctx);
 

@@ -1,0 +1,56 @@
+"""The C-ABI shared library loads without a GPU and exports every symbol include/afterqc_b200.h declares
+(no compute calls here)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "afterqc_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(aqc_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from afterqc_b200 import build, _native
+    lib_path = build.build()
+    assert os.path.exists(lib_path)
+    lib = ctypes.CDLL(lib_path)
+    syms = declared_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), "missing export " + s
+    assert sorted(_native.SYMBOLS) == syms, (set(syms) ^ set(_native.SYMBOLS))
+    L = _native.lib()
+    assert L.aqc_abi_version() == 1
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under afterqc_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "afterqc_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+                assert "aqc_oracle" not in src and "aqo_" not in src, fn
+
+
+def test_engine_fails_loudly_without_gpu_or_library(monkeypatch):
+    from afterqc_b200 import _abi, _native
+    import pytest
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        from afterqc_b200.engine import Engine, EngineError
+        with pytest.raises(EngineError):
+            Engine(_abi.Params.defaults())
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(_native, "LIB_PATH", "/nonexistent/libafterqc_b200.so")
+    with pytest.raises(ImportError):
+        _native.lib()

@@ -1,0 +1,32 @@
+"""GPU end-to-end: the full drop-in pipeline on the CUDA engine reproduces the reference's golden outputs
+(JSON + decompressed good/bad/overlap files), and the after.py command line runs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+import golden_util
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", golden_util.CASES)
+def test_pipeline_on_engine_matches_reference_golden(name, tmp_path):
+    from afterqc_b200.engine import Engine
+    problems = golden_util.run_case(name, tmp_path, lambda p: Engine(p))
+    assert not problems, problems
+
+
+def test_after_py_cli_runs_on_gpu(tmp_path):
+    import shutil
+    src = os.path.join(golden_util.GOLD, "pe150_default")
+    for fn in ("x_R1.fq.gz", "x_R2.fq.gz"):
+        shutil.copy(os.path.join(src, fn), str(tmp_path / fn))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "after.py"), "-1", str(tmp_path / "x_R1.fq.gz"), "-2", str(tmp_path / "x_R2.fq.gz"),
+                          "-g", str(tmp_path / "good")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Time used:" in out.stdout
+    for rel in ("good/x_R1.good.fq.gz", "bad/x_R2.bad.fq.gz", "QC/x_R1.fq.gz.json"):
+        assert os.path.exists(str(tmp_path / rel)), rel
