@@ -5,7 +5,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libafterqc_b200.so")
+LIB_PATH = os.environ.get("AQC_LIB_PATH") or os.path.join(_HERE, "libafterqc_b200.so")   # override: kernel tuning experiments
 
 # every symbol include/afterqc_b200.h declares
 SYMBOLS = [

@@ -306,6 +306,214 @@ __device__ __forceinline__ int polyx_exact(const uint8_t *s, int len, int maxPol
     return 0;
 }
 
+// ==========================================================================================
+// FAST PATH (reads made of A,C,G,T,N only -- every Illumina read in practice).
+// Codes come straight from the ASCII bits: code = (byte >> 1) & 3  ->  A0 C1 T2 G3, complement = code ^ 2
+// (flip plane 1).  'N' gets its own plane 2 with planes 0/1 forced to 0.  Each lane converts 8 consecutive
+// bases with SWAR arithmetic (one pass covers 256 bases), validates them with two PRMTs (re-encode the 2-bit
+// codes to ASCII and compare), and the 8-bit plane slices are gathered into the lane-per-word layout with 4
+// shuffles.  Any other byte (lowercase, IUPAC, ...) sends the PAIR to the general LUT/ballot path above.
+// ==========================================================================================
+__device__ __forceinline__ uint32_t bytemask_lo(int nbytes) {        // 0xFF for the first nbytes bytes (0..4)
+    return nbytes >= 4 ? 0xffffffffu : (nbytes <= 0 ? 0u : ((1u << (8 * nbytes)) - 1u));
+}
+
+// bytes s[x0 .. x0+7] (zero beyond len) from shared memory at any alignment; vm* = 0xFF per valid byte
+__device__ __forceinline__ void load8(const uint8_t *s, int x0, int len, uint32_t &v0, uint32_t &v1, uint32_t &vm0, uint32_t &vm1) {
+    v0 = v1 = vm0 = vm1 = 0;
+    const int nv = len - x0;
+    if (nv > 0) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(s + x0);
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        const int sh = (int)(a & 3) * 8;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+        vm0 = bytemask_lo(nv); vm1 = bytemask_lo(nv - 4);
+        v0 = __funnelshift_r(w0, w1, sh) & vm0;
+        v1 = __funnelshift_r(w1, w2, sh) & vm1;
+    }
+}
+
+__device__ __forceinline__ uint32_t gather4(uint32_t x01010101) {    // bit 0 of each byte -> 4-bit value
+    return (x01010101 * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ uint32_t hibit_nonzero(uint32_t x) {      // 0x80 in every byte of x that is non-zero
+    return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
+
+struct FastPlanes {
+    uint32_t P[4];      // P[0], P[1] code planes, P[2] = N plane, P[3] unused (0)
+    int n_count;        // exact number of 'N' bytes
+    bool hasN;          // warp-uniform
+    bool exotic;        // warp-uniform: some byte is not A,C,G,T,N -> general path required
+};
+
+// forward planes of a read (fast codes)
+__device__ __forceinline__ void fast_build(const uint8_t *s, int len, int lane, FastPlanes &F) {
+    F.P[0] = F.P[1] = F.P[2] = F.P[3] = 0;
+    F.n_count = 0; F.hasN = false; F.exotic = false;
+    const int npass = (len + 255) >> 8;
+    for (int p = 0; p < npass; p++) {
+        uint32_t v0, v1, vm0, vm1;
+        load8(s, (p << 8) + (lane << 3), len, v0, v1, vm0, vm1);
+        uint32_t t0 = (v0 >> 1) & 0x03030303u, t1 = (v1 >> 1) & 0x03030303u;
+        // re-encode the codes to ASCII (index 0 'A', 1 'C', 2 'T', 3 'G') and compare
+        const uint32_t e0 = __byte_perm(0x47544341u, 0u, __byte_perm(t0 | (t0 >> 4), 0u, 0x4420));
+        const uint32_t e1 = __byte_perm(0x47544341u, 0u, __byte_perm(t1 | (t1 >> 4), 0u, 0x4420));
+        const uint32_t bad0 = (e0 ^ v0) & vm0, bad1 = (e1 ^ v1) & vm1;
+        uint32_t nbyte = 0;
+        if (__ballot_sync(FULL, (bad0 | bad1) != 0u)) {            // warp-uniform: some non-ACGT byte in this pass
+            const uint32_t isN0 = ~hibit_nonzero(v0 ^ 0x4E4E4E4Eu) & 0x80808080u & vm0;
+            const uint32_t isN1 = ~hibit_nonzero(v1 ^ 0x4E4E4E4Eu) & 0x80808080u & vm1;
+            const uint32_t ex = (hibit_nonzero(bad0) & ~isN0) | (hibit_nonzero(bad1) & ~isN1);
+            if (__ballot_sync(FULL, ex != 0u)) F.exotic = true;
+            const uint32_t n0 = isN0 >> 7, n1 = isN1 >> 7;           // 0x01 per N byte
+            t0 &= ~(n0 * 3u); t1 &= ~(n1 * 3u);                      // planes 0/1 are 0 at N positions
+            nbyte = gather4(n0) | (gather4(n1) << 4);
+            const uint32_t nb = __ballot_sync(FULL, nbyte != 0u);
+            if (nb) { F.hasN = true; F.n_count += (int)__reduce_add_sync(FULL, (unsigned)__popc(nbyte)); }
+        }
+        const uint32_t p0b = gather4(t0 & 0x01010101u) | (gather4(t1 & 0x01010101u) << 4);
+        const uint32_t p1b = gather4((t0 >> 1) & 0x01010101u) | (gather4((t1 >> 1) & 0x01010101u) << 4);
+        const uint32_t v = p0b | (p1b << 8) | (nbyte << 16);
+        const int jj = (lane & 7) << 2;
+        const uint32_t b0 = __shfl_sync(FULL, v, jj), b1 = __shfl_sync(FULL, v, jj + 1);
+        const uint32_t b2 = __shfl_sync(FULL, v, jj + 2), b3 = __shfl_sync(FULL, v, jj + 3);
+        if ((lane >> 3) == p) {
+            const uint32_t x01 = __byte_perm(b0, b1, 0x5140), x23 = __byte_perm(b2, b3, 0x5140);
+            F.P[0] = __byte_perm(x01, x23, 0x5410);
+            F.P[1] = __byte_perm(x01, x23, 0x7632);
+            if (F.hasN) {
+                const uint32_t y01 = __byte_perm(b0, b1, 0x6262), y23 = __byte_perm(b2, b3, 0x6262);
+                F.P[2] = __byte_perm(y01, y23, 0x5410);
+            }
+        }
+    }
+}
+
+// planes of reverseComplement(read) from its forward fast planes: rc[i] = comp(fwd[len-1-i])
+__device__ __forceinline__ void fast_revcomp(const FastPlanes &F, int len, int lane, uint32_t (&RC)[4]) {
+    const int s = 1024 - len;
+    const int q = s >> 5, sh = s & 31;
+    const int np = F.hasN ? 3 : 2;
+    RC[0] = RC[1] = RC[2] = RC[3] = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (k < np) {
+            uint32_t r = __brev(__shfl_sync(FULL, F.P[k], 31 - lane));
+            RC[k] = plane_window(r, lane + q, sh);
+        }
+    }
+    RC[1] ^= lowmask(len - (lane << 5)) & ~RC[2];      // complement = code ^ 2, N stays 0
+}
+
+// lowQualityNum on 8 quality bytes per lane (thr in 1..127)
+__device__ __forceinline__ int count_lowq_fast(const uint8_t *q, int len, int thr, int lane) {
+    const uint32_t t4 = (uint32_t)thr * 0x01010101u;
+    int n = 0;
+    const int npass = (len + 255) >> 8;
+    for (int p = 0; p < npass; p++) {
+        uint32_t v0, v1, vm0, vm1;
+        load8(q, (p << 8) + (lane << 3), len, v0, v1, vm0, vm1);
+        // byte >= thr  <=>  high bit of ((byte | 0x80) - thr) | byte   (thr < 128)
+        const uint32_t ge0 = (((v0 | 0x80808080u) - t4) | v0) & 0x80808080u;
+        const uint32_t ge1 = (((v1 | 0x80808080u) - t4) | v1) & 0x80808080u;
+        n += __popc(~ge0 & 0x80808080u & vm0) + __popc(~ge1 & 0x80808080u & vm1);
+    }
+    return (int)__reduce_add_sync(FULL, (unsigned)n);
+}
+
+// run-length screen of hasPolyX on planes of EITHER code set (np planes), cheap version for m = R-1 <= 31
+__device__ __forceinline__ bool polyx_screen_fast(const uint32_t (&P)[4], int np, int len, int maxPoly, int mismatch, int lane) {
+    if (len < maxPoly) return false;
+    if (mismatch < 0) return false;
+    const int T = maxPoly - mismatch;
+    if (T <= 1) return true;
+    const int m = (T + mismatch) / (mismatch + 1) - 1;   // consecutive "same as previous" bits needed
+    if (m <= 0) return true;
+    if (m > 31) return true;                             // (caller falls back to the general screen)
+    uint32_t d = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (k < np) {
+            uint32_t up = __shfl_up_sync(FULL, P[k], 1);
+            if (lane == 0) up = 0;
+            d |= P[k] ^ __funnelshift_l(up, P[k], 1);
+        }
+    }
+    uint32_t y = ~d & lowmask(len - (lane << 5));
+    if (lane == 0) y &= ~1u;
+    // straddling runs: ones at the top of word j + ones at the bottom of word j+1
+    const int lead = __clz((int)~y);
+    int trail = __ffs((int)~y) - 1; if (trail < 0) trail = 32;
+    int nxt = __shfl_down_sync(FULL, trail, 1);
+    if (lane == 31) nxt = 0;
+    bool hit = (lead + nxt) >= m;
+    // runs inside a word
+    int t = 1;
+    while (t < m) { const int step = min(t, m - t); y &= y >> step; t += step; }
+    hit |= (y != 0u);
+    return __ballot_sync(FULL, hit) != 0u;
+}
+
+// leaner offset scan (same contract as scan_dir) for lenF >= 32
+template <int NP>
+__device__ __forceinline__ int scan_dir_fast(const uint32_t (&S)[4], const uint32_t (&F)[4], int lenS, int lenF, int lane,
+                                             int &ol_out, int &mm_out) {
+    const int nOff = lenS - 30;
+    if (nOff <= 0) return -1;
+    uint32_t f0[NP], a[NP];
+#pragma unroll
+    for (int k = 0; k < NP; k++) { f0[k] = __shfl_sync(FULL, F[k], 0); a[k] = __shfl_sync(FULL, S[k], 0); }
+    const int last = lenS - 31;                         // the only offset whose first window has 31 positions
+    for (int base = 0; base < nOff; base += 32) {
+        const int o = base + lane;
+        const int r1 = (base >> 5) + 1;
+        uint32_t x = 0;
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            const uint32_t b = __shfl_sync(FULL, S[k], r1 & 31);     // r1 <= 31 because lenS <= 1000
+            x |= __funnelshift_r(a[k], b, lane) ^ f0[k];
+            a[k] = b;
+        }
+        if (o == last) x &= 0x7fffffffu;
+        uint32_t sv = __ballot_sync(FULL, (o < nOff) && (__popc(x) < 3));
+        while (sv) {
+            const int l = __ffs(sv) - 1;
+            sv &= sv - 1;
+            const int oc = base + l;
+            const int olc = min(lenS - oc, lenF);
+            const int q = oc >> 5, sh = oc & 31;
+            uint32_t xx = 0;
+#pragma unroll
+            for (int k = 0; k < NP; k++) xx |= plane_window(S[k], lane + q, sh) ^ F[k];
+            const int lo = lane << 5;
+            xx &= lowmask(olc - lo);
+            const int mm = __reduce_add_sync(FULL, (unsigned)__popc(xx));
+            const int mm50 = __reduce_add_sync(FULL, (unsigned)__popc(xx & lowmask(min(50, olc) - lo)));
+            if (mm50 < 3 && (mm < 3 || olc >= 52)) { ol_out = olc; mm_out = mm; return oc; }
+        }
+    }
+    return -1;
+}
+
+template <int NP>
+__device__ __forceinline__ void overlap_fast(const uint32_t (&P1)[4], const uint32_t (&RC)[4], int len1, int len2, int lane,
+                                             int &offset, int &ol, int &diff) {
+    int o = (len2 >= 32) ? scan_dir_fast<NP>(P1, RC, len1, len2, lane, ol, diff) : scan_dir<NP>(P1, RC, len1, len2, lane, ol, diff);
+    if (o >= 0) { offset = o; return; }
+    o = (len1 >= 32) ? scan_dir_fast<NP>(RC, P1, len2, len1, lane, ol, diff) : scan_dir<NP>(RC, P1, len2, len1, lane, ol, diff);
+    if (o >= 0) { offset = -o; return; }
+    offset = 0; ol = 0; diff = 0;
+}
+
+// np = 2 (ACGT only), 3 (fast codes with N plane) or 4 (general LUT codes)
+__device__ __forceinline__ void overlap_np(int np, const uint32_t (&P1)[4], const uint32_t (&RC)[4], int len1, int len2,
+                                           int lane, int &offset, int &ol, int &diff) {
+    if (np == 2) overlap_fast<2>(P1, RC, len1, len2, lane, offset, ol, diff);
+    else if (np == 3) overlap_fast<3>(P1, RC, len1, len2, lane, offset, ol, diff);
+    else overlap_hm<4>(P1, RC, len1, len2, lane, offset, ol, diff);
+}
+
 // ------------------------------------------------------------------------------------------
 // shared-memory QC accumulators of one CTA (flushed to QcDev with 64-bit atomics)
 // ------------------------------------------------------------------------------------------

@@ -403,6 +403,7 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
         CK(cudaFuncGetAttributes(&fa, pair_kernel));
         ctx->max_dyn_smem = (size_t)optin - fa.sharedSizeBytes;
         CK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->max_dyn_smem));
+        CK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         for (int s = 0; s < AQC_NUM_QC; s++) { int r = alloc_qc(ctx, ctx->qc[s]); if (r) return r; }
         return aqc_reset(ctx);
     };

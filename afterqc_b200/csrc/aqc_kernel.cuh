@@ -13,6 +13,53 @@ __device__ __forceinline__ void py_trim(int len, int front, int tail, int &start
     start = s; newlen = e - s;
 }
 
+
+// Planes of both mates for the comparisons: fast ASCII-bit codes when every byte is A,C,G,T,N, else the
+// general LUT codes (np = 4).  Also N counts and the hasPolyX screen verdicts.
+struct PairPlanes {
+    uint32_t P1[4], RC[4];
+    int np, n1, n2;
+    bool cand1, cand2;      // hasPolyX candidates (screen passed)
+};
+
+__device__ __forceinline__ void prepare_pair(const uint8_t *r1, int len1, const uint8_t *r2, int len2, bool paired, bool want_poly,
+                                             int maxPoly, int mismatch, const uint8_t *lut1, int lane, PairPlanes &pp) {
+    FastPlanes F1, F2;
+    fast_build(r1, len1, lane, F1);
+    bool exotic = F1.exotic;
+    F2.hasN = false; F2.exotic = false; F2.n_count = 0;
+    if (paired) { fast_build(r2, len2, lane, F2); exotic |= F2.exotic; }
+    pp.cand1 = pp.cand2 = false;
+    if (!exotic) {
+        pp.np = (F1.hasN || F2.hasN) ? 3 : 2;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { pp.P1[k] = F1.P[k]; pp.RC[k] = 0; }
+        pp.n1 = F1.n_count; pp.n2 = F2.n_count;
+        if (want_poly) pp.cand1 = polyx_screen_fast(F1.P, F1.hasN ? 3 : 2, len1, maxPoly, mismatch, lane);
+        if (paired) {
+            if (want_poly) pp.cand2 = polyx_screen_fast(F2.P, F2.hasN ? 3 : 2, len2, maxPoly, mismatch, lane);
+            fast_revcomp(F2, len2, lane, pp.RC);
+        }
+    } else {
+        pp.np = 4;
+        bool e1 = false, e2 = false;
+        build_planes(r1, len1, false, lut1, lane, pp.P1, pp.n1, e1);
+        pp.n2 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) pp.RC[k] = 0;
+        if (want_poly) pp.cand1 = polyx_screen(pp.P1, e1, len1, maxPoly, mismatch, lane);
+        if (paired) {
+            build_planes(r2, len2, true, lut1, lane, pp.RC, pp.n2, e2);
+            if (want_poly) pp.cand2 = polyx_screen(pp.RC, e2, len2, maxPoly, mismatch, lane);
+        }
+    }
+}
+
+__device__ __forceinline__ int lowq_any(const uint8_t *q, int len, int thr, int lane) {
+    if (thr <= 0) return 0;
+    return thr < 128 ? count_lowq_fast(q, len, thr, lane) : count_lowq(q, len, thr, lane);
+}
+
 struct StageBuf {
     uint8_t *col[4];        // seq1, qual1, seq2, qual2
     uint32_t *off1, *off2;  // tile_pairs + 4 entries each
@@ -23,7 +70,10 @@ struct StageBuf {
 //   luts (768 B)
 //   qc acc  [2][5][max_len] u32, qc disc [2][max_len] u32
 //   overlap_hist [max_len+1] u32, distance_hist [max_len+1] u32
-__global__ void __launch_bounds__(THREADS, 2) pair_kernel(const __grid_constant__ KArgs A) {
+#ifndef AQC_MIN_BLOCKS
+#define AQC_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __grid_constant__ KArgs A) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[NSTAGES];
     __shared__ uint32_t tile_base[NSTAGES][2];      // 16-byte aligned column origin of the staged tile
@@ -176,21 +226,19 @@ __global__ void __launch_bounds__(THREADS, 2) pair_kernel(const __grid_constant_
                     if (paired) py_trim(olen2, A.p.trim_front2, A.p.trim_tail2, start2, len2);
                 }
                 const uint8_t *r1 = S1 + start1, *r1q = Q1 + start1;
-                uint32_t P1[4], RC[4] = {0, 0, 0, 0};
-                int n1 = 0, n2 = 0; bool ex1 = false, ex2 = false;
-                build_planes(r1, len1, false, lut1, lane, P1, n1, ex1);
-                int lowq1 = count_lowq(r1q, len1, A.p.qualified_quality_phred + 33, lane), lowq2 = 0;
+                const uint8_t *r2 = paired ? S2 + start2 : nullptr, *r2q = paired ? Q2 + start2 : nullptr;
+                PairPlanes pl;
+                prepare_pair(r1, len1, r2, len2, paired, true, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lut1, lane, pl);
+                const int n1 = pl.n1, n2 = pl.n2;
+                const int thr = A.p.qualified_quality_phred + 33;
+                int lowq1 = lowq_any(r1q, len1, thr, lane), lowq2 = 0;
                 int poly1 = 0, poly2 = 0;
-                if (polyx_screen(P1, ex1, len1, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lane))
-                    poly1 = polyx_exact(r1, len1, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lut2, lane);
+                if (pl.cand1) poly1 = polyx_exact(r1, len1, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lut2, lane);
                 int off = 0, ol = 0, diff = 0;
                 if (paired) {
-                    const uint8_t *r2 = S2 + start2, *r2q = Q2 + start2;
-                    build_planes(r2, len2, true, lut1, lane, RC, n2, ex2);
-                    lowq2 = count_lowq(r2q, len2, A.p.qualified_quality_phred + 33, lane);
-                    if (polyx_screen(RC, ex2, len2, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lane))
-                        poly2 = polyx_exact(r2, len2, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lut2, lane);
-                    overlap_any(ex1 || ex2, P1, RC, len1, len2, lane, off, ol, diff);
+                    lowq2 = lowq_any(r2q, len2, thr, lane);
+                    if (pl.cand2) poly2 = polyx_exact(r2, len2, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lut2, lane);
+                    overlap_np(pl.np, pl.P1, pl.RC, len1, len2, lane, off, ol, diff);
                 }
                 if (lane == 0) {
                     aqc_ops r;
@@ -208,9 +256,6 @@ __global__ void __launch_bounds__(THREADS, 2) pair_kernel(const __grid_constant_
             }
 
             // ================================ MODE_FILTER ================================
-            bump(AQC_C_TOTAL_READS, 1);
-            bump(AQC_C_TOTAL_BASES_R1, (unsigned long long)olen1);
-            bump(AQC_C_TOTAL_BASES_R2, (unsigned long long)olen2);
             uint32_t edits[4] = {0, 0, 0, 0};
             int n_edits = 0;
             int ov_off = 0, ov_len = 0, ov_diff = 0;
@@ -228,37 +273,35 @@ __global__ void __launch_bounds__(THREADS, 2) pair_kernel(const __grid_constant_
 
                 uint8_t *r1 = S1 + start1, *r1q = Q1 + start1;
                 uint8_t *r2 = paired ? S2 + start2 : nullptr, *r2q = paired ? Q2 + start2 : nullptr;
-                uint32_t P1[4], RC[4] = {0, 0, 0, 0};
-                int n1 = 0, n2 = 0; bool ex1 = false, ex2 = false;
-                build_planes(r1, len1, false, lut1, lane, P1, n1, ex1);
-                if (paired) build_planes(r2, len2, true, lut1, lane, RC, n2, ex2);
+                PairPlanes pl;
+                prepare_pair(r1, len1, r2, len2, paired, A.p.poly_size_limit > 0, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lut1, lane, pl);
 
                 if (A.p.poly_size_limit > 0) {                             // :482-490
                     bool poly = false;
-                    if (polyx_screen(P1, ex1, len1, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lane))
-                        poly = polyx_exact(r1, len1, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lut2, lane) != 0;
-                    if (!poly && paired && polyx_screen(RC, ex2, len2, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lane))
-                        poly = polyx_exact(r2, len2, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lut2, lane) != 0;
+                    if (pl.cand1) poly = polyx_exact(r1, len1, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lut2, lane) != 0;
+                    if (!poly && pl.cand2) poly = polyx_exact(r2, len2, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lut2, lane) != 0;
                     if (poly) { cls = AQC_BADPOL; break; }
                 }
                 if (A.p.unqualified_base_limit > 0) {                      // :493-501 (only lowQual1 tested, quirk Q2)
-                    int lowq1 = count_lowq(r1q, len1, A.p.qualified_quality_phred + 33, lane);
+                    int lowq1 = lowq_any(r1q, len1, A.p.qualified_quality_phred + 33, lane);
                     if (lowq1 > A.p.unqualified_base_limit) { cls = AQC_BADLQC; break; }
                 }
                 if (A.p.n_base_limit > 0) {                                // :504-512
-                    if (n1 > A.p.n_base_limit || n2 > A.p.n_base_limit) { cls = AQC_BADNCT; break; }
+                    if (pl.n1 > A.p.n_base_limit || pl.n2 > A.p.n_base_limit) { cls = AQC_BADNCT; break; }
                 }
                 if (paired && !A.p.no_overlap) {                           // :515-617
-                    const bool exo = ex1 || ex2;
+                    const int np = pl.np;
+                    uint32_t (&P1)[4] = pl.P1;
+                    uint32_t (&RC)[4] = pl.RC;
                     int offset, ol, distance;
-                    overlap_any(exo, P1, RC, len1, len2, lane, offset, ol, distance);     // :516
+                    overlap_np(np, P1, RC, len1, len2, lane, offset, ol, distance);       // :516
                     if (lane == 0) atomicAdd(&s_ovh[ol], 1u);                              // :517
                     if (offset < 0 && ol > 30) {                                          // :520 adapter trimming
                         // rc(r2[0:ol]) = last ol bases of rc(r2): shift the rc planes down by len2-ol
                         const int sh = len2 - ol;
                         if (sh > 0) {
 #pragma unroll
-                            for (int k = 0; k < 4; k++) RC[k] = plane_window(RC[k], lane + (sh >> 5), sh & 31);
+                            for (int k = 0; k < 4; k++) if (k < np) RC[k] = plane_window(RC[k], lane + (sh >> 5), sh & 31);
                         }
                         len1 = ol; len2 = ol;                                             // :522-525
                         bump(AQC_C_TRIMMED_ADAPTER_BASE, (unsigned long long)(2 * (-offset)));   // :526
@@ -267,7 +310,7 @@ __global__ void __launch_bounds__(THREADS, 2) pair_kernel(const __grid_constant_
                             ov_off = offset; ov_len = ol; ov_diff = distance;
                             cls = AQC_BADLEN; break;
                         }
-                        overlap_any(exo, P1, RC, len1, len2, lane, offset, ol, distance); // :534
+                        overlap_np(np, P1, RC, len1, len2, lane, offset, ol, distance);   // :534
                     }
                     ov_off = offset; ov_len = ol; ov_diff = distance;
                     if (lane == 0) atomicAdd(&s_dih[distance], 1u);                        // :536
@@ -281,12 +324,9 @@ __global__ void __launch_bounds__(THREADS, 2) pair_kernel(const __grid_constant_
                             // mismatch mask of the walk alignment r1[len1-ol+o] vs rc[o] (always this
                             // alignment, whatever offset was found: quirk Q8)
                             const int oc = len1 - ol;
-                            uint32_t xx = (plane_window(P1[0], lane + (oc >> 5), oc & 31) ^ RC[0]) |
-                                          (plane_window(P1[1], lane + (oc >> 5), oc & 31) ^ RC[1]);
-                            if (exo) {
-                                xx |= plane_window(P1[2], lane + (oc >> 5), oc & 31) ^ RC[2];
-                                xx |= plane_window(P1[3], lane + (oc >> 5), oc & 31) ^ RC[3];
-                            }
+                            uint32_t xx = 0;
+#pragma unroll
+                            for (int k = 0; k < 4; k++) if (k < np) xx |= plane_window(P1[k], lane + (oc >> 5), oc & 31) ^ RC[k];
                             xx &= lowmask(ol - (lane << 5));
                             int corrected = 0, masked = 0, skipped = 0;
                             int em_cell[3] = {-1, -1, -1};
@@ -404,6 +444,11 @@ __global__ void __launch_bounds__(THREADS, 2) pair_kernel(const __grid_constant_
             v = s_dih[i]; if (v) atomicAdd(&A.counters[AQC_C_DISTANCE_HIST + i], (unsigned long long)v);
         }
         if (wc0) atomicAdd(&A.counters[lane], wc0);
+        if (blockIdx.x == 0 && tid == 0) {      // TOTAL_READS / TOTAL_BASES (:416,:431,:433) are sums over the batch
+            atomicAdd(&A.counters[AQC_C_TOTAL_READS], (unsigned long long)A.n);
+            atomicAdd(&A.counters[AQC_C_TOTAL_BASES_R1], (unsigned long long)(A.off1[A.n] - A.off1[0]));
+            if (paired) atomicAdd(&A.counters[AQC_C_TOTAL_BASES_R2], (unsigned long long)(A.off2[A.n] - A.off2[0]));
+        }
         if (wc1 && lane < 16) atomicAdd(&A.counters[AQC_C_ERR_MATRIX + lane], wc1);
     }
 }
