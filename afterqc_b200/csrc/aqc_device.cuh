@@ -20,6 +20,14 @@
 
 namespace aqc {
 
+// Rare paths (statRead, exact hasPolyX, LUT plane build) stay inlined: out-of-line calls force the ABI register
+// convention onto the hot loop and cost 45 % of the throughput (measured, profiles/r01_notes.md).
+#ifdef AQC_NOINLINE_RARE
+#define AQC_RARE __noinline__
+#else
+#define AQC_RARE __forceinline__
+#endif
+
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARPS = 8;
 constexpr int THREADS = WARPS * 32;
@@ -66,6 +74,7 @@ struct KArgs {
     int mode;
     // parameters
     aqc_params p;
+    int poly_m;           // hasPolyX screen: consecutive 'same as previous' bits needed; -1 never flagged, 0 always candidate
     // stat gating (MODE_STAT): records with stat_lo <= global < stat_hi; order = order_base + g - stat_lo
     uint64_t stat_lo, stat_hi, order_base;
     // outputs
@@ -128,7 +137,7 @@ __device__ __forceinline__ uint32_t plane_window(uint32_t p, int word, int sh) {
 // rc-side code (this yields the planes of reverseComplement(read), util.py:42-51).
 // Also returns the exact count of 'N' bytes (nNumber, preprocesser.py:70-76) and whether any
 // position has a code >= 4 (then planes 2,3 are needed by the comparisons).
-__device__ __forceinline__ void build_planes(const uint8_t *s, int len, bool rev, const uint8_t *lut1, int lane,
+__device__ AQC_RARE void build_planes(const uint8_t *s, int len, bool rev, const uint8_t *lut1, int lane,
                                              uint32_t (&P)[4], int &n_count, bool &exotic) {
     P[0] = P[1] = P[2] = P[3] = 0;
     n_count = 0;
@@ -279,7 +288,7 @@ __device__ __forceinline__ bool polyx_screen(const uint32_t (&P)[4], bool exotic
 }
 
 // Exact hasPolyX on the raw bytes (taken only by screened candidates).  Returns the char or 0.
-__device__ __forceinline__ int polyx_exact(const uint8_t *s, int len, int maxPoly, int mismatch, const uint8_t *lut2, int lane) {
+__device__ AQC_RARE int polyx_exact(const uint8_t *s, int len, int maxPoly, int mismatch, const uint8_t *lut2, int lane) {
     if (len < maxPoly) return 0;
     const int T = maxPoly - mismatch;
     // first byte outside polyArray aborts the scan (:41-42)
@@ -422,15 +431,20 @@ __device__ __forceinline__ int count_lowq_fast(const uint8_t *q, int len, int th
     return (int)__reduce_add_sync(FULL, (unsigned)n);
 }
 
-// run-length screen of hasPolyX on planes of EITHER code set (np planes), cheap version for m = R-1 <= 31
-__device__ __forceinline__ bool polyx_screen_fast(const uint32_t (&P)[4], int np, int len, int maxPoly, int mismatch, int lane) {
-    if (len < maxPoly) return false;
-    if (mismatch < 0) return false;
-    const int T = maxPoly - mismatch;
-    if (T <= 1) return true;
-    const int m = (T + mismatch) / (mismatch + 1) - 1;   // consecutive "same as previous" bits needed
-    if (m <= 0) return true;
-    if (m > 31) return true;                             // (caller falls back to the general screen)
+// Run-length screen of hasPolyX (preprocesser.py:30-51) on the planes of either code set (np planes).
+// A flagged window holds >= T = maxPoly - mismatch equal bases with <= mismatch interruptions, i.e. a run of
+// >= R = ceil(T / (mismatch + 1)) identical bases, i.e. m = R - 1 consecutive "same as previous" bits.
+// m is computed once on the host (KArgs.poly_m): -1 = never flagged, 0 = every read is a candidate, > 31 = candidate.
+__device__ __forceinline__ uint32_t run_within_word(uint32_t y, int m) {   // bit x set <=> y[x..x+m-1] all ones (inside the word)
+    if (m == 10) { y &= y >> 1; y &= y >> 2; y &= y >> 4; y &= y >> 2; return y; }    // default -p 35 -a 2
+    int t = 1;
+    while (t < m) { const int step = min(t, m - t); y &= y >> step; t += step; }
+    return y;
+}
+
+__device__ __forceinline__ bool polyx_screen_fast(const uint32_t (&P)[4], int np, int len, int maxPoly, int m, int lane) {
+    if (len < maxPoly || m < 0) return false;
+    if (m == 0 || m > 31) return true;
     uint32_t d = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -448,11 +462,39 @@ __device__ __forceinline__ bool polyx_screen_fast(const uint32_t (&P)[4], int np
     int nxt = __shfl_down_sync(FULL, trail, 1);
     if (lane == 31) nxt = 0;
     bool hit = (lead + nxt) >= m;
-    // runs inside a word
-    int t = 1;
-    while (t < m) { const int step = min(t, m - t); y &= y >> step; t += step; }
-    hit |= (y != 0u);
+    hit |= (run_within_word(y, m) != 0u);
     return __ballot_sync(FULL, hit) != 0u;
+}
+
+// Both mates in one instruction stream (reads <= 512 bases): lanes 0-15 hold the words of mate 1, lanes 16-31 those of
+// mate 2 (forward fast planes A, B with the same np).  Returns bit 0 = mate 1 candidate, bit 1 = mate 2 candidate.
+__device__ __forceinline__ uint32_t polyx_screen_pair(const uint32_t (&A)[4], const uint32_t (&B)[4], int np, int len1, int len2,
+                                                      int maxPoly, int m, int lane) {
+    const bool hi = lane >= 16;
+    const int hl = lane & 15;
+    const int len = hi ? len2 : len1;
+    uint32_t d = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (k < np) {
+            const uint32_t b = __shfl_sync(FULL, B[k], hl);          // word hl of mate 2 (meaningful for lanes >= 16)
+            const uint32_t w = hi ? b : A[k];
+            uint32_t up = __shfl_up_sync(FULL, w, 1);
+            if (hl == 0) up = 0;
+            d |= w ^ __funnelshift_l(up, w, 1);
+        }
+    }
+    uint32_t y = ~d & lowmask(len - (hl << 5));
+    if (hl == 0) y &= ~1u;
+    const int lead = __clz((int)~y);
+    int trail = __ffs((int)~y) - 1; if (trail < 0) trail = 32;
+    int nxt = __shfl_down_sync(FULL, trail, 1);
+    if (hl == 15) nxt = 0;
+    bool hit = (lead + nxt) >= m;
+    hit |= (run_within_word(y, m) != 0u);
+    hit &= (len >= maxPoly);
+    const uint32_t hb = __ballot_sync(FULL, hit);
+    return ((hb & 0xFFFFu) ? 1u : 0u) | ((hb >> 16) ? 2u : 0u);
 }
 
 // leaner offset scan (same contract as scan_dir) for lenF >= 32
@@ -554,7 +596,7 @@ __device__ __forceinline__ void first_min(unsigned long long *addr, unsigned lon
 // seeds), while a k-mer X over COMP's alphabet seeds rc(X) only if X itself was not seeded earlier.  The side
 // table therefore keeps the first direct sighting (sfirst) and the first seeding by a foreign-byte k-mer (sseed)
 // apart, guarantees a slot for rc(X), and aqc_get_kmer_side resolves the partner rule on the host.
-__device__ __forceinline__ void stat_read(const uint8_t *s, const uint8_t *qv, int len, int mate, uint64_t order,
+__device__ AQC_RARE void stat_read(const uint8_t *s, const uint8_t *qv, int len, int mate, uint64_t order,
                                           const QcSmem &sm, const QcDev &qd, const uint8_t *lut1, const uint8_t *lut2, const uint8_t *lut3,
                                           int K, int lane, int *error_flag) {
     if (len <= 0) return;

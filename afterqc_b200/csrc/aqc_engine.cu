@@ -218,6 +218,12 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         if (slot >= 0) { A.qc[m] = ctx->qc[slot].d; A.qc[m].valid = 1; }
         else { A.qc[m] = ctx->qc[0].d; A.qc[m].valid = 0; }
     }
+    {   // hasPolyX screen constant (see polyx_screen_fast)
+        const int mismatch = ctx->p.allow_mismatch_in_poly, T = ctx->p.poly_size_limit - mismatch;
+        if (mismatch < 0) A.poly_m = -1;
+        else if (T <= 1) A.poly_m = 0;
+        else { int m = (T + mismatch) / (mismatch + 1) - 1; A.poly_m = m < 0 ? 0 : m; }
+    }
     size_t smem = smem_bytes_for(P, A.col_cap, maxl);
     while (smem > ctx->max_dyn_smem && P > 1) {
         P >>= 1;
@@ -226,7 +232,9 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
     }
     if (smem > ctx->max_dyn_smem) return fail(ctx, AQC_ERR_INVALID, "tile does not fit shared memory");
     int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_kernel, THREADS, smem));
+    if (x.mode == MODE_FILTER) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_kernel<MODE_FILTER>, THREADS, smem));
+    else if (x.mode == MODE_STAT) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_kernel<MODE_STAT>, THREADS, smem));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_kernel<MODE_OPS>, THREADS, smem));
     if (occ < 1) occ = 1;
     uint32_t grid = std::min<uint32_t>(A.num_tiles, (uint32_t)(ctx->sm_count * occ));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -240,7 +248,9 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         ctx->ev_used++;
         CK(cudaEventRecord(e0, stream));
     }
-    pair_kernel<<<grid, THREADS, smem, stream>>>(A);
+    if (x.mode == MODE_FILTER) pair_kernel<MODE_FILTER><<<grid, THREADS, smem, stream>>>(A);
+    else if (x.mode == MODE_STAT) pair_kernel<MODE_STAT><<<grid, THREADS, smem, stream>>>(A);
+    else pair_kernel<MODE_OPS><<<grid, THREADS, smem, stream>>>(A);
     CK(cudaGetLastError());
     if (timed) CK(cudaEventRecord(e1, stream));
     ctx->launches++;
@@ -399,11 +409,18 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
         CK(cudaMemcpy(ctx->d_luts, &L, sizeof L, cudaMemcpyHostToDevice));
         int optin = 0;
         CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-        cudaFuncAttributes fa;
-        CK(cudaFuncGetAttributes(&fa, pair_kernel));
-        ctx->max_dyn_smem = (size_t)optin - fa.sharedSizeBytes;
-        CK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->max_dyn_smem));
-        CK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        const void *kernels[3] = {(const void *)pair_kernel<MODE_FILTER>, (const void *)pair_kernel<MODE_STAT>, (const void *)pair_kernel<MODE_OPS>};
+        size_t max_static = 0;
+        for (const void *k : kernels) {
+            cudaFuncAttributes fa;
+            CK(cudaFuncGetAttributes(&fa, k));
+            max_static = std::max(max_static, fa.sharedSizeBytes);
+        }
+        ctx->max_dyn_smem = (size_t)optin - max_static - 64;
+        for (const void *k : kernels) {
+            CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->max_dyn_smem));
+            CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
         for (int s = 0; s < AQC_NUM_QC; s++) { int r = alloc_qc(ctx, ctx->qc[s]); if (r) return r; }
         return aqc_reset(ctx);
     };

@@ -23,7 +23,7 @@ struct PairPlanes {
 };
 
 __device__ __forceinline__ void prepare_pair(const uint8_t *r1, int len1, const uint8_t *r2, int len2, bool paired, bool want_poly,
-                                             int maxPoly, int mismatch, const uint8_t *lut1, int lane, PairPlanes &pp) {
+                                             int maxPoly, int poly_m, const uint8_t *lut1, int lane, PairPlanes &pp) {
     FastPlanes F1, F2;
     fast_build(r1, len1, lane, F1);
     bool exotic = F1.exotic;
@@ -35,11 +35,16 @@ __device__ __forceinline__ void prepare_pair(const uint8_t *r1, int len1, const 
 #pragma unroll
         for (int k = 0; k < 4; k++) { pp.P1[k] = F1.P[k]; pp.RC[k] = 0; }
         pp.n1 = F1.n_count; pp.n2 = F2.n_count;
-        if (want_poly) pp.cand1 = polyx_screen_fast(F1.P, F1.hasN ? 3 : 2, len1, maxPoly, mismatch, lane);
-        if (paired) {
-            if (want_poly) pp.cand2 = polyx_screen_fast(F2.P, F2.hasN ? 3 : 2, len2, maxPoly, mismatch, lane);
-            fast_revcomp(F2, len2, lane, pp.RC);
+        if (want_poly && poly_m >= 0) {
+            if (paired && poly_m >= 1 && poly_m <= 31 && len1 <= 512 && len2 <= 512) {
+                const uint32_t c = polyx_screen_pair(F1.P, F2.P, pp.np, len1, len2, maxPoly, poly_m, lane);
+                pp.cand1 = (c & 1u) != 0; pp.cand2 = (c & 2u) != 0;
+            } else {
+                pp.cand1 = polyx_screen_fast(F1.P, pp.np, len1, maxPoly, poly_m, lane);
+                if (paired) pp.cand2 = polyx_screen_fast(F2.P, pp.np, len2, maxPoly, poly_m, lane);
+            }
         }
+        if (paired) fast_revcomp(F2, len2, lane, pp.RC);
     } else {
         pp.np = 4;
         bool e1 = false, e2 = false;
@@ -47,10 +52,10 @@ __device__ __forceinline__ void prepare_pair(const uint8_t *r1, int len1, const 
         pp.n2 = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) pp.RC[k] = 0;
-        if (want_poly) pp.cand1 = polyx_screen(pp.P1, e1, len1, maxPoly, mismatch, lane);
+        if (want_poly) pp.cand1 = polyx_screen_fast(pp.P1, 4, len1, maxPoly, poly_m, lane);
         if (paired) {
             build_planes(r2, len2, true, lut1, lane, pp.RC, pp.n2, e2);
-            if (want_poly) pp.cand2 = polyx_screen(pp.RC, e2, len2, maxPoly, mismatch, lane);
+            if (want_poly) pp.cand2 = polyx_screen_fast(pp.RC, 4, len2, maxPoly, poly_m, lane);
         }
     }
 }
@@ -73,6 +78,7 @@ struct StageBuf {
 #ifndef AQC_MIN_BLOCKS
 #define AQC_MIN_BLOCKS 4
 #endif
+template <int MODE>
 __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __grid_constant__ KArgs A) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[NSTAGES];
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
             }
 
             // ================================ MODE_STAT ================================
-            if (A.mode == MODE_STAT) {
+            if (MODE == MODE_STAT) {
                 if (gidx >= A.stat_lo && gidx < A.stat_hi) {
                     uint64_t order = A.order_base + (gidx - A.stat_lo);
                     if (A.qc[0].valid) stat_read(S1, Q1, olen1, 0, order, qsm, A.qc[0], lut1, lut2, lut3, A.p.qc_kmer, lane, A.error_flag);
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
             int cls = AQC_GOOD;
             const bool do_trim = (A.p.trim_front > 0 || A.p.trim_tail > 0);   // gate keyed on R1 only (quirk Q4)
 
-            if (A.mode == MODE_OPS) {
+            if (MODE == MODE_OPS) {
                 if (do_trim) {
                     py_trim(olen1, A.p.trim_front, A.p.trim_tail, start1, len1);
                     if (paired) py_trim(olen2, A.p.trim_front2, A.p.trim_tail2, start2, len2);
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
                 const uint8_t *r1 = S1 + start1, *r1q = Q1 + start1;
                 const uint8_t *r2 = paired ? S2 + start2 : nullptr, *r2q = paired ? Q2 + start2 : nullptr;
                 PairPlanes pl;
-                prepare_pair(r1, len1, r2, len2, paired, true, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lut1, lane, pl);
+                prepare_pair(r1, len1, r2, len2, paired, true, A.p.poly_size_limit, A.poly_m, lut1, lane, pl);
                 const int n1 = pl.n1, n2 = pl.n2;
                 const int thr = A.p.qualified_quality_phred + 33;
                 int lowq1 = lowq_any(r1q, len1, thr, lane), lowq2 = 0;
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
                 uint8_t *r1 = S1 + start1, *r1q = Q1 + start1;
                 uint8_t *r2 = paired ? S2 + start2 : nullptr, *r2q = paired ? Q2 + start2 : nullptr;
                 PairPlanes pl;
-                prepare_pair(r1, len1, r2, len2, paired, A.p.poly_size_limit > 0, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lut1, lane, pl);
+                prepare_pair(r1, len1, r2, len2, paired, A.p.poly_size_limit > 0, A.p.poly_size_limit, A.poly_m, lut1, lane, pl);
 
                 if (A.p.poly_size_limit > 0) {                             // :482-490
                     bool poly = false;
@@ -438,7 +444,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
     // ---- epilogue: flush everything this CTA accumulated ----
     __syncthreads();
     flush_qc();
-    if (A.mode == MODE_FILTER) {
+    if (MODE == MODE_FILTER) {
         for (int i = tid; i <= A.max_len; i += THREADS) {
             uint32_t v = s_ovh[i]; if (v) atomicAdd(&A.counters[AQC_C_OVERLAP_HIST + i], (unsigned long long)v);
             v = s_dih[i]; if (v) atomicAdd(&A.counters[AQC_C_DISTANCE_HIST + i], (unsigned long long)v);

@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU (default = BASELINE config)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU sample (0 = auto)")
+    ap.add_argument("--qc-sample", type=int, default=QC_SAMPLE, help="--qc_sample of the workload (profiling runs on fewer pairs scale it to keep the 2%% mix)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -243,7 +244,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     n = args.pairs
-    params = _abi.Params.defaults(qc_sample=QC_SAMPLE)
+    QS = args.qc_sample
+    params = _abi.Params.defaults(qc_sample=QS)
     eng = Engine(params, device=local_rank)
     stream = torch.cuda.Stream(device)          # the launching stream of every kernel below (torch events time it)
     torch.cuda.set_stream(stream)
@@ -254,7 +256,7 @@ def run_ours(args):
     wb = make_device_workload(device, n, seed=20260927 + rank, first_index=first_index)
 
     # records of this shard inside the prefilter window [999, 999 + qc_sample) (global indices)
-    w_lo_g, w_hi_g = STAT_LO, STAT_LO + QC_SAMPLE
+    w_lo_g, w_hi_g = STAT_LO, STAT_LO + QS
     s_lo = max(w_lo_g, first_index) - first_index
     s_hi = min(w_hi_g, first_index + n) - first_index
     has_window = s_hi > s_lo
@@ -414,7 +416,7 @@ def run_ours(args):
             "value": value, "unit": "M read-pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu": n, "read_len": READ_LEN, "qc_sample": QC_SAMPLE,
+            "config": {"workload": WORKLOAD, "pairs_per_gpu": n, "read_len": READ_LEN, "qc_sample": QS,
                        "l2": "inputs (%.1f GB/GPU) exceed the 126 MB L2; no explicit flush" % (col_bytes / 1e9),
                        "parallelism": "read-sharded x%d, NCCL all-reduce of the counter blocks per step" % world if world > 1 else "1 GPU"},
             "clocks": clocks,
