@@ -29,7 +29,10 @@ namespace aqc {
 #endif
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int WARPS = 8;
+#ifndef AQC_WARPS
+#define AQC_WARPS 8
+#endif
+constexpr int WARPS = AQC_WARPS;
 constexpr int THREADS = WARPS * 32;
 constexpr int NSTAGES = 2;
 constexpr int MAX_TILE_PAIRS = 32;

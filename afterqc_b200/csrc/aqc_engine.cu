@@ -199,6 +199,7 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
     int maxl = std::max(b.max_len, 8);
     // tile: <= 32 pairs and <= ~24 KB of column bytes per mate column group
     int P = std::min(MAX_TILE_PAIRS, std::max(1, (24 * 1024) / (4 * maxl)));
+    if (const char *tp = getenv("AQC_TILE_PAIRS")) P = std::max(1, std::min(P, atoi(tp)));   // tuning knob
     // small batches: shrink tiles so that every SM gets work
     while (P > 8 && (b.n + P - 1) / P < (uint32_t)ctx->sm_count * 2) P >>= 1;
     A.tile_pairs = P;

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
     __shared__ __align__(8) uint64_t full_bar[NSTAGES];
     __shared__ uint32_t tile_base[NSTAGES][2];      // 16-byte aligned column origin of the staged tile
     __shared__ uint32_t qc_reads_since_flush;
+    __shared__ uint32_t tile_next[NSTAGES];        // AQC_DYNAMIC_CLAIM: next unclaimed pair of the staged tile
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool paired = A.seq2 != nullptr;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
     if (tid == 0) {
         for (int s = 0; s < NSTAGES; s++) mbar_init(&full_bar[s], 1);
         qc_reads_since_flush = 0;
+        for (int s = 0; s < NSTAGES; s++) tile_next[s] = 0;
         fence_mbar_init();
     }
     __syncthreads();
@@ -192,7 +194,15 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
         const uint32_t o0 = p0 & ~3u;
         const uint32_t g1 = tile_base[st][0], g2 = tile_base[st][1];
 
+#ifdef AQC_DYNAMIC_CLAIM
+        for (;;) {
+            uint32_t pp = 0;
+            if (lane == 0) pp = p0 + atomicAdd(&tile_next[st], 1u);
+            pp = __shfl_sync(FULL, pp, 0);
+            if (pp >= p1) break;
+#else
         for (uint32_t pp = p0 + warp; pp < p1; pp += WARPS) {
+#endif
             const uint32_t a1 = sb.off1[pp - o0], e1 = sb.off1[pp + 1 - o0];
             uint8_t *S1 = sb.col[0] + (a1 - g1);
             uint8_t *Q1 = sb.col[1] + (a1 - g1);
@@ -429,6 +439,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
         __syncthreads();
         if (tid == 0) {
             uint32_t nxt = tile + (uint32_t)NSTAGES * gridDim.x;
+            tile_next[st] = 0;
             if (nxt < A.num_tiles) issue_tile(nxt, st);
             qc_reads_since_flush += (p1 - p0);
         }
