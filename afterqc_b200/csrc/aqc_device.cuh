@@ -402,6 +402,86 @@ __device__ __forceinline__ void fast_build(const uint8_t *s, int len, int lane, 
     }
 }
 
+// Both mates in ONE instruction stream: lanes 0-15 convert mate 1, lanes 16-31 mate 2, 16 consecutive bases per lane
+// (256 bases per mate and pass).  Same arithmetic as fast_build on four words; the 16-bit plane slices of lanes
+// 2j, 2j+1 form plane word j, so the gather needs two shuffles per mate.  len2 = 0 for single-end input.
+__device__ __forceinline__ void fast_build2(const uint8_t *r1, int len1, const uint8_t *r2, int len2, int lane,
+                                            FastPlanes &F1, FastPlanes &F2) {
+    F1.P[0] = F1.P[1] = F1.P[2] = F1.P[3] = 0; F1.n_count = 0; F1.hasN = false; F1.exotic = false;
+    F2.P[0] = F2.P[1] = F2.P[2] = F2.P[3] = 0; F2.n_count = 0; F2.hasN = false; F2.exotic = false;
+    const bool hi = lane >= 16;
+    const int hl = lane & 15;
+    const uint8_t *s = hi ? r2 : r1;
+    const int len = hi ? len2 : len1;
+    const int npass = (max(len1, len2) + 255) >> 8;
+    for (int p = 0; p < npass; p++) {
+        const int x0 = (p << 8) + (hl << 4);
+        uint32_t v[4] = {0, 0, 0, 0}, vm[4] = {0, 0, 0, 0};
+        const int nv = len - x0;
+        if (nv > 0) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(s + x0);
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+            const int sh = (int)(a & 3) * 8;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+            vm[0] = bytemask_lo(nv); vm[1] = bytemask_lo(nv - 4); vm[2] = bytemask_lo(nv - 8); vm[3] = bytemask_lo(nv - 12);
+            v[0] = __funnelshift_r(w0, w1, sh) & vm[0];
+            v[1] = __funnelshift_r(w1, w2, sh) & vm[1];
+            v[2] = __funnelshift_r(w2, w3, sh) & vm[2];
+            v[3] = __funnelshift_r(w3, w4, sh) & vm[3];
+        }
+        uint32_t t[4], bad = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            t[i] = (v[i] >> 1) & 0x03030303u;
+            const uint32_t e = __byte_perm(0x47544341u, 0u, __byte_perm(t[i] | (t[i] >> 4), 0u, 0x4420));
+            bad |= (e ^ v[i]) & vm[i];
+        }
+        uint32_t nbits = 0;
+        const uint32_t anybad = __ballot_sync(FULL, bad != 0u);
+        if (anybad) {                                              // warp-uniform: some non-ACGT byte in this pass
+            uint32_t ex = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t isN = ~hibit_nonzero(v[i] ^ 0x4E4E4E4Eu) & 0x80808080u & vm[i];
+                const uint32_t e = __byte_perm(0x47544341u, 0u, __byte_perm(t[i] | (t[i] >> 4), 0u, 0x4420));
+                ex |= hibit_nonzero((e ^ v[i]) & vm[i]) & ~isN;
+                const uint32_t n01 = isN >> 7;
+                t[i] &= ~(n01 * 3u);
+                nbits |= gather4(n01) << (4 * i);
+            }
+            const uint32_t exb = __ballot_sync(FULL, ex != 0u);
+            if (exb & 0xFFFFu) F1.exotic = true;
+            if (exb >> 16) F2.exotic = true;
+            const uint32_t nb = __ballot_sync(FULL, nbits != 0u);
+            if (nb) {
+                const unsigned c = (unsigned)__popc(nbits);
+                if (nb & 0xFFFFu) { F1.hasN = true; F1.n_count += (int)__reduce_add_sync(FULL, hi ? 0u : c); }
+                if (nb >> 16) { F2.hasN = true; F2.n_count += (int)__reduce_add_sync(FULL, hi ? c : 0u); }
+            }
+        }
+        uint32_t p0 = 0, p1 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            p0 |= gather4(t[i] & 0x01010101u) << (4 * i);
+            p1 |= gather4((t[i] >> 1) & 0x01010101u) << (4 * i);
+        }
+        const uint32_t pv = p0 | (p1 << 16);
+        const int jj = (lane & 7) << 1;
+        const uint32_t a1 = __shfl_sync(FULL, pv, jj), b1 = __shfl_sync(FULL, pv, jj + 1);
+        const uint32_t a2 = __shfl_sync(FULL, pv, 16 + jj), b2 = __shfl_sync(FULL, pv, 17 + jj);
+        const bool mine = (lane >> 3) == p;
+        if (mine) {
+            F1.P[0] = __byte_perm(a1, b1, 0x5410); F1.P[1] = __byte_perm(a1, b1, 0x7632);
+            F2.P[0] = __byte_perm(a2, b2, 0x5410); F2.P[1] = __byte_perm(a2, b2, 0x7632);
+        }
+        if (F1.hasN || F2.hasN) {                                  // warp-uniform
+            const uint32_t na1 = __shfl_sync(FULL, nbits, jj), nb1 = __shfl_sync(FULL, nbits, jj + 1);
+            const uint32_t na2 = __shfl_sync(FULL, nbits, 16 + jj), nb2 = __shfl_sync(FULL, nbits, 17 + jj);
+            if (mine) { F1.P[2] = __byte_perm(na1, nb1, 0x5410); F2.P[2] = __byte_perm(na2, nb2, 0x5410); }
+        }
+    }
+}
+
 // planes of reverseComplement(read) from its forward fast planes: rc[i] = comp(fwd[len-1-i])
 __device__ __forceinline__ void fast_revcomp(const FastPlanes &F, int len, int lane, uint32_t (&RC)[4]) {
     const int s = 1024 - len;

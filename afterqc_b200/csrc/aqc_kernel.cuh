@@ -25,10 +25,8 @@ struct PairPlanes {
 __device__ __forceinline__ void prepare_pair(const uint8_t *r1, int len1, const uint8_t *r2, int len2, bool paired, bool want_poly,
                                              int maxPoly, int poly_m, const uint8_t *lut1, int lane, PairPlanes &pp) {
     FastPlanes F1, F2;
-    fast_build(r1, len1, lane, F1);
-    bool exotic = F1.exotic;
-    F2.hasN = false; F2.exotic = false; F2.n_count = 0;
-    if (paired) { fast_build(r2, len2, lane, F2); exotic |= F2.exotic; }
+    fast_build2(r1, len1, r2, paired ? len2 : 0, lane, F1, F2);
+    const bool exotic = F1.exotic || F2.exotic;
     pp.cand1 = pp.cand2 = false;
     if (!exotic) {
         pp.np = (F1.hasN || F2.hasN) ? 3 : 2;
