@@ -688,12 +688,21 @@ __device__ AQC_RARE void stat_read(const uint8_t *s, const uint8_t *qv, int len,
     uint32_t *dsc = sm.disc + (size_t)mate * sm.max_len;
     int gc = 0;
     const int nk = len - K;                         // k-mers start at i < len - K (quirk Q11)
+    const uint32_t km = (K >= 32) ? 0xffffffffu : ((1u << K) - 1u);
     // k-mer plane words of the previous chunk (positions base-32 .. base-1)
     uint32_t pk0 = 0, pk1 = 0, pkv = 0;
+    // software pipeline of the dense first-seen stamps: the load issued for chunk c-1 is consumed one iteration later
+    unsigned long long pend_val = 0, pend_when = 0;
+    uint32_t pend_idx = 0;
+    bool pend = false;
     const int nchunks = (len + 31) >> 5;
-    for (int c = 0; c <= nchunks; c++) {            // one extra iteration drains the k-mer pipeline
+    for (int c = 0; c <= nchunks + 1; c++) {        // +1: k-mers of the last chunk, +1: drain the stamp pipeline
         const int base = c << 5;
         const int pos = base + lane;
+        // ---- stage C: finish the stamp update whose load was issued in the previous iteration ----
+        if (pend && pend_val > pend_when) atomicMin(&qd.kfirst[pend_idx], pend_when);
+        pend = false;
+        if (c > nchunks) break;
         uint32_t k0 = 0, k1 = 0, kv = 0;
         if (c < nchunks) {
             bool valid = pos < len;
@@ -716,23 +725,20 @@ __device__ AQC_RARE void stat_read(const uint8_t *s, const uint8_t *qv, int len,
             kv = __ballot_sync(FULL, valid && (l2 & 0x40u));
         }
         if (c > 0) {
-            // k-mers starting in the previous chunk: i = base - 32 + lane
+            // ---- stage B: k-mers starting in the previous chunk: i = base - 32 + lane ----
             const int i = base - 32 + lane;
             if (i < nk) {
-                const uint32_t km = (K >= 32) ? 0xffffffffu : ((1u << K) - 1u);
                 uint32_t w0 = __funnelshift_r(pk0, k0, lane) & km;
                 uint32_t w1 = __funnelshift_r(pk1, k1, lane) & km;
                 uint32_t wv = __funnelshift_r(pkv, kv, lane) & km;
                 unsigned long long when = (order << 11) | ((unsigned long long)i << 1);
                 if (wv == km) {
-                    uint32_t idx = (w1 << K) | w0;
-                    // reverse complement: reverse the K positions, complement = invert both bits
-                    uint32_t r0 = (__brev(~w0) >> (32 - K)) & km;
-                    uint32_t r1 = (__brev(~w1) >> (32 - K)) & km;
-                    uint32_t ridx = (r1 << K) | r0;
+                    // dense table: count + DIRECT first sighting only; the stamp a k-mer gets from being seeded by its
+                    // reverse complement is derived at fetch: first[X] = min(direct[X], direct[rc(X)] | 1)
+                    const uint32_t idx = (w1 << K) | w0;
+                    pend_val = __ldcg(&qd.kfirst[idx]);
+                    pend_idx = idx; pend_when = when; pend = true;
                     atomicAdd(&qd.kcnt[idx], 1ULL);
-                    first_min(&qd.kfirst[idx], when);
-                    first_min(&qd.kfirst[ridx], when | 1ULL);
                 } else {
                     unsigned long long key = 0, rkey = 0;
                     bool foreign = false;

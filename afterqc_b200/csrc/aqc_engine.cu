@@ -629,16 +629,23 @@ int aqc_get_kmer_dense(aqc_ctx *ctx, int slot, uint64_t *counts, uint64_t *first
     std::vector<unsigned long long> c(q.dense_n), f(q.dense_n);
     CK(cudaMemcpy(c.data(), q.d.kcnt, q.dense_n * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(f.data(), q.d.kfirst, q.dense_n * 8, cudaMemcpyDeviceToHost));
-    // internal index (plane1 bits << K) | plane0 bits, bit t = base t  ->  natural index, base 0 most significant
+    // internal index (plane1 bits << K) | plane0 bits, bit t = base t  ->  natural index, base 0 most significant.
+    // The device keeps DIRECT first sightings; a k-mer is also inserted (with count 0) when its reverse complement is
+    // first seen (qualitycontrol.py:118-122): first[X] = min(direct[X], direct[rc(X)] | 1).
+    const uint32_t kmask = (1u << K) - 1u;
+    auto brevK = [&](uint32_t w) { uint32_t r = 0; for (int t = 0; t < K; t++) r |= ((w >> t) & 1u) << (K - 1 - t); return r; };
     for (size_t in = 0; in < q.dense_n; in++) {
-        uint32_t w0 = (uint32_t)in & ((1u << K) - 1u), w1 = (uint32_t)(in >> K);
+        uint32_t w0 = (uint32_t)in & kmask, w1 = (uint32_t)(in >> K);
         size_t nat = 0;
         for (int t = 0; t < K; t++) {
             uint32_t code = ((w0 >> t) & 1u) | (((w1 >> t) & 1u) << 1);
             nat |= (size_t)code << (2 * (K - 1 - t));
         }
+        const size_t rin = ((size_t)brevK(~w1 & kmask) << K) | brevK(~w0 & kmask);   // reverse complement (both code bits inverted)
+        unsigned long long fst = f[in];
+        if (f[rin] != AQC_KMER_NEVER) fst = std::min(fst, f[rin] | 1ULL);
         counts[nat] = c[in];
-        first[nat] = f[in];
+        first[nat] = fst;
     }
     return rc;
 }
