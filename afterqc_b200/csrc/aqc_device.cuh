@@ -624,19 +624,20 @@ __device__ __forceinline__ int scan_dir_fast(const uint32_t (&S)[4], const uint3
 template <int NP>
 __device__ __forceinline__ void overlap_fast(const uint32_t (&P1)[4], const uint32_t (&RC)[4], int len1, int len2, int lane,
                                              int &offset, int &ol, int &diff) {
-    int o = (len2 >= 32) ? scan_dir_fast<NP>(P1, RC, len1, len2, lane, ol, diff) : scan_dir<NP>(P1, RC, len1, len2, lane, ol, diff);
+    int o = scan_dir_fast<NP>(P1, RC, len1, len2, lane, ol, diff);      // forward  util.py:172-186
     if (o >= 0) { offset = o; return; }
-    o = (len1 >= 32) ? scan_dir_fast<NP>(RC, P1, len2, len1, lane, ol, diff) : scan_dir<NP>(RC, P1, len2, len1, lane, ol, diff);
+    o = scan_dir_fast<NP>(RC, P1, len2, len1, lane, ol, diff);          // reverse  util.py:194-209
     if (o >= 0) { offset = -o; return; }
     offset = 0; ol = 0; diff = 0;
 }
 
-// np = 2 (ACGT only), 3 (fast codes with N plane) or 4 (general LUT codes)
+// np = 2 (ACGT only), 3 (fast codes with N plane) or 4 (general LUT codes).  Mates shorter than 32 bases (rare) and
+// the LUT-coded pairs share the one general 4-plane scan (unused planes are zero on both sides).
 __device__ __forceinline__ void overlap_np(int np, const uint32_t (&P1)[4], const uint32_t (&RC)[4], int len1, int len2,
                                            int lane, int &offset, int &ol, int &diff) {
-    if (np == 2) overlap_fast<2>(P1, RC, len1, len2, lane, offset, ol, diff);
-    else if (np == 3) overlap_fast<3>(P1, RC, len1, len2, lane, offset, ol, diff);
-    else overlap_hm<4>(P1, RC, len1, len2, lane, offset, ol, diff);
+    if (np == 4 || len1 < 32 || len2 < 32) overlap_hm<4>(P1, RC, len1, len2, lane, offset, ol, diff);
+    else if (np == 2) overlap_fast<2>(P1, RC, len1, len2, lane, offset, ol, diff);
+    else overlap_fast<3>(P1, RC, len1, len2, lane, offset, ol, diff);
 }
 
 // ------------------------------------------------------------------------------------------

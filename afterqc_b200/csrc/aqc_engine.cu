@@ -118,6 +118,12 @@ size_t smem_bytes_for(int P, int col_cap, int max_len) {
     return NSTAGES * stage + 768 + acc + 64;
 }
 
+const void *kernel_for(int mode, bool paired) {
+    if (mode == MODE_FILTER) return paired ? (const void *)pair_kernel<MODE_FILTER, true> : (const void *)pair_kernel<MODE_FILTER, false>;
+    if (mode == MODE_STAT) return paired ? (const void *)pair_kernel<MODE_STAT, true> : (const void *)pair_kernel<MODE_STAT, false>;
+    return paired ? (const void *)pair_kernel<MODE_OPS, true> : (const void *)pair_kernel<MODE_OPS, false>;
+}
+
 int alloc_qc(aqc_ctx *ctx, QcHost &q) {
     q.dense_n = (size_t)1 << (2 * ctx->p.qc_kmer);
     int lg = ctx->p.kmer_side_log2 > 0 ? ctx->p.kmer_side_log2 : 20;
@@ -233,9 +239,9 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
     }
     if (smem > ctx->max_dyn_smem) return fail(ctx, AQC_ERR_INVALID, "tile does not fit shared memory");
     int occ = 1;
-    if (x.mode == MODE_FILTER) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_kernel<MODE_FILTER>, THREADS, smem));
-    else if (x.mode == MODE_STAT) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_kernel<MODE_STAT>, THREADS, smem));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_kernel<MODE_OPS>, THREADS, smem));
+    const bool pe = b.seq2 != nullptr;
+    const void *kern = kernel_for(x.mode, pe);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
     if (occ < 1) occ = 1;
     uint32_t grid = std::min<uint32_t>(A.num_tiles, (uint32_t)(ctx->sm_count * occ));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -249,9 +255,8 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         ctx->ev_used++;
         CK(cudaEventRecord(e0, stream));
     }
-    if (x.mode == MODE_FILTER) pair_kernel<MODE_FILTER><<<grid, THREADS, smem, stream>>>(A);
-    else if (x.mode == MODE_STAT) pair_kernel<MODE_STAT><<<grid, THREADS, smem, stream>>>(A);
-    else pair_kernel<MODE_OPS><<<grid, THREADS, smem, stream>>>(A);
+    void *kargs[1] = {(void *)&A};
+    CK(cudaLaunchKernel(kern, dim3(grid), dim3(THREADS), kargs, smem, stream));
     CK(cudaGetLastError());
     if (timed) CK(cudaEventRecord(e1, stream));
     ctx->launches++;
@@ -410,7 +415,8 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
         CK(cudaMemcpy(ctx->d_luts, &L, sizeof L, cudaMemcpyHostToDevice));
         int optin = 0;
         CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-        const void *kernels[3] = {(const void *)pair_kernel<MODE_FILTER>, (const void *)pair_kernel<MODE_STAT>, (const void *)pair_kernel<MODE_OPS>};
+        const void *kernels[6] = {kernel_for(MODE_FILTER, true), kernel_for(MODE_FILTER, false), kernel_for(MODE_STAT, true),
+                                  kernel_for(MODE_STAT, false), kernel_for(MODE_OPS, true), kernel_for(MODE_OPS, false)};
         size_t max_static = 0;
         for (const void *k : kernels) {
             cudaFuncAttributes fa;

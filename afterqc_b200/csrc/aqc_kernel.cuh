@@ -76,7 +76,7 @@ struct StageBuf {
 #ifndef AQC_MIN_BLOCKS
 #define AQC_MIN_BLOCKS 4
 #endif
-template <int MODE>
+template <int MODE, bool PAIRED>
 __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __grid_constant__ KArgs A) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[NSTAGES];
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
     __shared__ uint32_t tile_next[NSTAGES];        // AQC_DYNAMIC_CLAIM: next unclaimed pair of the staged tile
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool paired = A.seq2 != nullptr;
+    constexpr bool paired = PAIRED;
     const int P = A.tile_pairs;
     const int off_cap = ((P + 8) * 4 + 15) & ~15;        // P+1 entries from a 16-byte aligned start (<= P+4) + slack
     const int stage_bytes = (4 * A.col_cap + 2 * off_cap + 127) & ~127;
@@ -292,8 +292,12 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
 
                 if (A.p.poly_size_limit > 0) {                             // :482-490
                     bool poly = false;
-                    if (pl.cand1) poly = polyx_exact(r1, len1, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lut2, lane) != 0;
-                    if (!poly && pl.cand2) poly = polyx_exact(r2, len2, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lut2, lane) != 0;
+                    if (pl.cand1 || pl.cand2) {                             // rare: exact window test of the screened mates
+#pragma unroll 1
+                        for (int m = 0; m < 2 && !poly; m++)
+                            if (m ? pl.cand2 : pl.cand1)
+                                poly = polyx_exact(m ? r2 : r1, m ? len2 : len1, A.p.poly_size_limit, A.p.allow_mismatch_in_poly, lut2, lane) != 0;
+                    }
                     if (poly) { cls = AQC_BADPOL; break; }
                 }
                 if (A.p.unqualified_base_limit > 0) {                      // :493-501 (only lowQual1 tested, quirk Q2)
@@ -414,8 +418,10 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
                 bump(AQC_C_GOOD_BASES_R2, (unsigned long long)len2);
                 const uint64_t total_reads = gidx + 1;
                 if (A.p.qc_sample <= 0 || total_reads < (uint64_t)A.p.qc_sample) {       // :624
-                    stat_read(S1 + start1, Q1 + start1, len1, 0, gidx, qsm, A.qc[0], lut1, lut2, lut3, A.p.qc_kmer, lane, A.error_flag);
-                    if (paired) stat_read(S2 + start2, Q2 + start2, len2, 1, gidx, qsm, A.qc[1], lut1, lut2, lut3, A.p.qc_kmer, lane, A.error_flag);
+#pragma unroll 1
+                    for (int m = 0; m < (paired ? 2 : 1); m++)      // one inlined copy of statRead for both mates
+                        stat_read(m ? S2 + start2 : S1 + start1, m ? Q2 + start2 : Q1 + start1, m ? len2 : len1, m, gidx, qsm, A.qc[m],
+                                  lut1, lut2, lut3, A.p.qc_kmer, lane, A.error_flag);
                 }
             } else {
                 bump(AQC_C_BADTRIM1 + (cls - AQC_BADTRIM1), 1);
