@@ -231,11 +231,17 @@ __device__ __forceinline__ int scan_dir(const uint32_t (&S)[4], const uint32_t (
 template <int NP>
 __device__ __forceinline__ void overlap_hm(const uint32_t (&P1)[4], const uint32_t (&RC)[4], int len1, int len2, int lane,
                                            int &offset, int &ol, int &diff) {
-    int o = scan_dir<NP>(P1, RC, len1, len2, lane, ol, diff);      // forward  util.py:172-186
-    if (o >= 0) { offset = o; return; }
-    o = scan_dir<NP>(RC, P1, len2, len1, lane, ol, diff);          // reverse  util.py:194-209
-    if (o >= 0) { offset = -o; return; }
-    offset = 0; ol = 0; diff = 0;                                   // util.py:212
+    int o = -1, dir = 0;
+#pragma unroll 1
+    for (dir = 0; dir < 2; dir++) {                                  // forward util.py:172-186, reverse :194-209
+        uint32_t S[4], F[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { S[k] = dir ? RC[k] : P1[k]; F[k] = dir ? P1[k] : RC[k]; }
+        o = scan_dir<NP>(S, F, dir ? len2 : len1, dir ? len1 : len2, lane, ol, diff);
+        if (o >= 0) break;
+    }
+    if (o >= 0) offset = dir ? -o : o;
+    else { offset = 0; ol = 0; diff = 0; }                           // util.py:212
 }
 
 __device__ __forceinline__ void overlap_any(bool exotic, const uint32_t (&P1)[4], const uint32_t (&RC)[4], int len1, int len2,

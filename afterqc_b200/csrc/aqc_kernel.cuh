@@ -28,7 +28,7 @@ __device__ __forceinline__ void prepare_pair(const uint8_t *r1, int len1, const 
     fast_build2(r1, len1, r2, paired ? len2 : 0, lane, F1, F2);
     const bool exotic = F1.exotic || F2.exotic;
     pp.cand1 = pp.cand2 = false;
-    if (!exotic) {
+    if (__builtin_expect(!exotic, 1)) {
         pp.np = (F1.hasN || F2.hasN) ? 3 : 2;
 #pragma unroll
         for (int k = 0; k < 4; k++) { pp.P1[k] = F1.P[k]; pp.RC[k] = 0; }
@@ -43,17 +43,18 @@ __device__ __forceinline__ void prepare_pair(const uint8_t *r1, int len1, const 
             }
         }
         if (paired) fast_revcomp(F2, len2, lane, pp.RC);
-    } else {
+    } else {                                     // some byte outside A,C,G,T,N: LUT codes, 4 planes (rare)
         pp.np = 4;
-        bool e1 = false, e2 = false;
-        build_planes(r1, len1, false, lut1, lane, pp.P1, pp.n1, e1);
-        pp.n2 = 0;
+        pp.n1 = 0; pp.n2 = 0;
+#pragma unroll 1
+        for (int m = 0; m < (paired ? 2 : 1); m++) {                // one inlined copy of the LUT build for both mates
+            uint32_t Q[4]; int nn = 0; bool ee = false;
+            build_planes(m ? r2 : r1, m ? len2 : len1, m != 0, lut1, lane, Q, nn, ee);
+            const bool cand = want_poly && polyx_screen_fast(Q, 4, m ? len2 : len1, maxPoly, poly_m, lane);
+            if (m) { pp.n2 = nn; pp.cand2 = cand; }
+            else { pp.n1 = nn; pp.cand1 = cand; }
 #pragma unroll
-        for (int k = 0; k < 4; k++) pp.RC[k] = 0;
-        if (want_poly) pp.cand1 = polyx_screen_fast(pp.P1, 4, len1, maxPoly, poly_m, lane);
-        if (paired) {
-            build_planes(r2, len2, true, lut1, lane, pp.RC, pp.n2, e2);
-            if (want_poly) pp.cand2 = polyx_screen_fast(pp.RC, 4, len2, maxPoly, poly_m, lane);
+            for (int k = 0; k < 4; k++) { if (m) pp.RC[k] = Q[k]; else pp.P1[k] = Q[k]; }
         }
     }
 }
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
 
                 if (A.p.poly_size_limit > 0) {                             // :482-490
                     bool poly = false;
-                    if (pl.cand1 || pl.cand2) {                             // rare: exact window test of the screened mates
+                    if (__builtin_expect(pl.cand1 || pl.cand2, 0)) {        // rare: exact window test of the screened mates
 #pragma unroll 1
                         for (int m = 0; m < 2 && !poly; m++)
                             if (m ? pl.cand2 : pl.cand1)
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
                     int offset, ol, distance;
                     overlap_np(np, P1, RC, len1, len2, lane, offset, ol, distance);       // :516
                     if (lane == 0) atomicAdd(&s_ovh[ol], 1u);                              // :517
-                    if (offset < 0 && ol > 30) {                                          // :520 adapter trimming
+                    if (__builtin_expect(offset < 0 && ol > 30, 0)) {                     // :520 adapter trimming
                         // rc(r2[0:ol]) = last ol bases of rc(r2): shift the rc planes down by len2-ol
                         const int sh = len2 - ol;
                         if (sh > 0) {
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
                 bump(AQC_C_GOOD_BASES_R1, (unsigned long long)len1);
                 bump(AQC_C_GOOD_BASES_R2, (unsigned long long)len2);
                 const uint64_t total_reads = gidx + 1;
-                if (A.p.qc_sample <= 0 || total_reads < (uint64_t)A.p.qc_sample) {       // :624
+                if (__builtin_expect(A.p.qc_sample <= 0 || total_reads < (uint64_t)A.p.qc_sample, 0)) {       // :624
 #pragma unroll 1
                     for (int m = 0; m < (paired ? 2 : 1); m++)      // one inlined copy of statRead for both mates
                         stat_read(m ? S2 + start2 : S1 + start1, m ? Q2 + start2 : Q1 + start1, m ? len2 : len1, m, gidx, qsm, A.qc[m],
