@@ -13,7 +13,7 @@ SYMBOLS = [
     "aqc_last_error", "aqc_host_alloc", "aqc_host_free", "aqc_device_alloc", "aqc_device_free",
     "aqc_memcpy_h2d", "aqc_memcpy_d2h", "aqc_stat_reads", "aqc_filter_pairs", "aqc_ops_pairs", "aqc_sync",
     "aqc_get_counters", "aqc_add_counters", "aqc_get_qc", "aqc_get_kmer_dense", "aqc_get_kmer_side",
-    "aqc_launch_count", "aqc_last_kernel_ms", "aqc_set_stream", "aqc_device_ptr",
+    "aqc_launch_count", "aqc_last_kernel_ms", "aqc_set_stream", "aqc_device_ptr", "aqc_fastq_parse", "aqc_fastq_emit",
 ]
 
 _lib = None
@@ -59,6 +59,8 @@ def lib():
         "aqc_get_kmer_side": (i32, [vp, i32, vp, vp, vp, u32, C.POINTER(u32)]),
         "aqc_set_stream": (i32, [vp, vp]),
         "aqc_device_ptr": (i32, [vp, i32, i32, C.POINTER(vp), C.POINTER(u64)]),
+        "aqc_fastq_parse": (i32, [vp, u64, i32, u64, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), C.POINTER(u64), C.POINTER(i32), C.POINTER(u64)]),
+        "aqc_fastq_emit": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, u64, vp, u64, vp, u64, C.POINTER(u64)]),
         "aqc_launch_count": (u64, [vp]),
         "aqc_last_kernel_ms": (C.c_float, [vp]),
     }

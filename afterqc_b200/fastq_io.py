@@ -74,52 +74,34 @@ class FastqRecords:
 
 
 def _parse_block(buf, final):
-    """Parse complete records out of `buf` (bytes).  Returns (records|None, consumed_bytes, hit_eof)."""
-    data = np.frombuffer(buf, dtype=np.uint8)
-    nl = np.flatnonzero(data == 10)
-    nlines = len(nl)
-    ends = nl
-    if final and (len(data) > 0) and (nlines == 0 or nl[-1] != len(data) - 1):
-        ends = np.append(nl, len(data))          # last line without trailing newline
-        nlines += 1
-    if nlines == 0:
+    """Parse complete records out of `buf` (bytes) with the native parser (csrc/aqc_fastq.cpp).
+    Returns (records|None, consumed_bytes, hit_eof)."""
+    import ctypes as C
+    from . import _native
+    L = _native.lib()
+    n = len(buf)
+    if n == 0:
         return None, 0, final
-    starts = np.empty(nlines, dtype=np.int64)
-    starts[0] = 0
-    starts[1:] = ends[:-1] + 1
-    e = ends.astype(np.int64).copy()
-    # rstrip: drop trailing whitespace bytes
-    while True:
-        m = (e > starts) & _WS[data[np.maximum(e - 1, 0)]]
-        if not m.any():
-            break
-        e[m] -= 1
-    lens = e - starts
-    nrec = nlines // 4           # a partial trailing group is carried over (or dropped at EOF)
-    hit_eof = False
-    empty = np.flatnonzero(lens[:nrec * 4] == 0)
-    if len(empty):
-        # the first empty line ends the file (fastq.py:44-47); its record is incomplete
-        nrec = int(empty[0]) // 4
-        hit_eof = True
-    if nrec == 0:
-        return None, 0, hit_eof or final
-    consumed = int(ends[nrec * 4 - 1]) + 1
-
-    def column(k):
-        s = starts[k:nrec * 4:4]
-        l = lens[k:nrec * 4:4]
-        off = np.zeros(nrec + 1, dtype=np.int64)
-        np.cumsum(l, out=off[1:])
-        total = int(off[-1])
-        idx = np.repeat(s - off[:-1], l) + np.arange(total, dtype=np.int64)
-        return Column(data[idx], off)
-
-    rec = FastqRecords(column(0), column(1), column(2), column(3))
-    if not np.array_equal(rec.seqs.off, rec.quals.off):
-        bad = int(np.flatnonzero(np.diff(rec.seqs.off) != np.diff(rec.quals.off))[0])
-        raise ValueError("FASTQ record %d: quality line length differs from sequence length" % bad)
-    return rec, consumed, hit_eof or final
+    max_rec = n // 8 + 1                      # a record needs at least 4 x (1 byte + newline)
+    src = np.frombuffer(buf, dtype=np.uint8)
+    cols = [np.empty(n, dtype=np.uint8) for _ in range(4)]
+    offs = [np.zeros(max_rec + 1, dtype=np.uint64) for _ in range(4)]
+    pb = (C.c_void_p * 4)(*[c.ctypes.data for c in cols])
+    po = (C.c_void_p * 4)(*[o.ctypes.data for o in offs])
+    nrec, consumed, bad = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    eof = C.c_int(0)
+    rc = L.aqc_fastq_parse(src.ctypes.data, n, 1 if final else 0, max_rec, pb, po,
+                           C.byref(nrec), C.byref(consumed), C.byref(eof), C.byref(bad))
+    if rc:
+        raise ValueError("FASTQ record %d: quality line length differs from sequence length" % bad.value)
+    k = int(nrec.value)
+    if k == 0:
+        return None, int(consumed.value), bool(eof.value) or final
+    out = []
+    for c, o in zip(cols, offs):
+        o = o[:k + 1].astype(np.int64)
+        out.append(Column(c[:int(o[-1])].copy(), o))
+    return FastqRecords(*out), int(consumed.value), bool(eof.value) or final
 
 
 def iter_records(path, block_bytes=32 << 20):
@@ -167,6 +149,32 @@ def to_batch(rec1, rec2, lo, hi, first_index=None):
         return PackedBatch(s1, q1, o1, first_index=fi)
     s2, q2, o2 = cut(rec2)
     return PackedBatch(s1, q1, o1, s2, q2, o2, first_index=fi)
+
+
+def emit(rec, mate, which, rec_base, results):
+    """FASTQ text (bytes) of records rec_base.. of one mate selected by `which` (0 good, 1 bad, 2 overlap tails),
+    with the slices and edits of the aqc_result records applied (native, csrc/aqc_fastq.cpp)."""
+    import ctypes as C
+    from . import _native
+    L = _native.lib()
+    n = len(results)
+    if n == 0:
+        return b""
+    a, b = rec_base, rec_base + n
+    cap = int((rec.names.off[b] - rec.names.off[a]) + (rec.plus.off[b] - rec.plus.off[a]) + 2 * (rec.seqs.off[b] - rec.seqs.off[a])) + 20 * n + 64
+    out = np.empty(cap, dtype=np.uint8)
+    olen = C.c_uint64(0)
+    res = np.ascontiguousarray(results)
+    cols = [rec.names, rec.seqs, rec.plus, rec.quals]
+    for c in cols:
+        if c.off.dtype != np.int64 or not c.off.flags["C_CONTIGUOUS"]:
+            c.off = np.ascontiguousarray(c.off, dtype=np.int64)
+    rc = L.aqc_fastq_emit(mate, which, rec.names.data.ctypes.data, rec.names.off.ctypes.data, rec.seqs.data.ctypes.data,
+                          rec.seqs.off.ctypes.data, rec.plus.data.ctypes.data, rec.plus.off.ctypes.data, rec.quals.data.ctypes.data,
+                          rec_base, res.ctypes.data, n, out.ctypes.data, cap, C.byref(olen))
+    if rc:
+        raise RuntimeError("aqc_fastq_emit failed (%d)" % rc)
+    return out[:olen.value].tobytes()
 
 
 class Writer:

@@ -294,43 +294,16 @@ class seqFilter:
         return n
 
     def _write(self, writers, rec1, rec2, base, res):
-        good1, bad1, good2, bad2, ov1, ov2 = [], [], [], [], [], []
-        store_ov = "ov1" in writers
-        for j in range(len(res)):
-            r = res[j]
-            i = base + j
-            s2 = q2 = None
-            if rec2 is not None:
-                s2 = rec2.seqs.get(i); q2 = rec2.quals.get(i)
-            o1, p1, o2, p2 = apply_result(r, rec1.seqs.get(i), rec1.quals.get(i), s2, q2)
-            cls = int(r["cls"])
-            n1 = rec1.names.get(i)
-            if cls == _abi.GOOD:
-                _emit(good1, n1, o1, rec1.plus.get(i), p1)
-                if rec2 is not None:
-                    n2 = rec2.names.get(i)
-                    _emit(good2, n2, o2, rec2.plus.get(i), p2)
-                    if store_ov and int(r["ov_len"]) > 30:
-                        ne = int(r["n_edits"])
-                        corrected = sum(1 for e in r["edits"][:ne] if ((int(e) >> 10) & 3) < 2)
-                        d = int(r["ov_diff"])
-                        if d == 0 or d == corrected:          # preprocesser.py:615-617
-                            ol = int(r["ov_len"])
-                            _emit(ov1, n1, o1[len(o1) - ol:], rec1.plus.get(i), p1[len(p1) - ol:])
-                            _emit(ov2, n2, o2[len(o2) - ol:], rec2.plus.get(i), p2[len(p2) - ol:])
-            else:
-                flag = _abi.CLASS_FLAGS[cls].encode()
-                _emit(bad1, b"@" + flag + n1[1:], o1, rec1.plus.get(i), p1)     # preprocesser.py:212-213
-                if rec2 is not None:
-                    n2 = rec2.names.get(i)
-                    _emit(bad2, b"@" + flag + n2[1:], o2, rec2.plus.get(i), p2)
-        writers["good1"].write(b"".join(good1)); writers["bad1"].write(b"".join(bad1))
+        """good/bad(/overlap) text of one batch: slices, correction edits and @BADxxx names (preprocesser.py:206-232)."""
+        writers["good1"].write(fastq_io.emit(rec1, 1, 0, base, res))
+        writers["bad1"].write(fastq_io.emit(rec1, 1, 1, base, res))
         if rec2 is not None:
-            writers["good2"].write(b"".join(good2)); writers["bad2"].write(b"".join(bad2))
-        if store_ov:
-            writers["ov1"].write(b"".join(ov1))
+            writers["good2"].write(fastq_io.emit(rec2, 2, 0, base, res))
+            writers["bad2"].write(fastq_io.emit(rec2, 2, 1, base, res))
+        if "ov1" in writers:
             if rec2 is not None:
-                writers["ov2"].write(b"".join(ov2))
+                writers["ov1"].write(fastq_io.emit(rec1, 1, 2, base, res))
+                writers["ov2"].write(fastq_io.emit(rec2, 2, 2, base, res))
 
     def _build_stat(self, cnt, readLen, extra_total_bases):
         """preprocesser.py:660-778"""

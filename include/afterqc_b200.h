@@ -249,6 +249,23 @@ int aqc_get_kmer_dense(aqc_ctx *ctx, int slot, uint64_t *counts, uint64_t *first
 int aqc_get_kmer_side(aqc_ctx *ctx, int slot, uint64_t *keys, uint64_t *counts, uint64_t *first,
                       uint32_t cap, uint32_t *n_out);
 
+/* ---- host-side FASTQ ingest / egress on the packed columns (no GPU work; replaces fastq.py:17-104) ---- */
+/* Parse complete 4-line records of buf[0..n): lines are rstrip()'d, the first empty line ends the file (its record is
+ * dropped), a trailing partial record stays unconsumed unless `final`.  Column k (0 names, 1 bases, 2 '+' lines,
+ * 3 qualities) is appended to out_bytes[k] (capacity >= n) with offsets out_off[k][0..records] (caller sets [0]).
+ * AQC_ERR_INVALID + *bad_record when a quality line's length differs from its sequence line's. */
+int aqc_fastq_parse(const uint8_t *buf, uint64_t n, int final, uint64_t max_records,
+                    uint8_t *const out_bytes[4], uint64_t *const out_off[4],
+                    uint64_t *n_records, uint64_t *consumed, int *hit_eof, uint64_t *bad_record);
+/* FASTQ text of one mate's records selected by `which` (0 good, 1 bad with the "@BADxxx" name prefix of
+ * preprocesser.py:212-213, 2 overlapped tails for --store_overlap :615-617): final slice + correction edits of
+ * results[i] applied to column record rec_base + i.  AQC_ERR_NOMEM when out_cap is too small. */
+int aqc_fastq_emit(int mate, int which,
+                   const uint8_t *names, const uint64_t *name_off, const uint8_t *seqs, const uint64_t *seq_off,
+                   const uint8_t *plus, const uint64_t *plus_off, const uint8_t *quals,
+                   uint64_t rec_base, const aqc_result *results, uint64_t n,
+                   uint8_t *out, uint64_t out_cap, uint64_t *out_len);
+
 /* instrumentation for bench.py: kernels launched by this context so far, and the device
  * time in ms of the last filter/stat call's kernels (CUDA events on the launching stream) */
 uint64_t aqc_launch_count(const aqc_ctx *ctx);

@@ -157,3 +157,35 @@ def test_full_scale_properties():
     res2 = eng.fetch_results(d)
     assert res2.tobytes() == res.tobytes()
     d.free(); eng.close()
+
+
+def test_domain_errors_are_loud(backends, oracle_lib):
+    """Situations where the reference raises: the engine reports the same sticky error codes as the oracle."""
+    from afterqc_b200.batch import PackedBatch
+    from afterqc_b200.engine import Engine, EngineError
+    # statRead on a 3-base read (IndexError in the reference, qualitycontrol.py:106-108)
+    short = PackedBatch.from_reads([("ACG", "III"), ("ACGTACGTAC", "I" * 10)], [("ACGTA", "IIIII"), ("ACGTACGTAC", "I" * 10)])
+    for make in (lambda: oracle_lib.Oracle(_abi.Params.defaults()), lambda: Engine(_abi.Params.defaults())):
+        be = make()
+        with pytest.raises(Exception) as ei:
+            be.stat_reads(short, _abi.QC_R1_PRE, _abi.QC_R2_PRE)
+            be.counters()
+        assert getattr(ei.value, "code", None) == _abi.ERR_TOO_SHORT_STAT
+        be.close()
+    # a read longer than MAX_LEN
+    long_ = PackedBatch.from_reads([("A" * 1001, "I" * 1001)], [("ACGTA", "IIIII")])
+    eng = Engine(_abi.Params.defaults())
+    with pytest.raises(EngineError) as ei:
+        eng.filter_pairs(long_)
+    assert ei.value.code == _abi.ERR_TOO_LONG
+    eng.close()
+    # side-table overflow: 16-entry table, hundreds of distinct N-containing k-mers
+    import random
+    rng = random.Random(3)
+    reads = [("".join(rng.choice("ACGTN") for _ in range(100)), "I" * 100) for _ in range(64)]
+    eng = Engine(_abi.Params.defaults(kmer_side_log2=4))
+    with pytest.raises(EngineError) as ei:
+        eng.stat_reads(PackedBatch.from_reads(reads, reads), _abi.QC_R1_PRE, _abi.QC_R2_PRE)
+        eng.counters()
+    assert ei.value.code == _abi.ERR_KMER_TABLE_FULL
+    eng.close()
