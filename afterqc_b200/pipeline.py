@@ -268,15 +268,43 @@ class seqFilter:
         # quirk Q1: the reference only adds R2's bases when an index2 file is present, and the R1
         # record read just before a shorter R2 ran out is still counted (preprocesser.py:416-431)
         extra = int(rec1.lengths()[n]) if (self.paired and rec1.n > n and not opt.qc_only) else 0
+        figure_qcs = [("Read1" if self.paired else "", "before", "r1_pre", self.r1qc_prefilter),
+                      ("Read1" if self.paired else "", "after", "r1_post", self.r1qc_postfilter)]
+        if self.paired:
+            figure_qcs += [("Read2", "before", "r2_pre", self.r2qc_prefilter), ("Read2", "after", "r2_post", self.r2qc_postfilter)]
+        read_figs = []
+        if rank == 0:
+            from . import report
+            for mate_label, when, key, q in figure_qcs:             # before squeeze(): the GC plot needs readLen+1 bins
+                read_figs += report.read_figures(q, mate_label, when, key)
         stat = self._build_stat(cnt, readLen, extra)
         self.stat = stat
         if rank == 0:
             with open(os.path.join(qc_dir, os.path.basename(opt.read1_file) + ".json"), "w") as f:
                 f.write(json.dumps(stat, sort_keys=True, indent=4, separators=(',', ': ')))
+            self._write_html(os.path.join(qc_dir, os.path.basename(opt.read1_file) + ".html"), stat, cnt, read_figs)
         be.close()
         return stat
 
     # ------------------------------------------------------------------------------------------
+    def _write_html(self, path, stat, cnt, read_figs):
+        """the report of preprocesser.py:678-700,771-783 (figure order as the reference)"""
+        from . import report
+        opt = self.options
+        c = lambda name: int(cnt[_abi.CIDX[name]])
+        total = c("TOTAL_READS")
+        labels = ['good reads', 'has_polyX', 'low_quality', 'too_short', 'too_many_N']
+        counts = [c("GOOD_READS"), c("BADPOL"), c("BADLQC"), c("BADLEN") + c("BADTRIM1") + c("BADTRIM2"), c("BADNCT")]
+        if self.paired:
+            labels.append('bad_overlap'); counts.append(c("BADMISMATCH") + c("BADDIFF"))
+        labels = ["%s: %d(%s%%)" % (l, n, (100.0 * float(n) / total) if total > 0 else 0.0) for l, n in zip(labels, counts)]
+        figs = [report.filter_figure(labels, counts, total)]
+        if self.paired:
+            figs.append(report.error_figure(stat["afterqc_overlap"]["error_matrix"]))
+            figs.append(report.overlap_figure(self.overlap_histgram, stat["afterqc_main_summary"]["readlen"], total))
+        figs += read_figs
+        report.write_html(path, stat, getattr(opt, "version", "0.9.6"), figs)
+
     def _qc_only_stop(self, be, rec1, rec2, n):
         """--qc_only stops after the first GOOD pair whose TOTAL_READS >= qc_sample
         (preprocesser.py:630-631); find that index with a counter-free dry run."""

@@ -44,6 +44,8 @@ class QualityControl:
         self.topKmerCount = []
         self.totalKmer = 0
         self._kmers = None
+        self._sorted = None
+        self.gcHistogramFull = [0] * (MAX_LEN + 1)
 
     # ---- load the integer counters fetched from the engine ---------------------------------
     def load(self, counters, kmers):
@@ -51,7 +53,8 @@ class QualityControl:
         self.totalNum = counters["totalNum"].tolist()
         self.totalQual = counters["totalQual"].tolist()
         self.totalDiscontinuity = [float(x) for x in counters["totalDiscontinuity"].tolist()]
-        self.gcHistogram = counters["gcHistogram"].tolist()[:MAX_LEN]
+        self.gcHistogramFull = counters["gcHistogram"].tolist()
+        self.gcHistogram = self.gcHistogramFull[:MAX_LEN]
         for i, b in enumerate(ALL_BASES):
             self.baseCounts[b] = counters["baseCounts"][i].tolist()
             self.baseTotalQual[b] = counters["baseTotalQual"][i].tolist()
@@ -110,6 +113,42 @@ class QualityControl:
             name = _kmer_dense_str(int(present[j]), k) if j < nd else _kmer_side_str(skeys[j - nd], k)
             top.append((name, int(cnt[j])))
         self.topKmerCount = top
+
+    def strand_bias_points(self, max_points=1000):
+        """(forward, reverse) k-mer counts sampled along the sorted k-mer list, as strandBiasPlotly does
+        (qualitycontrol.py:238-257): skip the top min(50, n/2) k-mers, at most 1000 evenly spaced points."""
+        if self._sorted is None:
+            return [], []
+        order, present, skeys, cnt, nd = self._sorted
+        n = len(order)
+        shift = min(50, n // 2)
+        top = min(n - shift, max_points)
+        if top <= 0:
+            return [], []
+        step = max(1, (n - shift) // top)
+        k = self.kmerLen
+        dense_pos = {int(p): j for j, p in enumerate(present)}          # natural dense index -> entry
+        side_pos = {int(key): nd + j for j, key in enumerate(skeys)}
+        comp = {65: 84, 84: 65, 67: 71, 71: 67, 97: 116, 116: 97, 99: 103, 103: 99, 78: 78, 10: 10}
+        fwd, rev = [], []
+        for i in range(top):
+            idx = i * step + shift
+            if idx >= n:
+                break
+            j = int(order[idx])
+            fwd.append(int(cnt[j]))
+            if j < nd:
+                d = int(present[j]); r = 0
+                for _ in range(k):
+                    r = (r << 2) | (3 - (d & 3)); d >>= 2
+                jr = dense_pos.get(r)
+            else:
+                key = int(skeys[j - nd]); r = 0
+                for t in range(k):
+                    r |= comp.get((key >> (8 * (k - 1 - t))) & 0xFF, 78) << (8 * t)
+                jr = side_pos.get(r)
+            rev.append(int(cnt[jr]) if jr is not None else 0)
+        return fwd, rev
 
     def qc(self):
         self.calcReadLen()

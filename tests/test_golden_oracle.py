@@ -46,3 +46,22 @@ def test_known_answers_from_survey(oracle_lib):
     ops = o.ops_pairs(b)
     for i, p in enumerate(pairs):
         assert (int(ops[i]["ov_offset"]), int(ops[i]["ov_len"]), int(ops[i]["ov_diff"])) == p[2]
+
+
+def test_html_report_sections(tmp_path, oracle_lib):
+    """QC/<R1>.html: one section per figure of the reference's report (preprocesser.py:700,771-772,785-819)."""
+    import re
+    import refcmp
+    from afterqc_b200 import synth
+    for cfg, paired, nfig in (("pe150", True, 3 + 4 * 5), ("se100", False, 1 + 2 * 5)):
+        d = str(tmp_path / cfg)
+        batch = synth.generate(cfg, 1300)
+        refcmp.prepare_case(d, batch, subs=("new",))
+        refcmp.run_ours(d, "new", paired, [], lambda p: oracle_lib.Oracle(p))
+        html = open(os.path.join(d, "new", "QC", "x_R1.fq.html")).read()
+        assert html.count("Plotly.newPlot(") == nfig
+        titles = re.findall(r"<li class='menu-item'><a href='#[^']*'>\d+, ([^<]*)</a>", html)
+        assert titles[0] == "AfterQC summary" and titles[1] == "Good reads and bad reads after filtering"
+        assert ("Read1 kmer strand bias after filtering" in titles) == paired
+        assert ("Kmer strand bias after filtering" in titles) == (not paired)
+        assert "total reads:" in html and "auto trimming" in html
