@@ -3,15 +3,16 @@
 // Execution model: one WARP per read pair.  A persistent CTA (8 warps) walks tiles of <= 32
 // pairs; the four byte columns of a tile (bases/quals of both mates) are contiguous in HBM and
 // are staged into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier), double
-// buffered.  Inside a warp the bases of a mate are turned into BIT-PLANES with warp ballots
-// (lane j holds bits 32j..32j+31 of each plane), so that
+// buffered.  Inside a warp the bases of both mates are turned into BIT-PLANES (lane j holds bits
+// 32j..32j+31 of each plane) -- by SWAR arithmetic on 16 bases per lane for A/C/G/T/N reads
+// (fast_build2), by a LUT + warp ballots for anything else (build_planes) -- so that
 //   * the sliding-offset Hamming scan of util.overlap_hm (util.py:158-212) becomes: each lane
 //     scores ONE candidate offset with funnel-shift + XOR + popc on the first 32 positions,
 //     a ballot picks the survivors in scan order, and a warp-wide popc/redux evaluates the
 //     reference's acceptance rule exactly (closed form of the leaked loop variable, quirk Q6);
 //   * hasPolyX (preprocesser.py:30-51) is screened by a bit-parallel run-length test and only
 //     candidate reads take the exact sliding-window path;
-//   * N / low-quality counts are ballots + popc.
+//   * N counts are popcounts of the N plane, low-quality counts a SWAR byte compare.
 // All arithmetic is integer/byte work; there is no tensor-core use by design.
 #pragma once
 #include <cstdint>
@@ -244,58 +245,9 @@ __device__ __forceinline__ void overlap_hm(const uint32_t (&P1)[4], const uint32
     else { offset = 0; ol = 0; diff = 0; }                           // util.py:212
 }
 
-__device__ __forceinline__ void overlap_any(bool exotic, const uint32_t (&P1)[4], const uint32_t (&RC)[4], int len1, int len2,
-                                            int lane, int &offset, int &ol, int &diff) {
-    if (exotic) overlap_hm<4>(P1, RC, len1, len2, lane, offset, ol, diff);
-    else overlap_hm<2>(P1, RC, len1, len2, lane, offset, ol, diff);
-}
-
 // ------------------------------------------------------------------------------------------
 // hasPolyX (preprocesser.py:30-51)
 // ------------------------------------------------------------------------------------------
-// Shift a plane word array left by `s` positions (new[x] = old[x - s]).
-__device__ __forceinline__ uint32_t plane_shl(uint32_t y, int s, int lane) {
-    int q = s >> 5, r = s & 31;
-    int src_hi = lane - q, src_lo = lane - q - 1;
-    uint32_t hi = __shfl_sync(FULL, y, src_hi & 31);
-    uint32_t lo = __shfl_sync(FULL, y, src_lo & 31);
-    if (src_hi < 0) hi = 0;
-    if (src_lo < 0) lo = 0;
-    return __funnelshift_l(lo, hi, r);
-}
-
-// Necessary condition for hasPolyX != None: the read contains a run of >= R identical codes,
-// R = ceil(T / (mismatch + 1)), T = maxPoly - mismatch  (<= mismatch interruptions split the >= T
-// equal bases of a flagged window into <= mismatch + 1 runs).  Works on either orientation.
-__device__ __forceinline__ bool polyx_screen(const uint32_t (&P)[4], bool exotic, int len, int maxPoly, int mismatch, int lane) {
-    if (len < maxPoly) return false;               // :31-32
-    if (mismatch < 0) return false;                // count <= maxPoly < threshold: never flagged
-    int T = maxPoly - mismatch;
-    if (T <= 1) return true;
-    int R = (T + mismatch) / (mismatch + 1);
-    int m = R - 1;                                 // need m consecutive "same as previous" bits
-    if (m <= 0) return true;
-    uint32_t d = 0;
-    {
-        uint32_t prev;
-        prev = plane_shl(P[0], 1, lane); d |= P[0] ^ prev;
-        prev = plane_shl(P[1], 1, lane); d |= P[1] ^ prev;
-        if (exotic) {
-            prev = plane_shl(P[2], 1, lane); d |= P[2] ^ prev;
-            prev = plane_shl(P[3], 1, lane); d |= P[3] ^ prev;
-        }
-    }
-    uint32_t y = ~d & lowmask(len - (lane << 5));
-    if (lane == 0) y &= ~1u;                       // position 0 has no predecessor
-    int t = 1;
-    while (t < m) {                                // y_t[x] = AND_{i<t} same[x-i]
-        int step = min(t, m - t);
-        y &= plane_shl(y, step, lane);
-        t += step;
-    }
-    return __ballot_sync(FULL, y != 0) != 0;
-}
-
 // Exact hasPolyX on the raw bytes (taken only by screened candidates).  Returns the char or 0.
 __device__ AQC_RARE int polyx_exact(const uint8_t *s, int len, int maxPoly, int mismatch, const uint8_t *lut2, int lane) {
     if (len < maxPoly) return 0;
@@ -364,49 +316,6 @@ struct FastPlanes {
     bool hasN;          // warp-uniform
     bool exotic;        // warp-uniform: some byte is not A,C,G,T,N -> general path required
 };
-
-// forward planes of a read (fast codes)
-__device__ __forceinline__ void fast_build(const uint8_t *s, int len, int lane, FastPlanes &F) {
-    F.P[0] = F.P[1] = F.P[2] = F.P[3] = 0;
-    F.n_count = 0; F.hasN = false; F.exotic = false;
-    const int npass = (len + 255) >> 8;
-    for (int p = 0; p < npass; p++) {
-        uint32_t v0, v1, vm0, vm1;
-        load8(s, (p << 8) + (lane << 3), len, v0, v1, vm0, vm1);
-        uint32_t t0 = (v0 >> 1) & 0x03030303u, t1 = (v1 >> 1) & 0x03030303u;
-        // re-encode the codes to ASCII (index 0 'A', 1 'C', 2 'T', 3 'G') and compare
-        const uint32_t e0 = __byte_perm(0x47544341u, 0u, __byte_perm(t0 | (t0 >> 4), 0u, 0x4420));
-        const uint32_t e1 = __byte_perm(0x47544341u, 0u, __byte_perm(t1 | (t1 >> 4), 0u, 0x4420));
-        const uint32_t bad0 = (e0 ^ v0) & vm0, bad1 = (e1 ^ v1) & vm1;
-        uint32_t nbyte = 0;
-        if (__ballot_sync(FULL, (bad0 | bad1) != 0u)) {            // warp-uniform: some non-ACGT byte in this pass
-            const uint32_t isN0 = ~hibit_nonzero(v0 ^ 0x4E4E4E4Eu) & 0x80808080u & vm0;
-            const uint32_t isN1 = ~hibit_nonzero(v1 ^ 0x4E4E4E4Eu) & 0x80808080u & vm1;
-            const uint32_t ex = (hibit_nonzero(bad0) & ~isN0) | (hibit_nonzero(bad1) & ~isN1);
-            if (__ballot_sync(FULL, ex != 0u)) F.exotic = true;
-            const uint32_t n0 = isN0 >> 7, n1 = isN1 >> 7;           // 0x01 per N byte
-            t0 &= ~(n0 * 3u); t1 &= ~(n1 * 3u);                      // planes 0/1 are 0 at N positions
-            nbyte = gather4(n0) | (gather4(n1) << 4);
-            const uint32_t nb = __ballot_sync(FULL, nbyte != 0u);
-            if (nb) { F.hasN = true; F.n_count += (int)__reduce_add_sync(FULL, (unsigned)__popc(nbyte)); }
-        }
-        const uint32_t p0b = gather4(t0 & 0x01010101u) | (gather4(t1 & 0x01010101u) << 4);
-        const uint32_t p1b = gather4((t0 >> 1) & 0x01010101u) | (gather4((t1 >> 1) & 0x01010101u) << 4);
-        const uint32_t v = p0b | (p1b << 8) | (nbyte << 16);
-        const int jj = (lane & 7) << 2;
-        const uint32_t b0 = __shfl_sync(FULL, v, jj), b1 = __shfl_sync(FULL, v, jj + 1);
-        const uint32_t b2 = __shfl_sync(FULL, v, jj + 2), b3 = __shfl_sync(FULL, v, jj + 3);
-        if ((lane >> 3) == p) {
-            const uint32_t x01 = __byte_perm(b0, b1, 0x5140), x23 = __byte_perm(b2, b3, 0x5140);
-            F.P[0] = __byte_perm(x01, x23, 0x5410);
-            F.P[1] = __byte_perm(x01, x23, 0x7632);
-            if (F.hasN) {
-                const uint32_t y01 = __byte_perm(b0, b1, 0x6262), y23 = __byte_perm(b2, b3, 0x6262);
-                F.P[2] = __byte_perm(y01, y23, 0x5410);
-            }
-        }
-    }
-}
 
 // Both mates in ONE instruction stream: lanes 0-15 convert mate 1, lanes 16-31 mate 2, 16 consecutive bases per lane
 // (256 bases per mate and pass).  Same arithmetic as fast_build on four words; the 16-bit plane slices of lanes

@@ -67,13 +67,20 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_arm(sample_pairs, threads, steps=1, warmup=0):
-    """Oracle throughput on `sample_pairs` pairs of the workload, split over `threads` host threads.
+CPU_SAMPLE_CAP = 2_000_000
+
+
+def cpu_sample_size(pairs, threads, requested):
+    return requested or min(pairs, 100_000 * threads, CPU_SAMPLE_CAP)
+
+
+def cpu_arm(batch, threads, steps=1, warmup=0):
+    """Oracle throughput on the PackedBatch `batch` (a prefix of the workload), split over `threads` host threads.
     The sample keeps the workload's mix: the QC window is scaled to the same 2 % of the pairs."""
-    from afterqc_b200 import _abi, synth
+    from afterqc_b200 import _abi
     from oracle import oracle as orc_mod
     orc_mod.build()
-    batch = synth.generate("pe150", sample_pairs)
+    sample_pairs = batch.n
     qs = max(1000, sample_pairs * QC_SAMPLE // PAIRS_PER_GPU)
     params = _abi.Params.defaults(qc_sample=qs)
     per = (sample_pairs + threads - 1) // threads
@@ -104,13 +111,24 @@ def cpu_arm(sample_pairs, threads, steps=1, warmup=0):
             "sample_pairs": sample_pairs, "qc_sample_scaled": qs, "ms_per_step": 1e3 * total / len(times)}
 
 
+def host_sample(pairs, threads):
+    """CPU-generated prefix of the workload (reference arm: no GPU work at all)."""
+    import torch
+    from afterqc_b200 import synth
+    try:
+        torch.set_num_threads(max(1, min(threads, 32)))     # torchrun exports OMP_NUM_THREADS=1
+    except Exception:
+        pass
+    return synth.generate("pe150", pairs)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = host_threads()
-    sample = args.cpu_sample or min(args.pairs, 100_000 * threads)
-    r = cpu_arm(sample, threads, steps=args.steps, warmup=min(args.warmup, 1))
+    sample = cpu_sample_size(args.pairs, threads, args.cpu_sample)
+    r = cpu_arm(host_sample(sample, threads), threads, steps=args.steps, warmup=min(args.warmup, 1))
     mps = r["pairs_per_s"] / 1e6
     line = {
         "impl": "reference",
@@ -406,8 +424,18 @@ def run_ours(args):
         cpu = None
         if not args.no_cpu:
             threads = host_threads()
-            sample = args.cpu_sample or min(n, 100_000 * threads)
-            r = cpu_arm(sample, threads)
+            sample = cpu_sample_size(n, threads, args.cpu_sample)
+            # the first `sample` pairs of the resident batch, copied back to the host
+            from afterqc_b200.batch import PackedBatch, SLACK
+            o1 = wb.t["off1"][:sample + 1].cpu().numpy().astype(np.uint32); o2 = wb.t["off2"][:sample + 1].cpu().numpy().astype(np.uint32)
+
+            def hostcol(name, end):
+                a = np.zeros(end + SLACK, dtype=np.uint8)
+                a[:end] = wb.t[name][:end].cpu().numpy()
+                return a
+            hb = PackedBatch(hostcol("seq1", int(o1[-1])), hostcol("qual1", int(o1[-1])), o1,
+                             hostcol("seq2", int(o2[-1])), hostcol("qual2", int(o2[-1])), o2)
+            r = cpu_arm(hb, threads)
             cpu = {"value": r["pairs_per_s"] / 1e6, "unit": "M read-pairs/s", "cores": r["threads"], "kind": "port",
                    "sample": "%d pairs of the same PE150 workload (QC window scaled to %d reads, the same 2%% mix), %.1f s of wall time on %d threads; "
                              "C oracle oracle/aqc_oracle.c" % (sample, r["qc_sample_scaled"], r["seconds"], r["threads"])}
