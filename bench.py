@@ -144,7 +144,7 @@ def run_reference_arm(args):
         "e2e": {"value": mps, "unit": "M read-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_json(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -459,11 +459,32 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line))
+        emit_json(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Route everything any library prints to fd 1 (NCCL's version banner, ...) to stderr and keep the real stdout for the
+    ONE JSON line rank 0 emits."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_json(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
