@@ -62,36 +62,49 @@ class QualityControl:
         self._kmers = kmers
         return self
 
-    # ---- qualitycontrol.py:124-156 ---------------------------------------------------------
+    # ---- derived per-cycle statistics (qualitycontrol.py:124-153) ---------------------------
+    # numpy float64 division of exactly-converted integers is the same IEEE operation as the reference's
+    # float(a) / float(b), so the JSON text is identical; .tolist() yields python floats.
+    def _count_matrix(self):
+        return np.array([self.baseCounts[b] for b in ALL_BASES], dtype=np.int64)        # [4][MAX_LEN], A,T,C,G
+
     def calcReadLen(self):
-        for pos in range(MAX_LEN):
-            hasData = False
-            for base in ALL_BASES:
-                if self.baseCounts[base][pos] > 0:
-                    hasData = True
-            if not hasData:
-                self.readLen = pos
-                break
+        """first cycle without any A/T/C/G observation; stays 0 when all MAX_LEN cycles are populated (:124-132)"""
+        empty = np.flatnonzero(self._count_matrix().sum(axis=0) == 0)
+        if len(empty):
+            self.readLen = int(empty[0])
 
     def calcPercents(self):
-        for pos in range(self.readLen):
-            total = 0
-            for base in ALL_BASES:
-                total += self.baseCounts[base][pos]
-            for base in ALL_BASES:
-                self.percents[base][pos] = float(self.baseCounts[base][pos]) / float(total)
-            self.gcPercents[pos] = float(self.baseCounts['G'][pos] + self.baseCounts['C'][pos]) / float(total)
+        n = self.readLen
+        if n == 0:
+            return
+        cnt = self._count_matrix()[:, :n]
+        total = cnt.sum(axis=0).astype(np.float64)
+        for i, base in enumerate(ALL_BASES):
+            self.percents[base][:n] = (cnt[i].astype(np.float64) / total).tolist()
+        g, c = ALL_BASES.index('G'), ALL_BASES.index('C')
+        self.gcPercents[:n] = ((cnt[g] + cnt[c]).astype(np.float64) / total).tolist()
 
     def calcQualities(self):
-        for pos in range(self.readLen):
-            self.meanQual[pos] = float(self.totalQual[pos]) / float(self.totalNum[pos])
-            for base in ALL_BASES:
-                if self.baseCounts[base][pos] > 0:
-                    self.baseMeanQual[base][pos] = float(self.baseTotalQual[base][pos]) / float(self.baseCounts[base][pos])
+        n = self.readLen
+        if n == 0:
+            return
+        num = np.array(self.totalNum[:n], dtype=np.int64).astype(np.float64)
+        self.meanQual[:n] = (np.array(self.totalQual[:n], dtype=np.int64).astype(np.float64) / num).tolist()
+        cnt = self._count_matrix()[:, :n]
+        for i, base in enumerate(ALL_BASES):
+            q = np.array(self.baseTotalQual[base][:n], dtype=np.int64).astype(np.float64)
+            seen = cnt[i] > 0                                       # cycles where the base never occurs keep 0.0 (:148)
+            out = np.zeros(n, dtype=np.float64)
+            out[seen] = q[seen] / cnt[i][seen].astype(np.float64)
+            self.baseMeanQual[base][:n] = out.tolist()
 
     def calcDiscontinuity(self):
-        for pos in range(self.readLen):
-            self.meanDiscontinuity[pos] = float(self.totalDiscontinuity[pos]) / float(self.totalNum[pos])
+        n = self.readLen
+        if n == 0:
+            return
+        num = np.array(self.totalNum[:n], dtype=np.int64).astype(np.float64)
+        self.meanDiscontinuity[:n] = (np.array(self.totalDiscontinuity[:n], dtype=np.float64) / num).tolist()
 
     def sortKmer(self):
         """sorted(kmerCount.items(), key=count, reverse=True) over an insertion-ordered dict
@@ -173,44 +186,36 @@ class QualityControl:
             self.baseMeanQual[base] = self.baseMeanQual[base][0:n]
             self.baseTotalQual[base] = self.baseTotalQual[base][0:n]
 
-    # ---- qualitycontrol.py:359-408 ---------------------------------------------------------
-    def autoTrim(self):
-        center = int(self.readLen / 2)
-        front = center
-        tail = center
-        bad_in_front = False
-        bad_in_tail = False
-        for front in range(0, center)[::-1]:
-            if self.isAbnormalCycle(front, front + 1, 0.10):
-                bad_in_front = True
-                break
-        for tail in range(center + 1, self.readLen):
-            if self.isAbnormalCycle(tail, tail - 1, 0.05):
-                bad_in_tail = True
-                break
-        trimFront = 0
-        trimTail = 0
-        if bad_in_front:
-            trimFront = front + 1
-        if bad_in_tail:
-            trimTail = self.readLen - tail
-        trimFront = min(int(self.readLen * 0.1), trimFront)
-        trimTail = min(int(self.readLen * 0.05), trimTail)
-        return (trimFront, trimTail)
+    # ---- automatic trimming (qualitycontrol.py:359-408) ------------------------------------------
+    # Walk outwards from the middle cycle; the first abnormal cycle on each side bounds the good segment.
+    _BASE_RANGE = (0.15, 0.4)      # BASE_BOTTOM, BASE_TOP
+    _GC_RANGE = (0.3, 0.7)         # GC_BOTTOM, GC_TOP
+    _QUAL_BOTTOM = 20.0
 
     def isAbnormalCycle(self, this_cycle, comp_cycle, percent_change_threshold):
-        BASE_TOP = 0.4
-        BASE_BOTTOM = 0.15
-        GC_TOP = 0.7
-        GC_BOTTOM = 0.3
-        QUAL_BOTTOM = 20.0
-        if self.gcPercents[this_cycle] > GC_TOP or self.gcPercents[this_cycle] < GC_BOTTOM:
+        gc = self.gcPercents[this_cycle]
+        if gc > self._GC_RANGE[1] or gc < self._GC_RANGE[0]:
             return True
         for base in ALL_BASES:
-            if self.percents[base][this_cycle] > BASE_TOP or self.percents[base][this_cycle] < BASE_BOTTOM:
+            here = self.percents[base][this_cycle]
+            if here > self._BASE_RANGE[1] or here < self._BASE_RANGE[0]:
                 return True
-            if abs(self.percents[base][this_cycle] - self.percents[base][comp_cycle]) > percent_change_threshold:
+            if abs(here - self.percents[base][comp_cycle]) > percent_change_threshold:
                 return True
-            if self.baseMeanQual[base][this_cycle] < QUAL_BOTTOM:
+            if self.baseMeanQual[base][this_cycle] < self._QUAL_BOTTOM:
                 return True
         return False
+
+    def autoTrim(self):
+        n = self.readLen
+        center = int(n / 2)
+        trimFront = trimTail = 0
+        for front in range(center - 1, -1, -1):                     # towards the head, compared with the next cycle
+            if self.isAbnormalCycle(front, front + 1, 0.10):
+                trimFront = front + 1
+                break
+        for tail in range(center + 1, n):                           # towards the tail, compared with the previous cycle
+            if self.isAbnormalCycle(tail, tail - 1, 0.05):
+                trimTail = n - tail
+                break
+        return (min(int(n * 0.1), trimFront), min(int(n * 0.05), trimTail))
