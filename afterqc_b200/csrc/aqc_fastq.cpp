@@ -71,18 +71,20 @@ int aqc_fastq_emit(int mate, int which,
                    const uint8_t *plus, const uint64_t *plus_off, const uint8_t *quals,
                    uint64_t rec_base, const aqc_result *results, uint64_t n,
                    uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
-    if (mate != 1 && mate != 2) return AQC_ERR_INVALID;
+    if (mate < 0 || mate > 2) return AQC_ERR_INVALID;          // mate 0: index read, passed through whole and unedited
     uint64_t w = 0;
     for (uint64_t i = 0; i < n; i++) {
         const aqc_result &r = results[i];
         const bool good = r.cls == AQC_GOOD;
         if ((which == 1) == good) continue;
+        const uint64_t rec0 = rec_base + i;
         uint32_t start = mate == 1 ? r.start1 : r.start2, len = mate == 1 ? r.len1 : r.len2;
+        if (mate == 0) { start = 0; len = (uint32_t)(seq_off[rec0 + 1] - seq_off[rec0]); }
         int corrected = 0;
         for (int e = 0; e < r.n_edits && e < 4; e++) if (AQC_EDIT_KIND(r.edits[e]) < 2) corrected++;
         if (which == 2) {
             if (!(r.ov_len > 30 && (r.ov_diff == 0 || (int)r.ov_diff == corrected))) continue;
-            start += len - r.ov_len; len = r.ov_len;
+            if (mate != 0) { start += len - r.ov_len; len = r.ov_len; }
         }
         const uint64_t rec = rec_base + i;
         const uint64_t nl = name_off[rec + 1] - name_off[rec], pl = plus_off[rec + 1] - plus_off[rec];
@@ -105,7 +107,7 @@ int aqc_fastq_emit(int mate, int which,
         uint8_t *qo = out + w;
         memcpy(qo, q + start, len); w += len;
         out[w++] = '\n';
-        for (int e = 0; e < r.n_edits && e < 4; e++) {       // apply the correction-walk edits that fall inside the slice
+        for (int e = 0; mate != 0 && e < r.n_edits && e < 4; e++) {       // apply the correction-walk edits that fall inside the slice
             const uint32_t ed = r.edits[e], kind = AQC_EDIT_KIND(ed);
             uint32_t pos; bool has_base = false;
             if (kind == 0 && mate == 1) { pos = AQC_EDIT_POS(ed); has_base = true; }

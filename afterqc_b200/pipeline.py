@@ -129,11 +129,11 @@ class seqFilter:
             raise NotImplementedError("--debubble is outside the B200 hot-path scope (SURVEY.md section 2, #12)")
         if getattr(opt, "barcode", False):
             raise NotImplementedError("barcode (UMI) processing is outside the B200 hot-path scope (SURVEY.md section 2, #11)")
-        if opt.index1_file is not None or opt.index2_file is not None:
-            raise NotImplementedError("index files (-7/-5) are a 'next' row (SURVEY.md section 8(f) #4)")
-
         rec1 = fastq_io.read_all(opt.read1_file)
         rec2 = fastq_io.read_all(opt.read2_file) if self.paired else None
+        # index reads (-7 / -5) are carried along untouched (preprocesser.py:358-371,422-431)
+        idx_files = [(k, getattr(opt, k)) for k in ("index1_file", "index2_file") if getattr(opt, k) is not None]
+        idx_recs = {k: fastq_io.read_all(f) for k, f in idx_files}
 
         params = params_from_options(opt, self.paired)
         be = self.backend_factory(params)
@@ -214,11 +214,16 @@ class seqFilter:
                 writers["bad2"] = mk(bad_dir, opt.read2_file, ".bad.fq")
                 if opt.store_overlap:
                     writers["ov2"] = mk(overlap_dir, opt.read2_file, ".overlap.fq")
+            for k, f in idx_files:
+                writers["good_" + k] = mk(good_dir, f, ".good.fq")
+                writers["bad_" + k] = mk(bad_dir, f, ".bad.fq")
+                if opt.store_overlap and self.paired:
+                    writers["ov_" + k] = mk(overlap_dir, f, ".overlap.fq")
 
         # ---- the per-read loop, in batches (preprocesser.py:411-631) ----
         params = params_from_options(opt, self.paired)
         be.set_params(params)
-        n = min(rec1.n, rec2.n) if self.paired else rec1.n
+        n = min([rec1.n] + ([rec2.n] if self.paired else []) + [r.n for r in idx_recs.values()])   # loop ends at the shortest file
         stop = n
         if opt.qc_only:
             if world > 1:
@@ -232,6 +237,11 @@ class seqFilter:
             res = be.filter_pairs(batch)
             if not opt.qc_only:
                 self._write(writers, rec1, rec2, a, res)
+                for k, r in idx_recs.items():
+                    writers["good_" + k].write(fastq_io.emit(r, 0, 0, a, res))
+                    writers["bad_" + k].write(fastq_io.emit(r, 0, 1, a, res))
+                    if "ov_" + k in writers:
+                        writers["ov_" + k].write(fastq_io.emit(r, 0, 2, a, res))
         for w in writers.values():
             w.close()
         if world > 1 and not opt.qc_only:
@@ -267,7 +277,8 @@ class seqFilter:
 
         # quirk Q1: the reference only adds R2's bases when an index2 file is present, and the R1
         # record read just before a shorter R2 ran out is still counted (preprocesser.py:416-431)
-        extra = int(rec1.lengths()[n]) if (self.paired and rec1.n > n and not opt.qc_only) else 0
+        extra = int(rec1.lengths()[n]) if (rec1.n > n and not opt.qc_only) else 0
+        self._count_r2_bases = opt.index2_file is not None
         figure_qcs = [("Read1" if self.paired else "", "before", "r1_pre", self.r1qc_prefilter),
                       ("Read1" if self.paired else "", "after", "r1_post", self.r1qc_postfilter)]
         if self.paired:
@@ -338,8 +349,8 @@ class seqFilter:
         opt = self.options
         c = lambda name: int(cnt[_abi.CIDX[name]])
         result = {
-            'total_bases': c("TOTAL_BASES_R1") + extra_total_bases,
-            'good_bases': c("GOOD_BASES_R1"),
+            'total_bases': c("TOTAL_BASES_R1") + extra_total_bases + (c("TOTAL_BASES_R2") if self._count_r2_bases else 0),
+            'good_bases': c("GOOD_BASES_R1") + (c("GOOD_BASES_R2") if self._count_r2_bases else 0),
             'total_reads': c("TOTAL_READS"),
             'good_reads': c("GOOD_READS"),
             'bad_reads': c("TOTAL_READS") - c("GOOD_READS"),

@@ -259,7 +259,8 @@ int aqc_fastq_parse(const uint8_t *buf, uint64_t n, int final, uint64_t max_reco
                     uint64_t *n_records, uint64_t *consumed, int *hit_eof, uint64_t *bad_record);
 /* FASTQ text of one mate's records selected by `which` (0 good, 1 bad with the "@BADxxx" name prefix of
  * preprocesser.py:212-213, 2 overlapped tails for --store_overlap :615-617): final slice + correction edits of
- * results[i] applied to column record rec_base + i.  AQC_ERR_NOMEM when out_cap is too small. */
+ * results[i] applied to column record rec_base + i; mate 0 = index read (-7/-5 files), passed through whole.
+ * AQC_ERR_NOMEM when out_cap is too small. */
 int aqc_fastq_emit(int mate, int which,
                    const uint8_t *names, const uint64_t *name_off, const uint8_t *seqs, const uint64_t *seq_off,
                    const uint8_t *plus, const uint64_t *plus_off, const uint8_t *quals,
