@@ -125,7 +125,13 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // bit-plane helpers.  A "plane set" is uint32_t P[4]; lane j holds positions 32j..32j+31.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lowmask(int nbits) {   // nbits may be <= 0 or >= 32
+#ifdef AQC_NO_BMSK
     return nbits >= 32 ? 0xffffffffu : (nbits <= 0 ? 0u : ((1u << nbits) - 1u));
+#else
+    uint32_t m;
+    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(m) : "r"(0u), "r"((uint32_t)max(nbits, 0)));   // width clamps at 32
+    return m;
+#endif
 }
 
 // 32 bits of plane word array `p` starting at bit (32*word + sh), word may exceed 31 (-> zeros)
@@ -320,8 +326,9 @@ struct FastPlanes {
 // Both mates in ONE instruction stream: lanes 0-15 convert mate 1, lanes 16-31 mate 2, 16 consecutive bases per lane
 // (256 bases per mate and pass).  Same arithmetic as fast_build on four words; the 16-bit plane slices of lanes
 // 2j, 2j+1 form plane word j, so the gather needs two shuffles per mate.  len2 = 0 for single-end input.
+// bytemask16: shared-memory table, entry k (0..16) = 16 bytes with the first k bytes 0xFF (built once per CTA)
 __device__ __forceinline__ void fast_build2(const uint8_t *r1, int len1, const uint8_t *r2, int len2, int lane,
-                                            FastPlanes &F1, FastPlanes &F2) {
+                                            const uint4 *bytemask16, FastPlanes &F1, FastPlanes &F2) {
     F1.P[0] = F1.P[1] = F1.P[2] = F1.P[3] = 0; F1.n_count = 0; F1.hasN = false; F1.exotic = false;
     F2.P[0] = F2.P[1] = F2.P[2] = F2.P[3] = 0; F2.n_count = 0; F2.hasN = false; F2.exotic = false;
     const bool hi = lane >= 16;
@@ -338,7 +345,8 @@ __device__ __forceinline__ void fast_build2(const uint8_t *r1, int len1, const u
             const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
             const int sh = (int)(a & 3) * 8;
             const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-            vm[0] = bytemask_lo(nv); vm[1] = bytemask_lo(nv - 4); vm[2] = bytemask_lo(nv - 8); vm[3] = bytemask_lo(nv - 12);
+            const uint4 mk = bytemask16[min(nv, 16)];
+            vm[0] = mk.x; vm[1] = mk.y; vm[2] = mk.z; vm[3] = mk.w;
             v[0] = __funnelshift_r(w0, w1, sh) & vm[0];
             v[1] = __funnelshift_r(w1, w2, sh) & vm[1];
             v[2] = __funnelshift_r(w2, w3, sh) & vm[2];

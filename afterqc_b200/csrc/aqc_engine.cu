@@ -115,7 +115,7 @@ size_t smem_bytes_for(int P, int col_cap, int max_len) {
     int off_cap = ((P + 8) * 4 + 15) & ~15;
     size_t stage = ((size_t)4 * col_cap + 2 * off_cap + 127) & ~(size_t)127;
     size_t acc = (size_t)(2 * QC_CLASSES * max_len + 2 * max_len + 2 * (max_len + 1)) * 4;
-    return NSTAGES * stage + 768 + acc + 64;
+    return NSTAGES * stage + 768 + 272 + acc + 64;
 }
 
 const void *kernel_for(int mode, bool paired) {

@@ -23,9 +23,9 @@ struct PairPlanes {
 };
 
 __device__ __forceinline__ void prepare_pair(const uint8_t *r1, int len1, const uint8_t *r2, int len2, bool paired, bool want_poly,
-                                             int maxPoly, int poly_m, const uint8_t *lut1, int lane, PairPlanes &pp) {
+                                             int maxPoly, int poly_m, const uint8_t *lut1, const uint4 *bytemask16, int lane, PairPlanes &pp) {
     FastPlanes F1, F2;
-    fast_build2(r1, len1, r2, paired ? len2 : 0, lane, F1, F2);
+    fast_build2(r1, len1, r2, paired ? len2 : 0, lane, bytemask16, F1, F2);
     const bool exotic = F1.exotic || F2.exotic;
     pp.cand1 = pp.cand2 = false;
     if (__builtin_expect(!exotic, 1)) {
@@ -71,7 +71,7 @@ struct StageBuf {
 
 // dynamic shared memory layout:
 //   [NSTAGES][ 4 * col_cap + 2 * off_cap ]   tile staging (TMA destinations, 128-byte aligned)
-//   luts (768 B)
+//   luts (768 B) + byte-mask table (272 B)
 //   qc acc  [2][5][max_len] u32, qc disc [2][max_len] u32
 //   overlap_hist [max_len+1] u32, distance_hist [max_len+1] u32
 #ifndef AQC_MIN_BLOCKS
@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
 
     uint8_t *lutbase = smem_raw + (size_t)NSTAGES * stage_bytes;
     const uint8_t *lut1 = lutbase, *lut2 = lutbase + 256, *lut3 = lutbase + 512;
-    uint32_t *s_acc = reinterpret_cast<uint32_t *>(lutbase + 768);
+    uint4 *const bytemask16 = reinterpret_cast<uint4 *>(lutbase + 768);          // 17 entries
+    uint32_t *s_acc = reinterpret_cast<uint32_t *>(lutbase + 768 + 272);
     uint32_t *s_disc = s_acc + 2 * QC_CLASSES * A.max_len;
     uint32_t *s_ovh = s_disc + 2 * A.max_len;
     uint32_t *s_dih = s_ovh + (A.max_len + 1);
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
 
     // ---- one-time setup ----
     for (int i = tid; i < 768; i += THREADS) lutbase[i] = reinterpret_cast<const uint8_t *>(A.luts)[i];
+    for (int i = tid; i < 272; i += THREADS) lutbase[768 + i] = ((i & 15) < (i >> 4)) ? 0xFF : 0x00;   // entry k: first k bytes set
     for (int i = tid; i < n_acc_words; i += THREADS) s_acc[i] = 0;
     if (tid == 0) {
         for (int s = 0; s < NSTAGES; s++) mbar_init(&full_bar[s], 1);
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
                 const uint8_t *r1 = S1 + start1, *r1q = Q1 + start1;
                 const uint8_t *r2 = paired ? S2 + start2 : nullptr, *r2q = paired ? Q2 + start2 : nullptr;
                 PairPlanes pl;
-                prepare_pair(r1, len1, r2, len2, paired, true, A.p.poly_size_limit, A.poly_m, lut1, lane, pl);
+                prepare_pair(r1, len1, r2, len2, paired, true, A.p.poly_size_limit, A.poly_m, lut1, bytemask16, lane, pl);
                 const int n1 = pl.n1, n2 = pl.n2;
                 const int thr = A.p.qualified_quality_phred + 33;
                 int lowq1 = lowq_any(r1q, len1, thr, lane), lowq2 = 0;
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
                 uint8_t *r1 = S1 + start1, *r1q = Q1 + start1;
                 uint8_t *r2 = paired ? S2 + start2 : nullptr, *r2q = paired ? Q2 + start2 : nullptr;
                 PairPlanes pl;
-                prepare_pair(r1, len1, r2, len2, paired, A.p.poly_size_limit > 0, A.p.poly_size_limit, A.poly_m, lut1, lane, pl);
+                prepare_pair(r1, len1, r2, len2, paired, A.p.poly_size_limit > 0, A.p.poly_size_limit, A.poly_m, lut1, bytemask16, lane, pl);
 
                 if (A.p.poly_size_limit > 0) {                             // :482-490
                     bool poly = false;

@@ -30,3 +30,21 @@ def test_after_py_cli_runs_on_gpu(tmp_path):
     assert "Time used:" in out.stdout
     for rel in ("good/x_R1.good.fq.gz", "bad/x_R2.bad.fq.gz", "QC/x_R1.fq.gz.json"):
         assert os.path.exists(str(tmp_path / rel)), rel
+
+
+def test_directory_mode_on_gpu(tmp_path):
+    """after.py -d DIR: one job per *R1* file (after.py:101-171); outputs land in good/ bad/ QC/ next to the default names."""
+    import shutil
+    d = tmp_path / "run"
+    d.mkdir()
+    for tag, case in (("a", "pe150_default"), ("b", "pe150_small_head_fallback")):
+        src = os.path.join(golden_util.GOLD, case)
+        shutil.copy(os.path.join(src, "x_R1.fq.gz"), str(d / ("s%s_R1.fq.gz" % tag)))
+        shutil.copy(os.path.join(src, "x_R2.fq.gz"), str(d / ("s%s_R2.fq.gz" % tag)))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "after.py"), "-d", str(d), "-g", str(d / "good")],
+                         capture_output=True, text=True, timeout=900, cwd=str(d))
+    assert out.returncode == 0, out.stderr[-2000:]
+    for tag in ("a", "b"):
+        for rel in ("good/s%s_R1.good.fq.gz" % tag, "good/s%s_R2.good.fq.gz" % tag, "bad/s%s_R1.bad.fq.gz" % tag, "QC/s%s_R1.fq.gz.json" % tag,
+                    "QC/s%s_R1.fq.gz.html" % tag):
+            assert os.path.exists(str(d / rel)), rel
