@@ -72,6 +72,64 @@ class FastqRecords:
     def lengths(self):
         return np.diff(self.seqs.off.astype(np.int64))
 
+    def slice(self, a, b):
+        """records [a, b) as an independent FastqRecords (offsets rebased)"""
+        def cut(c):
+            lo, hi = int(c.off[a]), int(c.off[b])
+            return Column(c.data[lo:hi], (c.off[a:b + 1] - lo).astype(np.int64))
+        return FastqRecords(cut(self.names), cut(self.seqs), cut(self.plus), cut(self.quals))
+
+    @staticmethod
+    def concat(chunks):
+        if len(chunks) == 1:
+            return chunks[0]
+        return FastqRecords(*(Column.concat([getattr(c, k) for c in chunks]) for k in ("names", "seqs", "plus", "quals")))
+
+    @staticmethod
+    def empty():
+        z = np.zeros(1, dtype=np.int64)
+        e = np.zeros(0, dtype=np.uint8)
+        return FastqRecords(Column(e, z), Column(e, z), Column(e, z), Column(e, z))
+
+
+class RecordStream:
+    """Pull-based view of one FASTQ file: take(k) returns the next min(k, remaining) records."""
+
+    def __init__(self, path, block_bytes=32 << 20):
+        self._it = iter_records(path, block_bytes)
+        self._chunks = []       # pending FastqRecords
+        self._have = 0
+        self._ended = False
+
+    def _fill(self, k):
+        while self._have < k and not self._ended:
+            try:
+                c = next(self._it)
+            except StopIteration:
+                self._ended = True
+                break
+            self._chunks.append(c)
+            self._have += c.n
+
+    def available(self, k):
+        """number of records that can be taken now, up to k"""
+        self._fill(k)
+        return min(k, self._have)
+
+    def take(self, k):
+        self._fill(k)
+        k = min(k, self._have)
+        out = []
+        need = k
+        while need > 0:
+            c = self._chunks[0]
+            if c.n <= need:
+                out.append(c); self._chunks.pop(0); need -= c.n
+            else:
+                out.append(c.slice(0, need)); self._chunks[0] = c.slice(need, c.n); need = 0
+        self._have -= k
+        return FastqRecords.concat(out) if out else FastqRecords.empty()
+
 
 def _parse_block(buf, final):
     """Parse complete records out of `buf` (bytes) with the native parser (csrc/aqc_fastq.cpp).
@@ -127,11 +185,7 @@ def iter_records(path, block_bytes=32 << 20):
 
 def read_all(path):
     chunks = list(iter_records(path))
-    if not chunks:
-        z = np.zeros(1, dtype=np.int64)
-        e = np.zeros(0, dtype=np.uint8)
-        return FastqRecords(Column(e, z), Column(e, z), Column(e, z), Column(e, z))
-    return FastqRecords(*(Column.concat([getattr(c, k) for c in chunks]) for k in ("names", "seqs", "plus", "quals")))
+    return FastqRecords.concat(chunks) if chunks else FastqRecords.empty()
 
 
 def to_batch(rec1, rec2, lo, hi, first_index=None):

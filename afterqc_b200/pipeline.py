@@ -129,20 +129,32 @@ class seqFilter:
             raise NotImplementedError("--debubble is outside the B200 hot-path scope (SURVEY.md section 2, #12)")
         if getattr(opt, "barcode", False):
             raise NotImplementedError("barcode (UMI) processing is outside the B200 hot-path scope (SURVEY.md section 2, #11)")
-        rec1 = fastq_io.read_all(opt.read1_file)
-        rec2 = fastq_io.read_all(opt.read2_file) if self.paired else None
+        rank, world = self.shard
+        # One GPU: stream the files in bounded memory (two passes, like the reference).  Shards: every rank parses the
+        # files and takes its contiguous record range.
+        streaming = world == 1
         # index reads (-7 / -5) are carried along untouched (preprocesser.py:358-371,422-431)
         idx_files = [(k, getattr(opt, k)) for k in ("index1_file", "index2_file") if getattr(opt, k) is not None]
-        idx_recs = {k: fastq_io.read_all(f) for k, f in idx_files}
+        rec1 = rec2 = None
+        idx_recs = {}
+        if not streaming:
+            rec1 = fastq_io.read_all(opt.read1_file)
+            rec2 = fastq_io.read_all(opt.read2_file) if self.paired else None
+            idx_recs = {k: fastq_io.read_all(f) for k, f in idx_files}
 
         params = params_from_options(opt, self.paired)
         be = self.backend_factory(params)
         self.backend = be
 
         # ---- prefilter QC (preprocesser.py:247-251) ----
-        prefilter_stat(be, rec1, _abi.QC_R1_PRE, opt.qc_sample, self.batch_records, self.shard)
-        if self.paired:
-            prefilter_stat(be, rec2, _abi.QC_R2_PRE, opt.qc_sample, self.batch_records, self.shard)
+        if streaming:
+            self._prefilter_stream(be, opt.read1_file, _abi.QC_R1_PRE)
+            if self.paired:
+                self._prefilter_stream(be, opt.read2_file, _abi.QC_R2_PRE)
+        else:
+            prefilter_stat(be, rec1, _abi.QC_R1_PRE, opt.qc_sample, self.batch_records, self.shard)
+            if self.paired:
+                prefilter_stat(be, rec2, _abi.QC_R2_PRE, opt.qc_sample, self.batch_records, self.shard)
         self.r1qc_prefilter = QualityControl(opt.qc_sample, opt.qc_kmer).load(be.qc(_abi.QC_R1_PRE), be.kmers(_abi.QC_R1_PRE))
         self.r1qc_prefilter.qc()
         self.r2qc_prefilter = QualityControl(opt.qc_sample, opt.qc_kmer)
@@ -173,7 +185,6 @@ class seqFilter:
             if getattr(opt, k) < 0:
                 raise ValueError("%s=%d is outside the supported domain" % (k, getattr(opt, k)))
 
-        rank, world = self.shard
         if rank == 0:
             print(opt.read1_file + " options:")
             print(opt)
@@ -223,25 +234,26 @@ class seqFilter:
         # ---- the per-read loop, in batches (preprocesser.py:411-631) ----
         params = params_from_options(opt, self.paired)
         be.set_params(params)
-        n = min([rec1.n] + ([rec2.n] if self.paired else []) + [r.n for r in idx_recs.values()])   # loop ends at the shortest file
-        stop = n
-        if opt.qc_only:
-            if world > 1:
+        extra = 0
+        if streaming:
+            extra = self._filter_stream(be, writers, idx_files)
+        else:
+            n = min([rec1.n] + ([rec2.n] if self.paired else []) + [r.n for r in idx_recs.values()])   # loop ends at the shortest file
+            if opt.qc_only:
                 raise NotImplementedError("--qc_only stops at a data-dependent record; run it on one GPU")
-            stop = self._qc_only_stop(be, rec1, rec2, n)
-            be.reset_filter_counters()
-        s_lo, s_hi = (stop * rank) // world, (stop * (rank + 1)) // world
-        for a in range(s_lo, s_hi, self.batch_records):
-            b = min(s_hi, a + self.batch_records)
-            batch = fastq_io.to_batch(rec1, rec2, a, b)
-            res = be.filter_pairs(batch)
-            if not opt.qc_only:
+            s_lo, s_hi = (n * rank) // world, (n * (rank + 1)) // world
+            for a in range(s_lo, s_hi, self.batch_records):
+                b = min(s_hi, a + self.batch_records)
+                batch = fastq_io.to_batch(rec1, rec2, a, b)
+                res = be.filter_pairs(batch)
                 self._write(writers, rec1, rec2, a, res)
                 for k, r in idx_recs.items():
                     writers["good_" + k].write(fastq_io.emit(r, 0, 0, a, res))
                     writers["bad_" + k].write(fastq_io.emit(r, 0, 1, a, res))
                     if "ov_" + k in writers:
                         writers["ov_" + k].write(fastq_io.emit(r, 0, 2, a, res))
+            # the R1 record read just before a shorter mate/index file ran out is still counted (preprocesser.py:416-431)
+            extra = int(rec1.lengths()[n]) if rec1.n > n else 0
         for w in writers.values():
             w.close()
         if world > 1 and not opt.qc_only:
@@ -275,9 +287,7 @@ class seqFilter:
             self.r2qc_postfilter.load(be.qc(_abi.QC_R2_POST), be.kmers(_abi.QC_R2_POST))
             self.r2qc_postfilter.qc()
 
-        # quirk Q1: the reference only adds R2's bases when an index2 file is present, and the R1
-        # record read just before a shorter R2 ran out is still counted (preprocesser.py:416-431)
-        extra = int(rec1.lengths()[n]) if (rec1.n > n and not opt.qc_only) else 0
+        # quirk Q1: the reference only adds R2's bases when an index2 file is present (preprocesser.py:426-431,622-623)
         self._count_r2_bases = opt.index2_file is not None
         figure_qcs = [("Read1" if self.paired else "", "before", "r1_pre", self.r1qc_prefilter),
                       ("Read1" if self.paired else "", "after", "r1_post", self.r1qc_postfilter)]
@@ -316,21 +326,76 @@ class seqFilter:
         figs += read_figs
         report.write_html(path, stat, getattr(opt, "version", "0.9.6"), figs)
 
-    def _qc_only_stop(self, be, rec1, rec2, n):
-        """--qc_only stops after the first GOOD pair whose TOTAL_READS >= qc_sample
-        (preprocesser.py:630-631); find that index with a counter-free dry run."""
-        qs = self.options.qc_sample
-        for a in range(0, n, self.batch_records):
-            b = min(n, a + self.batch_records)
-            if b < qs:
-                continue
-            batch = fastq_io.to_batch(rec1, rec2, a, b)
+    def _prefilter_stream(self, be, path, slot):
+        """QualityControl.statFile (qualitycontrol.py:331-357) on a stream: window = records [999, 999+limit) (all when
+        limit <= 0); reading stops one record past the window (that is all statFile's counter needs); if fewer than
+        1000 records were counted in the window loop the first 999 are stat'd afterwards."""
+        opt = self.options
+        limit = opt.qc_sample
+        lo = READ_TO_SKIP - 1
+        hi = lo + limit if limit > 0 else None
+        stream = fastq_io.RecordStream(path)
+        g = 0
+        head = []
+        while True:
+            k = stream.available(self.batch_records)
+            if k == 0:
+                break
+            rec = stream.take(k)
+            a, b = g, g + rec.n
+            if a < lo:
+                head.append(rec.slice(0, min(rec.n, lo - a)))
+            wa, wb = max(a, lo), (b if hi is None else min(b, hi))
+            if wb > wa:
+                batch = fastq_io.to_batch(rec, None, wa - a, wb - a, first_index=wa)
+                be.stat_reads(batch, slot, -1, stat_lo=lo, stat_hi=(hi if hi is not None else 1 << 62), order_base=0)
+            g = b
+            if hi is not None and g > hi:
+                break
+        stat_reads_num = min(max(g - lo, 0), limit + 1) if limit > 0 else max(g - lo, 0)
+        if stat_reads_num < READ_TO_SKIP and head:
+            hrec = fastq_io.FastqRecords.concat(head)
+            batch = fastq_io.to_batch(hrec, None, 0, hrec.n, first_index=0)
+            be.stat_reads(batch, slot, -1, stat_lo=0, stat_hi=hrec.n, order_base=HEAD_ORDER_BASE)
+
+    def _filter_stream(self, be, writers, idx_files):
+        """The per-read loop over lock-stepped streams of R1 [, R2] [, I1] [, I2]; ends at the shortest file
+        (preprocesser.py:411-431).  Returns the bases of the R1 record that the reference reads (and counts) just before
+        another file runs out.  --qc_only: stop after the first GOOD pair whose TOTAL_READS >= qc_sample (:630-631)."""
+        opt = self.options
+        paths = [opt.read1_file] + ([opt.read2_file] if self.paired else []) + [f for _k, f in idx_files]
+        streams = [fastq_io.RecordStream(p) for p in paths]
+        keys = [k for k, _f in idx_files]
+        qs = opt.qc_sample
+        g = 0
+        stopped = False
+        while not stopped:
+            want = self.batch_records
+            if opt.qc_only:
+                want = 1 if g + 1 >= qs else min(want, qs - 1 - g)    # single pairs once the stop rule can fire
+            k = min(s.available(want) for s in streams)
+            if k == 0:
+                break
+            recs = [s.take(k) for s in streams]
+            rec1 = recs[0]
+            rec2 = recs[1] if self.paired else None
+            batch = fastq_io.to_batch(rec1, rec2, 0, k, first_index=g)
             res = be.filter_pairs(batch)
-            idx = np.arange(a, b) + 1
-            hit = np.flatnonzero((res["cls"] == _abi.GOOD) & (idx >= qs))
-            if len(hit):
-                return a + int(hit[0]) + 1
-        return n
+            if not opt.qc_only:
+                self._write(writers, rec1, rec2, 0, res)
+                for key, r in zip(keys, recs[(2 if self.paired else 1):]):
+                    writers["good_" + key].write(fastq_io.emit(r, 0, 0, 0, res))
+                    writers["bad_" + key].write(fastq_io.emit(r, 0, 1, 0, res))
+                    if "ov_" + key in writers:
+                        writers["ov_" + key].write(fastq_io.emit(r, 0, 2, 0, res))
+            g += k
+            if opt.qc_only and g >= qs and int(res["cls"][-1]) == _abi.GOOD:
+                stopped = True
+        if stopped or len(streams) == 1:
+            return 0
+        if streams[0].available(1) > 0:
+            return int(streams[0].take(1).lengths()[0])
+        return 0
 
     def _write(self, writers, rec1, rec2, base, res):
         """good/bad(/overlap) text of one batch: slices, correction edits and @BADxxx names (preprocesser.py:206-232)."""
