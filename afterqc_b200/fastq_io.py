@@ -17,11 +17,6 @@ import numpy as np
 
 from .batch import PackedBatch, SLACK
 
-_WS = np.zeros(256, dtype=bool)
-for _c in b" \t\n\r\x0b\x0c":
-    _WS[_c] = True
-
-
 def is_fastq(f):
     return f.endswith((".fq", ".fastq", ".fq.gz", ".fastq.gz", ".fq.bz2", ".fastq.bz2"))
 
@@ -231,6 +226,59 @@ def emit(rec, mate, which, rec_base, results):
     return out[:olen.value].tobytes()
 
 
+class _ParallelGzip:
+    """gzip output as a sequence of independent members (valid .gz: readers concatenate them), each block compressed
+    by a worker thread (zlib releases the GIL).  Content after decompression is what the reference writes; the
+    compressed bytes differ, as they already do between zlib builds (parity is on decompressed content, quirk Q14)."""
+
+    BLOCK = 8 << 20
+
+    def __init__(self, path, level, threads=4):
+        import concurrent.futures
+        self._f = open(path, "wb")
+        self._level = level
+        self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=threads)
+        self._pending = []
+        self._buf = []
+        self._size = 0
+
+    @staticmethod
+    def _member(data, level):
+        import zlib
+        c = zlib.compressobj(level, zlib.DEFLATED, 31)
+        return c.compress(data) + c.flush()
+
+    def write(self, data):
+        if not data:
+            return
+        self._buf.append(data)
+        self._size += len(data)
+        if self._size >= self.BLOCK:
+            self._submit()
+
+    def _submit(self):
+        if self._size == 0:
+            return
+        data = b"".join(self._buf)
+        self._buf, self._size = [], 0
+        self._pending.append(self._pool.submit(self._member, data, self._level))
+        while len(self._pending) > 8:                 # bounded queue, in-order write-out
+            self._f.write(self._pending.pop(0).result())
+
+    def flush(self):
+        pass
+
+    def close(self):
+        self._submit()
+        for fut in self._pending:
+            self._f.write(fut.result())
+        self._pending = []
+        if self._f.tell() == 0:                       # an empty .gz is still a gzip member
+            self._f.write(self._member(b"", self._level))
+        self._pool.shutdown()
+        self._f.close()
+
+
 class Writer:
     """fastq.Writer (fastq.py:57-104) on bytes."""
 
@@ -239,7 +287,7 @@ class Writer:
         if not self.filename.endswith(".gz") and force_gzip:
             self.filename = self.filename + ".gz"
         if self.filename.endswith(".gz"):
-            self._f = gzip.open(self.filename, "wb", compresslevel=gzip_compression)
+            self._f = _ParallelGzip(self.filename, gzip_compression)
         elif self.filename.endswith(".bz2"):
             print("ERROR: Write bzip2 stream is not supported")
             sys.exit(1)

@@ -101,3 +101,36 @@ def test_python_abi_mirror_matches_header():
     assert ctypes.sizeof(_abi.Params) == 24 * 4 and ctypes.sizeof(_abi.Batch) == 16 + 6 * 8
     names = re.findall(r"AQC_C_([A-Z0-9_]+)", hdr.split("enum {\n    AQC_C_TOTAL_READS")[1].split("AQC_C_ERR_MATRIX")[0])
     assert ["TOTAL_READS"] + names == list(_abi.CIDX)
+
+
+def test_parallel_gzip_writer_roundtrip(tmp_path):
+    import random
+    p = str(tmp_path / "o.fq.gz")
+    w = fastq_io.Writer(p, False, 2)
+    w._f.BLOCK = 1000                       # force several members
+    rng = random.Random(1)
+    chunks = [bytes(rng.choice(b"ACGT\n@+I") for _ in range(rng.randint(0, 700))) for _ in range(60)]
+    for c in chunks:
+        w.write(c)
+    w.close()
+    assert gzip.open(p).read() == b"".join(chunks)
+    q = str(tmp_path / "e.fq.gz")
+    fastq_io.Writer(q, False, 2).close()
+    assert gzip.open(q).read() == b""
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` prints exactly one JSON line with the contract's keys (CPU only)."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "4000"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0 and "workload" in d["config"]
