@@ -75,6 +75,14 @@ class Batch(C.Structure):
     ]
 
 
+class Records(C.Structure):
+    """aqc_records: one parsed batch of the streaming reader (views into the reader's slot buffers)."""
+    _fields_ = [
+        ("n", C.c_uint64), ("first_index", C.c_uint64), ("slot", C.c_uint32), ("max_len", C.c_uint32),
+        ("bytes", C.c_void_p * 4), ("off", C.c_void_p * 4), ("seq_off32", C.c_void_p),
+    ]
+
+
 RESULT_DTYPE = np.dtype([
     ("cls", "u1"), ("n_edits", "u1"), ("start1", "<u2"), ("len1", "<u2"), ("start2", "<u2"), ("len2", "<u2"),
     ("ov_offset", "<i2"), ("ov_len", "<u2"), ("ov_diff", "<u2"), ("edits", "<u4", (4,)),

@@ -7,8 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libafterqc_b200.so")
-SOURCES = ["aqc_engine.cu", "aqc_fastq.cpp"]
-DEPS = ["aqc_engine.cu", "aqc_fastq.cpp", "aqc_kernel.cuh", "aqc_device.cuh", os.path.join("..", "..", "include", "afterqc_b200.h")]
+SOURCES = ["aqc_engine.cu", "aqc_fastq.cpp", "aqc_stream.cpp"]
+DEPS = ["aqc_engine.cu", "aqc_fastq.cpp", "aqc_stream.cpp", "aqc_kernel.cuh", "aqc_device.cuh", os.path.join("..", "..", "include", "afterqc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -30,7 +30,7 @@ def up_to_date():
 def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + ["-lz", "-lpthread"]
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB
 

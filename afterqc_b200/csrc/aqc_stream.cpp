@@ -1,0 +1,235 @@
+// aqc_stream.cpp -- streaming FASTQ reader of libafterqc_b200.so: a background thread
+// inflates/reads one file and parses it into a ring of reusable packed-column buffers, so that the host loop only
+// hands ready batches to the device.  Mirrors fastq.Reader (fastq.py:17-55): .gz by extension, every line rstrip()'d,
+// the first empty line ends the file (quirk Q13).  No CUDA here.
+#include <zlib.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/afterqc_b200.h"
+
+namespace {
+
+constexpr size_t kReadBlock = 4u << 20;
+constexpr size_t kSlack = 64;
+constexpr uint64_t kMaxColumn = (1ull << 32) - 64;       // aqc_batch offsets are uint32
+
+struct Slot {
+    uint8_t *bytes[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t cap[4] = {0, 0, 0, 0};
+    uint64_t *off[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t *off32 = nullptr;
+    uint64_t n = 0, first = 0;
+    uint32_t max_len = 0;
+};
+
+bool ends_with(const std::string &s, const char *suf) {
+    size_t k = strlen(suf);
+    return s.size() >= k && s.compare(s.size() - k, k, suf) == 0;
+}
+
+}  // namespace
+
+struct aqc_reader {
+    std::string path, msg;
+    uint64_t batch = 0;
+    std::vector<Slot> slots;
+    std::deque<uint32_t> free_, ready;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::thread th;
+    std::atomic<bool> stop{false};
+    bool finished = false;
+    int err = 0;
+    // source (reader thread only)
+    gzFile gz = nullptr;
+    FILE *fp = nullptr;
+    std::vector<uint8_t> in;
+    size_t in_pos = 0, in_end = 0;
+    bool src_eof = false, file_end = false;
+    uint64_t next_index = 0;
+
+    bool grow(Slot &s, int c, size_t need) {
+        if (need <= s.cap[c]) return true;
+        size_t cap = s.cap[c] ? s.cap[c] : (size_t)1 << 20;
+        while (cap < need) cap += cap / 2;
+        uint8_t *p = (uint8_t *)realloc(s.bytes[c], cap);
+        if (!p) return false;
+        s.bytes[c] = p; s.cap[c] = cap;
+        return true;
+    }
+
+    // more input behind the unparsed tail; returns false on a read error
+    bool refill() {
+        if (in_pos > 0) {
+            memmove(in.data(), in.data() + in_pos, in_end - in_pos);
+            in_end -= in_pos; in_pos = 0;
+        }
+        if (in.size() < in_end + kReadBlock) in.resize(in_end + kReadBlock);
+        long got;
+        if (gz) {
+            got = gzread(gz, in.data() + in_end, (unsigned)kReadBlock);
+            if (got < 0) { int e; msg = std::string("gzip: ") + gzerror(gz, &e); return false; }
+            if (got == 0) {
+                int e = 0; const char *m = gzerror(gz, &e);
+                if (e != Z_OK && e != Z_STREAM_END) { msg = std::string("gzip: ") + m; return false; }
+            }
+        } else {
+            got = (long)fread(in.data() + in_end, 1, kReadBlock, fp);
+            if (got == 0 && ferror(fp)) { msg = "read error"; return false; }
+        }
+        if (got == 0) src_eof = true;
+        in_end += (size_t)got;
+        return true;
+    }
+
+    // parse up to `batch` records into s; returns 0 or an AQC_ERR_* code
+    int fill(Slot &s) {
+        s.n = 0; s.first = next_index; s.max_len = 0;
+        for (int c = 0; c < 4; c++) s.off[c][0] = 0;
+        while (s.n < batch && !file_end) {
+            if (stop.load(std::memory_order_relaxed)) { s.n = 0; return 0; }      // closing: drop the partial batch
+            const size_t avail = in_end - in_pos;
+            bool progressed = false;
+            if (avail > 0 || src_eof) {
+                for (int c = 0; c < 4; c++)
+                    if (!grow(s, c, (size_t)s.off[c][s.n] + avail + kSlack)) return AQC_ERR_NOMEM;
+                uint64_t *offp[4] = {s.off[0] + s.n, s.off[1] + s.n, s.off[2] + s.n, s.off[3] + s.n};
+                uint64_t nrec = 0, consumed = 0, bad = 0;
+                int hit = 0;
+                int rc = aqc_fastq_parse(in.data() + in_pos, avail, src_eof ? 1 : 0, batch - s.n, s.bytes, offp, &nrec, &consumed, &hit, &bad);
+                if (rc) {
+                    char t[128];
+                    snprintf(t, sizeof t, "FASTQ record %llu: quality line length differs from sequence length",
+                             (unsigned long long)(next_index + s.n + bad));
+                    msg = t;
+                    s.n += nrec;                         // records before the bad one are still delivered
+                    return rc;
+                }
+                s.n += nrec; in_pos += consumed;
+                progressed = nrec > 0;
+                if (hit) { file_end = true; break; }
+                if (s.n >= batch) break;
+            }
+            if (src_eof) { if (!progressed) file_end = true; continue; }
+            if (!refill()) return AQC_ERR_INVALID;
+        }
+        return 0;
+    }
+
+    void finish(Slot &s) {
+        if (s.off[1][s.n] > kMaxColumn) { err = AQC_ERR_INVALID; msg = "batch column exceeds uint32 offsets; use a smaller batch"; return; }
+        uint32_t m = 0;
+        for (uint64_t i = 0; i <= s.n; i++) s.off32[i] = (uint32_t)s.off[1][i];
+        for (uint64_t i = 0; i < s.n; i++) { uint32_t l = s.off32[i + 1] - s.off32[i]; if (l > m) m = l; }
+        s.max_len = m;
+        for (int c = 1; c <= 3; c += 2) {
+            if (!grow(s, c, (size_t)s.off[1][s.n] + kSlack)) { err = AQC_ERR_NOMEM; return; }
+            memset(s.bytes[c] + s.off[1][s.n], 0, kSlack);
+        }
+        next_index += s.n;
+    }
+
+    void run() {
+        for (;;) {
+            uint32_t id;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || !free_.empty(); });
+                if (stop) break;
+                id = free_.front(); free_.pop_front();
+            }
+            Slot &s = slots[id];
+            int rc = fill(s);
+            if (stop.load()) break;
+            int e2 = 0;
+            if (s.n) { finish(s); e2 = err; }
+            std::unique_lock<std::mutex> lk(mu);
+            if (s.n && !e2) ready.push_back(id); else free_.push_back(id);
+            if (rc || e2) { err = rc ? rc : e2; finished = true; }
+            else if (file_end || s.n == 0) finished = true;
+            cv.notify_all();
+            if (finished) break;
+        }
+    }
+};
+
+extern "C" {
+
+int aqc_reader_open(const char *path, uint64_t batch_records, uint32_t slots, aqc_reader **out) {
+    if (!path || !out || batch_records == 0) return AQC_ERR_INVALID;
+    if (slots < 2) slots = 2;
+    aqc_reader *r = new aqc_reader();
+    r->path = path; r->batch = batch_records;
+    if (ends_with(r->path, ".gz")) {
+        r->gz = gzopen(path, "rb");
+        if (r->gz) gzbuffer(r->gz, 1u << 20);
+    } else {
+        r->fp = fopen(path, "rb");
+    }
+    if (!r->gz && !r->fp) { delete r; return AQC_ERR_INVALID; }
+    r->slots.resize(slots);
+    for (uint32_t i = 0; i < slots; i++) {
+        Slot &s = r->slots[i];
+        for (int c = 0; c < 4; c++) s.off[c] = (uint64_t *)malloc((batch_records + 1) * sizeof(uint64_t));
+        s.off32 = (uint32_t *)malloc((batch_records + 1) * sizeof(uint32_t));
+        if (!s.off[0] || !s.off[1] || !s.off[2] || !s.off[3] || !s.off32) { aqc_reader_close(r); return AQC_ERR_NOMEM; }
+        r->free_.push_back(i);
+    }
+    r->th = std::thread([r] { r->run(); });
+    *out = r;
+    return 0;
+}
+
+int aqc_reader_next(aqc_reader *r, aqc_records *out) {
+    if (!r || !out) return AQC_ERR_INVALID;
+    std::unique_lock<std::mutex> lk(r->mu);
+    r->cv.wait(lk, [&] { return !r->ready.empty() || r->finished; });
+    memset(out, 0, sizeof *out);
+    if (r->ready.empty()) { out->slot = UINT32_MAX; return r->err; }       // end of file (or the error, after the good batches)
+    uint32_t id = r->ready.front(); r->ready.pop_front();
+    const Slot &s = r->slots[id];
+    out->n = s.n; out->first_index = s.first; out->slot = id; out->max_len = s.max_len;
+    for (int c = 0; c < 4; c++) { out->bytes[c] = s.bytes[c]; out->off[c] = s.off[c]; }
+    out->seq_off32 = s.off32;
+    return 0;
+}
+
+int aqc_reader_release(aqc_reader *r, uint32_t slot) {
+    if (!r || slot >= r->slots.size()) return AQC_ERR_INVALID;
+    std::unique_lock<std::mutex> lk(r->mu);
+    r->free_.push_back(slot);
+    r->cv.notify_all();
+    return 0;
+}
+
+const char *aqc_reader_error(const aqc_reader *r) { return r ? r->msg.c_str() : "null reader"; }
+
+void aqc_reader_close(aqc_reader *r) {
+    if (!r) return;
+    {
+        std::unique_lock<std::mutex> lk(r->mu);
+        r->stop = true;
+        r->cv.notify_all();
+    }
+    if (r->th.joinable()) r->th.join();
+    for (Slot &s : r->slots) {
+        for (int c = 0; c < 4; c++) { free(s.bytes[c]); free(s.off[c]); }
+        free(s.off32);
+    }
+    if (r->gz) gzclose(r->gz);
+    if (r->fp) fclose(r->fp);
+    delete r;
+}
+
+}  // extern "C"

@@ -48,12 +48,12 @@ class Column:
     def concat(cols):
         if len(cols) == 1:
             return cols[0]
-        data = np.concatenate([c.data for c in cols])
-        offs = [cols[0].off.astype(np.int64)]
-        base = int(cols[0].off[-1])
+        data = np.concatenate([c.data[int(c.off[0]):int(c.off[-1])] for c in cols])
+        offs = [cols[0].off.astype(np.int64) - int(cols[0].off[0])]
+        base = int(offs[0][-1])
         for c in cols[1:]:
-            offs.append(c.off[1:].astype(np.int64) + base)
-            base += int(c.off[-1])
+            offs.append(c.off[1:].astype(np.int64) - int(c.off[0]) + base)
+            base += int(c.off[-1]) - int(c.off[0])
         return Column(data, np.concatenate(offs))
 
 
@@ -73,6 +73,9 @@ class FastqRecords:
             lo, hi = int(c.off[a]), int(c.off[b])
             return Column(c.data[lo:hi], (c.off[a:b + 1] - lo).astype(np.int64))
         return FastqRecords(cut(self.names), cut(self.seqs), cut(self.plus), cut(self.quals))
+
+    def done(self):
+        """nothing to give back (RecordsView overrides this)"""
 
     @staticmethod
     def concat(chunks):
@@ -124,6 +127,132 @@ class RecordStream:
                 out.append(c.slice(0, need)); self._chunks[0] = c.slice(need, c.n); need = 0
         self._have -= k
         return FastqRecords.concat(out) if out else FastqRecords.empty()
+
+    def close(self):
+        self._it = iter(())
+        self._chunks, self._have, self._ended = [], 0, True
+
+
+def _view(ptr, nbytes, dtype=np.uint8):
+    """numpy view of native memory (no copy; the owner must outlive it)"""
+    import ctypes as C
+    if nbytes == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    return np.frombuffer((C.c_uint8 * nbytes).from_address(ptr), dtype=dtype)
+
+
+class RecordsView(FastqRecords):
+    """Records [lo, hi) of one batch of the native reader: columns are views into the reader's slot buffers, valid
+    until done().  `off32`/`seq_full`/`qual_full` are the aqc_batch columns of this mate (absolute offsets into the
+    slot's base/quality columns), so to_batch() builds a PackedBatch without copying."""
+
+    def __init__(self, owner, slot, cols, off32, max_len, lo, hi):
+        names, seqs, plus, quals = [Column(d, o[lo:hi + 1]) for d, o in cols]
+        FastqRecords.__init__(self, names, seqs, plus, quals)
+        self.n = hi - lo
+        self._owner, self._slot = owner, slot
+        self.off32 = off32[lo:hi + 1]
+        self.max_len = max_len
+        self._cols, self._off32_full, self._lo = cols, off32, lo
+
+    def slice(self, a, b):
+        """copying slice: the result does not depend on the slot"""
+        def cut(c):
+            lo, hi = int(c.off[a]), int(c.off[b])
+            return Column(c.data[lo:hi].copy(), (c.off[a:b + 1] - lo).astype(np.int64))
+        return FastqRecords(cut(self.names), cut(self.seqs), cut(self.plus), cut(self.quals))
+
+    def done(self):
+        """this view is no longer used (the slot goes back to the reader when all its views are done)"""
+        if self._owner is not None:
+            self._owner._view_done(self._slot)
+            self._owner = None
+
+
+class NativeStream:
+    """RecordStream on the native background reader (csrc/aqc_stream.cpp): available(k)/take(k) without copies.
+    Batches of all streams opened with the same batch size have the same record boundaries, so lock-stepped consumers
+    see the same k on every stream until the shortest file ends."""
+
+    def __init__(self, path, batch_records, slots=4):
+        import ctypes as C
+        from . import _native, _abi
+        self._L = _native.lib()
+        self._h = C.c_void_p()
+        self._rec_t = _abi.Records
+        rc = self._L.aqc_reader_open(path.encode(), int(batch_records), int(slots), C.byref(self._h))
+        if rc:
+            self._h = None
+            raise IOError("cannot open %s" % path)
+        self._cur = None            # (slot, cols, off32, max_len, n)
+        self._pos = 0
+        self._ended = False
+        self._out = {}              # slot -> outstanding views (+1 while it is the current batch)
+
+    def _fetch(self):
+        import ctypes as C
+        r = self._rec_t()
+        rc = self._L.aqc_reader_next(self._h, C.byref(r))
+        if rc:
+            raise ValueError(self._L.aqc_reader_error(self._h).decode() or "FASTQ reader failed (%d)" % rc)
+        if r.n == 0:
+            self._ended = True
+            self._cur = None
+            return
+        n = int(r.n)
+        offs = [_view(r.off[c], 8 * (n + 1), np.int64) for c in range(4)]
+        tot = [int(o[-1]) for o in offs]
+        cols = [(_view(r.bytes[0], tot[0]), offs[0]), (_view(r.bytes[1], tot[1] + 64), offs[1]),
+                (_view(r.bytes[2], tot[2]), offs[2]), (_view(r.bytes[3], tot[1] + 64), offs[1])]
+        self._cur = (int(r.slot), cols, _view(r.seq_off32, 4 * (n + 1), np.uint32), int(r.max_len), n)
+        self._pos = 0
+        self._out[int(r.slot)] = 1
+
+    def available(self, k):
+        if self._cur is None and not self._ended:
+            self._fetch()
+        if self._cur is None:
+            return 0
+        return min(k, self._cur[4] - self._pos)
+
+    def take(self, k):
+        k = self.available(k)
+        if k == 0:
+            return FastqRecords.empty()
+        slot, cols, off32, max_len, n = self._cur
+        v = RecordsView(self, slot, cols, off32, max_len, self._pos, self._pos + k)
+        self._out[slot] += 1
+        self._pos += k
+        if self._pos >= n:
+            self._cur = None
+            self._view_done(slot)
+        return v
+
+    def _view_done(self, slot):
+        self._out[slot] -= 1
+        if self._out[slot] == 0:
+            del self._out[slot]
+            if self._h is not None:
+                self._L.aqc_reader_release(self._h, slot)
+
+    def close(self):
+        if self._h is not None:
+            self._L.aqc_reader_close(self._h)
+            self._h = None
+            self._cur = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def open_stream(path, batch_records, slots=4):
+    """background native reader for plain/.gz files; the python reader for .bz2 (no bzip2 in the native library)"""
+    if path.endswith(".bz2"):
+        return RecordStream(path)
+    return NativeStream(path, batch_records, slots)
 
 
 def _parse_block(buf, final):
@@ -186,6 +315,8 @@ def read_all(path):
 def to_batch(rec1, rec2, lo, hi, first_index=None):
     """PackedBatch of records [lo, hi) of rec1 (and rec2 if not None)."""
     def cut(rec):
+        if isinstance(rec, RecordsView):      # zero copy: absolute offsets into the slot's columns
+            return rec._cols[1][0], rec._cols[3][0], rec.off32[lo:hi + 1]
         a, b = int(rec.seqs.off[lo]), int(rec.seqs.off[hi])
         s = np.zeros(b - a + SLACK, dtype=np.uint8)
         q = np.zeros(b - a + SLACK, dtype=np.uint8)
@@ -203,15 +334,23 @@ def to_batch(rec1, rec2, lo, hi, first_index=None):
 def emit(rec, mate, which, rec_base, results):
     """FASTQ text (bytes) of records rec_base.. of one mate selected by `which` (0 good, 1 bad, 2 overlap tails),
     with the slices and edits of the aqc_result records applied (native, csrc/aqc_fastq.cpp)."""
+    data, _ = emit_into(rec, mate, which, rec_base, results, None)
+    return data.tobytes() if len(data) else b""
+
+
+def emit_into(rec, mate, which, rec_base, results, scratch):
+    """emit() into a reusable uint8 scratch array: returns (view of the text, scratch to pass next time)."""
     import ctypes as C
     from . import _native
     L = _native.lib()
     n = len(results)
     if n == 0:
-        return b""
+        return np.zeros(0, dtype=np.uint8), scratch
     a, b = rec_base, rec_base + n
     cap = int((rec.names.off[b] - rec.names.off[a]) + (rec.plus.off[b] - rec.plus.off[a]) + 2 * (rec.seqs.off[b] - rec.seqs.off[a])) + 20 * n + 64
-    out = np.empty(cap, dtype=np.uint8)
+    if scratch is None or len(scratch) < cap:
+        scratch = np.empty(cap + cap // 8, dtype=np.uint8)
+    out = scratch
     olen = C.c_uint64(0)
     res = np.ascontiguousarray(results)
     cols = [rec.names, rec.seqs, rec.plus, rec.quals]
@@ -223,7 +362,7 @@ def emit(rec, mate, which, rec_base, results):
                           rec_base, res.ctypes.data, n, out.ctypes.data, cap, C.byref(olen))
     if rc:
         raise RuntimeError("aqc_fastq_emit failed (%d)" % rc)
-    return out[:olen.value].tobytes()
+    return out[:olen.value], scratch
 
 
 class _ParallelGzip:
@@ -249,8 +388,10 @@ class _ParallelGzip:
         return c.compress(data) + c.flush()
 
     def write(self, data):
-        if not data:
+        if not len(data):
             return
+        if not isinstance(data, bytes):
+            data = bytes(data)            # callers may reuse their buffer
         self._buf.append(data)
         self._size += len(data)
         if self._size >= self.BLOCK:

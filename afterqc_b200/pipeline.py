@@ -10,6 +10,7 @@ counter -> JSON assembly (:660-778).
 CUDA engine and there is NO CPU fallback (the import fails loudly without the built library).
 Tests inject the CPU oracle through the same hook to pin the host logic.
 """
+import collections
 import json
 import os
 
@@ -110,6 +111,28 @@ def apply_result(r, s1, q1, s2, q2):
         return o1, p1, None, None
     a2, l2 = int(r["start2"]), int(r["len2"])
     return o1, p1, bytes(s2[a2:a2 + l2]), bytes(q2[a2:a2 + l2])
+
+
+class _OutputLane:
+    """One output file of the streaming loop: formatting (native emit into a reused buffer) and writing run on the
+    lane's own thread, strictly in submission order; the native calls and zlib release the GIL."""
+
+    def __init__(self, writer):
+        import concurrent.futures
+        self.writer = writer
+        self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+        self._scratch = None
+
+    def submit(self, rec, mate, which, base, res):
+        return self._pool.submit(self._job, rec, mate, which, base, res)
+
+    def _job(self, rec, mate, which, base, res):
+        data, self._scratch = fastq_io.emit_into(rec, mate, which, base, res, self._scratch)
+        if len(data):
+            self.writer.write(data)
+
+    def shutdown(self):
+        self._pool.shutdown(wait=True)
 
 
 class seqFilter:
@@ -334,24 +357,28 @@ class seqFilter:
         limit = opt.qc_sample
         lo = READ_TO_SKIP - 1
         hi = lo + limit if limit > 0 else None
-        stream = fastq_io.RecordStream(path)
+        stream = fastq_io.open_stream(path, self.batch_records, slots=2)      # the window is short: little read-ahead
         g = 0
         head = []
-        while True:
-            k = stream.available(self.batch_records)
-            if k == 0:
-                break
-            rec = stream.take(k)
-            a, b = g, g + rec.n
-            if a < lo:
-                head.append(rec.slice(0, min(rec.n, lo - a)))
-            wa, wb = max(a, lo), (b if hi is None else min(b, hi))
-            if wb > wa:
-                batch = fastq_io.to_batch(rec, None, wa - a, wb - a, first_index=wa)
-                be.stat_reads(batch, slot, -1, stat_lo=lo, stat_hi=(hi if hi is not None else 1 << 62), order_base=0)
-            g = b
-            if hi is not None and g > hi:
-                break
+        try:
+            while True:
+                k = stream.available(self.batch_records)
+                if k == 0:
+                    break
+                rec = stream.take(k)
+                a, b = g, g + rec.n
+                if a < lo:
+                    head.append(rec.slice(0, min(rec.n, lo - a)))
+                wa, wb = max(a, lo), (b if hi is None else min(b, hi))
+                if wb > wa:
+                    batch = fastq_io.to_batch(rec, None, wa - a, wb - a, first_index=wa)
+                    be.stat_reads(batch, slot, -1, stat_lo=lo, stat_hi=(hi if hi is not None else 1 << 62), order_base=0)
+                rec.done()
+                g = b
+                if hi is not None and g > hi:
+                    break
+        finally:
+            stream.close()
         stat_reads_num = min(max(g - lo, 0), limit + 1) if limit > 0 else max(g - lo, 0)
         if stat_reads_num < READ_TO_SKIP and head:
             hrec = fastq_io.FastqRecords.concat(head)
@@ -361,41 +388,74 @@ class seqFilter:
     def _filter_stream(self, be, writers, idx_files):
         """The per-read loop over lock-stepped streams of R1 [, R2] [, I1] [, I2]; ends at the shortest file
         (preprocesser.py:411-431).  Returns the bases of the R1 record that the reference reads (and counts) just before
-        another file runs out.  --qc_only: stop after the first GOOD pair whose TOTAL_READS >= qc_sample (:630-631)."""
+        another file runs out.  --qc_only: stop after the first GOOD pair whose TOTAL_READS >= qc_sample (:630-631).
+
+        Three stages overlap: the native readers parse the next batches on their own threads, this thread runs the
+        device call, and every output file formats + (deflates +) writes its text on its own lane, in batch order."""
         opt = self.options
         paths = [opt.read1_file] + ([opt.read2_file] if self.paired else []) + [f for _k, f in idx_files]
-        streams = [fastq_io.RecordStream(p) for p in paths]
+        streams = [fastq_io.open_stream(p, self.batch_records) for p in paths]
+        lanes = {name: _OutputLane(w) for name, w in writers.items()}
         keys = [k for k, _f in idx_files]
         qs = opt.qc_sample
         g = 0
         stopped = False
-        while not stopped:
-            want = self.batch_records
-            if opt.qc_only:
-                want = 1 if g + 1 >= qs else min(want, qs - 1 - g)    # single pairs once the stop rule can fire
-            k = min(s.available(want) for s in streams)
-            if k == 0:
-                break
-            recs = [s.take(k) for s in streams]
-            rec1 = recs[0]
-            rec2 = recs[1] if self.paired else None
-            batch = fastq_io.to_batch(rec1, rec2, 0, k, first_index=g)
-            res = be.filter_pairs(batch)
-            if not opt.qc_only:
-                self._write(writers, rec1, rec2, 0, res)
-                for key, r in zip(keys, recs[(2 if self.paired else 1):]):
-                    writers["good_" + key].write(fastq_io.emit(r, 0, 0, 0, res))
-                    writers["bad_" + key].write(fastq_io.emit(r, 0, 1, 0, res))
-                    if "ov_" + key in writers:
-                        writers["ov_" + key].write(fastq_io.emit(r, 0, 2, 0, res))
-            g += k
-            if opt.qc_only and g >= qs and int(res["cls"][-1]) == _abi.GOOD:
-                stopped = True
-        if stopped or len(streams) == 1:
-            return 0
-        if streams[0].available(1) > 0:
-            return int(streams[0].take(1).lengths()[0])
-        return 0
+        inflight = collections.deque()
+
+        def retire(entry):
+            recs, futs = entry
+            for f in futs:
+                f.result()
+            for r in recs:
+                r.done()
+
+        try:
+            while not stopped:
+                want = self.batch_records
+                if opt.qc_only:
+                    want = 1 if g + 1 >= qs else min(want, qs - 1 - g)    # single pairs once the stop rule can fire
+                k = min(s.available(want) for s in streams)
+                if k == 0:
+                    break
+                recs = [s.take(k) for s in streams]
+                rec1 = recs[0]
+                rec2 = recs[1] if self.paired else None
+                batch = fastq_io.to_batch(rec1, rec2, 0, k, first_index=g)
+                res = be.filter_pairs(batch)
+                futs = []
+                if not opt.qc_only:
+                    futs = self._write_async(lanes, rec1, rec2, res)
+                    for key, r in zip(keys, recs[(2 if self.paired else 1):]):
+                        futs.append(lanes["good_" + key].submit(r, 0, 0, 0, res))
+                        futs.append(lanes["bad_" + key].submit(r, 0, 1, 0, res))
+                        if "ov_" + key in lanes:
+                            futs.append(lanes["ov_" + key].submit(r, 0, 2, 0, res))
+                inflight.append((recs, futs))
+                while len(inflight) > 2:
+                    retire(inflight.popleft())
+                g += k
+                if opt.qc_only and g >= qs and int(res["cls"][-1]) == _abi.GOOD:
+                    stopped = True
+            while inflight:
+                retire(inflight.popleft())
+            extra = 0
+            if not stopped and len(streams) > 1 and streams[0].available(1) > 0:
+                extra = int(streams[0].take(1).lengths()[0])
+            return extra
+        finally:
+            for lane in lanes.values():
+                lane.shutdown()
+            for s_ in streams:
+                s_.close()
+
+    def _write_async(self, lanes, rec1, rec2, res):
+        """_write() on the output lanes; returns the futures"""
+        futs = [lanes["good1"].submit(rec1, 1, 0, 0, res), lanes["bad1"].submit(rec1, 1, 1, 0, res)]
+        if rec2 is not None:
+            futs += [lanes["good2"].submit(rec2, 2, 0, 0, res), lanes["bad2"].submit(rec2, 2, 1, 0, res)]
+            if "ov1" in lanes:
+                futs += [lanes["ov1"].submit(rec1, 1, 2, 0, res), lanes["ov2"].submit(rec2, 2, 2, 0, res)]
+        return futs
 
     def _write(self, writers, rec1, rec2, base, res):
         """good/bad(/overlap) text of one batch: slices, correction edits and @BADxxx names (preprocesser.py:206-232)."""

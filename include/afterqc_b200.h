@@ -267,6 +267,30 @@ int aqc_fastq_emit(int mate, int which,
                    uint64_t rec_base, const aqc_result *results, uint64_t n,
                    uint8_t *out, uint64_t out_cap, uint64_t *out_len);
 
+/* ---- streaming reader: one FASTQ file -> packed record batches, parsed by a background thread into a ring of
+ * reusable buffers (replaces fastq.Reader, fastq.py:17-55; plain and .gz by file extension, :23-28; concatenated gzip
+ * members are read through).  Batches hold exactly `batch_records` records except the last; the columns of a batch stay
+ * valid until aqc_reader_release(slot).  bytes[1]/bytes[3] (bases/qualities) share the offsets off[1] (equal lengths are
+ * checked), carry >= 64 readable bytes after the data, and seq_off32 is off[1] as uint32: together they are the
+ * aqc_batch columns of one mate, without a copy. */
+typedef struct aqc_reader aqc_reader;
+typedef struct aqc_records {
+    uint64_t n;               /* records in this batch; 0 = end of file (no slot to release) */
+    uint64_t first_index;     /* index in the file of record 0 of the batch */
+    uint32_t slot;            /* pass to aqc_reader_release */
+    uint32_t max_len;         /* longest sequence in the batch */
+    const uint8_t *bytes[4];  /* names, bases, '+' lines, qualities */
+    const uint64_t *off[4];   /* n + 1 offsets per column */
+    const uint32_t *seq_off32;
+} aqc_records;
+int aqc_reader_open(const char *path, uint64_t batch_records, uint32_t slots, aqc_reader **out);
+/* blocks until the next batch is parsed.  AQC_ERR_INVALID (text in aqc_reader_error) on an unreadable / corrupt file or a
+ * record whose quality length differs from its sequence length; batches before the bad record are delivered first. */
+int aqc_reader_next(aqc_reader *r, aqc_records *out);
+int aqc_reader_release(aqc_reader *r, uint32_t slot);
+const char *aqc_reader_error(const aqc_reader *r);
+void aqc_reader_close(aqc_reader *r);
+
 /* instrumentation for bench.py: kernels launched by this context so far, and the device
  * time in ms of the last filter/stat call's kernels (CUDA events on the launching stream) */
 uint64_t aqc_launch_count(const aqc_ctx *ctx);
