@@ -83,6 +83,13 @@ class Records(C.Structure):
     ]
 
 
+class Columns(C.Structure):
+    """aqc_columns / aqc_columns_out (same layout)"""
+    _fields_ = [("names", C.c_void_p), ("name_off", C.c_void_p), ("seqs", C.c_void_p), ("seq_off", C.c_void_p), ("quals", C.c_void_p)]
+
+
+HOST_BADBCD1, HOST_BADBCD2 = 16, 17       # host-only pseudo classes of aqc_fastq_emit (barcode pre-pass)
+
 RESULT_DTYPE = np.dtype([
     ("cls", "u1"), ("n_edits", "u1"), ("start1", "<u2"), ("len1", "<u2"), ("start2", "<u2"), ("len2", "<u2"),
     ("ov_offset", "<i2"), ("ov_len", "<u2"), ("ov_diff", "<u2"), ("edits", "<u4", (4,)),

@@ -1,7 +1,9 @@
 // aqc_fastq.cpp -- host-side FASTQ ingest/egress of libafterqc_b200.so.
 // Replaces the python str-list I/O of the reference (fastq.py:17-104) on the packed-column layout: no CUDA here.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <vector>
 #include "../../include/afterqc_b200.h"
 
 namespace {
@@ -9,6 +11,54 @@ namespace {
 inline bool is_ws(uint8_t c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == 0x0b || c == 0x0c; }
 
 const char *const kFlags[AQC_NUM_CLASSES] = {"", "BADTRIM1", "BADTRIM2", "BADLEN", "BADPOL", "BADLQC", "BADNCT", "BADDIFF", "BADMISMATCH"};
+
+const char *flag_of(uint32_t cls) {
+    if (cls == AQC_HOST_BADBCD1) return "BADBCD1";
+    if (cls == AQC_HOST_BADBCD2) return "BADBCD2";
+    return kFlags[cls < AQC_NUM_CLASSES ? cls : 0];
+}
+
+// ---- barcode (UMI) helpers, barcodeprocesser.py ----
+inline int diff_number(const uint8_t *a, const uint8_t *b, int n) {          // diffNumber :9-14
+    int d = 0;
+    for (int i = 0; i < n; i++) d += a[i] != b[i];
+    return d;
+}
+
+// detectBarcode :19-32: where the barcode ends (design length, or one off), 0 = not found
+int detect_barcode(const uint8_t *seq, int64_t len, int blen, const uint8_t *verify, int vlen) {
+    if (len <= (int64_t)vlen + blen + 1) return 0;
+    if (diff_number(seq + blen, verify, vlen) <= 1) return blen;
+    if (diff_number(seq + blen - 1, verify, vlen) == 0) return blen - 1;
+    if (diff_number(seq + blen + 1, verify, vlen) == 0) return blen + 1;
+    return 0;
+}
+
+inline uint8_t comp_or_n(uint8_t c) {                                          // util.reverseComplement :42-51
+    switch (c) {
+        case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C';
+        case 'a': return 't'; case 't': return 'a'; case 'c': return 'g'; case 'g': return 'c';
+        case 'N': return 'N'; case '\n': return '\n';
+        default: return 'N';
+    }
+}
+
+// Levenshtein distance (util.editDistance :65-83; the editdistance module and libed.so compute the same number)
+int edit_distance(const uint8_t *a, int m, const uint8_t *b, int n, std::vector<int> &row) {
+    row.resize((size_t)n + 1);
+    for (int j = 0; j <= n; j++) row[j] = j;
+    for (int i = 1; i <= m; i++) {
+        int diag = row[0];
+        row[0] = i;
+        for (int j = 1; j <= n; j++) {
+            int up = row[j];
+            int v = std::min(std::min(up + 1, row[j - 1] + 1), diag + (a[i - 1] != b[j - 1]));
+            diag = up;
+            row[j] = v;
+        }
+    }
+    return row[n];
+}
 
 }  // namespace
 
@@ -92,7 +142,7 @@ int aqc_fastq_emit(int mate, int which,
         const uint8_t *nm = names + name_off[rec];
         if (which == 1) {
             out[w++] = '@';
-            const char *f = kFlags[r.cls < AQC_NUM_CLASSES ? r.cls : 0];
+            const char *f = flag_of(r.cls);
             size_t fl = strlen(f);
             memcpy(out + w, f, fl); w += fl;
             if (nl > 1) { memcpy(out + w, nm + 1, nl - 1); w += nl - 1; }
@@ -120,6 +170,90 @@ int aqc_fastq_emit(int mate, int which,
         }
     }
     *out_len = w;
+    return 0;
+}
+
+// Barcode (UMI) pre-pass of the per-read loop (preprocesser.py:435-452, barcodeprocesser.py): for every pair detect the
+// barcode of both mates, move it into the name ('@' + barcode + name[name.find(':'):], :34-46), drop barcode + verify
+// bases from the front and, for pairs, the read-through tail found by cleanBarcodeTail (:48-74).  Records are written
+// to `out*` in the input order; pairs without a barcode are copied unchanged with status 1 (BADBCD1) / 2 (BADBCD2).
+// Single-end input strips the DESIGN length whatever detectBarcode returned (:443-444).  removed[m] receives the bases
+// dropped from mate m+1 of the status-0 records.  Output capacity: names in.bytes + n * (barcode_length + 3); bases and
+// qualities in.bytes.
+int aqc_barcode_pairs(int barcode_length, const char *verify, uint64_t n, const aqc_columns *in1, const aqc_columns *in2,
+                      aqc_columns_out *out1, aqc_columns_out *out2, uint8_t *status, uint64_t removed[2]) {
+    if (!verify || !in1 || !out1 || !status || !removed || barcode_length < 1) return AQC_ERR_INVALID;
+    if ((in2 == nullptr) != (out2 == nullptr)) return AQC_ERR_INVALID;
+    const int vlen = (int)strlen(verify);
+    const uint8_t *vf = (const uint8_t *)verify;
+    const aqc_columns *in[2] = {in1, in2};
+    aqc_columns_out *out[2] = {out1, out2};
+    const int mates = in2 ? 2 : 1;
+    uint64_t wn[2] = {0, 0}, ws[2] = {0, 0};
+    removed[0] = removed[1] = 0;
+    for (int m = 0; m < mates; m++) { out[m]->name_off[0] = 0; out[m]->seq_off[0] = 0; }
+    std::vector<int> row;
+    std::vector<uint8_t> start[2], rev[2];
+    for (uint64_t i = 0; i < n; i++) {
+        const uint8_t *seq[2], *qual[2], *name[2];
+        int64_t slen[2], nlen[2];
+        for (int m = 0; m < mates; m++) {
+            seq[m] = in[m]->seqs + in[m]->seq_off[i]; qual[m] = in[m]->quals + in[m]->seq_off[i];
+            slen[m] = (int64_t)(in[m]->seq_off[i + 1] - in[m]->seq_off[i]);
+            name[m] = in[m]->names + in[m]->name_off[i];
+            nlen[m] = (int64_t)(in[m]->name_off[i + 1] - in[m]->name_off[i]);
+        }
+        int bl[2] = {0, 0};
+        uint8_t st = 0;
+        bl[0] = detect_barcode(seq[0], slen[0], barcode_length, vf, vlen);
+        if (bl[0] == 0) st = 1;
+        else if (mates == 2) { bl[1] = detect_barcode(seq[1], slen[1], barcode_length, vf, vlen); if (bl[1] == 0) st = 2; }
+        else bl[0] = barcode_length;
+        status[i] = st;
+        int64_t front[2] = {0, 0}, tail = 0;
+        if (st == 0) {
+            for (int m = 0; m < mates; m++) front[m] = std::min<int64_t>(slen[m], (int64_t)bl[m] + vlen);
+            if (mates == 2) {                                                  // cleanBarcodeTail on the stripped reads
+                for (int m = 0; m < 2; m++) {                                 // readStart = barcode + verify (the DESIGN verify)
+                    start[m].assign(seq[m], seq[m] + bl[m]);
+                    start[m].insert(start[m].end(), vf, vf + vlen);
+                    const size_t L = start[m].size();
+                    rev[m].resize(L);
+                    for (size_t k = 0; k < L; k++) rev[m][k] = comp_or_n(start[m][L - 1 - k]);
+                }
+                const int64_t L = (int64_t)std::min(start[0].size(), start[1].size());
+                const int64_t r1len = slen[0] - front[0], r2len = slen[1] - front[1];
+                for (int64_t k = 0; k < L; k++) {
+                    const int64_t comp = L - k;
+                    if (comp >= r1len || comp >= r2len) continue;
+                    const int d1 = edit_distance(seq[0] + slen[0] - comp, (int)comp, rev[1].data() + k, (int)(rev[1].size() - k), row);
+                    const int d2 = edit_distance(seq[1] + slen[1] - comp, (int)comp, rev[0].data() + k, (int)(rev[0].size() - k), row);
+                    const int thr = (int)(comp / 5);
+                    if (d1 <= thr && d2 <= thr) { tail = comp; break; }
+                }
+            }
+        }
+        for (int m = 0; m < mates; m++) {
+            uint8_t *nm = out[m]->names + wn[m];
+            if (st == 0) {
+                int64_t colon = -1;
+                for (int64_t k = 0; k < nlen[m]; k++) if (name[m][k] == ':') { colon = k; break; }
+                if (colon < 0) colon = nlen[m] > 0 ? nlen[m] - 1 : 0;          // name[-1:] when there is no ':' (python slice)
+                const int64_t bc = std::min<int64_t>(bl[m], slen[m]);
+                *nm++ = '@';
+                memcpy(nm, seq[m], (size_t)bc); nm += bc;
+                memcpy(nm, name[m] + colon, (size_t)(nlen[m] - colon)); nm += nlen[m] - colon;
+            } else { memcpy(nm, name[m], (size_t)nlen[m]); nm += nlen[m]; }
+            wn[m] = (uint64_t)(nm - out[m]->names);
+            out[m]->name_off[i + 1] = wn[m];
+            const int64_t keep = slen[m] - front[m] - tail;
+            memcpy(out[m]->seqs + ws[m], seq[m] + front[m], (size_t)keep);
+            memcpy(out[m]->quals + ws[m], qual[m] + front[m], (size_t)keep);
+            ws[m] += (uint64_t)keep;
+            out[m]->seq_off[i + 1] = ws[m];
+            if (st == 0) removed[m] += (uint64_t)(front[m] + tail);
+        }
+    }
     return 0;
 }
 

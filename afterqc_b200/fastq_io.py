@@ -331,6 +331,51 @@ def to_batch(rec1, rec2, lo, hi, first_index=None):
     return PackedBatch(s1, q1, o1, s2, q2, o2, first_index=fi)
 
 
+def barcode_transform(rec1, rec2, barcode_length, verify):
+    """The barcode (UMI) pre-pass of the per-read loop (native aqc_barcode_pairs; preprocesser.py:435-452): returns
+    (t1, t2, status, removed) -- the records in input order with barcodes moved into the names and barcode / verify /
+    read-through bases removed, status per pair (0 ok, 1 BADBCD1, 2 BADBCD2: copied unchanged), removed bases per mate."""
+    import ctypes as C
+    from . import _native, _abi
+    L = _native.lib()
+    n = rec1.n
+
+    def cin(rec):
+        for c in (rec.names, rec.seqs):
+            if c.off.dtype != np.int64 or not c.off.flags["C_CONTIGUOUS"]:
+                c.off = np.ascontiguousarray(c.off, dtype=np.int64)
+        return _abi.Columns(rec.names.data.ctypes.data, rec.names.off.ctypes.data, rec.seqs.data.ctypes.data,
+                            rec.seqs.off.ctypes.data, rec.quals.data.ctypes.data)
+
+    def cout(rec):
+        nb = int(rec.names.off[n] - rec.names.off[0]) + n * (barcode_length + 3)
+        sb = int(rec.seqs.off[n] - rec.seqs.off[0])
+        arrs = (np.empty(nb, dtype=np.uint8), np.zeros(n + 1, dtype=np.int64), np.zeros(sb + 64, dtype=np.uint8),
+                np.zeros(n + 1, dtype=np.int64), np.zeros(sb + 64, dtype=np.uint8))
+        return arrs, _abi.Columns(*[a.ctypes.data for a in arrs])
+
+    i1 = cin(rec1)
+    a1, o1 = cout(rec1)
+    i2 = o2 = a2 = None
+    if rec2 is not None:
+        i2 = cin(rec2)
+        a2, o2 = cout(rec2)
+    status = np.zeros(n, dtype=np.uint8)
+    removed = (C.c_uint64 * 2)()
+    rc = L.aqc_barcode_pairs(int(barcode_length), verify.encode("latin-1"), n, C.byref(i1), C.byref(i2) if i2 is not None else None,
+                             C.byref(o1), C.byref(o2) if o2 is not None else None, status.ctypes.data, removed)
+    if rc:
+        raise ValueError("aqc_barcode_pairs failed (%d): barcode_length must be >= 1" % rc)
+
+    def wrap(rec, arrs):
+        names, noff, seqs, soff, quals = arrs
+        lo, hi = int(rec.plus.off[0]), int(rec.plus.off[n])
+        plus = Column(rec.plus.data[lo:hi].copy(), (rec.plus.off[:n + 1] - lo).astype(np.int64))
+        return FastqRecords(Column(names[:int(noff[n])], noff), Column(seqs, soff), plus, Column(quals, soff))
+
+    return wrap(rec1, a1), (wrap(rec2, a2) if rec2 is not None else None), status, (int(removed[0]), int(removed[1]))
+
+
 def emit(rec, mate, which, rec_base, results):
     """FASTQ text (bytes) of records rec_base.. of one mate selected by `which` (0 good, 1 bad, 2 overlap tails),
     with the slices and edits of the aqc_result records applied (native, csrc/aqc_fastq.cpp)."""

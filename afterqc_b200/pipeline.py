@@ -150,9 +150,15 @@ class seqFilter:
         opt = self.options
         if getattr(opt, "debubble", False):
             raise NotImplementedError("--debubble is outside the B200 hot-path scope (SURVEY.md section 2, #12)")
-        if getattr(opt, "barcode", False):
-            raise NotImplementedError("barcode (UMI) processing is outside the B200 hot-path scope (SURVEY.md section 2, #11)")
         rank, world = self.shard
+        self._bcd = [0, 0]                # BADBCD1, BADBCD2: pairs rejected by the barcode pre-pass (never reach the device)
+        self._bcd_bases = [0, 0]          # bases the pre-pass kept from the device (R1, R2): TOTAL_BASES counts them (:416-431)
+        if getattr(opt, "barcode", False):
+            if world > 1:
+                raise NotImplementedError("barcode (UMI) files are processed on one GPU (the pre-pass runs in the streaming loop)")
+            if opt.barcode_length < 1:
+                raise ValueError("barcode_length=%d is outside the supported domain" % opt.barcode_length)
+            opt.trim_front = 0            # no front trim if the sequence is barcoded (preprocesser.py:241-243)
         # One GPU: stream the files in bounded memory (two passes, like the reference).  Shards: every rank parses the
         # files and takes its contiguous record range.
         streaming = world == 1
@@ -297,6 +303,11 @@ class seqFilter:
                         os.unlink(pth)
 
         cnt = be.counters()
+        if getattr(opt, "barcode", False):
+            cnt = cnt.copy()
+            cnt[_abi.CIDX["TOTAL_READS"]] += self._bcd[0] + self._bcd[1]
+            cnt[_abi.CIDX["TOTAL_BASES_R1"]] += self._bcd_bases[0]
+            cnt[_abi.CIDX["TOTAL_BASES_R2"]] += self._bcd_bases[1]
         self.counters = cnt
         hist_len = readLen + 1
         if cnt[_abi.C_OVERLAP_HIST + hist_len:_abi.C_OVERLAP_HIST + _abi.MAX_LEN + 1].any() or \
@@ -341,6 +352,8 @@ class seqFilter:
         counts = [c("GOOD_READS"), c("BADPOL"), c("BADLQC"), c("BADLEN") + c("BADTRIM1") + c("BADTRIM2"), c("BADNCT")]
         if self.paired:
             labels.append('bad_overlap'); counts.append(c("BADMISMATCH") + c("BADDIFF"))
+        if getattr(opt, "barcode", False):
+            labels.append('bad_barcode'); counts.append(self._bcd[0] + self._bcd[1])
         labels = ["%s: %d(%s%%)" % (l, n, (100.0 * float(n) / total) if total > 0 else 0.0) for l, n in zip(labels, counts)]
         figs = [report.filter_figure(labels, counts, total)]
         if self.paired:
@@ -420,8 +433,11 @@ class seqFilter:
                 recs = [s.take(k) for s in streams]
                 rec1 = recs[0]
                 rec2 = recs[1] if self.paired else None
-                batch = fastq_io.to_batch(rec1, rec2, 0, k, first_index=g)
-                res = be.filter_pairs(batch)
+                if getattr(opt, "barcode", False):
+                    rec1, rec2, res = self._barcode_batch(be, rec1, rec2, g)
+                else:
+                    batch = fastq_io.to_batch(rec1, rec2, 0, k, first_index=g)
+                    res = be.filter_pairs(batch)
                 futs = []
                 if not opt.qc_only:
                     futs = self._write_async(lanes, rec1, rec2, res)
@@ -447,6 +463,60 @@ class seqFilter:
                 lane.shutdown()
             for s_ in streams:
                 s_.close()
+
+    def _barcode_batch(self, be, rec1, rec2, g):
+        """Barcode (UMI) files: the pre-pass of preprocesser.py:435-452 on one batch, then the device loop on the pairs
+        that kept a barcode.  Returns the transformed records (input order, barcodes in the names) and one result per
+        input pair; BADBCD pairs carry a host-only class and their untouched reads.  The device sees compacted batches
+        whose first_index keeps the qc_sample gate (:624, TOTAL_READS counts the BADBCD pairs too) and the k-mer order
+        of the original indices: pairs before the gate run with the batch's own first index (compaction only lowers an
+        index), pairs at or beyond it with the original index of their first pair."""
+        from .batch import PackedBatch
+        opt = self.options
+        n = rec1.n
+        t1, t2, status, removed = fastq_io.barcode_transform(rec1, rec2, opt.barcode_length, opt.barcode_verify)
+        bad = status != 0
+        self._bcd[0] += int((status == 1).sum())
+        self._bcd[1] += int((status == 2).sum())
+        len1 = t1.lengths()
+        self._bcd_bases[0] += removed[0] + int(len1[bad].sum())
+        res = np.zeros(n, dtype=_abi.RESULT_DTYPE)
+        res["cls"][status == 1] = _abi.HOST_BADBCD1
+        res["cls"][status == 2] = _abi.HOST_BADBCD2
+        res["len1"][bad] = len1[bad]
+        if t2 is not None:
+            len2 = t2.lengths()
+            self._bcd_bases[1] += removed[1] + int(len2[bad].sum())
+            res["len2"][bad] = len2[bad]
+        idx = np.flatnonzero(~bad)
+        if len(idx):
+            def column(t):
+                off = t.seqs.off
+                if len(idx) == n:
+                    return t.seqs.data, t.quals.data, off.astype(np.uint32)
+                lens = (off[1:] - off[:-1])[idx]
+                noff = np.zeros(len(idx) + 1, dtype=np.int64)
+                np.cumsum(lens, out=noff[1:])
+                src = np.arange(int(noff[-1]), dtype=np.int64) + np.repeat(off[:-1][idx] - noff[:-1], lens)
+                seq = np.zeros(int(noff[-1]) + 64, dtype=np.uint8); qual = np.zeros(int(noff[-1]) + 64, dtype=np.uint8)
+                seq[:len(src)] = t.seqs.data[src]; qual[:len(src)] = t.quals.data[src]
+                return seq, qual, noff.astype(np.uint32)
+            s1, q1, o1 = column(t1)
+            s2 = q2 = o2 = None
+            if t2 is not None:
+                s2, q2, o2 = column(t2)
+            qs = opt.qc_sample
+            n_gate = int(np.searchsorted(g + idx + 1, qs, side="left")) if qs > 0 else len(idx)   # pairs with TOTAL_READS < qs
+            parts = []
+            for lo, hi, first in ((0, n_gate, g), (n_gate, len(idx), g + int(idx[min(n_gate, len(idx) - 1)]))):
+                if hi > lo:
+                    sub = PackedBatch(s1, q1, o1[lo:hi + 1], s2, q2, (o2[lo:hi + 1] if o2 is not None else None), first_index=first)
+                    parts.append(be.filter_pairs(sub))
+            res[idx] = np.concatenate(parts) if len(parts) > 1 else parts[0]
+        rec1.done()
+        if rec2 is not None:
+            rec2.done()
+        return t1, t2, res
 
     def _write_async(self, lanes, rec1, rec2, res):
         """_write() on the output lanes; returns the futures"""
@@ -479,7 +549,7 @@ class seqFilter:
             'total_reads': c("TOTAL_READS"),
             'good_reads': c("GOOD_READS"),
             'bad_reads': c("TOTAL_READS") - c("GOOD_READS"),
-            'bad_reads_with_bad_barcode': 0,
+            'bad_reads_with_bad_barcode': self._bcd[0] + self._bcd[1],
             'bad_reads_with_reads_in_bubble': 0,
             'bad_reads_with_bad_read_length': c("BADLEN") + c("BADTRIM1") + c("BADTRIM2"),
             'bad_reads_with_polyX': c("BADPOL"),

@@ -267,6 +267,26 @@ int aqc_fastq_emit(int mate, int which,
                    uint64_t rec_base, const aqc_result *results, uint64_t n,
                    uint8_t *out, uint64_t out_cap, uint64_t *out_len);
 
+/* ---- barcode (UMI) pre-pass on packed columns (host only; barcodeprocesser.py, preprocesser.py:435-452) ---- */
+#define AQC_HOST_BADBCD1 16   /* host-only pseudo classes for aqc_fastq_emit: pairs rejected before the device loop */
+#define AQC_HOST_BADBCD2 17
+typedef struct aqc_columns {       /* one mate's records; qualities share seq_off; offsets may be absolute */
+    const uint8_t *names; const uint64_t *name_off;
+    const uint8_t *seqs; const uint64_t *seq_off;
+    const uint8_t *quals;
+} aqc_columns;
+typedef struct aqc_columns_out {
+    uint8_t *names; uint64_t *name_off;
+    uint8_t *seqs; uint64_t *seq_off;
+    uint8_t *quals;
+} aqc_columns_out;
+/* detectBarcode on both mates, barcode moved into the name, barcode + verify bases and (pairs) the read-through tail of
+ * cleanBarcodeTail removed.  Records keep the input order; status[i] = 0 ok, 1 BADBCD1, 2 BADBCD2 (copied unchanged).
+ * in2/out2 NULL = single-end (strips the design length, preprocesser.py:443-444).  removed[m] = bases dropped from mate
+ * m+1 of the status-0 records.  Capacity: names in-bytes + n*(barcode_length+3); bases/qualities in-bytes. */
+int aqc_barcode_pairs(int barcode_length, const char *verify, uint64_t n, const aqc_columns *in1, const aqc_columns *in2,
+                      aqc_columns_out *out1, aqc_columns_out *out2, uint8_t *status, uint64_t removed[2]);
+
 /* ---- streaming reader: one FASTQ file -> packed record batches, parsed by a background thread into a ring of
  * reusable buffers (replaces fastq.Reader, fastq.py:17-55; plain and .gz by file extension, :23-28; concatenated gzip
  * members are read through).  Batches hold exactly `batch_records` records except the last; the columns of a batch stay

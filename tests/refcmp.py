@@ -64,6 +64,6 @@ def prepare_case(d, batch, subs=("ref", "new")):
         synth.write_fastq(batch, os.path.join(d, sub, "x_R1.fq"), os.path.join(d, sub, "x_R2.fq") if batch.paired else None)
 
 
-def load_json(d, sub):
-    with open(os.path.join(d, sub, "QC", "x_R1.fq.json")) as f:
+def load_json(d, sub, r1_name="x_R1.fq"):
+    with open(os.path.join(d, sub, "QC", r1_name + ".json")) as f:
         return json.load(f)

@@ -77,7 +77,7 @@ def main():
             os.unlink(u)
         in_bytes = os.path.getsize(r1) + os.path.getsize(r2)
         print("wrote %d pairs (%.1f MB on disk) in %.1fs" % (a.pairs, in_bytes / 1e6, time.time() - t), file=sys.stderr)
-        opts, _ = cli.parseCommand(["-1", r1, "-2", r2, "-f", "0", "-t", "0"])
+        opts, _ = cli.parseCommand(["-1", r1, "-2", r2, "-f", "0", "-t", "0", "-g", os.path.join(d, "good")])     # all outputs inside the scratch dir
         cli.normalize_options(opts); opts.barcode = False
         sf = seqFilter(opts, backend_factory=StubBackend)
         t = time.time()
