@@ -2,8 +2,8 @@
 (after.py:14-93 options, :186-225 main, :101-171 directory mode) so that it is a drop-in for
 the per-read path.  Options are declared as a table; semantics (defaults, string booleans via
 parseBool util.py:29-34, trim_front2/trim_tail2 mirroring, barcode detection by file name) follow
-the reference.  Features outside the hot-path scope (debubble, barcode, index files) are accepted
-on the command line and refused at run time with a clear message.
+the reference.  Index files and barcoded (UMI) files are handled on the host around the device loop; debubble is
+outside the scope: accepted on the command line and refused at run time with a clear message.
 """
 import copy
 import os

@@ -42,8 +42,59 @@ def sha(path):
         return hashlib.sha256(f.read()).hexdigest()
 
 
+BARCODE_GOLD = os.path.join(ROOT, "tests", "golden_barcode")
+BARCODE_CASES = [
+    # name, pairs, seed, paired, names with ':', extra CLI args
+    ("pe100_umi12", 900, 11, True, True, []),
+    ("pe100_umi12_gate_nocolon", 700, 12, True, False, ["--qc_sample", "150", "-t", "3", "--store_overlap", "on"]),
+    ("se100_umi11", 600, 13, False, True, ["--barcode_length", "11", "--barcode_verify", "CAGT"]),
+]
+
+
+def make_barcode_golden():
+    """tests/golden_barcode/<case>/: barcoded (UMI) inputs of tests/barcode_cases.py + the reference's outputs."""
+    import barcode_cases
+    os.makedirs(BARCODE_GOLD, exist_ok=True)
+    for name, n, seed, paired, colon, extra in BARCODE_CASES:
+        d = os.path.join(BARCODE_GOLD, name)
+        shutil.rmtree(d, ignore_errors=True)
+        os.makedirs(d)
+        r1s, r2s = barcode_cases.make(n, seed, paired=paired, colon=colon)
+        paths = []
+        for m, recs in ((1, r1s), (2, r2s)):
+            if recs is None:
+                continue
+            p = os.path.join(d, "x_barcode_R%d.fq.gz" % m)
+            with gzip.open(p, "wb", compresslevel=6) as f:
+                for nm, s, q in recs:
+                    f.write(("%s\n%s\n+\n%s\n" % (nm, s, q)).encode())
+            paths.append(p)
+        work = tempfile.mkdtemp()
+        args = ["-1", paths[0]] + (["-2", paths[1]] if paired else []) + ["-g", os.path.join(work, "good")] + extra
+        opt = ref_loader.run_cli(args)
+        assert opt.barcode is True
+        with open(os.path.join(work, "QC", "x_barcode_R1.fq.gz.json")) as f:
+            stat = json.load(f)
+        for k in ("read1_file", "read2_file", "good_output_folder"):
+            stat["command"][k] = None
+        outs = {}
+        for sub in ("good", "bad", "overlap"):
+            p = os.path.join(work, sub)
+            if os.path.isdir(p):
+                for fn in sorted(os.listdir(p)):
+                    outs[sub + "/" + fn] = sha(os.path.join(p, fn))
+        with open(os.path.join(d, "expected.json"), "w") as f:
+            json.dump({"args": extra, "stat": stat, "outputs_sha256": outs}, f, sort_keys=True, indent=1)
+        shutil.rmtree(work)
+        sm = stat["afterqc_main_summary"]
+        print(name, sm["good_reads"], "/", sm["total_reads"], "bad barcode", sm["bad_reads_with_bad_barcode"], list(outs))
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
+    if "--barcode-only" in sys.argv:
+        return make_barcode_golden()
+    make_barcode_golden()
     os.makedirs(GOLD, exist_ok=True)
     for name, cfg, n, jitter, extra in CASES:
         d = os.path.join(GOLD, name)

@@ -16,6 +16,13 @@ def test_pipeline_on_oracle_matches_reference_golden(name, tmp_path, oracle_lib)
     assert not problems, problems
 
 
+@pytest.mark.parametrize("name", golden_util.BARCODE_CASES)
+@pytest.mark.parametrize("batch_records", [1 << 18, 53])
+def test_barcode_pipeline_on_oracle_matches_reference_golden(name, batch_records, tmp_path, oracle_lib):
+    problems = golden_util.run_barcode_case(name, tmp_path, lambda p: oracle_lib.Oracle(p), batch_records)
+    assert not problems, problems
+
+
 def test_oracle_operators_match_reference_golden(oracle_lib):
     with open(os.path.join(golden_util.GOLD, "ops_adversarial.json")) as f:
         gold = json.load(f)
