@@ -270,6 +270,8 @@ class seqFilter:
             n = min([rec1.n] + ([rec2.n] if self.paired else []) + [r.n for r in idx_recs.values()])   # loop ends at the shortest file
             if opt.qc_only:
                 raise NotImplementedError("--qc_only stops at a data-dependent record; run it on one GPU")
+            if opt.index2_file is not None and not self.paired and n > 0:
+                raise TypeError("'NoneType' object is not subscriptable")       # preprocesser.py:426-431 without a read2 file
             s_lo, s_hi = (n * rank) // world, (n * (rank + 1)) // world
             for a in range(s_lo, s_hi, self.batch_records):
                 b = min(s_hi, a + self.batch_records)
@@ -430,6 +432,10 @@ class seqFilter:
                 k = min(s.available(want) for s in streams)
                 if k == 0:
                     break
+                if opt.index2_file is not None and not self.paired:
+                    # the reference adds len(r2[1]) whenever an index2 record was read (preprocesser.py:426-431, quirk Q1):
+                    # without a read2 file that is None[1] on the first complete record
+                    raise TypeError("'NoneType' object is not subscriptable")
                 recs = [s.take(k) for s in streams]
                 rec1 = recs[0]
                 rec2 = recs[1] if self.paired else None

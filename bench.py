@@ -392,6 +392,11 @@ def run_ours(args):
         e2e = {"value": world * n / (ms_e2e * 1e-3) / 1e6, "unit": "M read-pairs/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e_steps,
                "note": "aqc_stat_reads + aqc_filter_pairs with AQC_MEM_HOST on pinned host columns; chunked H2D/kernels/D2H pipeline inside"}
+        try:        # same pairs, same parameters: the host-buffer path must return the records of the resident path
+            torch.cuda.synchronize()
+            e2e["results_match_resident"] = bool(torch.equal(res_host.to(device, non_blocking=False), wb.results[:n * 32]))
+        except Exception:
+            e2e["results_match_resident"] = None
         del host, res_host
 
     # ---------------- roofline of the dominant kernel ----------------
