@@ -59,6 +59,7 @@ def random_case(rng):
     c["batch_records"] = rng.choice([1 << 18, 1 << 18, 97, 256, 1001])
     c["cfg"] = rng.choice(["pe150", "pe150_err3", "pe250", "pe150"]) if c["paired"] else "se100"
     c["jitter"] = rng.choice([0, 0, 17, 60])
+    c["flavour"] = rng.choice(["synth"] * 6 + ["adversarial", "long"]) if c["paired"] and not c["barcode"] else "synth"
     return c
 
 
@@ -78,7 +79,14 @@ def run_case(c, seed, d):
                     for nm, s, q in recs:
                         f.write("%s\n%s\n+\n%s\n" % (nm, s, q))
     else:
-        batch = synth.generate(c["cfg"], c["n"], seed=seed, len_jitter=c["jitter"])
+        if c.get("flavour") == "adversarial":
+            import cases
+            batch = cases.adversarial_batch(seed=seed)            # pairs on the decision boundaries of overlap / polyX / filters
+        elif c.get("flavour") == "long":
+            import cases
+            batch = cases.long_read_batch(seed=seed, n=min(c["n"], 400))      # 200-1000 bp reads
+        else:
+            batch = synth.generate(c["cfg"], c["n"], seed=seed, len_jitter=c["jitter"])
         for sub in ("ref", "new"):
             synth.write_fastq(batch, os.path.join(d, sub, stem + "_R1" + ext), os.path.join(d, sub, stem + "_R2" + ext) if batch.paired else None)
     paired = c["paired"]
