@@ -2,6 +2,10 @@
 // inflates/reads one file and parses it into a ring of reusable packed-column buffers, so that the host loop only
 // hands ready batches to the device.  Mirrors fastq.Reader (fastq.py:17-55): .gz by extension, every line rstrip()'d,
 // the first empty line ends the file (quirk Q13).  No CUDA here.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <atomic>
@@ -11,12 +15,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "../../include/afterqc_b200.h"
+#include "aqc_inflate.hpp"
 
 namespace {
 
@@ -31,6 +37,63 @@ struct Slot {
     uint32_t *off32 = nullptr;
     uint64_t n = 0, first = 0;
     uint32_t max_len = 0;
+};
+
+// Runs a blocking read(dst, cap) source (the gzip decoders) on its own thread, a few blocks ahead of the parser.
+class AsyncSource {
+  public:
+    using ReadFn = std::function<long(uint8_t *, size_t)>;
+    AsyncSource(ReadFn fn, size_t block_bytes, int blocks) : fn_(std::move(fn)) {
+        blocks_.resize(blocks);
+        for (auto &b : blocks_) b.data.resize(block_bytes);
+        for (int i = 0; i < blocks; i++) free_.push_back(i);
+        th_ = std::thread([this] { run(); });
+    }
+    ~AsyncSource() {
+        { std::unique_lock<std::mutex> lk(mu_); stop_ = true; cv_.notify_all(); }
+        if (th_.joinable()) th_.join();
+    }
+    // next block copied to dst (cap >= block_bytes): bytes, 0 at the end, -1 after a source error
+    long get(uint8_t *dst) {
+        int id;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return !ready_.empty() || done_; });
+            if (ready_.empty()) return failed_ ? -1 : 0;
+            id = ready_.front(); ready_.pop_front();
+        }
+        const long n = blocks_[id].n;
+        memcpy(dst, blocks_[id].data.data(), (size_t)n);
+        { std::unique_lock<std::mutex> lk(mu_); free_.push_back(id); cv_.notify_all(); }
+        return n;
+    }
+
+  private:
+    struct Block { std::vector<uint8_t> data; long n = 0; };
+    void run() {
+        for (;;) {
+            int id;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || !free_.empty(); });
+                if (stop_) return;
+                id = free_.front(); free_.pop_front();
+            }
+            long n = fn_(blocks_[id].data.data(), blocks_[id].data.size());
+            std::unique_lock<std::mutex> lk(mu_);
+            if (n > 0) { blocks_[id].n = n; ready_.push_back(id); }
+            else { failed_ = n < 0; done_ = true; }
+            cv_.notify_all();
+            if (n <= 0) return;
+        }
+    }
+    ReadFn fn_;
+    std::vector<Block> blocks_;
+    std::deque<int> free_, ready_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::thread th_;
+    bool stop_ = false, done_ = false, failed_ = false;
 };
 
 bool ends_with(const std::string &s, const char *suf) {
@@ -52,8 +115,13 @@ struct aqc_reader {
     bool finished = false;
     int err = 0;
     // source (reader thread only)
-    gzFile gz = nullptr;
+    gzFile gz = nullptr;                    // zlib path: pipes / non-mappable files, or AQC_INFLATE=zlib
     FILE *fp = nullptr;
+    aqc::GzipInflater *inf = nullptr;       // own decoder over the mapped .gz file
+    AsyncSource *async = nullptr;           // gz only: the decoder runs on its own thread, ahead of the parser
+    void *map = nullptr;
+    size_t map_len = 0;
+    int map_fd = -1;
     std::vector<uint8_t> in;
     size_t in_pos = 0, in_end = 0;
     bool src_eof = false, file_end = false;
@@ -69,6 +137,22 @@ struct aqc_reader {
         return true;
     }
 
+    // one block of decompressed bytes (gz inputs; runs on the AsyncSource thread): -1 + msg on error
+    long read_gz(uint8_t *dst, size_t cap) {
+        if (inf) {
+            long got = inf->read(dst, cap);
+            if (got < 0) msg = "gzip: " + inf->error() + " (AQC_INFLATE=zlib selects zlib's decoder)";
+            return got;
+        }
+        long got = gzread(gz, dst, (unsigned)cap);
+        if (got < 0) { int e; msg = std::string("gzip: ") + gzerror(gz, &e); return -1; }
+        if (got == 0) {
+            int e = 0; const char *m = gzerror(gz, &e);
+            if (e != Z_OK && e != Z_STREAM_END) { msg = std::string("gzip: ") + m; return -1; }
+        }
+        return got;
+    }
+
     // more input behind the unparsed tail; returns false on a read error
     bool refill() {
         if (in_pos > 0) {
@@ -77,7 +161,13 @@ struct aqc_reader {
         }
         if (in.size() < in_end + kReadBlock) in.resize(in_end + kReadBlock);
         long got;
-        if (gz) {
+        if (async) {
+            got = async->get(in.data() + in_end);
+            if (got < 0) return false;                                  // msg was set by the source thread
+        } else if (inf) {
+            got = inf->read(in.data() + in_end, kReadBlock);
+            if (got < 0) { msg = "gzip: " + inf->error() + " (AQC_INFLATE=zlib selects zlib's decoder)"; return false; }
+        } else if (gz) {
             got = gzread(gz, in.data() + in_end, (unsigned)kReadBlock);
             if (got < 0) { int e; msg = std::string("gzip: ") + gzerror(gz, &e); return false; }
             if (got == 0) {
@@ -172,12 +262,29 @@ int aqc_reader_open(const char *path, uint64_t batch_records, uint32_t slots, aq
     aqc_reader *r = new aqc_reader();
     r->path = path; r->batch = batch_records;
     if (ends_with(r->path, ".gz")) {
-        r->gz = gzopen(path, "rb");
-        if (r->gz) gzbuffer(r->gz, 1u << 20);
+        const char *sel = getenv("AQC_INFLATE");
+        if (!(sel && strcmp(sel, "zlib") == 0)) {                       // map the file for the own decoder
+            int fd = open(path, O_RDONLY);
+            struct stat st;
+            if (fd >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+                void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+                if (m != MAP_FAILED) {
+                    madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+                    r->map = m; r->map_len = (size_t)st.st_size; r->map_fd = fd;
+                    r->inf = new aqc::GzipInflater((const uint8_t *)m, r->map_len);
+                }
+            }
+            if (!r->inf && fd >= 0) close(fd);
+        }
+        if (!r->inf) {
+            r->gz = gzopen(path, "rb");
+            if (r->gz) gzbuffer(r->gz, 1u << 20);
+        }
     } else {
         r->fp = fopen(path, "rb");
     }
-    if (!r->gz && !r->fp) { delete r; return AQC_ERR_INVALID; }
+    if (!r->gz && !r->fp && !r->inf) { delete r; return AQC_ERR_INVALID; }
+    if (r->gz || r->inf) r->async = new AsyncSource([r](uint8_t *dst, size_t cap) { return r->read_gz(dst, cap); }, kReadBlock, 3);
     r->slots.resize(slots);
     for (uint32_t i = 0; i < slots; i++) {
         Slot &s = r->slots[i];
@@ -213,6 +320,29 @@ int aqc_reader_release(aqc_reader *r, uint32_t slot) {
     return 0;
 }
 
+// test / tool hook: gunzip a memory buffer with the reader's own decoder (all members); AQC_ERR_INVALID on a corrupt
+// stream, AQC_ERR_NOMEM when out_cap is too small.
+int aqc_gunzip_buffer(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_len, char *err, uint64_t err_cap) {
+    if (!in || !out_len) return AQC_ERR_INVALID;
+    aqc::GzipInflater inf(in, (size_t)n);
+    uint64_t w = 0;
+    for (;;) {
+        if (w == out_cap) {                                              // full: only fine if the stream ends here
+            uint8_t probe;
+            long g = inf.read(&probe, 1);
+            if (g == 0) break;
+            if (g < 0) { if (err && err_cap) snprintf(err, err_cap, "%s", inf.error().c_str()); return AQC_ERR_INVALID; }
+            return AQC_ERR_NOMEM;
+        }
+        long g = inf.read(out + w, (size_t)(out_cap - w));
+        if (g < 0) { if (err && err_cap) snprintf(err, err_cap, "%s", inf.error().c_str()); return AQC_ERR_INVALID; }
+        if (g == 0) break;
+        w += (uint64_t)g;
+    }
+    *out_len = w;
+    return 0;
+}
+
 const char *aqc_reader_error(const aqc_reader *r) { return r ? r->msg.c_str() : "null reader"; }
 
 void aqc_reader_close(aqc_reader *r) {
@@ -227,8 +357,12 @@ void aqc_reader_close(aqc_reader *r) {
         for (int c = 0; c < 4; c++) { free(s.bytes[c]); free(s.off[c]); }
         free(s.off32);
     }
+    delete r->async;                        // joins the decoder thread before its source goes away
     if (r->gz) gzclose(r->gz);
     if (r->fp) fclose(r->fp);
+    delete r->inf;
+    if (r->map) munmap(r->map, r->map_len);
+    if (r->map_fd >= 0) close(r->map_fd);
     delete r;
 }
 
