@@ -11,6 +11,7 @@ qualities + offsets) instead of python str lists.
 import bz2
 import gzip
 import io
+import os
 import sys
 
 import numpy as np
@@ -417,11 +418,14 @@ class _ParallelGzip:
 
     BLOCK = 8 << 20
 
-    def __init__(self, path, level, threads=4):
+    def __init__(self, path, level, threads=None):
         import concurrent.futures
+        if threads is None:                       # zlib level 2 deflates ~70 MB/s per thread: scale with the host, 4..12 per file
+            threads = max(4, min(12, (os.cpu_count() or 8) // 8))
         self._f = open(path, "wb")
         self._level = level
         self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=threads)
+        self._threads = threads
         self._pending = []
         self._buf = []
         self._size = 0
@@ -448,7 +452,7 @@ class _ParallelGzip:
         data = b"".join(self._buf)
         self._buf, self._size = [], 0
         self._pending.append(self._pool.submit(self._member, data, self._level))
-        while len(self._pending) > 8:                 # bounded queue, in-order write-out
+        while len(self._pending) > 2 * self._threads:  # bounded queue, in-order write-out
             self._f.write(self._pending.pop(0).result())
 
     def flush(self):
