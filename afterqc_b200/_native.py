@@ -14,7 +14,7 @@ SYMBOLS = [
     "aqc_memcpy_h2d", "aqc_memcpy_d2h", "aqc_stat_reads", "aqc_filter_pairs", "aqc_ops_pairs", "aqc_sync",
     "aqc_get_counters", "aqc_add_counters", "aqc_get_qc", "aqc_get_kmer_dense", "aqc_get_kmer_side",
     "aqc_launch_count", "aqc_last_kernel_ms", "aqc_set_stream", "aqc_device_ptr", "aqc_fastq_parse", "aqc_fastq_emit",
-    "aqc_barcode_pairs", "aqc_gunzip_buffer", "aqc_reader_open", "aqc_reader_next", "aqc_reader_release", "aqc_reader_error", "aqc_reader_close",
+    "aqc_barcode_pairs", "aqc_gunzip_buffer", "aqc_gunzip_buffer_mt", "aqc_reader_open", "aqc_reader_next", "aqc_reader_release", "aqc_reader_error", "aqc_reader_close",
 ]
 
 _lib = None
@@ -64,6 +64,7 @@ def lib():
         "aqc_fastq_emit": (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, u64, vp, u64, vp, u64, C.POINTER(u64)]),
         "aqc_barcode_pairs": (i32, [i32, C.c_char_p, u64, C.POINTER(_abi.Columns), C.POINTER(_abi.Columns), C.POINTER(_abi.Columns), C.POINTER(_abi.Columns), vp, C.POINTER(u64)]),
         "aqc_gunzip_buffer": (i32, [vp, u64, vp, u64, C.POINTER(u64), C.c_char_p, u64]),
+        "aqc_gunzip_buffer_mt": (i32, [vp, u64, vp, u64, C.POINTER(u64), i32, C.POINTER(u64), C.c_char_p, u64]),
         "aqc_reader_open": (i32, [C.c_char_p, u64, u32, C.POINTER(vp)]),
         "aqc_reader_next": (i32, [vp, C.POINTER(_abi.Records)]),
         "aqc_reader_release": (i32, [vp, u32]),

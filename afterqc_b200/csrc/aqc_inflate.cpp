@@ -56,13 +56,18 @@ bool GzipInflater::fail(const char *m) {
 // Canonical Huffman decode table: root table of 2^root_bits entries, codes longer than the root go through a
 // sub-table per root prefix (sized by the longest code sharing the prefix).  kind: 0 literal/length, 1 distance, 2 precode.
 bool GzipInflater::build(const uint8_t *lens, int n, int root_bits, int kind, std::vector<uint32_t> &tab) {
+    const char *e = build_table(lens, n, root_bits, kind, tab);
+    return e ? fail(e) : true;
+}
+
+const char *GzipInflater::build_table(const uint8_t *lens, int n, int root_bits, int kind, std::vector<uint32_t> &tab) {
     int count[16] = {0};
     for (int i = 0; i < n; i++) count[lens[i]]++;
     count[0] = 0;
     int left = 1;
     for (int l = 1; l <= 15; l++) {
         left = left * 2 - count[l];
-        if (left < 0) return fail("over-subscribed Huffman code");
+        if (left < 0) return "over-subscribed Huffman code";
     }
     uint32_t next[16];
     uint32_t code = 0;
@@ -83,7 +88,7 @@ bool GzipInflater::build(const uint8_t *lens, int n, int root_bits, int kind, st
     for (uint32_t p = 0; p < root_size; p++)
         if (sub_bits[p]) {
             uint32_t start = (uint32_t)tab.size();
-            if (start + (1u << sub_bits[p]) > 0xFFFF) return fail("Huffman table too large");
+            if (start + (1u << sub_bits[p]) > 0xFFFF) return "Huffman table too large";
             tab.resize(start + (1u << sub_bits[p]), 0);
             tab[p] = F_SUB | (start << 16) | ((uint32_t)sub_bits[p] << 8) | (uint32_t)root_bits;
         }
@@ -103,7 +108,27 @@ bool GzipInflater::build(const uint8_t *lens, int n, int root_bits, int kind, st
             for (uint32_t i = rev >> root_bits; i < (1u << sb); i += 1u << (l - root_bits)) tab[start + i] = e;
         }
     }
-    return true;
+    return nullptr;
+}
+
+// Two literals per lookup: when the root index holds a whole literal code AND the whole code of the literal that
+// follows, the entry carries both bytes (F_LIT | F_SUB, second byte in bits 24-31, bits 0-7 = both code lengths).
+// FASTQ text is literal-dominated with 2-4 bit codes, so most literal lookups emit two bytes.
+void GzipInflater::pair_literals(std::vector<uint32_t> &t, std::vector<uint32_t> &scratch) {
+    const uint32_t root_size = 1u << kLitBits;
+    scratch.assign(t.begin(), t.begin() + root_size);
+    for (uint32_t i = 0; i < root_size; i++) {
+        const uint32_t e1 = t[i];
+        if ((e1 & (F_LIT | F_SUB)) != F_LIT) continue;
+        const uint32_t l1 = e1 & 0xff;
+        if (l1 >= (uint32_t)kLitBits) continue;
+        const uint32_t e2 = t[i >> l1];                                  // the unknown high bits read as zeros: valid iff the code fits
+        if ((e2 & (F_LIT | F_SUB)) != F_LIT) continue;
+        const uint32_t l2 = e2 & 0xff;
+        if (l1 + l2 > (uint32_t)kLitBits) continue;
+        scratch[i] = F_LIT | F_SUB | (e1 & 0x00FF0000u) | ((e2 & 0x00FF0000u) << 8) | (l1 + l2);
+    }
+    memcpy(t.data(), scratch.data(), root_size * sizeof(uint32_t));
 }
 
 bool GzipInflater::need_bits(int n) {
@@ -231,26 +256,7 @@ bool GzipInflater::parse_block_header() {
     }
     if (!build(lens, nlit, kLitBits, 0, lit_)) return false;
     if (!build(lens + 288, ndist, kDistBits, 1, dist_)) return false;
-    // Two literals per lookup: when the root index holds a whole literal code AND the whole code of the literal that
-    // follows, the entry carries both bytes (F_LIT | F_SUB, second byte in bits 24-31, bits 0-7 = both code lengths).
-    // FASTQ text is literal-dominated with 2-4 bit codes, so most lookups emit two bytes.
-    {
-        const uint32_t root_size = 1u << kLitBits;
-        std::vector<uint32_t> &t = lit_;
-        pair_.assign(t.begin(), t.begin() + root_size);
-        for (uint32_t i = 0; i < root_size; i++) {
-            const uint32_t e1 = t[i];
-            if ((e1 & (F_LIT | F_SUB)) != F_LIT) continue;
-            const uint32_t l1 = e1 & 0xff;
-            if (l1 >= (uint32_t)kLitBits) continue;
-            const uint32_t e2 = t[i >> l1];                              // the unknown high bits read as zeros: valid iff the code fits
-            if ((e2 & (F_LIT | F_SUB)) != F_LIT) continue;
-            const uint32_t l2 = e2 & 0xff;
-            if (l1 + l2 > (uint32_t)kLitBits) continue;
-            pair_[i] = F_LIT | F_SUB | (e1 & 0x00FF0000u) | ((e2 & 0x00FF0000u) << 8) | (l1 + l2);
-        }
-        memcpy(t.data(), pair_.data(), root_size * sizeof(uint32_t));
-    }
+    pair_literals(lit_, pair_);
     st_ = HUFFMAN;
     return true;
 }

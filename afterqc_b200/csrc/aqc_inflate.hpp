@@ -20,8 +20,14 @@ class GzipInflater {
     long read(uint8_t *dst, size_t n);
     const std::string &error() const { return err_; }
 
-  private:
+    // shared with the parallel decoder (aqc_pinflate.cpp)
     static constexpr int kLitBits = 11, kDistBits = 8;
+    // canonical Huffman decode table (kind 0 literal/length, 1 distance, 2 precode); nullptr or an error text
+    static const char *build_table(const uint8_t *lens, int n, int root_bits, int kind, std::vector<uint32_t> &tab);
+    // two literals per root entry where both codes fit the root index
+    static void pair_literals(std::vector<uint32_t> &lit, std::vector<uint32_t> &scratch);
+
+  private:
     static constexpr size_t kWindow = 32768;
     static constexpr size_t kChunk = 1u << 20;       // bytes decoded per inner call (after the window)
 

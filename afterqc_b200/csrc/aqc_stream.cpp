@@ -23,6 +23,7 @@
 
 #include "../../include/afterqc_b200.h"
 #include "aqc_inflate.hpp"
+#include "aqc_pinflate.hpp"
 
 namespace {
 
@@ -96,6 +97,18 @@ class AsyncSource {
     bool stop_ = false, done_ = false, failed_ = false;
 };
 
+// decoder threads per .gz input: AQC_INFLATE_THREADS, else a quarter of the host's hardware threads (3..8, or 1);
+// AQC_INFLATE=serial keeps the single-threaded decoder
+int inflate_threads() {
+    const char *sel = getenv("AQC_INFLATE");
+    if (sel && strcmp(sel, "serial") == 0) return 1;
+    if (const char *e = getenv("AQC_INFLATE_THREADS")) { int v = atoi(e); return v < 1 ? 1 : (v > 64 ? 64 : v); }
+    unsigned hw = std::thread::hardware_concurrency();
+    int v = (int)(hw / 4);
+    if (v < 3) return 1;                      // the speculative decoder pays off from about 3 threads (16-bit symbols, two passes)
+    return v > 8 ? 8 : v;
+}
+
 bool ends_with(const std::string &s, const char *suf) {
     size_t k = strlen(suf);
     return s.size() >= k && s.compare(s.size() - k, k, suf) == 0;
@@ -118,6 +131,7 @@ struct aqc_reader {
     gzFile gz = nullptr;                    // zlib path: pipes / non-mappable files, or AQC_INFLATE=zlib
     FILE *fp = nullptr;
     aqc::GzipInflater *inf = nullptr;       // own decoder over the mapped .gz file
+    aqc::ParallelGunzip *pinf = nullptr;    // ... multi-threaded for large files
     AsyncSource *async = nullptr;           // gz only: the decoder runs on its own thread, ahead of the parser
     void *map = nullptr;
     size_t map_len = 0;
@@ -139,6 +153,11 @@ struct aqc_reader {
 
     // one block of decompressed bytes (gz inputs; runs on the AsyncSource thread): -1 + msg on error
     long read_gz(uint8_t *dst, size_t cap) {
+        if (pinf) {
+            long got = pinf->read(dst, cap);
+            if (got < 0) msg = "gzip: " + pinf->error() + " (AQC_INFLATE=zlib selects zlib's decoder)";
+            return got;
+        }
         if (inf) {
             long got = inf->read(dst, cap);
             if (got < 0) msg = "gzip: " + inf->error() + " (AQC_INFLATE=zlib selects zlib's decoder)";
@@ -271,20 +290,22 @@ int aqc_reader_open(const char *path, uint64_t batch_records, uint32_t slots, aq
                 if (m != MAP_FAILED) {
                     madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
                     r->map = m; r->map_len = (size_t)st.st_size; r->map_fd = fd;
-                    r->inf = new aqc::GzipInflater((const uint8_t *)m, r->map_len);
+                    int nt = inflate_threads();
+                    if (nt > 1 && r->map_len >= aqc::ParallelGunzip::kMinSize) r->pinf = new aqc::ParallelGunzip((const uint8_t *)m, r->map_len, nt);
+                    else r->inf = new aqc::GzipInflater((const uint8_t *)m, r->map_len);
                 }
             }
-            if (!r->inf && fd >= 0) close(fd);
+            if (!r->inf && !r->pinf && fd >= 0) close(fd);
         }
-        if (!r->inf) {
+        if (!r->inf && !r->pinf) {
             r->gz = gzopen(path, "rb");
             if (r->gz) gzbuffer(r->gz, 1u << 20);
         }
     } else {
         r->fp = fopen(path, "rb");
     }
-    if (!r->gz && !r->fp && !r->inf) { delete r; return AQC_ERR_INVALID; }
-    if (r->gz || r->inf) r->async = new AsyncSource([r](uint8_t *dst, size_t cap) { return r->read_gz(dst, cap); }, kReadBlock, 3);
+    if (!r->gz && !r->fp && !r->inf && !r->pinf) { delete r; return AQC_ERR_INVALID; }
+    if (r->gz || r->inf || r->pinf) r->async = new AsyncSource([r](uint8_t *dst, size_t cap) { return r->read_gz(dst, cap); }, kReadBlock, 3);
     r->slots.resize(slots);
     for (uint32_t i = 0; i < slots; i++) {
         Slot &s = r->slots[i];
@@ -343,6 +364,26 @@ int aqc_gunzip_buffer(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_
     return 0;
 }
 
+// the multi-threaded decoder on a memory buffer (no size threshold: for tests); stats: rounds, pieces, false starts
+int aqc_gunzip_buffer_mt(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_len, int threads,
+                         uint64_t stats[3], char *err, uint64_t err_cap) {
+    if (!in || !out_len) return AQC_ERR_INVALID;
+    aqc::ParallelGunzip inf(in, (size_t)n, threads);
+    uint64_t w = 0;
+    int rc = 0;
+    for (;;) {
+        uint8_t probe;
+        long g = w < out_cap ? inf.read(out + w, (size_t)(out_cap - w)) : inf.read(&probe, 1);
+        if (g < 0) { if (err && err_cap) snprintf(err, err_cap, "%s", inf.error().c_str()); rc = AQC_ERR_INVALID; break; }
+        if (g == 0) break;
+        if (w >= out_cap) { rc = AQC_ERR_NOMEM; break; }
+        w += (uint64_t)g;
+    }
+    if (stats) { stats[0] = inf.stats().rounds; stats[1] = inf.stats().pieces; stats[2] = inf.stats().false_starts; }
+    *out_len = w;
+    return rc;
+}
+
 const char *aqc_reader_error(const aqc_reader *r) { return r ? r->msg.c_str() : "null reader"; }
 
 void aqc_reader_close(aqc_reader *r) {
@@ -361,6 +402,7 @@ void aqc_reader_close(aqc_reader *r) {
     if (r->gz) gzclose(r->gz);
     if (r->fp) fclose(r->fp);
     delete r->inf;
+    delete r->pinf;
     if (r->map) munmap(r->map, r->map_len);
     if (r->map_fd >= 0) close(r->map_fd);
     delete r;

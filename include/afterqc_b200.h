@@ -312,6 +312,10 @@ const char *aqc_reader_error(const aqc_reader *r);
 /* the reader's own gzip/DEFLATE decoder on a memory buffer (all members; every member's CRC-32 and length verified):
  * AQC_ERR_INVALID + text in err on a corrupt or truncated stream, AQC_ERR_NOMEM when out_cap is too small. */
 int aqc_gunzip_buffer(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_len, char *err, uint64_t err_cap);
+/* ... and its multi-threaded form (speculative block search + symbolic windows, exact chaining; csrc/aqc_pinflate.hpp).
+ * stats receives rounds, accepted pieces, rejected search hits. */
+int aqc_gunzip_buffer_mt(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_len, int threads,
+                         uint64_t stats[3], char *err, uint64_t err_cap);
 void aqc_reader_close(aqc_reader *r);
 
 /* instrumentation for bench.py: kernels launched by this context so far, and the device
