@@ -141,3 +141,39 @@ def test_reader_with_decoder_threads_matches_zlib(tmp_path, monkeypatch):
     par = digest()
     monkeypatch.setenv("AQC_INFLATE", "zlib")
     assert digest() == par and par[0] == 120000
+
+
+def _realistic_fastq(n, seed):
+    """Illumina-like names, binned qualities in long runs, occasional N stretches and short reads"""
+    rng = np.random.default_rng(seed)
+    r = random.Random(seed)
+    L = r.choice([76, 101, 151])
+    out = []
+    for i in range(n):
+        name = b"@A00%d:%d:HXXXXDSXX:%d:%d:%d:%d 1:N:0:ACGT+TGCA" % (r.randrange(999), r.randrange(99), r.randrange(1, 5), 1101 + i // 5000,
+                                                                     r.randrange(30000), r.randrange(30000))
+        seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, L)].tobytes()
+        if r.random() < 0.02:
+            seq = seq[:r.randrange(1, L)] + b"NNNNN" + seq[:3]
+        q = bytearray()
+        while len(q) < len(seq):
+            q += bytes([r.choice(b"FFFFFFFF:,#")]) * r.randrange(1, 60)
+        out.append(name + b"\n" + seq + b"\n+\n" + bytes(q[:len(seq)]) + b"\n")
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_random_zlib_parameters_on_realistic_fastq(case):
+    r = random.Random(1000 + case)
+    data = _realistic_fastq(r.choice([30000, 60000]), case)
+    co = zlib.compressobj(r.randrange(1, 10), zlib.DEFLATED, 31, r.choice([8, 9, 5, 1]),
+                          r.choice([zlib.Z_DEFAULT_STRATEGY] * 3 + [zlib.Z_FILTERED, zlib.Z_RLE, zlib.Z_HUFFMAN_ONLY, zlib.Z_FIXED]))
+    step = r.choice([len(data), 1 << 20, 300000])
+    parts = []
+    for i in range(0, len(data), step):
+        parts.append(co.compress(data[i:i + step]))
+        if step < len(data) and r.random() < 0.5:
+            parts.append(co.flush(r.choice([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH])))      # pigz-style flush points
+    parts.append(co.flush())
+    out, stats = gunzip_mt(b"".join(parts), r.choice([2, 3, 4, 7]), len(data))
+    assert out == data, stats
