@@ -32,7 +32,12 @@ def lib():
         raise NativeLibraryMissing(
             "%s is missing: build it with `python -m afterqc_b200.build` (needs nvcc). "
             "The B200 engine has no CPU fallback." % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+    _lib = bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def bind(L):
+    """Attach the argument/return types of include/afterqc_b200.h to a loaded library and check its ABI version."""
     vp, i32, u32, u64, sz = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_size_t
     PB, PP = C.POINTER(_abi.Batch), C.POINTER(_abi.Params)
     sig = {
@@ -78,5 +83,4 @@ def lib():
         fn.restype, fn.argtypes = sig[name]
     if L.aqc_abi_version() != _abi.ABI_VERSION:
         raise ImportError("libafterqc_b200.so ABI %d != python ABI %d" % (L.aqc_abi_version(), _abi.ABI_VERSION))
-    _lib = L
     return L

@@ -93,6 +93,7 @@ struct KArgs {
 // ------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier + 1-D bulk async copy (TMA) + proxy fence
 // ------------------------------------------------------------------------------------------
+#ifndef AQC_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -110,9 +111,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) { }
-}
 // global -> shared bulk copy; dst, src and bytes are multiples of 16
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -120,12 +118,26 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#define AQC_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
+#else
+// host SIMT emulator build (tests/emu, test infrastructure): same contracts, modelled transaction counts
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { simt::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { simt::mbar_arrive_expect_tx(bar, bytes); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) { return simt::mbar_try_wait(bar, parity); }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) { simt::bulk_g2s(dst, src, bytes, bar); }
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void fence_mbar_init() {}
+#define AQC_DYN_SMEM(name) uint8_t *const name = simt::dyn_smem()
+#endif
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) { }
+}
 
 // ------------------------------------------------------------------------------------------
 // bit-plane helpers.  A "plane set" is uint32_t P[4]; lane j holds positions 32j..32j+31.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lowmask(int nbits) {   // nbits may be <= 0 or >= 32
-#ifdef AQC_NO_BMSK
+#if defined(AQC_NO_BMSK) || defined(AQC_EMU)
     return nbits >= 32 ? 0xffffffffu : (nbits <= 0 ? 0u : ((1u << nbits) - 1u));
 #else
     uint32_t m;

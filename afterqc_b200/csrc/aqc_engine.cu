@@ -118,11 +118,25 @@ size_t smem_bytes_for(int P, int col_cap, int max_len) {
     return NSTAGES * stage + 768 + 272 + acc + 64;
 }
 
+// A launchable kernel handle.  On the GPU this is the __global__ function itself; in the host SIMT emulator build
+// (tests/emu, test infrastructure) it is a trampoline that unpacks cudaLaunchKernel's argument array.
+#ifndef AQC_EMU
+#define AQC_KERNEL_HANDLE(...) ((const void *)(__VA_ARGS__))
+#else
+template <int MODE, bool PAIRED> void emu_pair_kernel(void **a) { pair_kernel<MODE, PAIRED>(*(const KArgs *)a[0]); }
+void emu_maxlen_kernel(void **a) { maxlen_kernel(*(const uint32_t **)a[0], *(const uint32_t **)a[1], *(uint32_t *)a[2], *(uint32_t **)a[3]); }
+#define pair_kernel emu_pair_kernel
+#define AQC_KERNEL_HANDLE(...) ((const void *)(simt::Entry)(__VA_ARGS__))
+#endif
+
 const void *kernel_for(int mode, bool paired) {
-    if (mode == MODE_FILTER) return paired ? (const void *)pair_kernel<MODE_FILTER, true> : (const void *)pair_kernel<MODE_FILTER, false>;
-    if (mode == MODE_STAT) return paired ? (const void *)pair_kernel<MODE_STAT, true> : (const void *)pair_kernel<MODE_STAT, false>;
-    return paired ? (const void *)pair_kernel<MODE_OPS, true> : (const void *)pair_kernel<MODE_OPS, false>;
+    if (mode == MODE_FILTER) return paired ? AQC_KERNEL_HANDLE(pair_kernel<MODE_FILTER, true>) : AQC_KERNEL_HANDLE(pair_kernel<MODE_FILTER, false>);
+    if (mode == MODE_STAT) return paired ? AQC_KERNEL_HANDLE(pair_kernel<MODE_STAT, true>) : AQC_KERNEL_HANDLE(pair_kernel<MODE_STAT, false>);
+    return paired ? AQC_KERNEL_HANDLE(pair_kernel<MODE_OPS, true>) : AQC_KERNEL_HANDLE(pair_kernel<MODE_OPS, false>);
 }
+#ifdef AQC_EMU
+#undef pair_kernel
+#endif
 
 int alloc_qc(aqc_ctx *ctx, QcHost &q) {
     q.dense_n = (size_t)1 << (2 * ctx->p.qc_kmer);
@@ -358,7 +372,15 @@ int run_device(aqc_ctx *ctx, const aqc_batch *b, const LaunchExtra &x) {
         uint32_t m = 0;
         CK(cudaMemsetAsync(ctx->d_maxlen, 0, 4, ctx->compute));
         if (b->n) {
-            maxlen_kernel<<<std::min<uint32_t>((b->n + 255) / 256, 1024u), 256, 0, ctx->compute>>>(b->off1, b->off2, b->n, ctx->d_maxlen);
+            const uint32_t *o1 = b->off1, *o2 = b->off2;
+            uint32_t nn = b->n, *dm = ctx->d_maxlen;
+            void *margs[4] = {(void *)&o1, (void *)&o2, (void *)&nn, (void *)&dm};
+#ifndef AQC_EMU
+            const void *mk = (const void *)maxlen_kernel;
+#else
+            const void *mk = (const void *)(simt::Entry)emu_maxlen_kernel;
+#endif
+            CK(cudaLaunchKernel(mk, dim3(std::min<uint32_t>((b->n + 255) / 256, 1024u)), dim3(256), margs, 0, ctx->compute));
             ctx->launches++;
         }
         CK(cudaMemcpyAsync(&m, ctx->d_maxlen, 4, cudaMemcpyDeviceToHost, ctx->compute));

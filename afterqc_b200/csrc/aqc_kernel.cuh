@@ -79,7 +79,7 @@ struct StageBuf {
 #endif
 template <int MODE, bool PAIRED>
 __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __grid_constant__ KArgs A) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
+    AQC_DYN_SMEM(smem_raw);
     __shared__ __align__(8) uint64_t full_bar[NSTAGES];
     __shared__ uint32_t tile_base[NSTAGES][2];      // 16-byte aligned column origin of the staged tile
     __shared__ uint32_t qc_reads_since_flush;
@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
                                 const uint8_t b2 = lut3[r2[p2]];                           // :565 util.complement
                                 const uint8_t qa = r1q[p1], qb = r2q[p2];                  // :566-567
                                 const int Qa = (int)qa - 33, Qb = (int)qb - 33;
+                                __syncwarp();      // every lane has read the bytes before lane 0 patches them
                                 bool fixed = false;
                                 uint32_t e = 0;
                                 if (Qa >= 30 && Qb <= 14) {                                // :571
