@@ -88,6 +88,9 @@ struct KArgs {
     QcDev qc[2];                  // [0] mate 1, [1] mate 2 for this launch
     int *error_flag;
     const Luts *luts;
+    // list mode (filter): tile i is the single pair list[i], i < *list_count -- the pairs lane_kernel hands over
+    const uint32_t *list;
+    const uint32_t *list_count;
 };
 
 // ------------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@
 #include <vector>
 #include <algorithm>
 #include "aqc_kernel.cuh"
+#include "aqc_lane_kernel.cuh"
 
 using namespace aqc;
 
@@ -44,6 +45,10 @@ struct aqc_ctx {
     Luts *d_luts = nullptr;
     int *d_error = nullptr;
     uint32_t *d_maxlen = nullptr;
+    // lane-per-pair filter path (aqc_lane_kernel.cuh): hand-over list of the pairs that need the general kernel
+    uint32_t *d_fb_list = nullptr, *d_fb_count = nullptr;
+    size_t fb_cap = 0;
+    int lane_mode = 0;             // 0 = warp-per-pair kernel only, 1 = lane-per-pair kernel for batches of short reads
     Staging stg[2];
     uint32_t chunk_pairs = 1u << 18;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -136,7 +141,25 @@ const void *kernel_for(int mode, bool paired) {
 }
 #ifdef AQC_EMU
 #undef pair_kernel
+template <bool PAIRED, int NW> void emu_lane_kernel(void **a) { lane_kernel<PAIRED, NW>(*(const LArgs *)a[0]); }
+#define lane_kernel emu_lane_kernel
 #endif
+
+// lane-per-pair filter kernel for mates of at most 32*NW bases
+int lane_words_for(int max_len) { return max_len <= 128 ? 4 : (max_len <= 160 ? 5 : (max_len <= 256 ? 8 : 0)); }
+const void *lane_kernel_for(bool paired, int nw) {
+    if (nw == 4) return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 4>) : AQC_KERNEL_HANDLE(lane_kernel<false, 4>);
+    if (nw == 5) return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 5>) : AQC_KERNEL_HANDLE(lane_kernel<false, 5>);
+    return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 8>) : AQC_KERNEL_HANDLE(lane_kernel<false, 8>);
+}
+#ifdef AQC_EMU
+#undef lane_kernel
+#endif
+
+size_t lane_smem_bytes(int nwarps, bool paired, int nw, int col_cap, int max_len) {
+    size_t acc = (size_t)(2 * QC_CLASSES * max_len + 2 * max_len + 2 * (max_len + 1) + 16) * 4;
+    return (size_t)nwarps * ((paired ? 3 : 2) * (size_t)col_cap + 4 * 32 * (size_t)nw) + 768 + acc + 64;
+}
 
 int alloc_qc(aqc_ctx *ctx, QcHost &q) {
     q.dense_n = (size_t)1 << (2 * ctx->p.qc_kmer);
@@ -209,6 +232,24 @@ struct LaunchExtra {
     void *out;                    // results / ops (device)
 };
 
+// tile geometry of pair_kernel for a batch whose longest read is maxl: fills tile_pairs / col_cap / num_tiles, returns smem bytes
+size_t pair_tiling(aqc_ctx *ctx, KArgs &A, uint32_t n_tiles_of, int maxl, int cap_pairs) {
+    // tile: <= 32 pairs and <= ~24 KB of column bytes per mate column group
+    int P = std::min(MAX_TILE_PAIRS, std::max(1, (24 * 1024) / (4 * maxl)));
+    P = std::min(P, cap_pairs);
+    if (const char *tp = getenv("AQC_TILE_PAIRS")) P = std::max(1, std::min(P, atoi(tp)));   // tuning knob
+    // small batches: shrink tiles so that every SM gets work
+    while (P > 8 && (n_tiles_of + P - 1) / P < (uint32_t)ctx->sm_count * 2) P >>= 1;
+    size_t smem;
+    for (;;) {
+        A.tile_pairs = P; A.col_cap = (P * maxl + 32 + 15) & ~15; A.num_tiles = (n_tiles_of + P - 1) / P;
+        smem = smem_bytes_for(P, A.col_cap, maxl);
+        if (smem <= ctx->max_dyn_smem || P == 1) break;
+        P >>= 1;
+    }
+    return smem;
+}
+
 int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t stream, bool timed) {
     if (b.n == 0) return 0;
     if (b.max_len > AQC_MAX_LEN) { ctx->sticky_err = AQC_ERR_TOO_LONG; return fail(ctx, AQC_ERR_TOO_LONG, "a read is longer than AQC_MAX_LEN"); }
@@ -216,16 +257,8 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
     memset(&A, 0, sizeof A);
     A.seq1 = b.seq1; A.qual1 = b.qual1; A.seq2 = b.seq2; A.qual2 = b.qual2; A.off1 = b.off1; A.off2 = b.off2;
     A.n = b.n; A.first_index = b.first_index;
-    int maxl = std::max(b.max_len, 8);
-    // tile: <= 32 pairs and <= ~24 KB of column bytes per mate column group
-    int P = std::min(MAX_TILE_PAIRS, std::max(1, (24 * 1024) / (4 * maxl)));
-    if (const char *tp = getenv("AQC_TILE_PAIRS")) P = std::max(1, std::min(P, atoi(tp)));   // tuning knob
-    // small batches: shrink tiles so that every SM gets work
-    while (P > 8 && (b.n + P - 1) / P < (uint32_t)ctx->sm_count * 2) P >>= 1;
-    A.tile_pairs = P;
-    A.col_cap = (P * maxl + 32 + 15) & ~15;
+    const int maxl = std::max(b.max_len, 8);
     A.max_len = maxl;
-    A.num_tiles = (b.n + P - 1) / P;
     A.mode = x.mode;
     A.p = ctx->p;
     A.stat_lo = x.stat_lo; A.stat_hi = x.stat_hi; A.order_base = x.order_base;
@@ -245,19 +278,9 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         else if (T <= 1) A.poly_m = 0;
         else { int m = (T + mismatch) / (mismatch + 1) - 1; A.poly_m = m < 0 ? 0 : m; }
     }
-    size_t smem = smem_bytes_for(P, A.col_cap, maxl);
-    while (smem > ctx->max_dyn_smem && P > 1) {
-        P >>= 1;
-        A.tile_pairs = P; A.col_cap = (P * maxl + 32 + 15) & ~15; A.num_tiles = (b.n + P - 1) / P;
-        smem = smem_bytes_for(P, A.col_cap, maxl);
-    }
-    if (smem > ctx->max_dyn_smem) return fail(ctx, AQC_ERR_INVALID, "tile does not fit shared memory");
-    int occ = 1;
     const bool pe = b.seq2 != nullptr;
-    const void *kern = kernel_for(x.mode, pe);
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
-    if (occ < 1) occ = 1;
-    uint32_t grid = std::min<uint32_t>(A.num_tiles, (uint32_t)(ctx->sm_count * occ));
+    const int nw = (x.mode == MODE_FILTER && ctx->lane_mode) ? lane_words_for(maxl) : 0;
+
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) {
         if (ctx->ev_used == ctx->ev_pool.size()) {
@@ -267,8 +290,73 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         }
         e0 = ctx->ev_pool[ctx->ev_used].first; e1 = ctx->ev_pool[ctx->ev_used].second;
         ctx->ev_used++;
-        CK(cudaEventRecord(e0, stream));
     }
+
+    if (nw) {
+        // ---- lane-per-pair kernel over the whole batch, then pair_kernel (list mode) over the pairs it handed over ----
+        if (b.n > ctx->fb_cap) {
+            cudaFree(ctx->d_fb_list); ctx->d_fb_list = nullptr; ctx->fb_cap = 0;
+            size_t cap = (size_t)b.n + (size_t)b.n / 4 + 1024;
+            CK(cudaMalloc(&ctx->d_fb_list, cap * sizeof(uint32_t)));
+            ctx->fb_cap = cap;
+        }
+        CK(cudaMemsetAsync(ctx->d_fb_count, 0, sizeof(uint32_t), stream));
+        LArgs L;
+        memset(&L, 0, sizeof L);
+        L.k = A;
+        L.k.tile_pairs = 32;
+        L.k.num_tiles = (b.n + 31) / 32;
+        L.fb_list = ctx->d_fb_list; L.fb_count = ctx->d_fb_count;
+        L.lane_col_cap = (32 * maxl + 96 + 15) & ~15;
+        const void *lk = lane_kernel_for(pe, nw);
+        int best_w = 0, best_occ = 0;
+        for (int w = LANE_MAX_WARPS; w >= 1; w--) {           // most resident warps per SM; ties go to the larger CTA
+            size_t sm = lane_smem_bytes(w, pe, nw, L.lane_col_cap, maxl);
+            if (sm > ctx->max_dyn_smem) continue;
+            int occ = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lk, w * 32, sm));
+            if (occ * w > best_occ * best_w) { best_w = w; best_occ = occ; }
+        }
+        if (const char *fw = getenv("AQC_LANE_WARPS")) {        // tuning knob
+            int w = std::max(1, std::min(LANE_MAX_WARPS, atoi(fw)));
+            size_t sm = lane_smem_bytes(w, pe, nw, L.lane_col_cap, maxl);
+            int occ = 0;
+            if (sm <= ctx->max_dyn_smem) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lk, w * 32, sm)); if (occ > 0) { best_w = w; best_occ = occ; } }
+        }
+        if (best_w == 0) return fail(ctx, AQC_ERR_INVALID, "lane kernel stage does not fit shared memory");
+        const size_t lsmem = lane_smem_bytes(best_w, pe, nw, L.lane_col_cap, maxl);
+        uint32_t want = (L.k.num_tiles + best_w - 1) / best_w;
+        uint32_t lgrid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * best_occ));
+        if (timed) CK(cudaEventRecord(e0, stream));
+        void *largs[1] = {(void *)&L};
+        CK(cudaLaunchKernel(lk, dim3(lgrid), dim3(best_w * 32), largs, lsmem, stream));
+        CK(cudaGetLastError());
+        ctx->launches++;
+        // general kernel over the hand-over list (usually empty: the count lives in device memory)
+        A.list = ctx->d_fb_list; A.list_count = ctx->d_fb_count;
+        size_t smem = pair_tiling(ctx, A, b.n, maxl, 1);
+        if (smem > ctx->max_dyn_smem) return fail(ctx, AQC_ERR_INVALID, "tile does not fit shared memory");
+        const void *kern = kernel_for(MODE_FILTER, pe);
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+        if (occ < 1) occ = 1;
+        uint32_t grid = std::min<uint32_t>(b.n, (uint32_t)(ctx->sm_count * occ));
+        void *kargs[1] = {(void *)&A};
+        CK(cudaLaunchKernel(kern, dim3(grid), dim3(THREADS), kargs, smem, stream));
+        CK(cudaGetLastError());
+        if (timed) CK(cudaEventRecord(e1, stream));
+        ctx->launches++;
+        return 0;
+    }
+
+    size_t smem = pair_tiling(ctx, A, b.n, maxl, MAX_TILE_PAIRS);
+    if (smem > ctx->max_dyn_smem) return fail(ctx, AQC_ERR_INVALID, "tile does not fit shared memory");
+    int occ = 1;
+    const void *kern = kernel_for(x.mode, pe);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+    if (occ < 1) occ = 1;
+    uint32_t grid = std::min<uint32_t>(A.num_tiles, (uint32_t)(ctx->sm_count * occ));
+    if (timed) CK(cudaEventRecord(e0, stream));
     void *kargs[1] = {(void *)&A};
     CK(cudaLaunchKernel(kern, dim3(grid), dim3(THREADS), kargs, smem, stream));
     CK(cudaGetLastError());
@@ -446,10 +534,24 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
             max_static = std::max(max_static, fa.sharedSizeBytes);
         }
         ctx->max_dyn_smem = (size_t)optin - max_static - 64;
+        const void *lanes[6] = {lane_kernel_for(true, 4), lane_kernel_for(false, 4), lane_kernel_for(true, 5),
+                                lane_kernel_for(false, 5), lane_kernel_for(true, 8), lane_kernel_for(false, 8)};
+        for (const void *k : lanes) {
+            cudaFuncAttributes fa;
+            CK(cudaFuncGetAttributes(&fa, k));
+            max_static = std::max(max_static, fa.sharedSizeBytes);
+        }
+        ctx->max_dyn_smem = (size_t)optin - max_static - 64;
         for (const void *k : kernels) {
             CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->max_dyn_smem));
             CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
+        for (const void *k : lanes) {
+            CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->max_dyn_smem));
+            CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
+        CK(cudaMalloc(&ctx->d_fb_count, sizeof(uint32_t)));
+        if (const char *lm = getenv("AQC_LANE_KERNEL")) ctx->lane_mode = atoi(lm) != 0;
         for (int s = 0; s < AQC_NUM_QC; s++) { int r = alloc_qc(ctx, ctx->qc[s]); if (r) return r; }
         return aqc_reset(ctx);
     };
@@ -472,6 +574,7 @@ void aqc_destroy(aqc_ctx *ctx) {
     }
     for (auto &ev : ctx->ev_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     cudaFree(ctx->d_counters); cudaFree(ctx->d_luts); cudaFree(ctx->d_error); cudaFree(ctx->d_maxlen);
+    cudaFree(ctx->d_fb_list); cudaFree(ctx->d_fb_count);
     if (ctx->own_compute) cudaStreamDestroy(ctx->own_compute);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);

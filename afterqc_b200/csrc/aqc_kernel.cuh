@@ -121,11 +121,17 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
     }
     __syncthreads();
 
+    // list mode: one listed pair per tile, the number of tiles is read from device memory
+    const bool listed = (MODE == MODE_FILTER) && A.list != nullptr;
+    const uint32_t num_tiles = listed ? *A.list_count : A.num_tiles;
+    auto tile_first = [&](uint32_t tile) -> uint32_t { return listed ? A.list[tile] : tile * (uint32_t)P; };
+    auto tile_end = [&](uint32_t p0) -> uint32_t { return listed ? p0 + 1u : min(A.n, p0 + (uint32_t)P); };
+
     // producer: issue the bulk copies of one tile into a stage (single thread)
     auto issue_tile = [&](uint32_t tile, int st) {
         StageBuf b = stage_ptr(st);
-        uint32_t p0 = tile * (uint32_t)P;
-        uint32_t p1 = min(A.n, p0 + (uint32_t)P);
+        uint32_t p0 = tile_first(tile);
+        uint32_t p1 = tile_end(p0);
         uint32_t a1 = A.off1[p0], e1 = A.off1[p1];
         uint32_t g1 = a1 & ~15u;
         uint32_t bytes1 = (e1 - g1 + 15u) & ~15u;
@@ -180,18 +186,18 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
     if (tid == 0) {
         for (int s = 0; s < NSTAGES; s++) {
             uint32_t t = blockIdx.x + (uint32_t)s * gridDim.x;
-            if (t < A.num_tiles) issue_tile(t, s);
+            if (t < num_tiles) issue_tile(t, s);
         }
     }
 
     uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < A.num_tiles; tile += gridDim.x, it++) {
+    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
         const int st = it % NSTAGES;
         const uint32_t parity = (it / NSTAGES) & 1u;
         mbar_wait(&full_bar[st], parity);
         StageBuf sb = stage_ptr(st);
-        const uint32_t p0 = tile * (uint32_t)P;
-        const uint32_t p1 = min(A.n, p0 + (uint32_t)P);
+        const uint32_t p0 = tile_first(tile);
+        const uint32_t p1 = tile_end(p0);
         const uint32_t o0 = p0 & ~3u;
         const uint32_t g1 = tile_base[st][0], g2 = tile_base[st][1];
 
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
         if (tid == 0) {
             uint32_t nxt = tile + (uint32_t)NSTAGES * gridDim.x;
             tile_next[st] = 0;
-            if (nxt < A.num_tiles) issue_tile(nxt, st);
+            if (nxt < num_tiles) issue_tile(nxt, st);
             qc_reads_since_flush += (p1 - p0);
         }
         __syncthreads();
@@ -469,7 +475,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
             v = s_dih[i]; if (v) atomicAdd(&A.counters[AQC_C_DISTANCE_HIST + i], (unsigned long long)v);
         }
         if (wc0) atomicAdd(&A.counters[lane], wc0);
-        if (blockIdx.x == 0 && tid == 0) {      // TOTAL_READS / TOTAL_BASES (:416,:431,:433) are sums over the batch
+        if (blockIdx.x == 0 && tid == 0 && !listed) {      // TOTAL_READS / TOTAL_BASES (:416,:431,:433) are sums over the batch
             atomicAdd(&A.counters[AQC_C_TOTAL_READS], (unsigned long long)A.n);
             atomicAdd(&A.counters[AQC_C_TOTAL_BASES_R1], (unsigned long long)(A.off1[A.n] - A.off1[0]));
             if (paired) atomicAdd(&A.counters[AQC_C_TOTAL_BASES_R2], (unsigned long long)(A.off2[A.n] - A.off2[0]));
