@@ -112,6 +112,7 @@ unsigned long long host_side_hash(unsigned long long k) {   // must match aqc::s
 
 int check_params(const aqc_params *p, char *err, size_t errn) {
     if (p->qc_kmer < 1 || p->qc_kmer > AQC_MAX_KMER) { snprintf(err, errn, "qc_kmer %d outside 1..%d", p->qc_kmer, AQC_MAX_KMER); return AQC_ERR_INVALID; }
+    if (p->filter_kernel < 0 || p->filter_kernel > 2) { snprintf(err, errn, "filter_kernel %d outside 0..2", p->filter_kernel); return AQC_ERR_INVALID; }
     if (p->trim_front < 0 || p->trim_tail < 0 || p->trim_front2 < 0 || p->trim_tail2 < 0) { snprintf(err, errn, "negative trim value (resolve auto-trim on the host first)"); return AQC_ERR_INVALID; }
     return 0;
 }
@@ -279,7 +280,8 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         else { int m = (T + mismatch) / (mismatch + 1) - 1; A.poly_m = m < 0 ? 0 : m; }
     }
     const bool pe = b.seq2 != nullptr;
-    const int nw = (x.mode == MODE_FILTER && ctx->lane_mode) ? lane_words_for(maxl) : 0;
+    const bool want_lane = ctx->p.filter_kernel == 2 || (ctx->p.filter_kernel == 0 && ctx->lane_mode);
+    const int nw = (x.mode == MODE_FILTER && want_lane) ? lane_words_for(maxl) : 0;
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) {

@@ -74,6 +74,9 @@ __device__ __forceinline__ void shr_bits(uint32_t (&X)[NW], int s) {
 
 // Planes of one read (bytes in the warp's stage, any alignment).  p0/p1 = bits 1/2 of the ASCII byte
 // (A0 C1 T2 G3), pn = 'N' (its code bits are cleared); exotic = some byte is not A,C,G,T,N.
+// The chunk loop is rolled (one copy of the SWAR code in the instruction cache): every iteration converts the next 32
+// bases into the TOP word of the plane registers and moves the others down one word, so after NW iterations word c
+// holds chunk c.
 template <int NW>
 __device__ __forceinline__ void lane_convert(const uint8_t *s, int len, LanePlanes<NW> &P, bool &exotic, int &n_count) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(s);
@@ -82,7 +85,11 @@ __device__ __forceinline__ void lane_convert(const uint8_t *s, int len, LanePlan
     exotic = false;
     n_count = 0;
     uint32_t prev = len > 0 ? w[0] : 0u;
+#ifdef AQC_LANE_UNROLL_CONVERT
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
     for (int c = 0; c < NW; c++) {
         uint32_t p0 = 0, p1 = 0, pn = 0;
         const int nvalid = len - 32 * c;
@@ -102,8 +109,9 @@ __device__ __forceinline__ void lane_convert(const uint8_t *s, int len, LanePlan
                 const uint32_t e = __byte_perm(0x47544341u, 0u, __byte_perm(tt | (tt >> 4), 0u, 0x4420));   // codes -> ASCII
                 bad |= e ^ v[j];
                 const uint32_t z = (tt | (t << 2)) & 0x11111111u;                               // bit0 = code bit 0, bit4 = code bit 1
-                const uint32_t r = (z * 0x01020408u) >> 24;                                     // nibble of plane 0 | nibble of plane 1 << 4
-                if (j < 4) rlo |= r << (8 * j); else rhi |= r << (8 * (j - 4));
+                const uint32_t r = z * 0x01020408u;                     // byte 3 = nibble of plane 0 | nibble of plane 1 << 4
+                constexpr uint32_t sel[4] = {0x3217u, 0x3270u, 0x3710u, 0x7210u};               // byte 3 of r -> byte j of the accumulator
+                if (j < 4) rlo = __byte_perm(rlo, r, sel[j & 3]); else rhi = __byte_perm(rhi, r, sel[j & 3]);
             }
             // de-interleave the nibbles: bytes of rlo/rhi hold (p1 nibble << 4 | p0 nibble) of 4 bases each
             {
@@ -135,7 +143,16 @@ __device__ __forceinline__ void lane_convert(const uint8_t *s, int len, LanePlan
                 n_count += __popc(nb);
             }
         }
+#ifdef AQC_LANE_UNROLL_CONVERT
         P.p0[c] = p0; P.p1[c] = p1; P.pn[c] = pn;
+#else
+#pragma unroll
+        for (int i = 0; i < NW; i++) {
+            P.p0[i] = (i + 1 < NW) ? P.p0[i + 1 < NW ? i + 1 : 0] : p0;
+            P.p1[i] = (i + 1 < NW) ? P.p1[i + 1 < NW ? i + 1 : 0] : p1;
+            P.pn[i] = (i + 1 < NW) ? P.pn[i + 1 < NW ? i + 1 : 0] : pn;
+        }
+#endif
     }
 }
 
@@ -204,7 +221,10 @@ __device__ __forceinline__ bool lane_scan_dir(uint32_t (&S0)[NW], uint32_t (&S1)
     const int maxOff = (int)__reduce_max_sync(FULL, (unsigned)max(nOff, 0));
     const int rounds = (maxOff + 31) >> 5;
     const bool slow = lenF < 32;                                // first window shorter than 32: every offset is evaluated exactly
-    const uint32_t f0 = F0[0], f1 = F1[0];
+    const uint32_t f0 = F0[0];
+#ifdef AQC_LANE_TWO_PLANE_FILTER
+    const uint32_t f1 = F1[0];
+#endif
     bool found = false;
 #pragma unroll 1
     for (int r = 0; r < rounds; r++) {
@@ -215,7 +235,13 @@ __device__ __forceinline__ bool lane_scan_dir(uint32_t (&S0)[NW], uint32_t (&S1)
             if (!slow) {
 #pragma unroll
                 for (int b = 0; b < 32; b++) {
+#ifdef AQC_LANE_TWO_PLANE_FILTER
                     const uint32_t x = (__funnelshift_r(S0[0], S0[1], b) ^ f0) | (__funnelshift_r(S1[0], S1[1], b) ^ f1);
+#else
+                    // one code bit is enough for a necessary condition: equal bases have equal bits, and 32 random positions
+                    // differ in fewer than 3 of them with probability 1.2e-7
+                    const uint32_t x = __funnelshift_r(S0[0], S0[1], b) ^ f0;
+#endif
                     if (__popc(x) < 3) cm |= 1u << b;
                 }
                 cm &= lowmask(rem);
@@ -289,7 +315,7 @@ __device__ __forceinline__ void lane_overlap(const LanePlanes<NW> &P1, const Lan
 //   luts (768 B)
 //   qc acc [2][5][max_len] u32, qc disc [2][max_len] u32, overlap_hist [max_len+1], distance_hist [max_len+1], err matrix [16]
 template <bool PAIRED, int NW>
-__global__ void __launch_bounds__(LANE_MAX_WARPS * 32, 4) lane_kernel(const __grid_constant__ LArgs L) {
+__global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_kernel(const __grid_constant__ LArgs L) {
     AQC_DYN_SMEM(smem_raw);
     __shared__ __align__(8) uint64_t full_bar[LANE_MAX_WARPS];
     const KArgs &A = L.k;
@@ -408,24 +434,34 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, 4) lane_kernel(const __gr
             if (live && len1 < A.p.seq_len_req) { cls = AQC_BADLEN; live = false; }   // :476-479 (R2 never checked, quirk Q3)
         }
         if (live) {
-            const uint8_t *r1 = stage + (a1 - g1) + start1;
-            bool ex1 = false, ex2 = false;
-            lane_convert<NW>(r1, len1, P1, ex1, n1);
-            if (paired) {
-                const uint8_t *r2 = stage + 2 * col_cap + (a2 - g2) + start2;
-                LanePlanes<NW> F2;
-                lane_convert<NW>(r2, len2, F2, ex2, n2);
-                if (A.p.poly_size_limit > 0) cand2 = lane_polyx_screen<NW>(F2.p0, F2.p1, F2.pn, len2, A.p.poly_size_limit, A.poly_m);
-                // reverseComplement (util.py:42-51): reverse the 32*NW-bit strings, shift the read down to bit 0, flip plane 1
+            bool ex = false;
+#pragma unroll 1
+            for (int m = 0; m < (paired ? 2 : 1); m++) {              // one copy of the conversion + screen code for both mates
+                const uint8_t *r = m ? stage + 2 * col_cap + (a2 - g2) + start2 : stage + (a1 - g1) + start1;
+                const int len = m ? len2 : len1;
+                LanePlanes<NW> F;
 #pragma unroll
-                for (int i = 0; i < NW; i++) { RC.p0[i] = __brev(F2.p0[NW - 1 - i]); RC.p1[i] = __brev(F2.p1[NW - 1 - i]); RC.pn[i] = __brev(F2.pn[NW - 1 - i]); }
-                shr_bits<NW>(RC.p0, MAXB - len2); shr_bits<NW>(RC.p1, MAXB - len2); shr_bits<NW>(RC.pn, MAXB - len2);
+                for (int i = 0; i < NW; i++) F.p0[i] = F.p1[i] = F.pn[i] = 0;
+                bool exm = false; int nn = 0;
+                lane_convert<NW>(r, len, F, exm, nn);
+                ex |= exm;
+                const bool cand = A.p.poly_size_limit > 0 && lane_polyx_screen<NW>(F.p0, F.p1, F.pn, len, A.p.poly_size_limit, A.poly_m);
+                if (m == 0) {
+                    n1 = nn; cand1 = cand;
 #pragma unroll
-                for (int i = 0; i < NW; i++) RC.p1[i] ^= lowmask(len2 - 32 * i) & ~RC.pn[i];
+                    for (int i = 0; i < NW; i++) { P1.p0[i] = F.p0[i]; P1.p1[i] = F.p1[i]; P1.pn[i] = F.pn[i]; }
+                } else {
+                    n2 = nn; cand2 = cand;
+                    // reverseComplement (util.py:42-51): reverse the 32*NW-bit strings, shift the read down to bit 0, flip plane 1
+#pragma unroll
+                    for (int i = 0; i < NW; i++) { RC.p0[i] = __brev(F.p0[NW - 1 - i]); RC.p1[i] = __brev(F.p1[NW - 1 - i]); RC.pn[i] = __brev(F.pn[NW - 1 - i]); }
+                    shr_bits<NW>(RC.p0, MAXB - len2); shr_bits<NW>(RC.p1, MAXB - len2); shr_bits<NW>(RC.pn, MAXB - len2);
+#pragma unroll
+                    for (int i = 0; i < NW; i++) RC.p1[i] ^= lowmask(len2 - 32 * i) & ~RC.pn[i];
+                }
             }
-            if (A.p.poly_size_limit > 0) cand1 = lane_polyx_screen<NW>(P1.p0, P1.p1, P1.pn, len1, A.p.poly_size_limit, A.poly_m);
             if (A.p.unqualified_base_limit > 0) lowq1 = lane_lowq(stage + col_cap + (a1 - g1) + start1, len1, A.p.qualified_quality_phred + 33);
-            if (ex1 || ex2) { fallback = true; live = false; cls = AQC_NUM_CLASSES; }
+            if (ex) { fallback = true; live = false; cls = AQC_NUM_CLASSES; }
         }
 
         // ---- the stage is free: prefetch the next tile while the registers are worked on ----
@@ -543,10 +579,11 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, 4) lane_kernel(const __gr
                         const int Qa = (int)qa - 33, Qb = (int)qb - 33;
                         bool fixed = false;
                         uint32_t e = 0;
+                        int cell = -1;
                         if (Qa >= 30 && Qb <= 14) {                                // :571
                             if (b1 != 'N' && b2 != 'N') {
                                 const uint32_t la = lut2[lut3[b1]], lc = lut2[lut3[b2]];
-                                if ((la & 0x40u) && (lc & 0x40u)) em_cell[done] = (int)((la & 7u) * 4u + (lc & 7u));   // :573
+                                if ((la & 0x40u) && (lc & 0x40u)) cell = (int)((la & 7u) * 4u + (lc & 7u));   // :573
                             }
                             if (!A.p.no_correction) {                              // :574-578
                                 const uint8_t nb = lut3[b1];
@@ -556,7 +593,7 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, 4) lane_kernel(const __gr
                         } else if (Qb >= 30 && Qa <= 14) {                         // :579
                             if (b1 != 'N' && b2 != 'N') {
                                 const uint32_t la = lut2[b2], lc = lut2[b1];
-                                if ((la & 0x40u) && (lc & 0x40u)) em_cell[done] = (int)((la & 7u) * 4u + (lc & 7u));   // :581
+                                if ((la & 0x40u) && (lc & 0x40u)) cell = (int)((la & 7u) * 4u + (lc & 7u));   // :581
                             }
                             if (!A.p.no_correction) {                              // :582-586
                                 corrected++; fixed = true;
@@ -572,10 +609,13 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, 4) lane_kernel(const __gr
                                 e = (uint32_t)(start1 + p1) | (3u << 10) | ((uint32_t)(start2 + p2) << 16);
                             }
                         }
-                        if (n_edits < 4) edits[n_edits++] = e;
+#pragma unroll
+                        for (int k = 0; k < 3; k++) if (k == done) { edits[k] = e; em_cell[k] = cell; }   // distance <= 3 here
                         done++;
                     }
+                    n_edits = done;
                     if (corrected + masked + skipped == distance) {               // :603-610
+#pragma unroll
                         for (int k = 0; k < 3; k++) if (em_cell[k] >= 0) atomicAdd(&s_em[em_cell[k]], 1u);
                         if (corrected > 0) t_read_corr = 1;
                         t_corr = (uint32_t)corrected; t_masked = (uint32_t)masked; t_skipped = (uint32_t)skipped;
@@ -660,9 +700,10 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, 4) lane_kernel(const __gr
                         for (int x = lane; x < bl2; x += 32) { sc_s2[x] = A.seq2[ba2 + bs2 + x]; sc_q2[x] = A.qual2[ba2 + bs2 + x]; }
                     __syncwarp();
                     if (lane == 0) {
-                        const uint32_t be[4] = {be0, be1, be2, be3};
-                        for (int k = 0; k < bne && k < 4; k++) {
-                            const uint32_t e = be[k];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            if (k >= bne) break;
+                            const uint32_t e = k == 0 ? be0 : (k == 1 ? be1 : (k == 2 ? be2 : be3));
                             const int kind = (int)AQC_EDIT_KIND(e), pos = (int)AQC_EDIT_POS(e);
                             if (kind == 0) { sc_s1[pos - bs1] = (uint8_t)AQC_EDIT_BASE(e); sc_q1[pos - bs1] = (uint8_t)AQC_EDIT_QUAL(e); }
                             else if (kind == 1) { sc_s2[pos - bs2] = (uint8_t)AQC_EDIT_BASE(e); sc_q2[pos - bs2] = (uint8_t)AQC_EDIT_QUAL(e); }

@@ -91,7 +91,11 @@ typedef struct aqc_params {
     int32_t qc_sample;               /* --qc_sample 200000 (postfilter gate, preprocesser.py:624) */
     int32_t qc_kmer;                 /* --qc_kmer 8 */
     int32_t kmer_side_log2;          /* log2 capacity of the non-ACGT k-mer side table (0 = default 20) */
-    int32_t reserved[7];
+    int32_t filter_kernel;           /* which kernel aqc_filter_pairs launches: 0 = engine default (environment AQC_LANE_KERNEL,
+                                        else 1), 1 = warp-per-pair (pair_kernel, any read length), 2 = lane-per-pair
+                                        (lane_kernel) for batches whose reads are <= 256 bases, pair_kernel otherwise.
+                                        Results are identical; this is a performance knob. */
+    int32_t reserved[6];
 } aqc_params;
 
 /* One packed batch.  off*[i]..off*[i+1] delimit record i in seq* and qual*.  seq2/qual2/off2

@@ -10,12 +10,16 @@ import compare
 from afterqc_b200 import _abi
 
 
-@pytest.fixture(scope="module")
-def backends(oracle_lib):
+@pytest.fixture(scope="module", params=["warp", "lane"])
+def backends(oracle_lib, request):
+    """warp = pair_kernel (one warp per pair); lane = lane_kernel (one lane per pair) + pair_kernel's list mode"""
     import emu
+    kernel = _abi.KERNEL_LANE if request.param == "lane" else _abi.KERNEL_WARP
 
     def make(params):
+        params.filter_kernel = kernel
         return oracle_lib.Oracle(params), emu.EmuEngine(params)
+    make.kernel = request.param
     return make
 
 
@@ -32,6 +36,8 @@ BATCHES = {
 @pytest.mark.parametrize("bname", ["adversarial", "pe150_jitter"])
 @pytest.mark.parametrize("pname", ["default_f0", "trim", "poly_wide"])
 def test_emu_ops_parity(backends, bname, pname):
+    if backends.kernel == "lane":
+        pytest.skip("the operator entry always runs pair_kernel")
     batch = BATCHES[bname]()
     orc, eng = backends(cases.make_params(pname))
     compare.assert_records_equal(batch, orc.ops_pairs(batch), eng.ops_pairs(batch), "emu ops %s/%s" % (bname, pname))
@@ -53,6 +59,8 @@ def test_emu_filter_parity(backends, bname, pname):
 
 
 def test_emu_stat_parity(backends):
+    if backends.kernel == "lane":
+        pytest.skip("the prefilter statistics entry always runs pair_kernel")
     batch = BATCHES["pe150_jitter"]()
     for kmer in (8, 4):
         orc, eng = backends(_abi.Params.defaults(qc_kmer=kmer))
@@ -74,3 +82,38 @@ def test_emu_single_end_and_resident(backends):
         compare.assert_records_equal(batch, a, b, "emu se100 %s" % pname)
         compare.compare_backends(orc, eng, (_abi.QC_R1_POST,), "emu se100 %s" % pname)
         d.free(); orc.close(); eng.close()
+
+
+def test_emu_lane_batch_split_and_sample_gate(backends):
+    """first_index gates the postfilter sample (quirk Q10) and counters add up over batches, whichever kernel runs"""
+    batch = cases.synthetic("pe150", 2500)
+    p = cases.make_params("default_f0"); p.qc_sample = 1500
+    orc, eng = backends(p)
+    orc.filter_pairs(batch)
+    for part in (batch.slice(0, 700), batch.slice(700, 1733), batch.slice(1733, 2500)):
+        eng.filter_pairs(part)
+    compare.compare_backends(orc, eng, (_abi.QC_R1_POST, _abi.QC_R2_POST), "emu split")
+    orc.close(); eng.close()
+
+
+def test_emu_lane_short_and_power_of_two_lengths(backends):
+    """reads of 32/64/128/256 bases (bank-conflict lengths for the lane kernel), very short mates, empty tail tile"""
+    import random
+    from afterqc_b200.batch import PackedBatch
+    rng = random.Random(11)
+    r1s, r2s = [], []
+    for L in (32, 33, 64, 100, 128, 129, 160, 161, 255, 256):
+        for _ in range(40):
+            frag = rng.randint(20, 2 * L + 40)
+            f = cases._rand_seq(rng, frag)
+            a = (f + cases._rand_seq(rng, L))[:L]
+            b = (cases.revcomp(f) + cases._rand_seq(rng, L))[:rng.choice([L, L, max(5, L - 7)])]
+            b = cases._mutate(rng, b, rng.choice([0, 0, 1, 2, 3, 5]), "ACGTN")
+            r1s.append((a, cases._rand_qual(rng, len(a)))); r2s.append((b, cases._rand_qual(rng, len(b))))
+    batch = PackedBatch.from_reads(r1s, r2s)
+    for pname in ("default_f0", "trim", "loose"):
+        orc, eng = backends(cases.make_params(pname))
+        a = orc.filter_pairs(batch); b = eng.filter_pairs(batch)
+        compare.assert_records_equal(batch, a, b, "emu lengths %s" % pname)
+        compare.compare_backends(orc, eng, (_abi.QC_R1_POST, _abi.QC_R2_POST), "emu lengths %s" % pname)
+        orc.close(); eng.close()
