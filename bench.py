@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU sample (0 = auto)")
     ap.add_argument("--qc-sample", type=int, default=QC_SAMPLE, help="--qc_sample of the workload (profiling runs on fewer pairs scale it to keep the 2%% mix)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--filter-kernel", default="auto", choices=["auto", "warp", "lane"],
+                    help="filter kernel: warp = pair_kernel (one warp per pair), lane = lane_kernel (one lane per pair); auto = lane "
+                         "only if it first proves bit-identical to warp on this GPU (child process with a timeout, then the full batch)")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -247,6 +250,73 @@ def cuda_tensor_view(ptr, n, torch_dtype, device):
     return torch.as_tensor(s, device=device)
 
 
+def lane_child_check(local_rank, pairs, timeout_s=300):
+    """tests/lane_gpu_check.py `full` in a child process with a timeout: both filter kernels on `pairs` pairs of the bench
+    workload, every output compared.  lane_kernel was committed without having run on hardware, so a hang or a mismatch
+    must not take the benchmark down: anything but a clean 'identical' keeps the warp-per-pair kernel."""
+    env = dict(os.environ)
+    ids = [x for x in env.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip() != ""]
+    env["CUDA_VISIBLE_DEVICES"] = (ids[local_rank] if local_rank < len(ids) else ids[0]) if ids else str(local_rank)
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "lane_gpu_check.py"), "full", str(pairs)]
+    t0 = time.time()
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+    except subprocess.TimeoutExpired:
+        return {"ok": False, "why": "child timed out after %d s" % timeout_s}
+    except Exception as e:      # noqa: BLE001
+        return {"ok": False, "why": "child could not run: %r" % (e,)}
+    out = {"ok": False, "seconds": round(time.time() - t0, 1)}
+    if r.returncode != 0:
+        out["why"] = "child exit %d: %s" % (r.returncode, (r.stderr or r.stdout)[-300:].replace("\n", " | "))
+        return out
+    for ln in r.stdout.splitlines():
+        ln = ln.strip()
+        if ln.startswith("{"):
+            try:
+                j = json.loads(ln)
+            except ValueError:
+                continue
+            out.update(j)
+            out["ok"] = bool(j.get("identical"))
+    if not out["ok"]:
+        out.setdefault("why", "no verdict in the child's output")
+    return out
+
+
+def lane_full_size_check(wb, n, qs, local_rank, stream):
+    """Both kernels once over the resident full-size batch in this process: records, scalar counters, histograms, error
+    matrix, postfilter per-cycle statistics and k-mer tables must be identical."""
+    import torch
+    from afterqc_b200 import _abi
+    from afterqc_b200.engine import Engine
+    ref = None
+    for k in (_abi.KERNEL_WARP, _abi.KERNEL_LANE):
+        e = Engine(_abi.Params.defaults(qc_sample=qs, filter_kernel=k), device=local_rank)
+        e.set_stream(stream.cuda_stream)
+        res = torch.empty(max(1, n) * 32, dtype=torch.uint8, device=wb.results.device)
+        b = wb.struct()
+        e._check(e._L.aqc_filter_pairs(e._h, C.byref(b), _abi.MEM_DEVICE, res.data_ptr()))
+        e.sync()
+        got = (res, e.counters(), [e.qc(s) for s in (_abi.QC_R1_POST, _abi.QC_R2_POST)], [e.kmers(s) for s in (_abi.QC_R1_POST, _abi.QC_R2_POST)])
+        e.close()
+        if ref is None:
+            ref = got
+            continue
+        if not bool(torch.equal(ref[0], got[0])):
+            return False, "records differ"
+        if not np.array_equal(ref[1], got[1]):
+            return False, "counters differ"
+        for a, c in zip(ref[2], got[2]):
+            for f in a.dtype.names:
+                if not np.array_equal(a[f], c[f]):
+                    return False, "QC field %s differs" % f
+        for a, c in zip(ref[3], got[3]):
+            for x, y in zip(a, c):
+                if not np.array_equal(x, y):
+                    return False, "k-mer tables differ"
+    return True, "identical"
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -264,15 +334,38 @@ def run_ours(args):
     device = torch.device("cuda", local_rank)
     n = args.pairs
     QS = args.qc_sample
-    params = _abi.Params.defaults(qc_sample=QS)
-    eng = Engine(params, device=local_rank)
     stream = torch.cuda.Stream(device)          # the launching stream of every kernel below (torch events time it)
     torch.cuda.set_stream(stream)
+    first_index = rank * n
+
+    # ---------------- which filter kernel ----------------
+    selection = {"requested": args.filter_kernel}
+    use_lane = args.filter_kernel == "lane"
+    child = None
+    if args.filter_kernel == "auto":
+        child = lane_child_check(local_rank, min(n, 2_000_000))
+        selection["child_check"] = child
+        use_lane = bool(child.get("ok"))
+    wb = make_device_workload(device, n, seed=20260927 + rank, first_index=first_index)
+    if use_lane and args.filter_kernel == "auto":
+        try:
+            ok, why = lane_full_size_check(wb, n, QS, local_rank, stream)
+        except Exception as e:      # noqa: BLE001
+            ok, why = False, "full-size check raised %r" % (e,)
+        selection["full_size_check"] = why
+        use_lane = ok
+    if world > 1:       # every rank runs the same kernel
+        flag = torch.tensor([1 if use_lane else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        use_lane = bool(flag.item())
+    selection["used"] = "lane" if use_lane else "warp"
+    kernel_label = ("aqc::lane_kernel (one lane per pair) + aqc::pair_kernel list mode" if use_lane
+                    else "aqc::pair_kernel (MODE_FILTER, one warp per pair)")
+
+    params = _abi.Params.defaults(qc_sample=QS, filter_kernel=_abi.KERNEL_LANE if use_lane else _abi.KERNEL_WARP)
+    eng = Engine(params, device=local_rank)
     eng.set_stream(stream.cuda_stream)
     L = eng._L
-
-    first_index = rank * n
-    wb = make_device_workload(device, n, seed=20260927 + rank, first_index=first_index)
 
     # records of this shard inside the prefilter window [999, 999 + qc_sample) (global indices)
     w_lo_g, w_hi_g = STAT_LO, STAT_LO + QS
@@ -412,8 +505,8 @@ def run_ours(args):
     algo_bytes = col_bytes + 32 * n + 8 * n
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_filter_kernel_dram_bytes.json")
-    if os.path.exists(tp):
+    tp = os.path.join(ROOT, "profiles", "r01_filter_kernel_dram_bytes.json")     # ncu capture of pair_kernel
+    if os.path.exists(tp) and not use_lane:
         try:
             with open(tp) as f:
                 tj = json.load(f)
@@ -421,7 +514,7 @@ def run_ours(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "aqc::pair_kernel (MODE_FILTER, %d pairs/launch)" % n, "kernel_ms": kernel_ms,
+                "kernel": "%s, %d pairs/launch" % (kernel_label, n), "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                 "note": "integer ALU-bound kernel: see DESIGN.md (instruction budget per pair vs HBM budget)"}
 
@@ -451,6 +544,7 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_gpu": n, "read_len": READ_LEN, "qc_sample": QS,
+                       "filter_kernel": selection,
                        "l2": "inputs (%.1f GB/GPU) exceed the 126 MB L2; no explicit flush" % (col_bytes / 1e9),
                        "parallelism": "read-sharded x%d, NCCL all-reduce of the counter blocks per step" % world if world > 1 else "1 GPU"},
             "clocks": clocks,

@@ -1,0 +1,119 @@
+"""GPU parity of the lane-per-pair filter kernel (aqc_params.filter_kernel = 2), run as a script so that callers
+(tests/test_gpu_zzz_lane_kernel.py, bench.py) can put it in a child process with a timeout: the kernel was written in a
+round without GPU time left and had only been run under the SIMT emulator (tests/emu) when it was committed.
+
+  python tests/lane_gpu_check.py parity          lane engine vs the CPU oracle, bit-exact, on the parity-test batches
+  python tests/lane_gpu_check.py full [pairs]    lane engine vs the warp-per-pair engine on the full-size bench batch
+                                                 (HBM-resident entry); prints one JSON line with both kernel times
+Exit code 0 = identical everywhere.
+"""
+import json
+import os
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+
+def parity():
+    import cases
+    import compare
+    from afterqc_b200 import _abi
+    from afterqc_b200.engine import Engine
+    from oracle import oracle
+    oracle.build()
+    batches = {
+        "adversarial": (cases.adversarial_batch(), list(cases.PARAM_SETS)),
+        "pe150": (cases.synthetic("pe150", 20000), list(cases.PARAM_SETS)),
+        "pe150_err3": (cases.synthetic("pe150_err3", 12000), ["default_f0", "trim", "strict"]),
+        "pe150_jitter": (cases.synthetic("pe150", 8000, len_jitter=60), ["default_f0", "trim", "mask"]),
+        "pe250": (cases.synthetic("pe250", 6000), ["default_f0", "trim", "poly_wide"]),
+        "long": (cases.long_read_batch(), ["default_f0"]),           # > 256 bases: must fall through to pair_kernel
+    }
+    n_cases = 0
+    for bname, (batch, pnames) in batches.items():
+        for pname in pnames:
+            p = cases.make_params(pname)
+            p.filter_kernel = _abi.KERNEL_LANE
+            orc, eng = oracle.Oracle(p), Engine(p)
+            a = orc.filter_pairs(batch)
+            b = eng.filter_pairs(batch)
+            what = "lane %s/%s" % (bname, pname)
+            compare.assert_records_equal(batch, a, b, what)
+            compare.compare_backends(orc, eng, (_abi.QC_R1_POST, _abi.QC_R2_POST), what)
+            # the HBM-resident entry
+            eng.reset()
+            d = eng.upload(batch)
+            eng.filter_pairs(d)
+            compare.assert_records_equal(batch, a, eng.fetch_results(d), what + " resident")
+            compare.assert_counters_equal(orc.counters(), eng.counters(), what + " resident")
+            d.free(); orc.close(); eng.close()
+            n_cases += 1
+    se = cases.synthetic("se100", 30000)
+    for pname in ("default_f0", "trim", "loose"):
+        p = cases.make_params(pname, paired=False)
+        p.filter_kernel = _abi.KERNEL_LANE
+        orc, eng = oracle.Oracle(p), Engine(p)
+        compare.assert_records_equal(se, orc.filter_pairs(se), eng.filter_pairs(se), "lane se100 %s" % pname)
+        compare.compare_backends(orc, eng, (_abi.QC_R1_POST,), "lane se100 %s" % pname)
+        orc.close(); eng.close()
+        n_cases += 1
+    print("lane kernel parity ok: %d cases" % n_cases)
+
+
+def full(pairs):
+    """Both kernels on the bench workload, resident in HBM: records, counters and the postfilter QC slots must match."""
+    import torch
+    from afterqc_b200 import _abi, synth
+    from afterqc_b200.batch import PackedBatch
+    from afterqc_b200.engine import Engine
+    t = synth.generate_device("pe150", pairs, device="cuda")
+    host = PackedBatch(t["seq1"].cpu().numpy(), t["qual1"].cpu().numpy(), t["off1"].cpu().numpy().astype(np.uint32),
+                       t["seq2"].cpu().numpy(), t["qual2"].cpu().numpy(), t["off2"].cpu().numpy().astype(np.uint32))
+    del t
+    torch.cuda.empty_cache()
+    out = {}
+    ref = None
+    for name, k in (("warp", _abi.KERNEL_WARP), ("lane", _abi.KERNEL_LANE)):
+        eng = Engine(_abi.Params.defaults(filter_kernel=k))
+        d = eng.upload(host)
+        eng.filter_pairs(d); eng.sync()                      # warm-up
+        eng.reset()
+        eng.filter_pairs(d); eng.sync()
+        ms = eng.last_kernel_ms()
+        res = eng.fetch_results(d)
+        cnt = eng.counters()
+        qc = [eng.qc(s) for s in (_abi.QC_R1_POST, _abi.QC_R2_POST)]
+        km = [eng.kmers(s) for s in (_abi.QC_R1_POST, _abi.QC_R2_POST)]
+        out[name + "_ms"] = round(ms, 4)
+        if ref is None:
+            ref = (res, cnt, qc, km)
+        else:
+            assert res.tobytes() == ref[0].tobytes(), "records differ between the kernels"
+            assert np.array_equal(cnt, ref[1]), "counters differ between the kernels"
+            for a, b in zip(qc, ref[2]):
+                for f in a.dtype.names:
+                    assert np.array_equal(a[f], b[f]), "QC field %s differs between the kernels" % f
+            for a, b in zip(km, ref[3]):
+                for x, y in zip(a, b):
+                    assert np.array_equal(x, y), "k-mer tables differ between the kernels"
+        d.free(); eng.close()
+    out["pairs"] = pairs
+    out["identical"] = True
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    t0 = time.time()
+    mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
+    if mode == "parity":
+        parity()
+    else:
+        full(int(sys.argv[2]) if len(sys.argv) > 2 else 10_000_000)
+    sys.stderr.write("lane_gpu_check %s: %.1f s\n" % (mode, time.time() - t0))
