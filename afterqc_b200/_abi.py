@@ -21,6 +21,7 @@ ERR_NAMES = {
 
 MEM_HOST, MEM_DEVICE = 0, 1
 KERNEL_DEFAULT, KERNEL_WARP, KERNEL_LANE = 0, 1, 2     # aqc_params.filter_kernel
+BATCH_QUAL2_IN_PLACE = 1 << 16                         # aqc_batch.flags
 
 # pair classes, reference priority order (preprocesser.py:436-614)
 GOOD, BADTRIM1, BADTRIM2, BADLEN, BADPOL, BADLQC, BADNCT, BADDIFF, BADMISMATCH = range(9)

@@ -122,6 +122,20 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 #define AQC_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
+// explicit shared-memory word loads (the compiler falls back to generic LD once a pointer went through integer arithmetic)
+typedef uint32_t smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(const void *p) { return smem_u32(p); }
+__device__ __forceinline__ uint32_t lds_u32(smem_addr_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+// PRMT without __byte_perm's selector sanitising (selector nibbles must be 0..7)
+__device__ __forceinline__ uint32_t prmt_raw(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
 #else
 // host SIMT emulator build (tests/emu, test infrastructure): same contracts, modelled transaction counts
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { simt::mbar_init(bar, count); }
@@ -131,6 +145,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ void fence_proxy_async() {}
 __device__ __forceinline__ void fence_mbar_init() {}
 #define AQC_DYN_SMEM(name) uint8_t *const name = simt::dyn_smem()
+typedef uintptr_t smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(const void *p) { return reinterpret_cast<uintptr_t>(p); }
+__device__ __forceinline__ uint32_t lds_u32(smem_addr_t a) { return *reinterpret_cast<const uint32_t *>(a); }
+__device__ __forceinline__ uint32_t prmt_raw(uint32_t a, uint32_t b, uint32_t sel) {
+    if (sel & 0x8888u) simt::fail("prmt_raw: selector nibble > 7");
+    return __byte_perm(a, b, sel);
+}
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) { }

@@ -224,6 +224,7 @@ struct DevBatch {    // device-visible view of a (chunk of a) batch
     uint32_t n;
     uint64_t first_index;
     int max_len;
+    bool qual2_in_sysmem = false;    // qual2 points into page-locked host memory: plain loads only, no bulk copies from it
 };
 
 struct LaunchExtra {
@@ -249,6 +250,23 @@ size_t pair_tiling(aqc_ctx *ctx, KArgs &A, uint32_t n_tiles_of, int maxl, int ca
         P >>= 1;
     }
     return smem;
+}
+
+bool lane_path(const aqc_ctx *ctx, int mode, int max_len) {
+    const bool want_lane = ctx->p.filter_kernel == 2 || (ctx->p.filter_kernel == 0 && ctx->lane_mode);
+    return mode == MODE_FILTER && want_lane && lane_words_for(std::max(max_len, 8)) != 0;
+}
+
+// device-side address of a page-locked host range, or nullptr when the device cannot address all of it
+const uint8_t *device_view_of_host(const uint8_t *p, size_t first, size_t last) {
+    if (!p || last < first) return nullptr;
+    cudaPointerAttributes a0, a1;
+    if (cudaPointerGetAttributes(&a0, p + first) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaPointerGetAttributes(&a1, p + last) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost || !a0.devicePointer || !a1.devicePointer) return nullptr;
+    const uint8_t *d0 = (const uint8_t *)a0.devicePointer, *d1 = (const uint8_t *)a1.devicePointer;
+    if ((size_t)(d1 - d0) != last - first) return nullptr;          // not one mapping
+    return d0 - first;
 }
 
 int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t stream, bool timed) {
@@ -280,8 +298,7 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         else { int m = (T + mismatch) / (mismatch + 1) - 1; A.poly_m = m < 0 ? 0 : m; }
     }
     const bool pe = b.seq2 != nullptr;
-    const bool want_lane = ctx->p.filter_kernel == 2 || (ctx->p.filter_kernel == 0 && ctx->lane_mode);
-    const int nw = (x.mode == MODE_FILTER && want_lane) ? lane_words_for(maxl) : 0;
+    const int nw = lane_path(ctx, x.mode, maxl) ? lane_words_for(maxl) : 0;
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) {
@@ -419,9 +436,13 @@ int run_host(aqc_ctx *ctx, const aqc_batch *b, const LaunchExtra &x0, void *out_
         CK(cudaMemcpyAsync(s.col[0], b->seq1 + g1, e1 - g1, cudaMemcpyHostToDevice, ctx->copy_in));
         CK(cudaMemcpyAsync(s.col[1], b->qual1 + g1, e1 - g1, cudaMemcpyHostToDevice, ctx->copy_in));
         CK(cudaMemcpyAsync(s.off[0], b->off1 + lo, (size_t)(cn + 1) * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+        // mate-2 qualities may stay in page-locked host memory when the lane-per-pair kernel runs (AQC_BATCH_QUAL2_IN_PLACE)
+        const uint8_t *q2_in_place = nullptr;
+        if (paired && (b->flags & AQC_BATCH_QUAL2_IN_PLACE) && e2 > a2 && lane_path(ctx, x0.mode, maxl))
+            q2_in_place = device_view_of_host(b->qual2, a2, e2 - 1);
         if (paired) {
             CK(cudaMemcpyAsync(s.col[2], b->seq2 + g2, e2 - g2, cudaMemcpyHostToDevice, ctx->copy_in));
-            CK(cudaMemcpyAsync(s.col[3], b->qual2 + g2, e2 - g2, cudaMemcpyHostToDevice, ctx->copy_in));
+            if (!q2_in_place) CK(cudaMemcpyAsync(s.col[3], b->qual2 + g2, e2 - g2, cudaMemcpyHostToDevice, ctx->copy_in));
             CK(cudaMemcpyAsync(s.off[1], b->off2 + lo, (size_t)(cn + 1) * 4, cudaMemcpyHostToDevice, ctx->copy_in));
         }
         CK(cudaEventRecord(s.h2d_done, ctx->copy_in));
@@ -429,9 +450,10 @@ int run_host(aqc_ctx *ctx, const aqc_batch *b, const LaunchExtra &x0, void *out_
         DevBatch d;
         // virtual column bases so that the absolute offsets of the chunk index the staged bytes
         d.seq1 = s.col[0] - g1; d.qual1 = s.col[1] - g1;
-        d.seq2 = paired ? s.col[2] - g2 : nullptr; d.qual2 = paired ? s.col[3] - g2 : nullptr;
+        d.seq2 = paired ? s.col[2] - g2 : nullptr; d.qual2 = paired ? (q2_in_place ? q2_in_place : s.col[3] - g2) : nullptr;
         d.off1 = s.off[0]; d.off2 = paired ? s.off[1] : nullptr;
         d.n = cn; d.first_index = b->first_index + lo; d.max_len = maxl;
+        d.qual2_in_sysmem = q2_in_place != nullptr;
         LaunchExtra x = x0;
         x.out = s.res;
         rc = launch(ctx, d, x, ctx->compute, true);

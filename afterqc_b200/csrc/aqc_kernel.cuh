@@ -182,8 +182,27 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
         }
     };
 
+    // list mode stages its single-pair tiles with plain loads (a rare path; and mate-2 qualities may live in page-locked
+    // host memory there, AQC_BATCH_QUAL2_IN_PLACE, which bulk copies are not used on)
+    auto stage_listed = [&](uint32_t tile, int st) {     // all threads; ends with a CTA barrier
+        StageBuf b = stage_ptr(st);
+        const uint32_t p0 = tile_first(tile), p1 = tile_end(p0);
+        const uint32_t o0 = p0 & ~3u;
+        const uint32_t a1 = A.off1[p0], e1 = A.off1[p1], g1 = a1 & ~15u;
+        uint32_t a2 = 0, e2 = 0, g2 = 0;
+        if (paired) { a2 = A.off2[p0]; e2 = A.off2[p1]; g2 = a2 & ~15u; }
+        for (uint32_t i = a1 - g1 + tid; i < e1 - g1; i += THREADS) { b.col[0][i] = A.seq1[g1 + i]; b.col[1][i] = A.qual1[g1 + i]; }
+        for (uint32_t i = tid; i <= p1 - o0; i += THREADS) b.off1[i] = A.off1[o0 + i];
+        if (paired) {
+            for (uint32_t i = a2 - g2 + tid; i < e2 - g2; i += THREADS) { b.col[2][i] = A.seq2[g2 + i]; b.col[3][i] = A.qual2[g2 + i]; }
+            for (uint32_t i = tid; i <= p1 - o0; i += THREADS) b.off2[i] = A.off2[o0 + i];
+        }
+        if (tid == 0) { tile_base[st][0] = g1; tile_base[st][1] = g2; }
+        __syncthreads();
+    };
+
     // ---- prologue: prefetch the first NSTAGES tiles of this CTA ----
-    if (tid == 0) {
+    if (tid == 0 && !listed) {
         for (int s = 0; s < NSTAGES; s++) {
             uint32_t t = blockIdx.x + (uint32_t)s * gridDim.x;
             if (t < num_tiles) issue_tile(t, s);
@@ -194,7 +213,8 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
     for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
         const int st = it % NSTAGES;
         const uint32_t parity = (it / NSTAGES) & 1u;
-        mbar_wait(&full_bar[st], parity);
+        if (listed) stage_listed(tile, st);
+        else mbar_wait(&full_bar[st], parity);
         StageBuf sb = stage_ptr(st);
         const uint32_t p0 = tile_first(tile);
         const uint32_t p1 = tile_end(p0);
@@ -454,7 +474,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
         if (tid == 0) {
             uint32_t nxt = tile + (uint32_t)NSTAGES * gridDim.x;
             tile_next[st] = 0;
-            if (nxt < num_tiles) issue_tile(nxt, st);
+            if (nxt < num_tiles && !listed) issue_tile(nxt, st);
             qc_reads_since_flush += (p1 - p0);
         }
         __syncthreads();

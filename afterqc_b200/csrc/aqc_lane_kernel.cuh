@@ -79,12 +79,12 @@ __device__ __forceinline__ void shr_bits(uint32_t (&X)[NW], int s) {
 // holds chunk c.
 template <int NW>
 __device__ __forceinline__ void lane_convert(const uint8_t *s, int len, LanePlanes<NW> &P, bool &exotic, int &n_count) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(s);
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const smem_addr_t a = smem_addr(s);
+    const smem_addr_t w = a & ~(smem_addr_t)3;
     const int sh = (int)(a & 3) * 8;
     exotic = false;
     n_count = 0;
-    uint32_t prev = len > 0 ? w[0] : 0u;
+    uint32_t prev = len > 0 ? lds_u32(w) : 0u;
 #ifdef AQC_LANE_UNROLL_CONVERT
 #pragma unroll
 #else
@@ -97,7 +97,7 @@ __device__ __forceinline__ void lane_convert(const uint8_t *s, int len, LanePlan
             uint32_t v[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const uint32_t cur = w[8 * c + j + 1];
+                const uint32_t cur = lds_u32(w + 4 * (8 * c + j + 1));
                 v[j] = __funnelshift_r(prev, cur, sh);
                 prev = cur;
             }
@@ -106,9 +106,10 @@ __device__ __forceinline__ void lane_convert(const uint8_t *s, int len, LanePlan
             for (int j = 0; j < 8; j++) {
                 const uint32_t t = v[j] & 0x06060606u;
                 const uint32_t tt = t >> 1;                                                     // 2-bit codes
-                const uint32_t e = __byte_perm(0x47544341u, 0u, __byte_perm(tt | (tt >> 4), 0u, 0x4420));   // codes -> ASCII
+                // codes -> ASCII: the four codes of the word become the four selector nibbles of a table lookup
+                const uint32_t e = prmt_raw(0x47544341u, 0u, prmt_raw(tt + (tt >> 4), 0u, 0x4420u));
                 bad |= e ^ v[j];
-                const uint32_t z = (tt | (t << 2)) & 0x11111111u;                               // bit0 = code bit 0, bit4 = code bit 1
+                const uint32_t z = ((t << 2) + tt) & 0x11111111u;                               // bit0 = code bit 0, bit4 = code bit 1
                 const uint32_t r = z * 0x01020408u;                     // byte 3 = nibble of plane 0 | nibble of plane 1 << 4
                 constexpr uint32_t sel[4] = {0x3217u, 0x3270u, 0x3710u, 0x7210u};               // byte 3 of r -> byte j of the accumulator
                 if (j < 4) rlo = __byte_perm(rlo, r, sel[j & 3]); else rhi = __byte_perm(rhi, r, sel[j & 3]);
@@ -164,8 +165,8 @@ __device__ __forceinline__ int lane_lowq(const uint8_t *q, int len, int thr) {
         for (int i = 0; i < len; i++) n += (int)q[i] < thr;
         return n;
     }
-    const uintptr_t a = reinterpret_cast<uintptr_t>(q);
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const smem_addr_t a = smem_addr(q);
+    const smem_addr_t w = a & ~(smem_addr_t)3;
     const int lead = (int)(a & 3);
     const int total = lead + len;                              // bytes from the aligned start to the end of the read
     const int nwords = (total + 3) >> 2;
@@ -173,7 +174,7 @@ __device__ __forceinline__ int lane_lowq(const uint8_t *q, int len, int thr) {
     uint32_t acc = 0;
     int n = 0;
     for (int j = 0; j < nwords; j++) {
-        const uint32_t v = w[j];
+        const uint32_t v = lds_u32(w + 4 * j);
         uint32_t low = ~(((v | 0x80808080u) - t4) | v) & 0x80808080u;      // 0x80 per byte < thr
         if (j == 0) low &= ~bytemask_lo(lead);
         if (j == nwords - 1) low &= bytemask_lo(total - 4 * j);

@@ -119,14 +119,18 @@ class Engine:
         b = batch.as_struct()
         self._check(self._L.aqc_stat_reads(self._h, C.byref(b), mem, qc1, qc2, stat_lo, stat_hi, order_base))
 
-    def filter_pairs(self, batch, out=None):
-        """Host batch: returns the result records (copies inside).  DeviceBatch: asynchronous, results stay in HBM."""
+    def filter_pairs(self, batch, out=None, qual2_in_place=False):
+        """Host batch: returns the result records (copies inside).  DeviceBatch: asynchronous, results stay in HBM.
+        qual2_in_place: the host batch's qual2 column is page-locked (aqc_host_alloc / cudaHostAlloc): with the lane-per-pair
+        kernel the engine may read it in place over PCIe instead of copying it (AQC_BATCH_QUAL2_IN_PLACE)."""
         if isinstance(batch, DeviceBatch):
             b = batch.as_struct()
             self._check(self._L.aqc_filter_pairs(self._h, C.byref(b), _abi.MEM_DEVICE, batch.results))
             return None
         res = out if out is not None else np.zeros(batch.n, dtype=_abi.RESULT_DTYPE)
         b = batch.as_struct()
+        if qual2_in_place:
+            b.flags |= _abi.BATCH_QUAL2_IN_PLACE
         self._check(self._L.aqc_filter_pairs(self._h, C.byref(b), _abi.MEM_HOST, res.ctypes.data))
         return res
 

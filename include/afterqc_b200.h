@@ -105,12 +105,21 @@ typedef struct aqc_params {
 typedef struct aqc_batch {
     uint64_t first_index;
     uint32_t n;
-    uint32_t flags;             /* reserved, 0 */
+    uint32_t flags;             /* bits 0-15: optional hint, the longest read of the batch (0 = unknown);
+                                   AQC_BATCH_QUAL2_IN_PLACE: see below; other bits 0 */
     const uint8_t *seq1, *qual1;
     const uint32_t *off1;
     const uint8_t *seq2, *qual2;
     const uint32_t *off2;
 } aqc_batch;
+
+/* aqc_batch.flags, AQC_MEM_HOST batches of aqc_filter_pairs only: qual2 lives in page-locked host memory that the device
+ * can address (aqc_host_alloc / cudaHostAlloc / cudaHostRegister).  The loop reads qualities of mate 2 only in the correction
+ * walk (two bytes per visited mismatch, preprocesser.py:566-567) and in the sampled statRead (:624-627), so with the
+ * lane-per-pair kernel the engine may leave that column where it is and let the kernel fetch those bytes over PCIe instead of
+ * copying a quarter of the batch.  The engine checks the pointer (cudaPointerGetAttributes) and silently copies as usual when
+ * the condition does not hold.  Results are identical either way. */
+#define AQC_BATCH_QUAL2_IN_PLACE (1u << 16)
 
 /* Per-pair outcome, 32 bytes.  start/len are the final coordinates into the ORIGINAL read after
  * front/tail trim and adapter cut (what the good/bad writer must emit).  edits are the byte

@@ -248,6 +248,15 @@ enum { cudaSharedmemCarveoutMaxShared = 100 };
 struct cudaDeviceProp { int multiProcessorCount; char name[64]; };
 struct cudaFuncAttributes { size_t sharedSizeBytes; int numRegs; };
 
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; void *devicePointer; void *hostPointer; };
+// every host pointer is "device accessible" here unless AQC_EMU_PAGEABLE=1 (to exercise the copy fall-back)
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p) {
+    const bool pageable = getenv("AQC_EMU_PAGEABLE") != nullptr;
+    a->type = pageable ? cudaMemoryTypeUnregistered : cudaMemoryTypeHost;
+    a->device = 0; a->devicePointer = pageable ? nullptr : const_cast<void *>(p); a->hostPointer = const_cast<void *>(p);
+    return cudaSuccess;
+}
 static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }

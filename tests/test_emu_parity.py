@@ -117,3 +117,24 @@ def test_emu_lane_short_and_power_of_two_lengths(backends):
         compare.assert_records_equal(batch, a, b, "emu lengths %s" % pname)
         compare.compare_backends(orc, eng, (_abi.QC_R1_POST, _abi.QC_R2_POST), "emu lengths %s" % pname)
         orc.close(); eng.close()
+
+
+def test_emu_lane_qual2_in_place(backends, monkeypatch):
+    """AQC_BATCH_QUAL2_IN_PLACE: mate-2 qualities stay in (page-locked) host memory; identical results, also through the
+    general kernel's list mode (foreign bytes) and when the pointer turns out not to be device-accessible (copy fall-back)."""
+    if backends.kernel != "lane":
+        pytest.skip("only the lane-per-pair path leaves the column in place")
+    for bname in ("adversarial", "pe150_err3"):
+        batch = BATCHES[bname]()
+        for pageable in (False, True):
+            if pageable:
+                monkeypatch.setenv("AQC_EMU_PAGEABLE", "1")
+            else:
+                monkeypatch.delenv("AQC_EMU_PAGEABLE", raising=False)
+            p = cases.make_params("default_f0"); p.qc_sample = 700
+            orc, eng = backends(p)
+            a = orc.filter_pairs(batch)
+            b = eng.filter_pairs(batch, qual2_in_place=True)
+            compare.assert_records_equal(batch, a, b, "emu in-place %s" % bname)
+            compare.compare_backends(orc, eng, (_abi.QC_R1_POST, _abi.QC_R2_POST), "emu in-place %s" % bname)
+            orc.close(); eng.close()
