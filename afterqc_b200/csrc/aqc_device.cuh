@@ -40,7 +40,7 @@ constexpr int MAX_TILE_PAIRS = 32;
 constexpr int QC_CLASSES = 5;              // A, T, C, G, other  (ALL_BASES order, qualitycontrol.py:24)
 constexpr uint32_t QC_FLUSH_READS = 4000;  // packed smem word = count(12 bit) << 20 | byte sum (20 bit)
 
-enum Mode { MODE_FILTER = 0, MODE_STAT = 1, MODE_OPS = 2 };
+enum Mode { MODE_FILTER = 0, MODE_STAT = 1, MODE_OPS = 2, MODE_LIST = 3 };   // MODE_LIST: filter over a list of single pairs
 
 // lut1[b]: low nibble = comparison code of b as an R1 byte, high nibble = code of COMP[b] (rc side)
 //   codes: A0 C1 G2 T3 N4 a8 c9 g10 t11 '\n'12, any other R1 byte 15 (never equal to an rc code)

@@ -137,6 +137,7 @@ void emu_maxlen_kernel(void **a) { maxlen_kernel(*(const uint32_t **)a[0], *(con
 
 const void *kernel_for(int mode, bool paired) {
     if (mode == MODE_FILTER) return paired ? AQC_KERNEL_HANDLE(pair_kernel<MODE_FILTER, true>) : AQC_KERNEL_HANDLE(pair_kernel<MODE_FILTER, false>);
+    if (mode == MODE_LIST) return paired ? AQC_KERNEL_HANDLE(pair_kernel<MODE_LIST, true>) : AQC_KERNEL_HANDLE(pair_kernel<MODE_LIST, false>);
     if (mode == MODE_STAT) return paired ? AQC_KERNEL_HANDLE(pair_kernel<MODE_STAT, true>) : AQC_KERNEL_HANDLE(pair_kernel<MODE_STAT, false>);
     return paired ? AQC_KERNEL_HANDLE(pair_kernel<MODE_OPS, true>) : AQC_KERNEL_HANDLE(pair_kernel<MODE_OPS, false>);
 }
@@ -355,7 +356,8 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         A.list = ctx->d_fb_list; A.list_count = ctx->d_fb_count;
         size_t smem = pair_tiling(ctx, A, b.n, maxl, 1);
         if (smem > ctx->max_dyn_smem) return fail(ctx, AQC_ERR_INVALID, "tile does not fit shared memory");
-        const void *kern = kernel_for(MODE_FILTER, pe);
+        const void *kern = kernel_for(MODE_LIST, pe);
+        A.mode = MODE_LIST;
         int occ = 1;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
         if (occ < 1) occ = 1;
@@ -549,8 +551,9 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
         CK(cudaMemcpy(ctx->d_luts, &L, sizeof L, cudaMemcpyHostToDevice));
         int optin = 0;
         CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-        const void *kernels[6] = {kernel_for(MODE_FILTER, true), kernel_for(MODE_FILTER, false), kernel_for(MODE_STAT, true),
-                                  kernel_for(MODE_STAT, false), kernel_for(MODE_OPS, true), kernel_for(MODE_OPS, false)};
+        const void *kernels[8] = {kernel_for(MODE_FILTER, true), kernel_for(MODE_FILTER, false), kernel_for(MODE_STAT, true),
+                                  kernel_for(MODE_STAT, false), kernel_for(MODE_OPS, true), kernel_for(MODE_OPS, false),
+                                  kernel_for(MODE_LIST, true), kernel_for(MODE_LIST, false)};
         size_t max_static = 0;
         for (const void *k : kernels) {
             cudaFuncAttributes fa;

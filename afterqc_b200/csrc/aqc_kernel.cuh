@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
     __syncthreads();
 
     // list mode: one listed pair per tile, the number of tiles is read from device memory
-    const bool listed = (MODE == MODE_FILTER) && A.list != nullptr;
+    constexpr bool listed = (MODE == MODE_LIST);     // its own instantiation: the regular filter kernel carries none of this
     const uint32_t num_tiles = listed ? *A.list_count : A.num_tiles;
     auto tile_first = [&](uint32_t tile) -> uint32_t { return listed ? A.list[tile] : tile * (uint32_t)P; };
     auto tile_end = [&](uint32_t p0) -> uint32_t { return listed ? p0 + 1u : min(A.n, p0 + (uint32_t)P); };
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
     // ---- epilogue: flush everything this CTA accumulated ----
     __syncthreads();
     flush_qc();
-    if (MODE == MODE_FILTER) {
+    if (MODE == MODE_FILTER || MODE == MODE_LIST) {
         for (int i = tid; i <= A.max_len; i += THREADS) {
             uint32_t v = s_ovh[i]; if (v) atomicAdd(&A.counters[AQC_C_OVERLAP_HIST + i], (unsigned long long)v);
             v = s_dih[i]; if (v) atomicAdd(&A.counters[AQC_C_DISTANCE_HIST + i], (unsigned long long)v);
