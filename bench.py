@@ -385,15 +385,18 @@ def run_ours(args):
             p, cnt = eng.device_ptr(7, slot)
             reduce_views.append(("min", cuda_tensor_view(p, cnt, torch.int64, device)))
 
+    sum_views = [v for op, v in reduce_views if op == "sum"]
+    min_views = [v for op, v in reduce_views if op == "min"]
+
     def step_resident():
         if has_window:
             b = wb.struct(s_lo_al, s_hi)
             eng._check(L.aqc_stat_reads(eng._h, C.byref(b), _abi.MEM_DEVICE, _abi.QC_R1_PRE, _abi.QC_R2_PRE, w_lo_g, w_hi_g, 0))
         b = wb.struct()
         eng._check(L.aqc_filter_pairs(eng._h, C.byref(b), _abi.MEM_DEVICE, wb.results.data_ptr()))
-        if world > 1:   # the path's only exchange: reduce (copies of) the counter blocks over NVLink
-            for op, v in reduce_views:
-                c = v.clone()
+        if world > 1:   # the path's only exchange: reduce (copies of) the counter blocks over NVLink -- one SUM, one MIN
+            for op, views in (("sum", sum_views), ("min", min_views)):
+                c = torch.cat(views)
                 dist.all_reduce(c, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MIN)
 
     def barrier():
