@@ -169,20 +169,17 @@ __device__ __forceinline__ int lane_lowq(const uint8_t *q, int len, int thr) {
     const smem_addr_t w = a & ~(smem_addr_t)3;
     const int lead = (int)(a & 3);
     const int total = lead + len;                              // bytes from the aligned start to the end of the read
-    const int nwords = (total + 3) >> 2;
+    const int last = (total - 1) >> 2;                         // index of the last word (<= 64: per-byte sums stay below 256)
     const uint32_t t4 = (uint32_t)thr * 0x01010101u;
-    uint32_t acc = 0;
-    int n = 0;
-    for (int j = 0; j < nwords; j++) {
-        const uint32_t v = lds_u32(w + 4 * j);
-        uint32_t low = ~(((v | 0x80808080u) - t4) | v) & 0x80808080u;      // 0x80 per byte < thr
-        if (j == 0) low &= ~bytemask_lo(lead);
-        if (j == nwords - 1) low &= bytemask_lo(total - 4 * j);
-        acc += low >> 7;
-        if ((j & 63) == 63) { n += (int)((acc * 0x01010101u) >> 24); acc = 0; }
-    }
-    n += (int)((acc * 0x01010101u) >> 24);
-    return n;
+    // 0x80 in every byte < thr:  byte >= thr  <=>  high bit of ((byte | 0x80) - thr) | byte   (thr < 128)
+    auto low_of = [&](uint32_t v) -> uint32_t { return ~(((v | 0x80808080u) - t4) | v) & 0x80808080u; };
+    uint32_t first = low_of(lds_u32(w)) & ~bytemask_lo(lead);
+    if (last == 0) first &= bytemask_lo(total);
+    uint32_t acc = first >> 7;
+    for (int j = 1; j < last; j++) acc += low_of(lds_u32(w + 4 * j)) >> 7;
+    if (last > 0) acc += (low_of(lds_u32(w + 4 * last)) & bytemask_lo(total - 4 * last)) >> 7;
+    const uint32_t h = (acc & 0x00FF00FFu) + ((acc >> 8) & 0x00FF00FFu);     // the four byte sums can add up to more than 255
+    return (int)((h + (h >> 16)) & 0xFFFFu);
 }
 
 // Run-length screen of hasPolyX (see polyx_screen_fast): true = the read needs the exact test.

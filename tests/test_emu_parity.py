@@ -110,6 +110,8 @@ def test_emu_lane_short_and_power_of_two_lengths(backends):
             b = (cases.revcomp(f) + cases._rand_seq(rng, L))[:rng.choice([L, L, max(5, L - 7)])]
             b = cases._mutate(rng, b, rng.choice([0, 0, 1, 2, 3, 5]), "ACGTN")
             r1s.append((a, cases._rand_qual(rng, len(a)))); r2s.append((b, cases._rand_qual(rng, len(b))))
+    for L in (255, 256):                                    # every quality low: the count does not fit in a byte
+        r1s.append((cases._rand_seq(rng, L), "#" * L)); r2s.append((cases._rand_seq(rng, L), "#" * L))
     batch = PackedBatch.from_reads(r1s, r2s)
     for pname in ("default_f0", "trim", "loose"):
         orc, eng = backends(cases.make_params(pname))
