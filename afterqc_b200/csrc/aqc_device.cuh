@@ -642,7 +642,10 @@ __device__ __forceinline__ void first_min(unsigned long long *addr, unsigned lon
 __device__ AQC_RARE void stat_read(const uint8_t *s, const uint8_t *qv, int len, int mate, uint64_t order,
                                           const QcSmem &sm, const QcDev &qd, const uint8_t *lut1, const uint8_t *lut2, const uint8_t *lut3,
                                           int K, int lane, int *error_flag) {
-    if (len <= 0) return;
+    if (len <= 0) {     // an empty read runs no loop of statRead but is still counted: gcHistogram[0] += 1 (qualitycontrol.py:112)
+        if (lane == 0) { atomicAdd(&qd.gchist[0], 1ULL); atomicAdd(&qd.scal[1], 1ULL); }
+        return;
+    }
     if (len < 5) { if (lane == 0) atomicExch(error_flag, AQC_ERR_TOO_SHORT_STAT); return; }
     uint32_t *acc = sm.acc + (size_t)mate * QC_CLASSES * sm.max_len;
     uint32_t *dsc = sm.disc + (size_t)mate * sm.max_len;

@@ -140,3 +140,26 @@ def test_emu_lane_qual2_in_place(backends, monkeypatch):
             compare.assert_records_equal(batch, a, b, "emu in-place %s" % bname)
             compare.compare_backends(orc, eng, (_abi.QC_R1_POST, _abi.QC_R2_POST), "emu in-place %s" % bname)
             orc.close(); eng.close()
+
+
+def _empty_mate_batch():
+    import random
+    from afterqc_b200.batch import PackedBatch
+    rng = random.Random(5)
+    r1s, r2s = [], []
+    for i in range(40):
+        a = cases._rand_seq(rng, 100)
+        b = "" if i % 3 == 0 else cases._rand_seq(rng, 100)
+        r1s.append((a, "I" * len(a))); r2s.append((b, "I" * len(b)))
+    return PackedBatch.from_reads(r1s, r2s)
+
+
+def test_emu_empty_mate_reaches_statread(backends):
+    """an empty mate 2 in a good pair (R2 is never length-checked, quirk Q3) still counts in statRead: gcHistogram[0] += 1"""
+    batch = _empty_mate_batch()
+    orc, eng = backends(cases.make_params("default_f0"))
+    a = orc.filter_pairs(batch); b = eng.filter_pairs(batch)
+    compare.assert_records_equal(batch, a, b, "emu empty mate")
+    compare.compare_backends(orc, eng, (_abi.QC_R1_POST, _abi.QC_R2_POST), "emu empty mate")
+    assert int(orc.qc(_abi.QC_R2_POST)["gcHistogram"][0]) >= 13
+    orc.close(); eng.close()

@@ -104,6 +104,27 @@ def test_batch_split_invariance(backends):
     orc.close(); eng.close()
 
 
+def test_empty_mate_reaches_statread(backends):
+    """an empty mate 2 in a good pair (R2 is never length-checked, quirk Q3) still counts in statRead: gcHistogram[0] += 1"""
+    import random
+    from afterqc_b200.batch import PackedBatch
+    rng = random.Random(5)
+    r1s, r2s = [], []
+    for i in range(40):
+        a = cases._rand_seq(rng, 100)
+        b = "" if i % 3 == 0 else cases._rand_seq(rng, 100)
+        r1s.append((a, "I" * len(a))); r2s.append((b, "I" * len(b)))
+    batch = PackedBatch.from_reads(r1s, r2s)
+    orc, eng = backends(cases.make_params("default_f0"))
+    a = orc.filter_pairs(batch); b = eng.filter_pairs(batch)
+    compare.assert_records_equal(batch, a, b, "empty mate")
+    compare.compare_backends(orc, eng, (_abi.QC_R1_POST, _abi.QC_R2_POST), "empty mate")
+    for be in (orc, eng):
+        be.stat_reads(batch, _abi.QC_R1_PRE, _abi.QC_R2_PRE)
+    compare.compare_backends(orc, eng, (_abi.QC_R1_PRE, _abi.QC_R2_PRE), "empty mate, prefilter")
+    orc.close(); eng.close()
+
+
 def test_operator_interface(backends):
     """util.overlap / hasPolyX / lowQualityNum / nNumber through the GPU; KATs from the reference."""
     from afterqc_b200.engine import Engine
