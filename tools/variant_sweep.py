@@ -47,6 +47,9 @@ def run(argv):
     ap.add_argument("--pairs", type=int, default=10000000)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--parity", action="store_true")
+    ap.add_argument("--filter-kernel", default="warp", choices=["warp", "lane"],
+                    help="lane: benchmark lane_kernel (variants: -DAQC_LANE_TWO_PLANE_FILTER, -DAQC_LANE_UNROLL_CONVERT; env AQC_LANE_WARPS); "
+                         "--parity then runs tests/lane_gpu_check.py parity instead of the pair_kernel tests")
     a = ap.parse_args(argv)
     with open(os.path.join(VDIR, "variants.json")) as f:
         meta = json.load(f)
@@ -56,14 +59,18 @@ def run(argv):
         env = dict(os.environ, AQC_LIB_PATH=os.path.join(VDIR, name + ".so"))
         row = {"variant": name, **meta[name]}
         if a.parity:
-            p = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-x", "-q", "-k", "filter_parity or stat_parity or single_end"],
-                               cwd=ROOT, env=env, capture_output=True, text=True)
+            if a.filter_kernel == "lane":
+                p = subprocess.run([sys.executable, "tests/lane_gpu_check.py", "parity"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+            else:
+                p = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-x", "-q", "-k", "filter_parity or stat_parity or single_end"],
+                                   cwd=ROOT, env=env, capture_output=True, text=True)
             row["parity"] = "pass" if p.returncode == 0 else "FAIL"
             if p.returncode:
                 row["parity_tail"] = p.stdout[-400:]
                 rows.append(row)
                 continue
-        p = subprocess.run([sys.executable, "bench.py", "--pairs", str(a.pairs), "--steps", str(a.steps), "--warmup", "3", "--no-e2e", "--no-cpu"],
+        p = subprocess.run([sys.executable, "bench.py", "--pairs", str(a.pairs), "--steps", str(a.steps), "--warmup", "3", "--no-e2e", "--no-cpu",
+                            "--filter-kernel", a.filter_kernel],
                            cwd=ROOT, env=env, capture_output=True, text=True)
         try:
             j = json.loads(p.stdout.strip().splitlines()[-1])
