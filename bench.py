@@ -346,6 +346,9 @@ def run_ours(args):
         child = lane_child_check(local_rank, min(n, 2_000_000))
         selection["child_check"] = child
         use_lane = bool(child.get("ok"))
+        if use_lane and not (child.get("lane_ms", 0) < child.get("warp_ms", 0)):      # identical but not faster here: keep pair_kernel
+            use_lane = False
+            selection["note"] = "lane kernel identical but not faster in the child check"
     wb = make_device_workload(device, n, seed=20260927 + rank, first_index=first_index)
     if use_lane and args.filter_kernel == "auto":
         try:
