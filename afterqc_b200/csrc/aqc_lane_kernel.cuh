@@ -238,7 +238,12 @@ __device__ __forceinline__ bool lane_scan_dir(uint32_t (&S0)[NW], uint32_t (&S1)
 #else
                     // one code bit is enough for a necessary condition: equal bases have equal bits, and 32 random positions
                     // differ in fewer than 3 of them with probability 1.2e-7
+#ifdef AQC_LANE_IMAD_SHIFT
+                    // tuning variant: the window as two multiplies (FMA pipe) instead of one funnel shift (ALU pipe, the busy one)
+                    const uint32_t x = (b == 0 ? S0[0] : __umulhi(S0[0], 1u << ((32 - b) & 31)) + S0[1] * (1u << ((32 - b) & 31))) ^ f0;
+#else
                     const uint32_t x = __funnelshift_r(S0[0], S0[1], b) ^ f0;
+#endif
 #endif
                     if (__popc(x) < 3) cm |= 1u << b;
                 }

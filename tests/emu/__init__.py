@@ -13,7 +13,10 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "afterqc_b200", "csrc")
-OUT = os.path.join(HERE, "_build", "libafterqc_b200_emu.so")
+# AQC_EMU_DEFINES="-DAQC_LANE_IMAD_SHIFT,..." builds (and loads) a tuning variant of the kernels under the emulator
+_DEFINES = [d for d in os.environ.get("AQC_EMU_DEFINES", "").split(",") if d]
+_TAG = ("_" + "".join(c if c.isalnum() else "_" for c in "".join(_DEFINES))) if _DEFINES else ""
+OUT = os.path.join(HERE, "_build", "libafterqc_b200_emu%s.so" % _TAG)
 SOURCES = ["aqc_engine.cu", "aqc_fastq.cpp", "aqc_stream.cpp", "aqc_inflate.cpp", "aqc_pinflate.cpp"]
 
 _lib = None
@@ -29,7 +32,7 @@ def build(force=False):
     if not force and os.path.exists(OUT) and all(os.path.getmtime(p) <= os.path.getmtime(OUT) for p in _deps()):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = ["g++", "-O2", "-g", "-std=c++17", "-DAQC_EMU", "-I" + HERE, "-fPIC", "-shared", "-x", "c++"]
+    cmd = ["g++", "-O2", "-g", "-std=c++17", "-DAQC_EMU"] + _DEFINES + ["-I" + HERE, "-fPIC", "-shared", "-x", "c++"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(HERE, "simt_emu.cpp"), "-o", OUT, "-lz", "-lpthread"]
     subprocess.check_call(cmd)
     return OUT

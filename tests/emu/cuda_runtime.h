@@ -91,6 +91,7 @@ static inline uint32_t __funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t sh) {
     const uint64_t v = ((uint64_t)hi << 32) | lo;
     return (uint32_t)(v >> (sh > 32u ? 32u : sh));
 }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 template <class T> static inline T __ldcg(const T *p) { return *p; }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 
