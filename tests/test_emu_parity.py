@@ -163,3 +163,20 @@ def test_emu_empty_mate_reaches_statread(backends):
     compare.compare_backends(orc, eng, (_abi.QC_R1_POST, _abi.QC_R2_POST), "emu empty mate")
     assert int(orc.qc(_abi.QC_R2_POST)["gcHistogram"][0]) >= 13
     orc.close(); eng.close()
+
+
+@pytest.mark.parametrize("kernel", ["warp", "lane"])
+@pytest.mark.parametrize("name", ["pe150_default", "pe150_err3_mask_overlap", "pe250_k5_strict", "se100_f0"])
+def test_emu_pipeline_matches_reference_golden(name, kernel, tmp_path):
+    """the whole drop-in pipeline (readers, packed columns, engine calls, writers, JSON) on the emulated engine reproduces
+    the reference's golden outputs -- the same check tests/test_gpu_golden.py makes on the GPU"""
+    import emu
+    import golden_util
+    if name not in golden_util.CASES:
+        pytest.skip("golden case %s not present" % name)
+
+    def factory(p):
+        p.filter_kernel = _abi.KERNEL_LANE if kernel == "lane" else _abi.KERNEL_WARP
+        return emu.EmuEngine(p)
+    problems = golden_util.run_case(name, tmp_path, factory)
+    assert not problems, problems

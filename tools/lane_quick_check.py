@@ -48,7 +48,41 @@ def make(n, L=150, seed=1):
     return PackedBatch(col(b1), col(q1), off, col(b2), col(q2), off.copy())
 
 
+def tiled(host, k):
+    """the batch repeated k times (fast way to a multi-million-pair workload)"""
+    n, L = host.n, 150
+    def rep(c):
+        return np.concatenate([np.tile(c[:n * L], k), np.zeros(SLACK, dtype=np.uint8)])
+    off = (np.arange(n * k + 1, dtype=np.int64) * L).astype(np.uint32)
+    return PackedBatch(rep(host.seq1), rep(host.qual1), off, rep(host.seq2), rep(host.qual2), off.copy())
+
+
+def timing(n, k):
+    """kernel times only: pair_kernel and lane_kernel with the bench's 2 % statistics mix, lane_kernel without statistics"""
+    host = tiled(make(n), k)
+    out = {"pairs": host.n, "t_generate_s": round(time.time() - t_start, 2)}
+    sums = {}
+    for name, kern, qs in (("warp", _abi.KERNEL_WARP, host.n // 50), ("lane", _abi.KERNEL_LANE, host.n // 50), ("lane_nostat", _abi.KERNEL_LANE, 1)):
+        eng = Engine(_abi.Params.defaults(filter_kernel=kern, qc_sample=max(1, qs)))
+        d = eng.upload(host)
+        eng.filter_pairs(d); eng.sync()
+        ms = []
+        for _ in range(3):
+            eng.filter_pairs(d); eng.sync()
+            ms.append(round(eng.last_kernel_ms(), 4))
+        out[name + "_ms"] = ms
+        out[name + "_Mpairs_s"] = round(host.n / (max(min(ms), 1e-6) * 1e-3) / 1e6, 1)
+        r = eng.fetch_results(d)
+        sums[name] = int(r.view(np.uint32).sum(dtype=np.uint64))
+        d.free(); eng.close()
+    out["records_checksum_equal"] = sums["warp"] == sums["lane"] == sums["lane_nostat"]
+    out["t_total_s"] = round(time.time() - t_start, 2)
+    print(json.dumps(out))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "timing":
+        return timing(int(sys.argv[2]), int(sys.argv[3]))
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
     host = make(n)
     out = {"pairs": n, "t_generate_s": round(time.time() - t_start, 2)}
