@@ -1,0 +1,31 @@
+#!/bin/bash
+# First GPU call of round 2 (one B200): everything round 1 could not measure for lane_kernel, in one go.
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+# Outputs under gpurun_out/: lane_parity.log (oracle matrix on hardware), bench.json (auto-selected kernel), bench_warp.json,
+# launches.csv (ncu launch list of one bench step), lane_full.ncu-rep (+ lane_full_raw.csv), sweep (lane tuning variants).
+set -u
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+
+echo "== lane kernel: full oracle matrix ==" | tee gpurun_out/lane_parity.log
+timeout 900 python tests/lane_gpu_check.py parity >> gpurun_out/lane_parity.log 2>&1; echo "exit $?" | tee -a gpurun_out/lane_parity.log
+
+echo "== gpu test suite =="
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "exit $?" | tee -a gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log
+
+echo "== bench: auto selection, then the warp kernel for reference =="
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 600 gpurun_out/bench.json
+timeout 600 python bench.py --filter-kernel warp --no-cpu > gpurun_out/bench_warp.json 2> gpurun_out/bench_warp.err
+
+echo "== ncu: launch list of one short bench run, then a full capture of lane_kernel =="
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --filter-kernel lane --pairs 2000000 --qc-sample 40000 --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/launches_bench.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:lane_kernel -s 3 -c 1 -o gpurun_out/lane_full \
+    python bench.py --filter-kernel lane --pairs 2000000 --qc-sample 40000 --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/lane_full_bench.log 2>&1
+ncu -i gpurun_out/lane_full.ncu-rep --page raw --csv > gpurun_out/lane_full_raw.csv 2>/dev/null
+
+echo "== lane tuning variants (built here with nvcc, benchmarked with parity) =="
+python tools/variant_sweep.py build lane_base= lane_imad=-DAQC_LANE_IMAD_SHIFT lane_2plane=-DAQC_LANE_TWO_PLANE_FILTER lane_unrollconv=-DAQC_LANE_UNROLL_CONVERT > gpurun_out/sweep_build.log 2>&1
+timeout 1200 python tools/variant_sweep.py run --filter-kernel lane --steps 10 > gpurun_out/sweep_run.log 2>&1
+for w in 1 2 3; do AQC_LANE_WARPS=$w timeout 200 python bench.py --filter-kernel lane --no-e2e --no-cpu --steps 10 > gpurun_out/bench_lane_warps$w.json 2>/dev/null; done
+echo done
