@@ -268,8 +268,11 @@ static inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { 
 static inline cudaError_t cudaFuncGetAttributes(cudaFuncAttributes *a, const void *) { a->sharedSizeBytes = 1024; a->numRegs = 64; return cudaSuccess; }
 static inline cudaError_t cudaFuncSetAttribute(const void *, cudaFuncAttribute, int) { return cudaSuccess; }
 static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, const void *, int, size_t) { *n = simt_env_int("AQC_EMU_OCC", 2); return cudaSuccess; }
-template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)aligned_alloc(256, (n + 255) & ~(size_t)255); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+// device allocations end (16-byte granular) right at an inaccessible guard page: a kernel or bulk copy that reads or writes
+// 16 bytes or more past the end of a buffer faults under the emulator (the GPU would read garbage or raise an illegal address)
+namespace simt { void *guarded_alloc(size_t n); void guarded_free(void *p); }
+template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)simt::guarded_alloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+static inline cudaError_t cudaFree(void *p) { simt::guarded_free(p); return cudaSuccess; }
 static inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { *p = aligned_alloc(256, (n + 255) & ~(size_t)255); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }

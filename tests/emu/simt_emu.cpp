@@ -5,6 +5,8 @@
 // not complete yet; the scheduler then resumes the next fiber whose wait condition has changed.  A pass over
 // all fibers without progress is a deadlock (on the GPU: a hang) and aborts with a diagnosis.
 #include <sys/mman.h>
+#include <unistd.h>
+#include <map>
 #include <vector>
 #include "cuda_runtime.h"
 
@@ -118,6 +120,32 @@ void fail(const char *msg) {
     abort();
 }
 
+namespace {
+std::map<void *, std::pair<void *, size_t>> g_allocs;     // user pointer -> (mapping base, mapping length)
+}
+
+void *guarded_alloc(size_t n) {
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    const size_t body = ((n ? n : 1) + 15) & ~(size_t)15;
+    const size_t len = ((body + page - 1) / page) * page + page;
+    void *m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (m == MAP_FAILED) return nullptr;
+    char *guard = (char *)m + len - page;
+    mprotect(guard, page, PROT_NONE);
+    void *p = guard - body;
+    memset(p, 0xA5, body);                                   // device memory is not zero-initialised
+    g_allocs[p] = {m, len};
+    return p;
+}
+
+void guarded_free(void *p) {
+    if (!p) return;
+    auto it = g_allocs.find(p);
+    if (it == g_allocs.end()) fail("cudaFree of a pointer cudaMalloc did not return");
+    munmap(it->second.first, it->second.second);
+    g_allocs.erase(it);
+}
+
 int lane_id() { return cur->tid & 31; }
 uint8_t *dyn_smem() { return g_smem; }
 
@@ -150,10 +178,18 @@ void wait_word_change(volatile uint32_t *w, uint32_t seen) { block_on(w, seen, "
 void launch(uint32_t grid, uint32_t block, size_t smem_bytes, Entry fn, void **args) {
     if (block == 0 || block > MAX_THREADS || (block & 31u)) fail("block size must be a multiple of 32 and <= 1024");
     if (smem_bytes > 232448) fail("dynamic shared memory beyond the 227 KB opt-in limit");
-    if (smem_bytes + 128 > g_smem_cap) {
-        free(g_smem);
-        g_smem_cap = smem_bytes + 128;
-        g_smem = (uint8_t *)aligned_alloc(1024, (g_smem_cap + 1023) & ~(size_t)1023);
+    {   // dynamic shared memory ends (128-byte granular) at a guard page: reads past the launch's allocation fault
+        static void *map_base = nullptr; static size_t map_len = 0;
+        const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+        const size_t body = (smem_bytes + 127) & ~(size_t)127;
+        if (map_base) munmap(map_base, map_len);
+        map_len = ((body + page - 1) / page) * page + 2 * page;
+        map_base = mmap(nullptr, map_len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (map_base == MAP_FAILED) fail("mmap of shared memory failed");
+        char *guard = (char *)map_base + map_len - page;
+        mprotect(guard, page, PROT_NONE);
+        g_smem = (uint8_t *)(guard - body);
+        g_smem_cap = body;
     }
     g_entry = fn; g_args = args;
     n_threads = (int)block;

@@ -180,3 +180,39 @@ def test_emu_pipeline_matches_reference_golden(name, kernel, tmp_path):
         return emu.EmuEngine(p)
     problems = golden_util.run_case(name, tmp_path, factory)
     assert not problems, problems
+
+
+def test_emu_resident_columns_need_only_16_bytes_of_slack(backends):
+    """the emulator's device buffers end at guard pages: with resident columns that carry exactly the 16 bytes of slack the
+    ABI asks for, neither the bulk copies nor the kernels' word loads may touch memory 16 bytes or more past a buffer"""
+    import ctypes as C
+
+    def upload_exact(eng, host):
+        from afterqc_b200.engine import DeviceBatch
+        d = DeviceBatch.__new__(DeviceBatch)
+        d.engine = eng; d.n = host.n; d.first_index = host.first_index; d.paired = host.paired
+        d.max_len = host.max_len(); d._ptrs = []
+
+        def up(arr):
+            p = C.c_void_p()
+            eng._check(eng._L.aqc_device_alloc(eng._h, arr.nbytes, C.byref(p)))
+            eng._check(eng._L.aqc_memcpy_h2d(eng._h, p, arr.ctypes.data, arr.nbytes))
+            d._ptrs.append(p)
+            return p
+        d.seq1, d.qual1, d.off1 = up(host.seq1), up(host.qual1), up(host.off1)
+        if host.paired:
+            d.seq2, d.qual2, d.off2 = up(host.seq2), up(host.qual2), up(host.off2)
+        else:
+            d.seq2 = d.qual2 = d.off2 = None
+        d.results = C.c_void_p()
+        eng._check(eng._L.aqc_device_alloc(eng._h, max(1, d.n) * 32, C.byref(d.results)))
+        d._ptrs.append(d.results)
+        return d
+
+    for batch in (cases.synthetic("pe150", 1000), cases.synthetic("pe150", 777, len_jitter=60), cases.adversarial_batch(), cases.synthetic("se100", 999)):
+        orc, eng = backends(cases.make_params("default_f0", paired=batch.paired))
+        a = orc.filter_pairs(batch)
+        d = upload_exact(eng, batch)
+        eng.filter_pairs(d)
+        compare.assert_records_equal(batch, a, eng.fetch_results(d), "emu exact slack")
+        d.free(); orc.close(); eng.close()
