@@ -579,6 +579,10 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
         }
         CK(cudaMalloc(&ctx->d_fb_count, sizeof(uint32_t)));
         if (const char *lm = getenv("AQC_LANE_KERNEL")) ctx->lane_mode = atoi(lm) != 0;
+        if (const char *cp = getenv("AQC_CHUNK_PAIRS")) {          // host-path chunk size (tests exercise the multi-chunk pipeline with small batches)
+            long v = atol(cp);
+            if (v >= 4) ctx->chunk_pairs = (uint32_t)std::min<long>(v & ~3L, 1L << 24);
+        }
         for (int s = 0; s < AQC_NUM_QC; s++) { int r = alloc_qc(ctx, ctx->qc[s]); if (r) return r; }
         return aqc_reset(ctx);
     };

@@ -216,3 +216,22 @@ def test_emu_resident_columns_need_only_16_bytes_of_slack(backends):
         eng.filter_pairs(d)
         compare.assert_records_equal(batch, a, eng.fetch_results(d), "emu exact slack")
         d.free(); orc.close(); eng.close()
+
+
+def test_emu_host_path_many_chunks(backends, monkeypatch):
+    """the chunked H2D -> kernels -> D2H pipeline of the host-buffer entry (double-buffered staging, per-chunk first_index,
+    16-byte aligned chunk origins) with chunks of a few hundred pairs, also with mate-2 qualities left in place"""
+    monkeypatch.setenv("AQC_CHUNK_PAIRS", "372")
+    batch = cases.synthetic("pe150", 2600, len_jitter=37)
+    p = cases.make_params("trim"); p.qc_sample = 1500
+    for in_place in (False, True):
+        orc, eng = backends(p)
+        a = orc.filter_pairs(batch)
+        b = eng.filter_pairs(batch, qual2_in_place=in_place)
+        compare.assert_records_equal(batch, a, b, "emu chunks")
+        compare.compare_backends(orc, eng, (_abi.QC_R1_POST, _abi.QC_R2_POST), "emu chunks")
+        lo, hi = 100, 2100
+        for be in (orc, eng):
+            be.stat_reads(batch, _abi.QC_R1_PRE, _abi.QC_R2_PRE, stat_lo=lo, stat_hi=hi, order_base=0)
+        compare.compare_backends(orc, eng, (_abi.QC_R1_PRE, _abi.QC_R2_PRE), "emu chunks stat")
+        orc.close(); eng.close()
