@@ -20,7 +20,7 @@ ERR_NAMES = {
 }
 
 MEM_HOST, MEM_DEVICE = 0, 1
-KERNEL_DEFAULT, KERNEL_WARP, KERNEL_LANE = 0, 1, 2     # aqc_params.filter_kernel
+KERNEL_DEFAULT, KERNEL_WARP, KERNEL_LANE, KERNEL_LANE2 = 0, 1, 2, 3     # aqc_params.filter_kernel
 BATCH_QUAL2_IN_PLACE = 1 << 16                         # aqc_batch.flags
 
 # pair classes, reference priority order (preprocesser.py:436-614)

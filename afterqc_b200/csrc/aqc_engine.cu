@@ -10,6 +10,7 @@
 #include <algorithm>
 #include "aqc_kernel.cuh"
 #include "aqc_lane_kernel.cuh"
+#include "aqc_lane2_kernel.cuh"
 
 using namespace aqc;
 
@@ -112,7 +113,7 @@ unsigned long long host_side_hash(unsigned long long k) {   // must match aqc::s
 
 int check_params(const aqc_params *p, char *err, size_t errn) {
     if (p->qc_kmer < 1 || p->qc_kmer > AQC_MAX_KMER) { snprintf(err, errn, "qc_kmer %d outside 1..%d", p->qc_kmer, AQC_MAX_KMER); return AQC_ERR_INVALID; }
-    if (p->filter_kernel < 0 || p->filter_kernel > 2) { snprintf(err, errn, "filter_kernel %d outside 0..2", p->filter_kernel); return AQC_ERR_INVALID; }
+    if (p->filter_kernel < 0 || p->filter_kernel > 3) { snprintf(err, errn, "filter_kernel %d outside 0..3", p->filter_kernel); return AQC_ERR_INVALID; }
     if (p->trim_front < 0 || p->trim_tail < 0 || p->trim_front2 < 0 || p->trim_tail2 < 0) { snprintf(err, errn, "negative trim value (resolve auto-trim on the host first)"); return AQC_ERR_INVALID; }
     return 0;
 }
@@ -156,11 +157,21 @@ const void *lane_kernel_for(bool paired, int nw) {
 }
 #ifdef AQC_EMU
 #undef lane_kernel
+template <bool PAIRED, int NW> void emu_lane2_kernel(void **a) { lane2_kernel<PAIRED, NW>(*(const LArgs *)a[0]); }
+#define lane2_kernel emu_lane2_kernel
+#endif
+const void *lane2_kernel_for(bool paired, int nw) {
+    if (nw == 4) return paired ? AQC_KERNEL_HANDLE(lane2_kernel<true, 4>) : AQC_KERNEL_HANDLE(lane2_kernel<false, 4>);
+    if (nw == 5) return paired ? AQC_KERNEL_HANDLE(lane2_kernel<true, 5>) : AQC_KERNEL_HANDLE(lane2_kernel<false, 5>);
+    return paired ? AQC_KERNEL_HANDLE(lane2_kernel<true, 8>) : AQC_KERNEL_HANDLE(lane2_kernel<false, 8>);
+}
+#ifdef AQC_EMU
+#undef lane2_kernel
 #endif
 
-size_t lane_smem_bytes(int nwarps, bool paired, int nw, int col_cap, int max_len) {
+size_t lane_smem_bytes(int nwarps, int ncols, int nw, int col_cap, int max_len) {
     size_t acc = (size_t)(2 * QC_CLASSES * max_len + 2 * max_len + 2 * (max_len + 1) + 16) * 4;
-    return (size_t)nwarps * ((paired ? 3 : 2) * (size_t)col_cap + 4 * 32 * (size_t)nw) + 768 + acc + 64;
+    return (size_t)nwarps * (ncols * (size_t)col_cap + 4 * 32 * (size_t)nw) + 768 + acc + 64;
 }
 
 int alloc_qc(aqc_ctx *ctx, QcHost &q) {
@@ -254,7 +265,7 @@ size_t pair_tiling(aqc_ctx *ctx, KArgs &A, uint32_t n_tiles_of, int maxl, int ca
 }
 
 bool lane_path(const aqc_ctx *ctx, int mode, int max_len) {
-    const bool want_lane = ctx->p.filter_kernel == 2 || (ctx->p.filter_kernel == 0 && ctx->lane_mode);
+    const bool want_lane = ctx->p.filter_kernel == 2 || ctx->p.filter_kernel == 3 || (ctx->p.filter_kernel == 0 && ctx->lane_mode);
     return mode == MODE_FILTER && want_lane && lane_words_for(std::max(max_len, 8)) != 0;
 }
 
@@ -320,7 +331,7 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
             CK(cudaMalloc(&ctx->d_fb_list, cap * sizeof(uint32_t)));
             ctx->fb_cap = cap;
         }
-        CK(cudaMemsetAsync(ctx->d_fb_count, 0, sizeof(uint32_t), stream));
+        CK(cudaMemsetAsync(ctx->d_fb_count, 0, 2 * sizeof(uint32_t), stream));      // [0] hand-over count, [1] tile counter
         LArgs L;
         memset(&L, 0, sizeof L);
         L.k = A;
@@ -328,10 +339,13 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         L.k.num_tiles = (b.n + 31) / 32;
         L.fb_list = ctx->d_fb_list; L.fb_count = ctx->d_fb_count;
         L.lane_col_cap = (32 * maxl + 96 + 15) & ~15;
-        const void *lk = lane_kernel_for(pe, nw);
+        L.tile_counter = ctx->d_fb_count + 1;
+        const bool gen2 = ctx->p.filter_kernel == 3;
+        const int ncols = (pe && !gen2) ? 3 : 2;
+        const void *lk = gen2 ? lane2_kernel_for(pe, nw) : lane_kernel_for(pe, nw);
         int best_w = 0, best_occ = 0;
         for (int w = LANE_MAX_WARPS; w >= 1; w--) {           // most resident warps per SM; ties go to the larger CTA
-            size_t sm = lane_smem_bytes(w, pe, nw, L.lane_col_cap, maxl);
+            size_t sm = lane_smem_bytes(w, ncols, nw, L.lane_col_cap, maxl);
             if (sm > ctx->max_dyn_smem) continue;
             int occ = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lk, w * 32, sm));
@@ -339,12 +353,12 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         }
         if (const char *fw = getenv("AQC_LANE_WARPS")) {        // tuning knob
             int w = std::max(1, std::min(LANE_MAX_WARPS, atoi(fw)));
-            size_t sm = lane_smem_bytes(w, pe, nw, L.lane_col_cap, maxl);
+            size_t sm = lane_smem_bytes(w, ncols, nw, L.lane_col_cap, maxl);
             int occ = 0;
             if (sm <= ctx->max_dyn_smem) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lk, w * 32, sm)); if (occ > 0) { best_w = w; best_occ = occ; } }
         }
         if (best_w == 0) return fail(ctx, AQC_ERR_INVALID, "lane kernel stage does not fit shared memory");
-        const size_t lsmem = lane_smem_bytes(best_w, pe, nw, L.lane_col_cap, maxl);
+        const size_t lsmem = lane_smem_bytes(best_w, ncols, nw, L.lane_col_cap, maxl);
         uint32_t want = (L.k.num_tiles + best_w - 1) / best_w;
         uint32_t lgrid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * best_occ));
         if (timed) CK(cudaEventRecord(e0, stream));
@@ -561,8 +575,10 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
             max_static = std::max(max_static, fa.sharedSizeBytes);
         }
         ctx->max_dyn_smem = (size_t)optin - max_static - 64;
-        const void *lanes[6] = {lane_kernel_for(true, 4), lane_kernel_for(false, 4), lane_kernel_for(true, 5),
-                                lane_kernel_for(false, 5), lane_kernel_for(true, 8), lane_kernel_for(false, 8)};
+        const void *lanes[12] = {lane_kernel_for(true, 4), lane_kernel_for(false, 4), lane_kernel_for(true, 5),
+                                 lane_kernel_for(false, 5), lane_kernel_for(true, 8), lane_kernel_for(false, 8),
+                                 lane2_kernel_for(true, 4), lane2_kernel_for(false, 4), lane2_kernel_for(true, 5),
+                                 lane2_kernel_for(false, 5), lane2_kernel_for(true, 8), lane2_kernel_for(false, 8)};
         for (const void *k : lanes) {
             cudaFuncAttributes fa;
             CK(cudaFuncGetAttributes(&fa, k));
@@ -577,7 +593,7 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
             CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->max_dyn_smem));
             CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
-        CK(cudaMalloc(&ctx->d_fb_count, sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->d_fb_count, 2 * sizeof(uint32_t)));
         if (const char *lm = getenv("AQC_LANE_KERNEL")) ctx->lane_mode = atoi(lm) != 0;
         if (const char *cp = getenv("AQC_CHUNK_PAIRS")) {          // host-path chunk size (tests exercise the multi-chunk pipeline with small batches)
             long v = atol(cp);

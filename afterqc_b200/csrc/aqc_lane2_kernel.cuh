@@ -1,334 +1,36 @@
-// aqc_lane_kernel.cuh -- the filter path for short reads (every mate <= 32*NW bases, NW <= 8): ONE LANE PER PAIR.
+// aqc_lane2_kernel.cuh -- second generation of the lane-per-pair filter kernel (aqc_params.filter_kernel = 3).
 //
-// pair_kernel (aqc_kernel.cuh) gives a whole warp to one pair: simple and length-agnostic, but a 150-base mate fills
-// only 5 of the 32 lanes of a plane set and every piece of per-pair bookkeeping is executed 32 times.  For Illumina
-// lengths the planes of both mates fit in registers (2 x NW words per plane), so here a warp takes a tile of 32 pairs
-// and every lane runs the whole reference loop body (preprocesser.py:455-631) for its own pair:
-//   * the warp's private shared-memory stage receives the tile's three byte columns (bases 1, qualities 1, bases 2;
-//     qualities 2 are only ever touched by the correction walk and the statistics) with 1-D TMA bulk copies; the lane
-//     converts its own reads to bit-planes (SWAR, 4 bases per 32-bit word: codes from the ASCII bits, re-encoding
-//     check for foreign bytes, multiply-gather of the code bits) and counts low qualities; after that the stage is
-//     free and the next tile's copy overlaps the rest of the work;
-//   * util.overlap_hm (util.py:158-212): per 32 candidate offsets the lane funnel-shifts two plane words, XORs them with
-//     the fixed mate's first word and keeps the offsets with < 3 mismatches in the first 32 positions as a bit mask
-//     (a necessary condition of the acceptance rule); the lanes then evaluate their candidates exactly, in scan order,
-//     in lock step; the scanned mate's words are rotated one register per round so that the code does not depend on
-//     the round;
-//   * hasPolyX is screened by a multi-word run-length test per lane; adapter cut, rescan, correction walk and the
-//     classifier are per-lane code on registers, reading the few bytes the walk needs from HBM (L2);
-//   * rare work that is better done by a whole warp is handed over by ballot: exact hasPolyX of screened reads,
-//     statRead of the sampled good pairs (the trimmed, corrected reads are rebuilt in a per-warp scratch from the
-//     result record), and pairs holding a byte outside A,C,G,T,N, which are appended to a list that pair_kernel
-//     processes in its list mode right after this kernel.
-// Counters: per-tile packed warp reductions into lane-owned 64-bit registers; histograms and the error matrix are
-// shared-memory atomics.  Results are bit-identical to pair_kernel and the oracle.
+// Same per-lane algorithm and device functions as lane_kernel (aqc_lane_kernel.cuh), which is the kernel that has been
+// checked on hardware and is therefore left untouched.  Two scheduling changes, both aimed at what its first GPU timing
+// showed (31 % of the issue slots with 12 resident warps per SM; the statistics tiles at the head of the batch all landing
+// on the first warps of a static round-robin):
+//   * two columns per warp instead of three: the qualities of mate 1 are copied over the bases of mate 1 as soon as those
+//     are converted (their copy overlaps the conversion of mate 2), so a 4-warp CTA needs 51 KB instead of 70 KB at PE150 and
+//     a fourth CTA fits on the SM (16 warps);
+//   * tiles are claimed from a counter in HBM, one ahead, instead of a static stride.
+// Written without GPU access (verified under the SIMT emulator only); bench.py tries it before lane_kernel and keeps it only
+// if it is identical and faster on the GPU it runs on.
 #pragma once
-#include "aqc_device.cuh"
+#include "aqc_lane_kernel.cuh"
 
 namespace aqc {
 
-constexpr int LANE_MAX_WARPS = 4;
-
-struct LArgs {
-    KArgs k;                      // batch, parameters, outputs (tile_pairs/col_cap as used by this kernel)
-    uint32_t *fb_list;            // pairs that need the general (warp-per-pair) path
-    uint32_t *fb_count;
-    int lane_col_cap;             // bytes reserved per column in a warp's stage
-    uint32_t *tile_counter;       // lane2_kernel: next unclaimed tile (zeroed before the launch)
-};
-
-template <int NW> struct LanePlanes {
-    uint32_t p0[NW], p1[NW], pn[NW];
-};
-
-// python slice semantics of trim() (preprocesser.py:19-28)
-__device__ __forceinline__ void lane_py_trim(int len, int front, int tail, int &start, int &newlen) {
-    int s = front < len ? front : len;
-    int e = tail > 0 ? len - tail : len;
-    if (e < 0) e = 0;
-    if (e < s) e = s;
-    start = s; newlen = e - s;
-}
-
-// multi-word logical right shift by s bits, 0 <= s < 32*NW (zeros enter at the top)
-template <int NW>
-__device__ __forceinline__ void shr_bits(uint32_t (&X)[NW], int s) {
-    static_assert(NW >= 2 && NW <= 8, "NW in 2..8");
-    const int q = s >> 5, sh = s & 31;
-    if (q) {
-        if (q & 1) {
-#pragma unroll
-            for (int i = 0; i < NW; i++) X[i] = (i + 1 < NW) ? X[i + 1 < NW ? i + 1 : 0] : 0u;
-        }
-        if (q & 2) {
-#pragma unroll
-            for (int i = 0; i < NW; i++) X[i] = (i + 2 < NW) ? X[i + 2 < NW ? i + 2 : 0] : 0u;
-        }
-        if (q & 4) {
-#pragma unroll
-            for (int i = 0; i < NW; i++) X[i] = (i + 4 < NW) ? X[i + 4 < NW ? i + 4 : 0] : 0u;
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < NW; i++) X[i] = __funnelshift_r(X[i], (i + 1 < NW) ? X[i + 1 < NW ? i + 1 : 0] : 0u, sh);
-}
-
-// Planes of one read (bytes in the warp's stage, any alignment).  p0/p1 = bits 1/2 of the ASCII byte
-// (A0 C1 T2 G3), pn = 'N' (its code bits are cleared); exotic = some byte is not A,C,G,T,N.
-// The chunk loop is rolled (one copy of the SWAR code in the instruction cache): every iteration converts the next 32
-// bases into the TOP word of the plane registers and moves the others down one word, so after NW iterations word c
-// holds chunk c.
-template <int NW>
-__device__ __forceinline__ void lane_convert(const uint8_t *s, int len, LanePlanes<NW> &P, bool &exotic, int &n_count) {
-    const smem_addr_t a = smem_addr(s);
-    const smem_addr_t w = a & ~(smem_addr_t)3;
-    const int sh = (int)(a & 3) * 8;
-    exotic = false;
-    n_count = 0;
-    uint32_t prev = len > 0 ? lds_u32(w) : 0u;
-#ifdef AQC_LANE_UNROLL_CONVERT
-#pragma unroll
-#else
-#pragma unroll 1
-#endif
-    for (int c = 0; c < NW; c++) {
-        uint32_t p0 = 0, p1 = 0, pn = 0;
-        const int nvalid = len - 32 * c;
-        if (nvalid > 0) {
-            uint32_t v[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const uint32_t cur = lds_u32(w + 4 * (8 * c + j + 1));
-                v[j] = __funnelshift_r(prev, cur, sh);
-                prev = cur;
-            }
-            uint32_t rlo = 0, rhi = 0, bad = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const uint32_t t = v[j] & 0x06060606u;
-                const uint32_t tt = t >> 1;                                                     // 2-bit codes
-                // codes -> ASCII: the four codes of the word become the four selector nibbles of a table lookup
-                const uint32_t e = prmt_raw(0x47544341u, 0u, prmt_raw(tt + (tt >> 4), 0u, 0x4420u));
-                bad |= e ^ v[j];
-                const uint32_t z = ((t << 2) + tt) & 0x11111111u;                               // bit0 = code bit 0, bit4 = code bit 1
-                const uint32_t r = z * 0x01020408u;                     // byte 3 = nibble of plane 0 | nibble of plane 1 << 4
-                constexpr uint32_t sel[4] = {0x3217u, 0x3270u, 0x3710u, 0x7210u};               // byte 3 of r -> byte j of the accumulator
-                if (j < 4) rlo = __byte_perm(rlo, r, sel[j & 3]); else rhi = __byte_perm(rhi, r, sel[j & 3]);
-            }
-            // de-interleave the nibbles: bytes of rlo/rhi hold (p1 nibble << 4 | p0 nibble) of 4 bases each
-            {
-                const uint32_t l0 = rlo & 0x0F0F0F0Fu, h0 = rhi & 0x0F0F0F0Fu;
-                const uint32_t l1 = (rlo >> 4) & 0x0F0F0F0Fu, h1 = (rhi >> 4) & 0x0F0F0F0Fu;
-                const uint32_t a0 = (l0 | (l0 >> 4)) & 0x00FF00FFu, b0 = (h0 | (h0 >> 4)) & 0x00FF00FFu;
-                const uint32_t a1 = (l1 | (l1 >> 4)) & 0x00FF00FFu, b1 = (h1 | (h1 >> 4)) & 0x00FF00FFu;
-                p0 = __byte_perm(a0, b0, 0x6420);
-                p1 = __byte_perm(a1, b1, 0x6420);
-            }
-            const uint32_t vm = lowmask(nvalid);
-            p0 &= vm; p1 &= vm;
-            if (__builtin_expect(bad != 0u, 0)) {           // some byte of the 32 is not A,C,G,T (maybe beyond the read)
-                uint32_t nb = 0, xb = 0;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const uint32_t t = v[j] & 0x06060606u;
-                    const uint32_t tt = t >> 1;
-                    const uint32_t e = __byte_perm(0x47544341u, 0u, __byte_perm(tt | (tt >> 4), 0u, 0x4420));
-                    const uint32_t isn = ~hibit_nonzero(v[j] ^ 0x4E4E4E4Eu) & 0x80808080u;
-                    const uint32_t isbad = hibit_nonzero(e ^ v[j]);
-                    nb |= gather4(isn >> 7) << (4 * j);
-                    xb |= gather4((isbad & ~isn) >> 7) << (4 * j);
-                }
-                nb &= vm; xb &= vm;
-                if (xb) exotic = true;
-                pn = nb;
-                p0 &= ~nb; p1 &= ~nb;
-                n_count += __popc(nb);
-            }
-        }
-#ifdef AQC_LANE_UNROLL_CONVERT
-        P.p0[c] = p0; P.p1[c] = p1; P.pn[c] = pn;
-#else
-#pragma unroll
-        for (int i = 0; i < NW; i++) {
-            P.p0[i] = (i + 1 < NW) ? P.p0[i + 1 < NW ? i + 1 : 0] : p0;
-            P.p1[i] = (i + 1 < NW) ? P.p1[i + 1 < NW ? i + 1 : 0] : p1;
-            P.pn[i] = (i + 1 < NW) ? P.pn[i + 1 < NW ? i + 1 : 0] : pn;
-        }
-#endif
-    }
-}
-
-// lowQualityNum (preprocesser.py:61-68) on the lane's own quality bytes: aligned words, byte-masked at both ends
-__device__ __forceinline__ int lane_lowq(const uint8_t *q, int len, int thr) {
-    if (len <= 0 || thr <= 0) return 0;
-    if (thr >= 128) {                                          // outside the SWAR domain (never with sane -q): byte loop
-        int n = 0;
-        for (int i = 0; i < len; i++) n += (int)q[i] < thr;
-        return n;
-    }
-    const smem_addr_t a = smem_addr(q);
-    const smem_addr_t w = a & ~(smem_addr_t)3;
-    const int lead = (int)(a & 3);
-    const int total = lead + len;                              // bytes from the aligned start to the end of the read
-    const int last = (total - 1) >> 2;                         // index of the last word (<= 64: per-byte sums stay below 256)
-    const uint32_t t4 = (uint32_t)thr * 0x01010101u;
-    // 0x80 in every byte < thr:  byte >= thr  <=>  high bit of ((byte | 0x80) - thr) | byte   (thr < 128)
-    auto low_of = [&](uint32_t v) -> uint32_t { return ~(((v | 0x80808080u) - t4) | v) & 0x80808080u; };
-    uint32_t first = low_of(lds_u32(w)) & ~bytemask_lo(lead);
-    if (last == 0) first &= bytemask_lo(total);
-    uint32_t acc = first >> 7;
-    for (int j = 1; j < last; j++) acc += low_of(lds_u32(w + 4 * j)) >> 7;
-    if (last > 0) acc += (low_of(lds_u32(w + 4 * last)) & bytemask_lo(total - 4 * last)) >> 7;
-    const uint32_t h = (acc & 0x00FF00FFu) + ((acc >> 8) & 0x00FF00FFu);     // the four byte sums can add up to more than 255
-    return (int)((h + (h >> 16)) & 0xFFFFu);
-}
-
-// Run-length screen of hasPolyX (see polyx_screen_fast): true = the read needs the exact test.
-template <int NW>
-__device__ __forceinline__ bool lane_polyx_screen(const uint32_t (&p0)[NW], const uint32_t (&p1)[NW], const uint32_t (&pn)[NW],
-                                                  int len, int maxPoly, int m) {
-    if (len < maxPoly || m < 0) return false;
-    if (m == 0 || m > 31) return true;
-    uint32_t y[NW];
-#pragma unroll
-    for (int i = 0; i < NW; i++) {
-        const uint32_t u0 = i ? p0[i - 1 >= 0 ? i - 1 : 0] : 0u, u1 = i ? p1[i - 1 >= 0 ? i - 1 : 0] : 0u, un = i ? pn[i - 1 >= 0 ? i - 1 : 0] : 0u;
-        const uint32_t d = (p0[i] ^ __funnelshift_l(u0, p0[i], 1)) | (p1[i] ^ __funnelshift_l(u1, p1[i], 1)) | (pn[i] ^ __funnelshift_l(un, pn[i], 1));
-        y[i] = ~d & lowmask(len - 32 * i);                     // bit x: base x equals base x-1
-    }
-    y[0] &= ~1u;
-    int t = 1;
-    while (t < m) {                                             // y[x] := run of m "same as previous" bits starts at x
-        const int step = min(t, m - t);
-#pragma unroll
-        for (int i = 0; i < NW; i++) y[i] &= __funnelshift_r(y[i], (i + 1 < NW) ? y[i + 1 < NW ? i + 1 : 0] : 0u, step);
-        t += step;
-    }
-    uint32_t any = 0;
-#pragma unroll
-    for (int i = 0; i < NW; i++) any |= y[i];
-    return any != 0u;
-}
-
-// util.overlap_hm (util.py:158-212), one direction, lane-per-pair.  S is scanned at offsets 0 .. lenS-31 against the
-// fixed read F; `active` lanes take part, the others idle through the warp-uniform loops.
-template <int NW>
-__device__ __forceinline__ bool lane_scan_dir(uint32_t (&S0)[NW], uint32_t (&S1)[NW], uint32_t (&SN)[NW], int lenS,
-                                              const uint32_t (&F0)[NW], const uint32_t (&F1)[NW], const uint32_t (&FN)[NW], int lenF,
-                                              bool active, int &o_out, int &ol_out, int &mm_out) {
-    const int nOff = active ? lenS - 30 : 0;                    // overlap_require = 30 (util.py:164)
-    const int maxOff = (int)__reduce_max_sync(FULL, (unsigned)max(nOff, 0));
-    const int rounds = (maxOff + 31) >> 5;
-    const bool slow = lenF < 32;                                // first window shorter than 32: every offset is evaluated exactly
-    const uint32_t f0 = F0[0];
-#ifdef AQC_LANE_TWO_PLANE_FILTER
-    const uint32_t f1 = F1[0];
-#endif
-    bool found = false;
-#pragma unroll 1
-    for (int r = 0; r < rounds; r++) {
-        const int rem = nOff - (r << 5);
-        if (!__any_sync(FULL, !found && rem > 0)) break;
-        uint32_t cm = 0;
-        if (!found && rem > 0) {
-            if (!slow) {
-#pragma unroll
-                for (int b = 0; b < 32; b++) {
-#ifdef AQC_LANE_TWO_PLANE_FILTER
-                    const uint32_t x = (__funnelshift_r(S0[0], S0[1], b) ^ f0) | (__funnelshift_r(S1[0], S1[1], b) ^ f1);
-#else
-                    // one code bit is enough for a necessary condition: equal bases have equal bits, and 32 random positions
-                    // differ in fewer than 3 of them with probability 1.2e-7
-#ifdef AQC_LANE_IMAD_SHIFT
-                    // tuning variant: the window as two multiplies (FMA pipe) instead of one funnel shift (ALU pipe, the busy one)
-                    const uint32_t x = (b == 0 ? S0[0] : __umulhi(S0[0], 1u << ((32 - b) & 31)) + S0[1] * (1u << ((32 - b) & 31))) ^ f0;
-#else
-                    const uint32_t x = __funnelshift_r(S0[0], S0[1], b) ^ f0;
-#endif
-#endif
-                    if (__popc(x) < 3) cm |= 1u << b;
-                }
-                cm &= lowmask(rem);
-                if (rem <= 32) cm |= 1u << (rem - 1);           // offset lenS-31 sees only 31 positions: always evaluated exactly
-            } else {
-                cm = lowmask(rem);
-            }
-        }
-        while (__any_sync(FULL, cm != 0u)) {                    // candidates in scan order, all lanes in lock step
-            if (cm) {
-                const int b = __ffs(cm) - 1;
-                cm &= cm - 1;
-                const int oc = (r << 5) + b;
-                const int olc = min(lenS - oc, lenF);
-                const int l50 = min(50, olc);
-                int mm = 0, mm50 = 0;
-#pragma unroll
-                for (int w = 0; w < NW; w++) {
-                    const uint32_t n0 = (w + 1 < NW) ? S0[w + 1 < NW ? w + 1 : 0] : 0u;
-                    const uint32_t n1 = (w + 1 < NW) ? S1[w + 1 < NW ? w + 1 : 0] : 0u;
-                    const uint32_t nn = (w + 1 < NW) ? SN[w + 1 < NW ? w + 1 : 0] : 0u;
-                    uint32_t xw = (__funnelshift_r(S0[w], n0, b) ^ F0[w]) | (__funnelshift_r(S1[w], n1, b) ^ F1[w]) | (__funnelshift_r(SN[w], nn, b) ^ FN[w]);
-                    xw &= lowmask(olc - 32 * w);
-                    mm += __popc(xw);
-                    if (w < 2) mm50 += __popc(xw & lowmask(l50 - 32 * w));
-                }
-                if (mm50 < 3 && (mm < 3 || olc >= 52)) {        // closed form of the leaked loop variable (quirk Q6)
-                    found = true; o_out = oc; ol_out = olc; mm_out = mm; cm = 0;
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < NW; i++) {                           // next round: word i+1 becomes word i
-            S0[i] = (i + 1 < NW) ? S0[i + 1 < NW ? i + 1 : 0] : 0u;
-            S1[i] = (i + 1 < NW) ? S1[i + 1 < NW ? i + 1 : 0] : 0u;
-            SN[i] = (i + 1 < NW) ? SN[i + 1 < NW ? i + 1 : 0] : 0u;
-        }
-    }
-    return found;
-}
-
-// util.overlap(r1, r2) for the active lanes: forward offsets, then reverse (util.py:172-209), else (0,0,0) (:212)
-template <int NW>
-__device__ __forceinline__ void lane_overlap(const LanePlanes<NW> &P1, const LanePlanes<NW> &RC, int len1, int len2, bool active,
-                                             int &offset, int &ol, int &diff) {
-    bool found = false;
-    int o = 0;
-#pragma unroll 1
-    for (int dir = 0; dir < 2; dir++) {
-        uint32_t S0[NW], S1[NW], SN[NW], F0[NW], F1[NW], FN[NW];
-#pragma unroll
-        for (int i = 0; i < NW; i++) {
-            S0[i] = dir ? RC.p0[i] : P1.p0[i]; S1[i] = dir ? RC.p1[i] : P1.p1[i]; SN[i] = dir ? RC.pn[i] : P1.pn[i];
-            F0[i] = dir ? P1.p0[i] : RC.p0[i]; F1[i] = dir ? P1.p1[i] : RC.p1[i]; FN[i] = dir ? P1.pn[i] : RC.pn[i];
-        }
-        const bool act = active && !found;
-        if (!__any_sync(FULL, act)) break;
-        int oo = 0, ool = 0, omm = 0;
-        const bool f = lane_scan_dir<NW>(S0, S1, SN, dir ? len2 : len1, F0, F1, FN, dir ? len1 : len2, act, oo, ool, omm);
-        if (f) { found = true; o = dir ? -oo : oo; ol = ool; diff = omm; }
-    }
-    if (active) {
-        if (found) offset = o;
-        else { offset = 0; ol = 0; diff = 0; }
-    }
-}
-
 // dynamic shared memory of one CTA:
-//   [nwarps][ 3 * lane_col_cap ]           per-warp stage: bases 1 | qualities 1 | bases 2 (TMA destinations)
+//   [nwarps][ 2 * lane_col_cap ]           per-warp stage: column 0 = bases 1, later qualities 1 | column 1 = bases 2 (or qualities 1, single-end)
 //   [nwarps][ 4 * 32*NW ]                  per-warp scratch of the statistics hand-over
 //   luts (768 B)
 //   qc acc [2][5][max_len] u32, qc disc [2][max_len] u32, overlap_hist [max_len+1], distance_hist [max_len+1], err matrix [16]
 template <bool PAIRED, int NW>
-__global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_kernel(const __grid_constant__ LArgs L) {
+__global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane2_kernel(const __grid_constant__ LArgs L) {
     AQC_DYN_SMEM(smem_raw);
-    __shared__ __align__(8) uint64_t full_bar[LANE_MAX_WARPS];
+    __shared__ __align__(8) uint64_t full_bar[2 * LANE_MAX_WARPS];      // per warp: [0] bases landed, [1] qualities landed
     const KArgs &A = L.k;
     constexpr bool paired = PAIRED;
     constexpr int MAXB = 32 * NW;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
     const int col_cap = L.lane_col_cap;
-    const int ncols = paired ? 3 : 2;
+    const int ncols = 2;
 
     uint8_t *stage = smem_raw + (size_t)warp * ncols * col_cap;
     uint8_t *scratch = smem_raw + (size_t)nwarps * ncols * col_cap + (size_t)warp * 4 * MAXB;
@@ -345,7 +47,7 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_ke
     for (int i = tid; i < 768; i += blockDim.x) lutbase[i] = reinterpret_cast<const uint8_t *>(A.luts)[i];
     for (int i = tid; i < n_acc_words; i += blockDim.x) s_acc[i] = 0;
     if (tid == 0) {
-        for (int s = 0; s < nwarps; s++) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < 2 * nwarps; s++) mbar_init(&full_bar[s], 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -357,9 +59,14 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_ke
     // lane i owns scalar counter i
     unsigned long long wc0 = 0;
 
-    const uint32_t gw = blockIdx.x * (uint32_t)nwarps + (uint32_t)warp;
-    const uint32_t W = gridDim.x * (uint32_t)nwarps;
-    uint64_t *bar = &full_bar[warp];
+    uint64_t *bar = &full_bar[2 * warp], *qbar = &full_bar[2 * warp + 1];
+    // tiles are claimed from a counter in HBM, one tile ahead of the one being worked on: warps that meet expensive tiles
+    // (the statistics window sits at the head of the batch) simply take fewer
+    auto claim_tile = [&]() -> uint32_t {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(L.tile_counter, 1u);
+        return __shfl_sync(FULL, t, 0);
+    };
 
     // offsets of the lane's pair in tile t (pairs beyond n: empty records at the end of the columns)
     auto load_offsets = [&](uint32_t t, uint32_t &a1, uint32_t &e1, uint32_t &a2, uint32_t &e2) {
@@ -368,33 +75,43 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_ke
         a2 = 0; e2 = 0;
         if (paired) { a2 = A.off2[pp]; e2 = A.off2[pq]; }
     };
-    // producer (whole warp computes, lane 0 issues): bulk copies of the tile's columns into the warp's stage
+    // producer (whole warp computes, lane 0 issues).  Paired input: the bases of both mates first; the qualities of mate 1
+    // follow into column 0 once mate 1 has been converted (issue_quals) -- two columns per warp instead of three, so that a
+    // fourth CTA fits on the SM.  Single-end input: bases and qualities together, as in lane_kernel.
     auto issue_tile = [&](uint32_t a1, uint32_t e1, uint32_t a2, uint32_t e2) {
         const uint32_t f1 = __shfl_sync(FULL, a1, 0), l1 = __shfl_sync(FULL, e1, 31);
         const uint32_t f2 = __shfl_sync(FULL, a2, 0), l2 = __shfl_sync(FULL, e2, 31);
         if (lane == 0) {
             const uint32_t g1 = f1 & ~15u, bytes1 = (l1 - g1 + 15u) & ~15u;
             const uint32_t g2 = f2 & ~15u, bytes2 = paired ? ((l2 - g2 + 15u) & ~15u) : 0u;
-            mbar_expect_tx(bar, 2 * bytes1 + bytes2);
+            mbar_expect_tx(bar, paired ? bytes1 + bytes2 : 2 * bytes1);
             if (bytes1) {
                 bulk_g2s(stage, A.seq1 + g1, bytes1, bar);
-                bulk_g2s(stage + col_cap, A.qual1 + g1, bytes1, bar);
+                if (!paired) bulk_g2s(stage + col_cap, A.qual1 + g1, bytes1, bar);
             }
-            if (paired && bytes2) bulk_g2s(stage + 2 * col_cap, A.seq2 + g2, bytes2, bar);
+            if (paired && bytes2) bulk_g2s(stage + col_cap, A.seq2 + g2, bytes2, bar);
+        }
+    };
+    auto issue_quals = [&](uint32_t a1, uint32_t e1) {          // paired only: qualities of mate 1 over the bases of mate 1
+        const uint32_t f1 = __shfl_sync(FULL, a1, 0), l1 = __shfl_sync(FULL, e1, 31);
+        if (lane == 0) {
+            const uint32_t g1 = f1 & ~15u, bytes1 = (l1 - g1 + 15u) & ~15u;
+            mbar_expect_tx(qbar, bytes1);
+            if (bytes1) bulk_g2s(stage, A.qual1 + g1, bytes1, qbar);
         }
     };
 
     uint32_t a1 = 0, e1 = 0, a2 = 0, e2 = 0;
-    uint32_t t = gw;
+    uint32_t t = claim_tile();
     if (t < A.num_tiles) {
         load_offsets(t, a1, e1, a2, e2);
         issue_tile(a1, e1, a2, e2);
     }
-    uint32_t parity = 0;
+    uint32_t parity = 0, qparity = 0;
 
 #pragma unroll 1
-    for (; t < A.num_tiles; t += W) {
-        const uint32_t tn = t + W;
+    for (; t < A.num_tiles;) {
+        const uint32_t tn = claim_tile();
         uint32_t na1 = 0, ne1 = 0, na2 = 0, ne2 = 0;
         if (tn < A.num_tiles) load_offsets(tn, na1, ne1, na2, ne2);
 
@@ -437,35 +154,46 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_ke
             }
             if (live && len1 < A.p.seq_len_req) { cls = AQC_BADLEN; live = false; }   // :476-479 (R2 never checked, quirk Q3)
         }
-        if (live) {
+        const bool want_lowq = A.p.unqualified_base_limit > 0;     // warp-uniform
+        {
             bool ex = false;
 #pragma unroll 1
             for (int m = 0; m < (paired ? 2 : 1); m++) {              // one copy of the conversion + screen code for both mates
-                const uint8_t *r = m ? stage + 2 * col_cap + (a2 - g2) + start2 : stage + (a1 - g1) + start1;
-                const int len = m ? len2 : len1;
-                LanePlanes<NW> F;
+                if (live) {
+                    const uint8_t *r = m ? stage + col_cap + (a2 - g2) + start2 : stage + (a1 - g1) + start1;
+                    const int len = m ? len2 : len1;
+                    LanePlanes<NW> F;
 #pragma unroll
-                for (int i = 0; i < NW; i++) F.p0[i] = F.p1[i] = F.pn[i] = 0;
-                bool exm = false; int nn = 0;
-                lane_convert<NW>(r, len, F, exm, nn);
-                ex |= exm;
-                const bool cand = A.p.poly_size_limit > 0 && lane_polyx_screen<NW>(F.p0, F.p1, F.pn, len, A.p.poly_size_limit, A.poly_m);
-                if (m == 0) {
-                    n1 = nn; cand1 = cand;
+                    for (int i = 0; i < NW; i++) F.p0[i] = F.p1[i] = F.pn[i] = 0;
+                    bool exm = false; int nn = 0;
+                    lane_convert<NW>(r, len, F, exm, nn);
+                    ex |= exm;
+                    const bool cand = A.p.poly_size_limit > 0 && lane_polyx_screen<NW>(F.p0, F.p1, F.pn, len, A.p.poly_size_limit, A.poly_m);
+                    if (m == 0) {
+                        n1 = nn; cand1 = cand;
 #pragma unroll
-                    for (int i = 0; i < NW; i++) { P1.p0[i] = F.p0[i]; P1.p1[i] = F.p1[i]; P1.pn[i] = F.pn[i]; }
-                } else {
-                    n2 = nn; cand2 = cand;
-                    // reverseComplement (util.py:42-51): reverse the 32*NW-bit strings, shift the read down to bit 0, flip plane 1
+                        for (int i = 0; i < NW; i++) { P1.p0[i] = F.p0[i]; P1.p1[i] = F.p1[i]; P1.pn[i] = F.pn[i]; }
+                    } else {
+                        n2 = nn; cand2 = cand;
+                        // reverseComplement (util.py:42-51): reverse the 32*NW-bit strings, shift the read down to bit 0, flip plane 1
 #pragma unroll
-                    for (int i = 0; i < NW; i++) { RC.p0[i] = __brev(F.p0[NW - 1 - i]); RC.p1[i] = __brev(F.p1[NW - 1 - i]); RC.pn[i] = __brev(F.pn[NW - 1 - i]); }
-                    shr_bits<NW>(RC.p0, MAXB - len2); shr_bits<NW>(RC.p1, MAXB - len2); shr_bits<NW>(RC.pn, MAXB - len2);
+                        for (int i = 0; i < NW; i++) { RC.p0[i] = __brev(F.p0[NW - 1 - i]); RC.p1[i] = __brev(F.p1[NW - 1 - i]); RC.pn[i] = __brev(F.pn[NW - 1 - i]); }
+                        shr_bits<NW>(RC.p0, MAXB - len2); shr_bits<NW>(RC.p1, MAXB - len2); shr_bits<NW>(RC.pn, MAXB - len2);
 #pragma unroll
-                    for (int i = 0; i < NW; i++) RC.p1[i] ^= lowmask(len2 - 32 * i) & ~RC.pn[i];
+                        for (int i = 0; i < NW; i++) RC.p1[i] ^= lowmask(len2 - 32 * i) & ~RC.pn[i];
+                    }
+                }
+                if (paired && m == 0 && want_lowq) {     // the bases of mate 1 are in registers: their column takes the qualities
+                    fence_proxy_async();
+                    __syncwarp();
+                    issue_quals(a1, e1);
                 }
             }
-            if (A.p.unqualified_base_limit > 0) lowq1 = lane_lowq(stage + col_cap + (a1 - g1) + start1, len1, A.p.qualified_quality_phred + 33);
-            if (ex) { fallback = true; live = false; cls = AQC_NUM_CLASSES; }
+            if (want_lowq) {
+                if (paired) { mbar_wait(qbar, qparity); qparity ^= 1u; }
+                if (live) lowq1 = lane_lowq(stage + (paired ? 0 : col_cap) + (a1 - g1) + start1, len1, A.p.qualified_quality_phred + 33);
+            }
+            if (live && ex) { fallback = true; live = false; cls = AQC_NUM_CLASSES; }
         }
 
         // ---- the stage is free: prefetch the next tile while the registers are worked on ----
@@ -743,6 +471,7 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_ke
         }
 
         a1 = na1; e1 = ne1; a2 = na2; e2 = ne2;
+        t = tn;
     }
 
     // ---- epilogue: flush everything this CTA accumulated ----

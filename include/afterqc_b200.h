@@ -93,7 +93,8 @@ typedef struct aqc_params {
     int32_t kmer_side_log2;          /* log2 capacity of the non-ACGT k-mer side table (0 = default 20) */
     int32_t filter_kernel;           /* which kernel aqc_filter_pairs launches: 0 = engine default (environment AQC_LANE_KERNEL,
                                         else 1), 1 = warp-per-pair (pair_kernel, any read length), 2 = lane-per-pair
-                                        (lane_kernel) for batches whose reads are <= 256 bases, pair_kernel otherwise.
+                                        (lane_kernel) for batches whose reads are <= 256 bases, pair_kernel otherwise; 3 = lane2_kernel, the
+                                        same with two staged columns per warp and dynamic tile claiming (experimental).
                                         Results are identical; this is a performance knob. */
     int32_t reserved[6];
 } aqc_params;

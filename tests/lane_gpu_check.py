@@ -3,7 +3,8 @@
 round without GPU time left and had only been run under the SIMT emulator (tests/emu) when it was committed.
 
   python tests/lane_gpu_check.py parity          lane engine vs the CPU oracle, bit-exact, on the parity-test batches
-  python tests/lane_gpu_check.py full [pairs]    lane engine vs the warp-per-pair engine on the full-size bench batch
+  python tests/lane_gpu_check.py full [pairs] [lane|lane2]
+                                                 that kernel vs the warp-per-pair kernel on the bench workload
                                                  (HBM-resident entry); prints one JSON line with both kernel times
 Exit code 0 = identical everywhere.
 """
@@ -21,7 +22,7 @@ for p in (ROOT, HERE):
 import numpy as np  # noqa: E402
 
 
-def parity():
+def parity(candidate="lane"):
     import cases
     import compare
     from afterqc_b200 import _abi
@@ -40,7 +41,7 @@ def parity():
     for bname, (batch, pnames) in batches.items():
         for pname in pnames:
             p = cases.make_params(pname)
-            p.filter_kernel = _abi.KERNEL_LANE
+            p.filter_kernel = {"lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}[candidate]
             orc, eng = oracle.Oracle(p), Engine(p)
             a = orc.filter_pairs(batch)
             b = eng.filter_pairs(batch)
@@ -58,17 +59,18 @@ def parity():
     se = cases.synthetic("se100", 30000)
     for pname in ("default_f0", "trim", "loose"):
         p = cases.make_params(pname, paired=False)
-        p.filter_kernel = _abi.KERNEL_LANE
+        p.filter_kernel = {"lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}[candidate]
         orc, eng = oracle.Oracle(p), Engine(p)
         compare.assert_records_equal(se, orc.filter_pairs(se), eng.filter_pairs(se), "lane se100 %s" % pname)
         compare.compare_backends(orc, eng, (_abi.QC_R1_POST,), "lane se100 %s" % pname)
         orc.close(); eng.close()
         n_cases += 1
-    print("lane kernel parity ok: %d cases" % n_cases)
+    print("%s kernel parity ok: %d cases" % (candidate, n_cases))
 
 
-def full(pairs):
-    """Both kernels on the bench workload, resident in HBM: records, counters and the postfilter QC slots must match."""
+def full(pairs, candidate="lane"):
+    """pair_kernel and a lane-per-pair kernel (lane / lane2) on the bench workload, resident in HBM: records, counters and
+    the postfilter QC slots must match."""
     import torch
     from afterqc_b200 import _abi, synth
     from afterqc_b200.batch import PackedBatch
@@ -80,7 +82,9 @@ def full(pairs):
     torch.cuda.empty_cache()
     out = {}
     ref = None
-    for name, k in (("warp", _abi.KERNEL_WARP), ("lane", _abi.KERNEL_LANE)):
+    cand_id = {"lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}[candidate]
+    out["candidate"] = candidate
+    for name, k in (("warp", _abi.KERNEL_WARP), ("lane", cand_id)):      # key "lane_ms" = the candidate's time
         eng = Engine(_abi.Params.defaults(filter_kernel=k))
         d = eng.upload(host)
         eng.filter_pairs(d); eng.sync()                      # warm-up
@@ -134,7 +138,7 @@ if __name__ == "__main__":
     t0 = time.time()
     mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
     if mode == "parity":
-        parity()
+        parity(sys.argv[2] if len(sys.argv) > 2 else "lane")
     else:
-        full(int(sys.argv[2]) if len(sys.argv) > 2 else 10_000_000)
+        full(int(sys.argv[2]) if len(sys.argv) > 2 else 10_000_000, sys.argv[3] if len(sys.argv) > 3 else "lane")
     sys.stderr.write("lane_gpu_check %s: %.1f s\n" % (mode, time.time() - t0))

@@ -10,11 +10,12 @@ import compare
 from afterqc_b200 import _abi
 
 
-@pytest.fixture(scope="module", params=["warp", "lane"])
+@pytest.fixture(scope="module", params=["warp", "lane", "lane2"])
 def backends(oracle_lib, request):
-    """warp = pair_kernel (one warp per pair); lane = lane_kernel (one lane per pair) + pair_kernel's list mode"""
+    """warp = pair_kernel (one warp per pair); lane = lane_kernel (one lane per pair) + pair_kernel's list mode;
+    lane2 = lane2_kernel (two staged columns per warp, dynamic tile claiming)"""
     import emu
-    kernel = _abi.KERNEL_LANE if request.param == "lane" else _abi.KERNEL_WARP
+    kernel = {"warp": _abi.KERNEL_WARP, "lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}[request.param]
 
     def make(params):
         params.filter_kernel = kernel
@@ -36,7 +37,7 @@ BATCHES = {
 @pytest.mark.parametrize("bname", ["adversarial", "pe150_jitter"])
 @pytest.mark.parametrize("pname", ["default_f0", "trim", "poly_wide"])
 def test_emu_ops_parity(backends, bname, pname):
-    if backends.kernel == "lane":
+    if backends.kernel != "warp":
         pytest.skip("the operator entry always runs pair_kernel")
     batch = BATCHES[bname]()
     orc, eng = backends(cases.make_params(pname))
@@ -59,7 +60,7 @@ def test_emu_filter_parity(backends, bname, pname):
 
 
 def test_emu_stat_parity(backends):
-    if backends.kernel == "lane":
+    if backends.kernel != "warp":
         pytest.skip("the prefilter statistics entry always runs pair_kernel")
     batch = BATCHES["pe150_jitter"]()
     for kmer in (8, 4):
@@ -124,7 +125,7 @@ def test_emu_lane_short_and_power_of_two_lengths(backends):
 def test_emu_lane_qual2_in_place(backends, monkeypatch):
     """AQC_BATCH_QUAL2_IN_PLACE: mate-2 qualities stay in (page-locked) host memory; identical results, also through the
     general kernel's list mode (foreign bytes) and when the pointer turns out not to be device-accessible (copy fall-back)."""
-    if backends.kernel != "lane":
+    if backends.kernel == "warp":
         pytest.skip("only the lane-per-pair path leaves the column in place")
     for bname in ("adversarial", "pe150_err3"):
         batch = BATCHES[bname]()
@@ -165,7 +166,7 @@ def test_emu_empty_mate_reaches_statread(backends):
     orc.close(); eng.close()
 
 
-@pytest.mark.parametrize("kernel", ["warp", "lane"])
+@pytest.mark.parametrize("kernel", ["warp", "lane", "lane2"])
 @pytest.mark.parametrize("name", ["pe150_default", "pe150_err3_mask_overlap", "pe250_k5_strict", "se100_f0"])
 def test_emu_pipeline_matches_reference_golden(name, kernel, tmp_path):
     """the whole drop-in pipeline (readers, packed columns, engine calls, writers, JSON) on the emulated engine reproduces
@@ -176,7 +177,7 @@ def test_emu_pipeline_matches_reference_golden(name, kernel, tmp_path):
         pytest.skip("golden case %s not present" % name)
 
     def factory(p):
-        p.filter_kernel = _abi.KERNEL_LANE if kernel == "lane" else _abi.KERNEL_WARP
+        p.filter_kernel = {"warp": _abi.KERNEL_WARP, "lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}[kernel]
         return emu.EmuEngine(p)
     problems = golden_util.run_case(name, tmp_path, factory)
     assert not problems, problems

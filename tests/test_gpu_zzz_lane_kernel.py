@@ -36,3 +36,15 @@ def test_lane_kernel_parity_vs_oracle():
 def test_lane_kernel_equals_warp_kernel_at_bench_size():
     out = _run(["full", "2000000"], 600)
     assert '"identical": true' in out
+
+
+@pytest.mark.xfail(reason="lane2_kernel has not run on hardware yet (written after the round's GPU budget was spent); emulator-verified", strict=False)
+def test_lane2_kernel_equals_warp_kernel_at_bench_size():
+    out = _run(["full", "2000000", "lane2"], 600)
+    assert '"identical": true' in out
+
+
+@pytest.mark.xfail(reason="lane2_kernel has not run on hardware yet (written after the round's GPU budget was spent); emulator-verified", strict=False)
+def test_lane2_kernel_parity_vs_oracle():
+    out = _run(["parity", "lane2"], 600)
+    assert "lane2 kernel parity ok" in out

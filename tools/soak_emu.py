@@ -99,7 +99,7 @@ def one_case(rng, k):
     batch = PackedBatch.from_reads([p[0] for p in pairs], [p[1] for p in pairs] if paired else None, first_index=rng.choice([0, 0, 17, 199990]))
     p = rand_params(rng, paired)
     results = {}
-    for kern in (_abi.KERNEL_WARP, _abi.KERNEL_LANE):
+    for kern in (_abi.KERNEL_WARP, _abi.KERNEL_LANE, _abi.KERNEL_LANE2):
         p.filter_kernel = kern
         orc, eng = oracle.Oracle(p), emu.EmuEngine(p)
         try:
