@@ -201,9 +201,23 @@ void launch(uint32_t grid, uint32_t block, size_t smem_bytes, Entry fn, void **a
         cta_arrived = 0; cta_gen = 0;
         for (int t = 0; t < (int)block; t++) prepare(fibers[t], t);
         int remaining = (int)block;
+        // fiber order of a scheduling pass: AQC_EMU_SCHED=reverse|random shakes out code that relies on lane 0 (or warp 0)
+        // running first; the default is thread order
+        static const char *sched = getenv("AQC_EMU_SCHED");
+        static uint64_t rng = 0x9E3779B97F4A7C15ull;
+        static int order[MAX_THREADS];
+        for (int t = 0; t < (int)block; t++) order[t] = (sched && sched[0] == 'r' && sched[1] == 'e') ? (int)block - 1 - t : t;
         while (remaining > 0) {
             bool progressed = false;
-            for (int t = 0; t < (int)block; t++) {
+            if (sched && sched[0] == 'r' && sched[1] == 'a') {
+                for (int t = (int)block - 1; t > 0; t--) {
+                    rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+                    const int j = (int)(rng % (uint64_t)(t + 1));
+                    const int tmp = order[t]; order[t] = order[j]; order[j] = tmp;
+                }
+            }
+            for (int oi = 0; oi < (int)block; oi++) {
+                const int t = order[oi];
                 Fiber &f = fibers[t];
                 if (f.done) continue;
                 if (f.wait_ptr) {
