@@ -134,10 +134,35 @@ def full(pairs, candidate="lane"):
     print(json.dumps(out))
 
 
+def smoke():
+    """lane_kernel and lane2_kernel against the oracle on two small batches (adversarial reads incl. foreign bytes -> list
+    mode, synthetic PE150); called from __graft_entry__.smoke() in a child process."""
+    import cases
+    import compare
+    from afterqc_b200 import _abi
+    from afterqc_b200.engine import Engine
+    from oracle import oracle
+    oracle.build()
+    for cand, kid in (("lane", _abi.KERNEL_LANE), ("lane2", _abi.KERNEL_LANE2)):
+        try:
+            for bname, batch in (("adversarial", cases.adversarial_batch()), ("pe150", cases.synthetic("pe150", 4096))):
+                p = cases.make_params("default_f0"); p.qc_sample = 3000; p.filter_kernel = kid
+                orc, eng = oracle.Oracle(p), Engine(p)
+                a = orc.filter_pairs(batch); b = eng.filter_pairs(batch)
+                compare.assert_records_equal(batch, a, b, "%s smoke %s" % (cand, bname))
+                compare.compare_backends(orc, eng, (_abi.QC_R1_POST, _abi.QC_R2_POST), "%s smoke %s" % (cand, bname))
+                orc.close(); eng.close()
+            print("%s kernel smoke ok (bit-exact vs the oracle: adversarial + pe150)" % cand)
+        except Exception as e:      # noqa: BLE001
+            print("%s kernel smoke FAILED: %s" % (cand, str(e)[:300]))
+
+
 if __name__ == "__main__":
     t0 = time.time()
     mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
-    if mode == "parity":
+    if mode == "smoke":
+        smoke()
+    elif mode == "parity":
         parity(sys.argv[2] if len(sys.argv) > 2 else "lane")
     else:
         full(int(sys.argv[2]) if len(sys.argv) > 2 else 10_000_000, sys.argv[3] if len(sys.argv) > 3 else "lane")
