@@ -21,6 +21,7 @@ ERR_NAMES = {
 
 MEM_HOST, MEM_DEVICE = 0, 1
 KERNEL_DEFAULT, KERNEL_WARP, KERNEL_LANE, KERNEL_LANE2 = 0, 1, 2, 3     # aqc_params.filter_kernel
+STAT_DEFAULT, STAT_WARP, STAT_LANE = 0, 1, 2                            # aqc_params.stat_kernel
 BATCH_QUAL2_IN_PLACE = 1 << 16                         # aqc_batch.flags
 
 # pair classes, reference priority order (preprocesser.py:436-614)
@@ -53,7 +54,7 @@ class Params(C.Structure):
         "paired", "trim_front", "trim_tail", "trim_front2", "trim_tail2", "seq_len_req",
         "poly_size_limit", "allow_mismatch_in_poly", "qualified_quality_phred",
         "unqualified_base_limit", "n_base_limit", "no_overlap", "no_correction", "mask_mismatch",
-        "qc_sample", "qc_kmer", "kmer_side_log2", "filter_kernel")] + [("reserved", C.c_int32 * 6)]
+        "qc_sample", "qc_kmer", "kmer_side_log2", "filter_kernel", "stat_kernel")] + [("reserved", C.c_int32 * 5)]
 
     @classmethod
     def defaults(cls, **kw):
@@ -61,7 +62,7 @@ class Params(C.Structure):
         p = cls(paired=1, trim_front=0, trim_tail=0, trim_front2=0, trim_tail2=0, seq_len_req=35,
                 poly_size_limit=35, allow_mismatch_in_poly=2, qualified_quality_phred=15,
                 unqualified_base_limit=60, n_base_limit=5, no_overlap=0, no_correction=0,
-                mask_mismatch=0, qc_sample=200000, qc_kmer=8, kmer_side_log2=0, filter_kernel=0)
+                mask_mismatch=0, qc_sample=200000, qc_kmer=8, kmer_side_log2=0, filter_kernel=0, stat_kernel=0)
         for k, v in kw.items():
             if not hasattr(p, k):
                 raise KeyError(k)

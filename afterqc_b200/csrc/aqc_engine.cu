@@ -114,6 +114,7 @@ unsigned long long host_side_hash(unsigned long long k) {   // must match aqc::s
 int check_params(const aqc_params *p, char *err, size_t errn) {
     if (p->qc_kmer < 1 || p->qc_kmer > AQC_MAX_KMER) { snprintf(err, errn, "qc_kmer %d outside 1..%d", p->qc_kmer, AQC_MAX_KMER); return AQC_ERR_INVALID; }
     if (p->filter_kernel < 0 || p->filter_kernel > 3) { snprintf(err, errn, "filter_kernel %d outside 0..3", p->filter_kernel); return AQC_ERR_INVALID; }
+    if (p->stat_kernel < 0 || p->stat_kernel > 2) { snprintf(err, errn, "stat_kernel %d outside 0..2", p->stat_kernel); return AQC_ERR_INVALID; }
     if (p->trim_front < 0 || p->trim_tail < 0 || p->trim_front2 < 0 || p->trim_tail2 < 0) { snprintf(err, errn, "negative trim value (resolve auto-trim on the host first)"); return AQC_ERR_INVALID; }
     return 0;
 }
@@ -144,30 +145,54 @@ const void *kernel_for(int mode, bool paired) {
 }
 #ifdef AQC_EMU
 #undef pair_kernel
-template <bool PAIRED, int NW> void emu_lane_kernel(void **a) { lane_kernel<PAIRED, NW>(*(const LArgs *)a[0]); }
+template <bool PAIRED, int NW, bool STAT2 = false> void emu_lane_kernel(void **a) { lane_kernel<PAIRED, NW, STAT2>(*(const LArgs *)a[0]); }
 #define lane_kernel emu_lane_kernel
 #endif
 
 // lane-per-pair filter kernel for mates of at most 32*NW bases
 int lane_words_for(int max_len) { return max_len <= 128 ? 4 : (max_len <= 160 ? 5 : (max_len <= 256 ? 8 : 0)); }
-const void *lane_kernel_for(bool paired, int nw) {
+const void *lane_kernel_for(bool paired, int nw, bool stat2) {     // stat2: sampled statRead with one lane per read (aqc_stat2.cuh)
+    if (stat2) {
+        if (nw == 4) return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 4, true>) : AQC_KERNEL_HANDLE(lane_kernel<false, 4, true>);
+        if (nw == 5) return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 5, true>) : AQC_KERNEL_HANDLE(lane_kernel<false, 5, true>);
+        return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 8, true>) : AQC_KERNEL_HANDLE(lane_kernel<false, 8, true>);
+    }
     if (nw == 4) return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 4>) : AQC_KERNEL_HANDLE(lane_kernel<false, 4>);
     if (nw == 5) return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 5>) : AQC_KERNEL_HANDLE(lane_kernel<false, 5>);
     return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 8>) : AQC_KERNEL_HANDLE(lane_kernel<false, 8>);
 }
 #ifdef AQC_EMU
 #undef lane_kernel
-template <bool PAIRED, int NW> void emu_lane2_kernel(void **a) { lane2_kernel<PAIRED, NW>(*(const LArgs *)a[0]); }
+template <bool PAIRED, int NW, bool STAT2 = false> void emu_lane2_kernel(void **a) { lane2_kernel<PAIRED, NW, STAT2>(*(const LArgs *)a[0]); }
 #define lane2_kernel emu_lane2_kernel
 #endif
-const void *lane2_kernel_for(bool paired, int nw) {
+const void *lane2_kernel_for(bool paired, int nw, bool stat2) {
+    if (stat2) {
+        if (nw == 4) return paired ? AQC_KERNEL_HANDLE(lane2_kernel<true, 4, true>) : AQC_KERNEL_HANDLE(lane2_kernel<false, 4, true>);
+        if (nw == 5) return paired ? AQC_KERNEL_HANDLE(lane2_kernel<true, 5, true>) : AQC_KERNEL_HANDLE(lane2_kernel<false, 5, true>);
+        return paired ? AQC_KERNEL_HANDLE(lane2_kernel<true, 8, true>) : AQC_KERNEL_HANDLE(lane2_kernel<false, 8, true>);
+    }
     if (nw == 4) return paired ? AQC_KERNEL_HANDLE(lane2_kernel<true, 4>) : AQC_KERNEL_HANDLE(lane2_kernel<false, 4>);
     if (nw == 5) return paired ? AQC_KERNEL_HANDLE(lane2_kernel<true, 5>) : AQC_KERNEL_HANDLE(lane2_kernel<false, 5>);
     return paired ? AQC_KERNEL_HANDLE(lane2_kernel<true, 8>) : AQC_KERNEL_HANDLE(lane2_kernel<false, 8>);
 }
 #ifdef AQC_EMU
 #undef lane2_kernel
+template <bool PAIRED, int NW> void emu_stat_lane_kernel(void **a) { stat_lane_kernel<PAIRED, NW>(*(const KArgs *)a[0]); }
+#define stat_lane_kernel emu_stat_lane_kernel
 #endif
+// prefilter statistics with one lane per read (aqc_params.stat_kernel = 2)
+const void *stat_lane_kernel_for(bool paired, int nw) {
+    if (nw == 4) return paired ? AQC_KERNEL_HANDLE(stat_lane_kernel<true, 4>) : AQC_KERNEL_HANDLE(stat_lane_kernel<false, 4>);
+    if (nw == 5) return paired ? AQC_KERNEL_HANDLE(stat_lane_kernel<true, 5>) : AQC_KERNEL_HANDLE(stat_lane_kernel<false, 5>);
+    return paired ? AQC_KERNEL_HANDLE(stat_lane_kernel<true, 8>) : AQC_KERNEL_HANDLE(stat_lane_kernel<false, 8>);
+}
+#ifdef AQC_EMU
+#undef stat_lane_kernel
+#endif
+size_t stat_lane_smem_bytes(int nwarps, int nw, int max_len) {
+    return (size_t)nwarps * 2 * 32 * (size_t)nw + 768 + (size_t)(2 * QC_CLASSES * max_len + 2 * max_len) * 4 + 64;
+}
 
 size_t lane_smem_bytes(int nwarps, int ncols, int nw, int col_cap, int max_len) {
     size_t acc = (size_t)(2 * QC_CLASSES * max_len + 2 * max_len + 2 * (max_len + 1) + 16) * 4;
@@ -342,7 +367,8 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         L.tile_counter = ctx->d_fb_count + 1;
         const bool gen2 = ctx->p.filter_kernel == 3;
         const int ncols = (pe && !gen2) ? 3 : 2;
-        const void *lk = gen2 ? lane2_kernel_for(pe, nw) : lane_kernel_for(pe, nw);
+        const bool stat2 = ctx->p.stat_kernel == 2;
+        const void *lk = gen2 ? lane2_kernel_for(pe, nw, stat2) : lane_kernel_for(pe, nw, stat2);
         int best_w = 0, best_occ = 0;
         for (int w = LANE_MAX_WARPS; w >= 1; w--) {           // most resident warps per SM; ties go to the larger CTA
             size_t sm = lane_smem_bytes(w, ncols, nw, L.lane_col_cap, maxl);
@@ -378,6 +404,28 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         uint32_t grid = std::min<uint32_t>(b.n, (uint32_t)(ctx->sm_count * occ));
         void *kargs[1] = {(void *)&A};
         CK(cudaLaunchKernel(kern, dim3(grid), dim3(THREADS), kargs, smem, stream));
+        CK(cudaGetLastError());
+        if (timed) CK(cudaEventRecord(e1, stream));
+        ctx->launches++;
+        return 0;
+    }
+
+    if (x.mode == MODE_STAT && ctx->p.stat_kernel == 2 && lane_words_for(maxl) != 0) {
+        // ---- prefilter statistics with one lane per read (aqc_stat2.cuh) ----
+        const int snw = lane_words_for(maxl);
+        const void *sk = stat_lane_kernel_for(pe, snw);
+        A.tile_pairs = 32;
+        A.num_tiles = (b.n + 31) / 32;
+        const size_t ssmem = stat_lane_smem_bytes(STAT2_WARPS, snw, maxl);
+        if (ssmem > 64 * 1024) return fail(ctx, AQC_ERR_INVALID, "statistics accumulators do not fit shared memory");
+        int socc = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&socc, sk, STAT2_WARPS * 32, ssmem));
+        if (socc < 1) socc = 1;
+        const uint32_t swant = (A.num_tiles + STAT2_WARPS - 1) / STAT2_WARPS;
+        const uint32_t sgrid = std::min<uint32_t>(swant, (uint32_t)(ctx->sm_count * socc));
+        if (timed) CK(cudaEventRecord(e0, stream));
+        void *sargs[1] = {(void *)&A};
+        CK(cudaLaunchKernel(sk, dim3(sgrid), dim3(STAT2_WARPS * 32), sargs, ssmem, stream));
         CK(cudaGetLastError());
         if (timed) CK(cudaEventRecord(e1, stream));
         ctx->launches++;
@@ -575,10 +623,14 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
             max_static = std::max(max_static, fa.sharedSizeBytes);
         }
         ctx->max_dyn_smem = (size_t)optin - max_static - 64;
-        const void *lanes[12] = {lane_kernel_for(true, 4), lane_kernel_for(false, 4), lane_kernel_for(true, 5),
-                                 lane_kernel_for(false, 5), lane_kernel_for(true, 8), lane_kernel_for(false, 8),
-                                 lane2_kernel_for(true, 4), lane2_kernel_for(false, 4), lane2_kernel_for(true, 5),
-                                 lane2_kernel_for(false, 5), lane2_kernel_for(true, 8), lane2_kernel_for(false, 8)};
+        std::vector<const void *> lanes;
+        for (int nw : {4, 5, 8})
+            for (bool pe : {true, false}) {
+                for (bool st2 : {false, true}) { lanes.push_back(lane_kernel_for(pe, nw, st2)); lanes.push_back(lane2_kernel_for(pe, nw, st2)); }
+                // stat_lane_kernel: small accumulators only, and it re-reads each 32-byte sector of a read eight times (word loads
+                // per lane), so it keeps the default carve-out (a large L1)
+                CK(cudaFuncSetAttribute(stat_lane_kernel_for(pe, nw), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            }
         for (const void *k : lanes) {
             cudaFuncAttributes fa;
             CK(cudaFuncGetAttributes(&fa, k));

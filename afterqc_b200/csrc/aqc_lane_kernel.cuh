@@ -313,12 +313,16 @@ __device__ __forceinline__ void lane_overlap(const LanePlanes<NW> &P1, const Lan
     }
 }
 
+}  // namespace aqc
+#include "aqc_stat2.cuh"      // stat_tile: statRead with one lane per read (needs LanePlanes / shr_bits above)
+namespace aqc {
+
 // dynamic shared memory of one CTA:
 //   [nwarps][ 3 * lane_col_cap ]           per-warp stage: bases 1 | qualities 1 | bases 2 (TMA destinations)
 //   [nwarps][ 4 * 32*NW ]                  per-warp scratch of the statistics hand-over
 //   luts (768 B)
 //   qc acc [2][5][max_len] u32, qc disc [2][max_len] u32, overlap_hist [max_len+1], distance_hist [max_len+1], err matrix [16]
-template <bool PAIRED, int NW>
+template <bool PAIRED, int NW, bool STAT2 = false>
 __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_kernel(const __grid_constant__ LArgs L) {
     AQC_DYN_SMEM(smem_raw);
     __shared__ __align__(8) uint64_t full_bar[LANE_MAX_WARPS];
@@ -688,6 +692,19 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_ke
             if (__builtin_expect(sbm != 0u, 0)) {
                 stat_since_flush += (uint32_t)__popc(sbm);
                 uint8_t *sc_s1 = scratch, *sc_q1 = scratch + MAXB, *sc_s2 = scratch + 2 * MAXB, *sc_q2 = scratch + 3 * MAXB;
+                uint32_t need[2] = {sbm, sbm};                    // per mate: lanes whose read still needs stat_read
+                if constexpr (STAT2) {                            // one lane per read for everything made of A,C,G,T,N (aqc_stat2.cuh)
+#pragma unroll 1
+                    for (int m = 0; m < (paired ? 2 : 1); m++) {
+                        MatePatches mp;
+                        mate_patches(edits, n_edits, m, start1, start2, mp);
+                        const uint8_t *gs = m ? A.seq2 + a2 + start2 : A.seq1 + a1 + start1;
+                        const uint8_t *gq = m ? A.qual2 + a2 + start2 : A.qual1 + a1 + start1;
+                        const bool done = stat_tile<NW>(want, gs, gq, m ? len2 : len1, gidx, m, mp, qsm, A.qc[m], A.p.qc_kmer, lane, A.error_flag);
+                        need[m] = __ballot_sync(FULL, want && !done);
+                    }
+                    sbm = need[0] | (paired ? need[1] : 0u);
+                }
                 while (sbm) {
                     const int src = __ffs(sbm) - 1;
                     sbm &= sbm - 1;
@@ -716,8 +733,10 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_ke
                     }
                     __syncwarp();
 #pragma unroll 1
-                    for (int m = 0; m < (paired ? 2 : 1); m++)
+                    for (int m = 0; m < (paired ? 2 : 1); m++) {
+                        if constexpr (STAT2) { if (!((need[m] >> src) & 1u)) continue; }
                         stat_read(m ? sc_s2 : sc_s1, m ? sc_q2 : sc_q1, m ? bl2 : bl1, m, bg, qsm, A.qc[m], lut1, lut2, lut3, A.p.qc_kmer, lane, A.error_flag);
+                    }
                 }
                 __syncwarp();
                 if (stat_since_flush + 32u > flush_limit) {      // packed shared accumulators: count field is 12 bits

@@ -96,7 +96,11 @@ typedef struct aqc_params {
                                         (lane_kernel) for batches whose reads are <= 256 bases, pair_kernel otherwise; 3 = lane2_kernel, the
                                         same with two staged columns per warp and dynamic tile claiming (experimental).
                                         Results are identical; this is a performance knob. */
-    int32_t reserved[6];
+    int32_t stat_kernel;             /* how statRead (qualitycontrol.py:73-122) is executed: 0 / 1 = one warp per read (stat_read);
+                                        2 = one lane per read with per-cycle warp reductions (stat_tile, aqc_stat2.cuh) in
+                                        aqc_stat_reads and in the sampled statistics of the lane-per-pair filter kernels, for batches
+                                        whose reads are <= 256 bases (experimental, emulator-verified).  Results are identical. */
+    int32_t reserved[5];
 } aqc_params;
 
 /* One packed batch.  off*[i]..off*[i+1] delimit record i in seq* and qual*.  seq2/qual2/off2

@@ -10,17 +10,23 @@ import compare
 from afterqc_b200 import _abi
 
 
-@pytest.fixture(scope="module", params=["warp", "lane", "lane2"])
+KERNELS = {"warp": _abi.KERNEL_WARP, "lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}
+
+
+@pytest.fixture(scope="module", params=["warp", "lane", "lane2", "lane_st2", "lane2_st2"])
 def backends(oracle_lib, request):
     """warp = pair_kernel (one warp per pair); lane = lane_kernel (one lane per pair) + pair_kernel's list mode;
-    lane2 = lane2_kernel (two staged columns per warp, dynamic tile claiming)"""
+    lane2 = lane2_kernel (two staged columns per warp, dynamic tile claiming); *_st2 = the same with aqc_params.stat_kernel = 2
+    (statRead with one lane per read, aqc_stat2.cuh: stat_tile in the sampled statistics, stat_lane_kernel for aqc_stat_reads)"""
     import emu
-    kernel = {"warp": _abi.KERNEL_WARP, "lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}[request.param]
+    name, _, st2 = request.param.partition("_")
 
     def make(params):
-        params.filter_kernel = kernel
+        params.filter_kernel = KERNELS[name]
+        params.stat_kernel = _abi.STAT_LANE if st2 else _abi.STAT_DEFAULT
         return oracle_lib.Oracle(params), emu.EmuEngine(params)
-    make.kernel = request.param
+    make.kernel = name
+    make.stat2 = bool(st2)
     return make
 
 
@@ -50,6 +56,8 @@ def test_emu_ops_parity(backends, bname, pname):
 def test_emu_filter_parity(backends, bname, pname):
     if bname not in ("adversarial", "pe150") and pname not in ("default_f0", "trim", "strict"):
         pytest.skip("reduced matrix on the emulator")
+    if backends.stat2 and (pname not in ("default_f0", "trim", "mask", "nocorr_mask") or (backends.kernel == "lane2" and bname not in ("adversarial", "pe250"))):
+        pytest.skip("reduced matrix for the stat_kernel = 2 variants (the filter part is the base kernel's)")
     batch = BATCHES[bname]()
     orc, eng = backends(cases.make_params(pname))
     a = orc.filter_pairs(batch)
@@ -60,15 +68,18 @@ def test_emu_filter_parity(backends, bname, pname):
 
 
 def test_emu_stat_parity(backends):
-    if backends.kernel != "warp":
-        pytest.skip("the prefilter statistics entry always runs pair_kernel")
-    batch = BATCHES["pe150_jitter"]()
-    for kmer in (8, 4):
+    """aqc_stat_reads: pair_kernel<MODE_STAT> (warp) and stat_lane_kernel (lane_st2: stat_kernel = 2)"""
+    if not (backends.kernel == "warp" or (backends.kernel == "lane" and backends.stat2)):
+        pytest.skip("the prefilter statistics entry does not depend on the filter kernel")
+    for bname, kmer in (("pe150_jitter", 8), ("pe150_jitter", 4), ("adversarial", 8), ("pe250", 8), ("long", 8), ("adversarial", 1)):
+        if not backends.stat2 and bname != "pe150_jitter":
+            continue
+        batch = BATCHES[bname]()
         orc, eng = backends(_abi.Params.defaults(qc_kmer=kmer))
         lo, hi = batch.n // 10, batch.n - batch.n // 7
         for be in (orc, eng):
             be.stat_reads(batch, _abi.QC_R1_PRE, _abi.QC_R2_PRE, stat_lo=lo, stat_hi=hi, order_base=0)
-        compare.compare_backends(orc, eng, (_abi.QC_R1_PRE, _abi.QC_R2_PRE), "emu stat k=%d" % kmer)
+        compare.compare_backends(orc, eng, (_abi.QC_R1_PRE, _abi.QC_R2_PRE), "emu stat %s k=%d" % (bname, kmer))
         orc.close(); eng.close()
 
 
@@ -166,7 +177,7 @@ def test_emu_empty_mate_reaches_statread(backends):
     orc.close(); eng.close()
 
 
-@pytest.mark.parametrize("kernel", ["warp", "lane", "lane2"])
+@pytest.mark.parametrize("kernel", ["warp", "lane", "lane2", "lane_st2"])
 @pytest.mark.parametrize("name", ["pe150_default", "pe150_err3_mask_overlap", "pe250_k5_strict", "se100_f0"])
 def test_emu_pipeline_matches_reference_golden(name, kernel, tmp_path):
     """the whole drop-in pipeline (readers, packed columns, engine calls, writers, JSON) on the emulated engine reproduces
@@ -177,7 +188,8 @@ def test_emu_pipeline_matches_reference_golden(name, kernel, tmp_path):
         pytest.skip("golden case %s not present" % name)
 
     def factory(p):
-        p.filter_kernel = {"warp": _abi.KERNEL_WARP, "lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}[kernel]
+        p.filter_kernel = KERNELS[kernel.partition("_")[0]]
+        p.stat_kernel = _abi.STAT_LANE if kernel.endswith("_st2") else _abi.STAT_DEFAULT
         return emu.EmuEngine(p)
     problems = golden_util.run_case(name, tmp_path, factory)
     assert not problems, problems
