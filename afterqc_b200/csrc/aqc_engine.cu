@@ -50,6 +50,7 @@ struct aqc_ctx {
     uint32_t *d_fb_list = nullptr, *d_fb_count = nullptr;
     size_t fb_cap = 0;
     int lane_mode = 0;             // 0 = warp-per-pair kernel only, 1 = lane-per-pair kernel for batches of short reads
+    int stat_mode = 0;             // AQC_STAT_KERNEL=2: statRead with one lane per read when aqc_params.stat_kernel is 0
     Staging stg[2];
     uint32_t chunk_pairs = 1u << 18;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -289,6 +290,8 @@ size_t pair_tiling(aqc_ctx *ctx, KArgs &A, uint32_t n_tiles_of, int maxl, int ca
     return smem;
 }
 
+bool stat2_on(const aqc_ctx *ctx) { return ctx->p.stat_kernel == 2 || (ctx->p.stat_kernel == 0 && ctx->stat_mode); }
+
 bool lane_path(const aqc_ctx *ctx, int mode, int max_len) {
     const bool want_lane = ctx->p.filter_kernel == 2 || ctx->p.filter_kernel == 3 || (ctx->p.filter_kernel == 0 && ctx->lane_mode);
     return mode == MODE_FILTER && want_lane && lane_words_for(std::max(max_len, 8)) != 0;
@@ -367,7 +370,7 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         L.tile_counter = ctx->d_fb_count + 1;
         const bool gen2 = ctx->p.filter_kernel == 3;
         const int ncols = (pe && !gen2) ? 3 : 2;
-        const bool stat2 = ctx->p.stat_kernel == 2;
+        const bool stat2 = stat2_on(ctx);
         const void *lk = gen2 ? lane2_kernel_for(pe, nw, stat2) : lane_kernel_for(pe, nw, stat2);
         int best_w = 0, best_occ = 0;
         for (int w = LANE_MAX_WARPS; w >= 1; w--) {           // most resident warps per SM; ties go to the larger CTA
@@ -410,7 +413,7 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         return 0;
     }
 
-    if (x.mode == MODE_STAT && ctx->p.stat_kernel == 2 && lane_words_for(maxl) != 0) {
+    if (x.mode == MODE_STAT && stat2_on(ctx) && lane_words_for(maxl) != 0) {
         // ---- prefilter statistics with one lane per read (aqc_stat2.cuh) ----
         const int snw = lane_words_for(maxl);
         const void *sk = stat_lane_kernel_for(pe, snw);
@@ -647,6 +650,7 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
         }
         CK(cudaMalloc(&ctx->d_fb_count, 2 * sizeof(uint32_t)));
         if (const char *lm = getenv("AQC_LANE_KERNEL")) ctx->lane_mode = atoi(lm) != 0;
+        if (const char *sk = getenv("AQC_STAT_KERNEL")) ctx->stat_mode = atoi(sk) == 2;       // opt-in for callers that pass stat_kernel = 0
         if (const char *cp = getenv("AQC_CHUNK_PAIRS")) {          // host-path chunk size (tests exercise the multi-chunk pipeline with small batches)
             long v = atol(cp);
             if (v >= 4) ctx->chunk_pairs = (uint32_t)std::min<long>(v & ~3L, 1L << 24);

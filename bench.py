@@ -56,6 +56,9 @@ def parse_args():
     ap.add_argument("--filter-kernel", default="auto", choices=["auto", "warp", "lane", "lane2"],
                     help="filter kernel: warp = pair_kernel (one warp per pair), lane = lane_kernel (one lane per pair); auto = lane "
                          "only if it first proves bit-identical to warp on this GPU (child process with a timeout, then the full batch)")
+    ap.add_argument("--stat-kernel", default="auto", choices=["auto", "warp", "lane"],
+                    help="statRead kernel (aqc_params.stat_kernel): warp = stat_read (one warp per read), lane = stat_tile / "
+                         "stat_lane_kernel (one lane per read); auto = lane only after the same two-stage identity check, and only if faster")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -283,21 +286,26 @@ def lane_child_check(local_rank, pairs, timeout_s=300, candidate="lane"):
     return out
 
 
-def lane_full_size_check(wb, n, qs, local_rank, stream, cand_kernel):
+def lane_full_size_check(wb, n, qs, local_rank, stream, cand_kernel, cand_stat=0, window=None):
     """Both kernels once over the resident full-size batch in this process: records, scalar counters, histograms, error
-    matrix, postfilter per-cycle statistics and k-mer tables must be identical."""
+    matrix, per-cycle statistics and k-mer tables must be identical (with a candidate statistics kernel: also the prefilter
+    slots after aqc_stat_reads over `window` = (first record, end record, global lo, global hi))."""
     import torch
     from afterqc_b200 import _abi
     from afterqc_b200.engine import Engine
     ref = None
-    for k in (_abi.KERNEL_WARP, cand_kernel):
-        e = Engine(_abi.Params.defaults(qc_sample=qs, filter_kernel=k), device=local_rank)
+    slots = (_abi.QC_R1_POST, _abi.QC_R2_POST) + ((_abi.QC_R1_PRE, _abi.QC_R2_PRE) if (cand_stat and window) else ())
+    for k, sk in ((_abi.KERNEL_WARP, _abi.STAT_DEFAULT), (cand_kernel, cand_stat)):
+        e = Engine(_abi.Params.defaults(qc_sample=qs, filter_kernel=k, stat_kernel=sk), device=local_rank)
         e.set_stream(stream.cuda_stream)
         res = torch.empty(max(1, n) * 32, dtype=torch.uint8, device=wb.results.device)
+        if cand_stat and window:
+            b = wb.struct(window[0], window[1])
+            e._check(e._L.aqc_stat_reads(e._h, C.byref(b), _abi.MEM_DEVICE, _abi.QC_R1_PRE, _abi.QC_R2_PRE, window[2], window[3], 0))
         b = wb.struct()
         e._check(e._L.aqc_filter_pairs(e._h, C.byref(b), _abi.MEM_DEVICE, res.data_ptr()))
         e.sync()
-        got = (res, e.counters(), [e.qc(s) for s in (_abi.QC_R1_POST, _abi.QC_R2_POST)], [e.kmers(s) for s in (_abi.QC_R1_POST, _abi.QC_R2_POST)])
+        got = (res, e.counters(), [e.qc(s) for s in slots], [e.kmers(s) for s in slots])
         e.close()
         if ref is None:
             ref = got
@@ -345,26 +353,47 @@ def run_ours(args):
     KID = {"warp": _abi.KERNEL_WARP, "lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}
     selection = {"requested": args.filter_kernel}
     chosen = args.filter_kernel if args.filter_kernel != "auto" else "warp"
+    stat2 = args.stat_kernel == "lane"          # aqc_params.stat_kernel = 2 (statRead with one lane per read, aqc_stat2.cuh)
     child = None
     if args.filter_kernel == "auto":
         best_ms = None
         for cand in ("lane", "lane2"):
-            c = lane_child_check(local_rank, min(n, 2_000_000), candidate=cand)
+            c = lane_child_check(local_rank, min(n, 2_000_000), timeout_s=240 if cand == "lane" else 150, candidate=cand)
             selection["child_check_" + cand] = c
             if not c.get("ok"):
                 continue
             ms, wms = c.get("lane_ms", 0), c.get("warp_ms", 0)
             if ms > 0 and ms < wms and (best_ms is None or ms < best_ms):
                 best_ms, chosen, child = ms, cand, c
+    if args.stat_kernel == "auto":
+        # the statistics kernel: the chosen filter kernel with stat_kernel = 2 must be identical in a child process and
+        # faster on filter + prefilter statistics together (written without GPU access, emulator-verified when committed)
+        c = lane_child_check(local_rank, min(n, 2_000_000), timeout_s=150, candidate=chosen + "_st2")
+        selection["child_check_" + chosen + "_st2"] = c
+        if c.get("ok"):
+            base_ms = child.get("lane_ms", 0) if child else c.get("warp_ms", 0)      # the chosen filter kernel with stat_read
+            old_ms, new_ms = base_ms + c.get("stat_warp_ms", 0), c.get("lane_ms", 0) + c.get("stat_ms", 0)
+            stat2 = 0 < new_ms < old_ms
     wb = make_device_workload(device, n, seed=20260927 + rank, first_index=first_index)
-    if chosen != "warp" and args.filter_kernel == "auto":
-        try:
-            ok, why = lane_full_size_check(wb, n, QS, local_rank, stream, KID[chosen])
-        except Exception as e:      # noqa: BLE001
-            ok, why = False, "full-size check raised %r" % (e,)
-        selection["full_size_check"] = why
-        if not ok:
-            chosen = "warp"
+    # records of this shard inside the prefilter window [999, 999 + qc_sample) (global indices)
+    w_lo_g, w_hi_g = STAT_LO, STAT_LO + QS
+    s_lo = max(w_lo_g, first_index) - first_index
+    s_hi = min(w_hi_g, first_index + n) - first_index
+    has_window = s_hi > s_lo
+    s_lo_al = (s_lo // 4) * 4
+    if (chosen != "warp" or stat2) and (args.filter_kernel == "auto" or args.stat_kernel == "auto"):
+        attempts = [(chosen, stat2)] + ([(chosen, False)] if (stat2 and chosen != "warp") else [])
+        chosen, stat2 = "warp", False
+        for cand, st in attempts:       # a failing statistics kernel must not cost the filter kernel its place
+            try:
+                ok, why = lane_full_size_check(wb, n, QS, local_rank, stream, KID[cand], _abi.STAT_LANE if st else _abi.STAT_DEFAULT,
+                                               (s_lo_al, s_hi, w_lo_g, w_hi_g) if has_window else None)
+            except Exception as e:      # noqa: BLE001
+                ok, why = False, "full-size check raised %r" % (e,)
+            selection["full_size_check_%s%s" % (cand, "_st2" if st else "")] = why
+            if ok:
+                chosen, stat2 = cand, st
+                break
     if world > 1:       # every rank runs the same kernel: the most conservative choice any rank made
         flag = torch.tensor([KID[chosen]], dtype=torch.int32, device=device)
         flags = [torch.zeros_like(flag) for _ in range(world)]
@@ -377,23 +406,21 @@ def run_ours(args):
         else:
             agreed = _abi.KERNEL_LANE
         chosen = {v: k for k, v in KID.items()}[agreed]
+        sflag = torch.tensor([1 if stat2 else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(sflag, op=dist.ReduceOp.MIN)
+        stat2 = bool(sflag.item())
     use_lane = chosen != "warp"
     selection["used"] = chosen
+    selection["stat_kernel_requested"] = args.stat_kernel
+    selection["stat_kernel_used"] = "lane (stat_tile / stat_lane_kernel)" if stat2 else "warp (stat_read)"
     kernel_label = {"warp": "aqc::pair_kernel (MODE_FILTER, one warp per pair)",
                     "lane": "aqc::lane_kernel (one lane per pair) + aqc::pair_kernel list mode",
                     "lane2": "aqc::lane2_kernel (one lane per pair, 2-column stage, dynamic tiles) + aqc::pair_kernel list mode"}[chosen]
 
-    params = _abi.Params.defaults(qc_sample=QS, filter_kernel=KID[chosen])
+    params = _abi.Params.defaults(qc_sample=QS, filter_kernel=KID[chosen], stat_kernel=_abi.STAT_LANE if stat2 else _abi.STAT_DEFAULT)
     eng = Engine(params, device=local_rank)
     eng.set_stream(stream.cuda_stream)
     L = eng._L
-
-    # records of this shard inside the prefilter window [999, 999 + qc_sample) (global indices)
-    w_lo_g, w_hi_g = STAT_LO, STAT_LO + QS
-    s_lo = max(w_lo_g, first_index) - first_index
-    s_hi = min(w_hi_g, first_index + n) - first_index
-    has_window = s_hi > s_lo
-    s_lo_al = (s_lo // 4) * 4
 
     reduce_views = []
     if world > 1:

@@ -3,9 +3,10 @@
 round without GPU time left and had only been run under the SIMT emulator (tests/emu) when it was committed.
 
   python tests/lane_gpu_check.py parity          lane engine vs the CPU oracle, bit-exact, on the parity-test batches
-  python tests/lane_gpu_check.py full [pairs] [lane|lane2]
+  python tests/lane_gpu_check.py full [pairs] [lane|lane2|warp_st2|lane_st2|lane2_st2]
                                                  that kernel vs the warp-per-pair kernel on the bench workload
-                                                 (HBM-resident entry); prints one JSON line with both kernel times
+                                                 (HBM-resident entry); prints one JSON line with both kernel times;
+                                                 *_st2 = with aqc_params.stat_kernel = 2 (also compares aqc_stat_reads)
 Exit code 0 = identical everywhere.
 """
 import json
@@ -22,6 +23,16 @@ for p in (ROOT, HERE):
 import numpy as np  # noqa: E402
 
 
+def kernel_ids(candidate):
+    """'lane' | 'lane2' | 'warp', optionally with '_st2' (aqc_params.stat_kernel = 2: statRead with one lane per read)"""
+    from afterqc_b200 import _abi
+    base, _, st2 = candidate.partition("_")
+    fk = {"warp": _abi.KERNEL_WARP, "lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}[base]
+    if st2 not in ("", "st2"):
+        raise SystemExit("unknown candidate %r" % candidate)
+    return fk, (_abi.STAT_LANE if st2 else _abi.STAT_DEFAULT)
+
+
 def parity(candidate="lane"):
     import cases
     import compare
@@ -29,6 +40,7 @@ def parity(candidate="lane"):
     from afterqc_b200.engine import Engine
     from oracle import oracle
     oracle.build()
+    fk, sk = kernel_ids(candidate)
     batches = {
         "adversarial": (cases.adversarial_batch(), list(cases.PARAM_SETS)),
         "pe150": (cases.synthetic("pe150", 20000), list(cases.PARAM_SETS)),
@@ -41,11 +53,11 @@ def parity(candidate="lane"):
     for bname, (batch, pnames) in batches.items():
         for pname in pnames:
             p = cases.make_params(pname)
-            p.filter_kernel = {"lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}[candidate]
+            p.filter_kernel = fk; p.stat_kernel = sk
             orc, eng = oracle.Oracle(p), Engine(p)
             a = orc.filter_pairs(batch)
             b = eng.filter_pairs(batch)
-            what = "lane %s/%s" % (bname, pname)
+            what = "%s %s/%s" % (candidate, bname, pname)
             compare.assert_records_equal(batch, a, b, what)
             compare.compare_backends(orc, eng, (_abi.QC_R1_POST, _abi.QC_R2_POST), what)
             # the HBM-resident entry
@@ -54,12 +66,17 @@ def parity(candidate="lane"):
             eng.filter_pairs(d)
             compare.assert_records_equal(batch, a, eng.fetch_results(d), what + " resident")
             compare.assert_counters_equal(orc.counters(), eng.counters(), what + " resident")
+            if sk and pname == pnames[0]:                 # the prefilter statistics entry (stat_lane_kernel), window inside the batch
+                lo, hi = batch.n // 10, batch.n - batch.n // 7
+                for be, bb in ((orc, batch), (eng, d)):
+                    be.stat_reads(bb, _abi.QC_R1_PRE, _abi.QC_R2_PRE, stat_lo=lo, stat_hi=hi, order_base=3)
+                compare.compare_backends(orc, eng, (_abi.QC_R1_PRE, _abi.QC_R2_PRE), what + " prefilter statistics")
             d.free(); orc.close(); eng.close()
             n_cases += 1
     se = cases.synthetic("se100", 30000)
     for pname in ("default_f0", "trim", "loose"):
         p = cases.make_params(pname, paired=False)
-        p.filter_kernel = {"lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}[candidate]
+        p.filter_kernel = fk; p.stat_kernel = sk
         orc, eng = oracle.Oracle(p), Engine(p)
         compare.assert_records_equal(se, orc.filter_pairs(se), eng.filter_pairs(se), "lane se100 %s" % pname)
         compare.compare_backends(orc, eng, (_abi.QC_R1_POST,), "lane se100 %s" % pname)
@@ -82,11 +99,28 @@ def full(pairs, candidate="lane"):
     torch.cuda.empty_cache()
     out = {}
     ref = None
-    cand_id = {"lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}[candidate]
+    cand_id, cand_stat = kernel_ids(candidate)
     out["candidate"] = candidate
-    for name, k in (("warp", _abi.KERNEL_WARP), ("lane", cand_id)):      # key "lane_ms" = the candidate's time
-        eng = Engine(_abi.Params.defaults(filter_kernel=k))
+    sref = None
+    s_lo, s_hi = 999, 999 + min(200000, max(1, pairs // 2))       # bench.py's prefilter window
+    for name, k, sk in (("warp", _abi.KERNEL_WARP, _abi.STAT_DEFAULT), ("lane", cand_id, cand_stat)):      # key "lane_ms" = the candidate's time
+        eng = Engine(_abi.Params.defaults(filter_kernel=k, stat_kernel=sk))
         d = eng.upload(host)
+        if cand_stat:                                        # aqc_stat_reads: pair_kernel<MODE_STAT> vs stat_lane_kernel
+            eng.stat_reads(d, _abi.QC_R1_PRE, _abi.QC_R2_PRE, s_lo, s_hi, 0); eng.sync()
+            eng.reset()
+            eng.stat_reads(d, _abi.QC_R1_PRE, _abi.QC_R2_PRE, s_lo, s_hi, 0); eng.sync()
+            out["stat_warp_ms" if name == "warp" else "stat_ms"] = round(eng.last_kernel_ms(), 4)
+            sgot = ([eng.qc(x) for x in (_abi.QC_R1_PRE, _abi.QC_R2_PRE)], [eng.kmers(x) for x in (_abi.QC_R1_PRE, _abi.QC_R2_PRE)])
+            if sref is None:
+                sref = sgot
+            else:
+                for a, b in zip(sgot[0], sref[0]):
+                    for f in a.dtype.names:
+                        assert np.array_equal(a[f], b[f]), "prefilter QC field %s differs between the statistics kernels" % f
+                for a, b in zip(sgot[1], sref[1]):
+                    for x, y in zip(a, b):
+                        assert np.array_equal(x, y), "prefilter k-mer tables differ between the statistics kernels"
         eng.filter_pairs(d); eng.sync()                      # warm-up
         eng.reset()
         eng.filter_pairs(d); eng.sync()
@@ -107,7 +141,7 @@ def full(pairs, candidate="lane"):
             for a, b in zip(km, ref[3]):
                 for x, y in zip(a, b):
                     assert np.array_equal(x, y), "k-mer tables differ between the kernels"
-        if name == "lane":
+        if name == "lane" and cand_id != _abi.KERNEL_WARP and not cand_stat:
             # host-buffer entry, mate-2 qualities copied vs left in page-locked host memory (AQC_BATCH_QUAL2_IN_PLACE)
             try:
                 import ctypes as C
@@ -143,14 +177,19 @@ def smoke():
     from afterqc_b200.engine import Engine
     from oracle import oracle
     oracle.build()
-    for cand, kid in (("lane", _abi.KERNEL_LANE), ("lane2", _abi.KERNEL_LANE2)):
+    for cand in ("lane", "lane2", "lane_st2"):
+        kid, sk = kernel_ids(cand)
         try:
             for bname, batch in (("adversarial", cases.adversarial_batch()), ("pe150", cases.synthetic("pe150", 4096))):
-                p = cases.make_params("default_f0"); p.qc_sample = 3000; p.filter_kernel = kid
+                p = cases.make_params("default_f0"); p.qc_sample = 3000; p.filter_kernel = kid; p.stat_kernel = sk
                 orc, eng = oracle.Oracle(p), Engine(p)
                 a = orc.filter_pairs(batch); b = eng.filter_pairs(batch)
                 compare.assert_records_equal(batch, a, b, "%s smoke %s" % (cand, bname))
                 compare.compare_backends(orc, eng, (_abi.QC_R1_POST, _abi.QC_R2_POST), "%s smoke %s" % (cand, bname))
+                if sk:
+                    for be in (orc, eng):
+                        be.stat_reads(batch, _abi.QC_R1_PRE, _abi.QC_R2_PRE, stat_lo=7, stat_hi=batch.n - 5, order_base=0)
+                    compare.compare_backends(orc, eng, (_abi.QC_R1_PRE, _abi.QC_R2_PRE), "%s smoke %s prefilter" % (cand, bname))
                 orc.close(); eng.close()
             print("%s kernel smoke ok (bit-exact vs the oracle: adversarial + pe150)" % cand)
         except Exception as e:      # noqa: BLE001

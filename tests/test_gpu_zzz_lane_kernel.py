@@ -40,11 +40,27 @@ def test_lane_kernel_equals_warp_kernel_at_bench_size():
 
 @pytest.mark.xfail(reason="lane2_kernel has not run on hardware yet (written after the round's GPU budget was spent); emulator-verified", strict=False)
 def test_lane2_kernel_equals_warp_kernel_at_bench_size():
-    out = _run(["full", "2000000", "lane2"], 600)
+    out = _run(["full", "2000000", "lane2"], 240)
     assert '"identical": true' in out
 
 
 @pytest.mark.xfail(reason="lane2_kernel has not run on hardware yet (written after the round's GPU budget was spent); emulator-verified", strict=False)
 def test_lane2_kernel_parity_vs_oracle():
-    out = _run(["parity", "lane2"], 600)
+    out = _run(["parity", "lane2"], 300)
     assert "lane2 kernel parity ok" in out
+
+
+ST2_REASON = "stat_tile / stat_lane_kernel (aqc_params.stat_kernel = 2) were written after the round's GPU budget was spent; emulator-verified"
+
+
+@pytest.mark.xfail(reason=ST2_REASON, strict=False)
+@pytest.mark.parametrize("cand", ["warp_st2", "lane_st2"])
+def test_stat2_equals_warp_statistics_at_bench_size(cand):
+    out = _run(["full", "2000000", cand], 240)
+    assert '"identical": true' in out
+
+
+@pytest.mark.xfail(reason=ST2_REASON, strict=False)
+def test_stat2_parity_vs_oracle():
+    out = _run(["parity", "lane_st2"], 300)
+    assert "lane_st2 kernel parity ok" in out

@@ -99,8 +99,10 @@ def one_case(rng, k):
     batch = PackedBatch.from_reads([p[0] for p in pairs], [p[1] for p in pairs] if paired else None, first_index=rng.choice([0, 0, 17, 199990]))
     p = rand_params(rng, paired)
     results = {}
-    for kern in (_abi.KERNEL_WARP, _abi.KERNEL_LANE, _abi.KERNEL_LANE2):
+    # (filter kernel, statistics kernel): the lane-per-read statistics (stat_kernel = 2) ride on every filter kernel
+    for kern, sk in ((_abi.KERNEL_WARP, 0), (_abi.KERNEL_LANE, 0), (_abi.KERNEL_LANE2, 0), (_abi.KERNEL_WARP, 2), (_abi.KERNEL_LANE, 2), (_abi.KERNEL_LANE2, 2)):
         p.filter_kernel = kern
+        p.stat_kernel = sk
         orc, eng = oracle.Oracle(p), emu.EmuEngine(p)
         try:
             err_o = err_e = None
@@ -113,15 +115,15 @@ def one_case(rng, k):
             except Exception as e:      # noqa: BLE001
                 err_e = getattr(e, "code", repr(e))
             if err_o is not None or err_e is not None:
-                assert err_o == err_e, "case %d kernel %d: oracle error %r engine error %r" % (k, kern, err_o, err_e)
-                results[kern] = "both raise %r" % (err_o,)
+                assert err_o == err_e, "case %d kernel %d/%d: oracle error %r engine error %r" % (k, kern, sk, err_o, err_e)
+                results[(kern, sk)] = "both raise %r" % (err_o,)
                 continue
-            what = "case %d kernel %d" % (k, kern)
+            what = "case %d kernel %d stat_kernel %d" % (k, kern, sk)
             compare.assert_records_equal(batch, a, b, what)
             slots = (_abi.QC_R1_POST, _abi.QC_R2_POST) if paired else (_abi.QC_R1_POST,)
             compare.compare_backends(orc, eng, slots, what)
-            results[kern] = "ok"
-            if kern == _abi.KERNEL_WARP:        # the operator and prefilter-statistics entries (always pair_kernel)
+            results[(kern, sk)] = "ok"
+            if kern == _abi.KERNEL_WARP:        # the operator and prefilter-statistics entries (pair_kernel; stat_lane_kernel with stat_kernel = 2)
                 compare.assert_records_equal(batch, orc.ops_pairs(batch), eng.ops_pairs(batch), what + " ops")
                 lo = batch.first_index + rng.randint(0, max(0, batch.n - 1)); hi = lo + rng.randint(0, batch.n)
                 errs = []
