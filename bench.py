@@ -371,9 +371,13 @@ def run_ours(args):
         c = lane_child_check(local_rank, min(n, 2_000_000), timeout_s=150, candidate=chosen + "_st2")
         selection["child_check_" + chosen + "_st2"] = c
         if c.get("ok"):
-            base_ms = child.get("lane_ms", 0) if child else c.get("warp_ms", 0)      # the chosen filter kernel with stat_read
-            old_ms, new_ms = base_ms + c.get("stat_warp_ms", 0), c.get("lane_ms", 0) + c.get("stat_ms", 0)
-            stat2 = 0 < new_ms < old_ms
+            # the chosen filter kernel with stat_read: timed by its own child check, or the warp kernel of this one
+            base_ms = child.get("lane_ms", 0) if child else (c.get("warp_ms", 0) if chosen == "warp" else None)
+            if base_ms is None:         # explicit --filter-kernel: only the prefilter launches are comparable
+                stat2 = 0 < c.get("stat_ms", 0) < c.get("stat_warp_ms", 0)
+            else:
+                old_ms, new_ms = base_ms + c.get("stat_warp_ms", 0), c.get("lane_ms", 0) + c.get("stat_ms", 0)
+                stat2 = 0 < new_ms < old_ms
     wb = make_device_workload(device, n, seed=20260927 + rank, first_index=first_index)
     # records of this shard inside the prefilter window [999, 999 + qc_sample) (global indices)
     w_lo_g, w_hi_g = STAT_LO, STAT_LO + QS
