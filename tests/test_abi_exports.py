@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -54,3 +56,18 @@ def test_engine_fails_loudly_without_gpu_or_library(monkeypatch):
     monkeypatch.setattr(_native, "LIB_PATH", "/nonexistent/libafterqc_b200.so")
     with pytest.raises(ImportError):
         _native.lib()
+
+
+def test_hardware_verified_kernels_are_unchanged():
+    """profiles/sass_fingerprints.json lists the kernels whose parity was seen green on a B200; a refactoring of the shared
+    headers must leave their SASS untouched (same nvcc), or the file is updated after they are verified on the GPU again:
+    `python tools/sass_fingerprint.py --update`."""
+    import shutil
+    import sys
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_fingerprint
+    from afterqc_b200 import build
+    build.build()
+    assert sass_fingerprint.compare() == []
