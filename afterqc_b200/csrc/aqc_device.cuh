@@ -608,6 +608,46 @@ struct QcSmem {
     int max_len;
 };
 
+// Flush of the packed accumulators by ONE warp while the CTA's other warps keep adding: every word is exchanged with 0.
+__device__ __forceinline__ void qc_flush_warp(const QcDev (&qc)[2], uint32_t *s_acc, uint32_t *s_disc, int max_len, int lane) {
+    for (int m = 0; m < 2; m++) {
+        const QcDev &qd = qc[m];
+        if (!qd.valid) continue;
+        for (int i = lane; i < QC_CLASSES * max_len; i += 32) {
+            const uint32_t v = atomicExch(&s_acc[m * QC_CLASSES * max_len + i], 0u);
+            if (v) {
+                const int c = i / max_len, pos = i - c * max_len;
+                atomicAdd(&qd.cls_cnt[c * AQC_MAX_LEN + pos], (unsigned long long)(v >> 20));
+                atomicAdd(&qd.cls_qsum[c * AQC_MAX_LEN + pos], (unsigned long long)(v & 0xFFFFFu));
+            }
+        }
+        for (int i = lane; i < max_len; i += 32) {
+            const uint32_t v = atomicExch(&s_disc[m * max_len + i], 0u);
+            if (v) atomicAdd(&qd.disc[i], (unsigned long long)v);
+        }
+    }
+}
+
+// Final flush by the whole CTA (after a __syncthreads: nobody adds any more).
+__device__ __forceinline__ void qc_flush_cta(const QcDev (&qc)[2], const uint32_t *s_acc, const uint32_t *s_disc, int max_len, int tid, unsigned nthreads) {
+    for (int m = 0; m < 2; m++) {
+        const QcDev &qd = qc[m];
+        if (!qd.valid) continue;
+        for (int i = tid; i < QC_CLASSES * max_len; i += nthreads) {
+            const uint32_t v = s_acc[m * QC_CLASSES * max_len + i];
+            if (v) {
+                const int c = i / max_len, pos = i - c * max_len;
+                atomicAdd(&qd.cls_cnt[c * AQC_MAX_LEN + pos], (unsigned long long)(v >> 20));
+                atomicAdd(&qd.cls_qsum[c * AQC_MAX_LEN + pos], (unsigned long long)(v & 0xFFFFFu));
+            }
+        }
+        for (int i = tid; i < max_len; i += nthreads) {
+            const uint32_t v = s_disc[m * max_len + i];
+            if (v) atomicAdd(&qd.disc[i], (unsigned long long)v);
+        }
+    }
+}
+
 __device__ __forceinline__ unsigned long long side_hash(unsigned long long k) {
     k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
     return k;

@@ -464,22 +464,7 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane2_k
                 }
                 __syncwarp();
                 if (stat_since_flush + 32u > flush_limit) {      // packed shared accumulators: count field is 12 bits
-                    for (int m = 0; m < 2; m++) {
-                        const QcDev &qd = A.qc[m];
-                        if (!qd.valid) continue;
-                        for (int i = lane; i < QC_CLASSES * A.max_len; i += 32) {
-                            const uint32_t v = atomicExch(&s_acc[m * QC_CLASSES * A.max_len + i], 0u);
-                            if (v) {
-                                const int c = i / A.max_len, pos = i - c * A.max_len;
-                                atomicAdd(&qd.cls_cnt[c * AQC_MAX_LEN + pos], (unsigned long long)(v >> 20));
-                                atomicAdd(&qd.cls_qsum[c * AQC_MAX_LEN + pos], (unsigned long long)(v & 0xFFFFFu));
-                            }
-                        }
-                        for (int i = lane; i < A.max_len; i += 32) {
-                            const uint32_t v = atomicExch(&s_disc[m * A.max_len + i], 0u);
-                            if (v) atomicAdd(&qd.disc[i], (unsigned long long)v);
-                        }
-                    }
+                    qc_flush_warp(A.qc, s_acc, s_disc, A.max_len, lane);
                     stat_since_flush = 0;
                 }
             }
@@ -491,22 +476,7 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane2_k
 
     // ---- epilogue: flush everything this CTA accumulated ----
     __syncthreads();
-    for (int m = 0; m < 2; m++) {
-        const QcDev &qd = A.qc[m];
-        if (!qd.valid) continue;
-        for (int i = tid; i < QC_CLASSES * A.max_len; i += blockDim.x) {
-            const uint32_t v = s_acc[m * QC_CLASSES * A.max_len + i];
-            if (v) {
-                const int c = i / A.max_len, pos = i - c * A.max_len;
-                atomicAdd(&qd.cls_cnt[c * AQC_MAX_LEN + pos], (unsigned long long)(v >> 20));
-                atomicAdd(&qd.cls_qsum[c * AQC_MAX_LEN + pos], (unsigned long long)(v & 0xFFFFFu));
-            }
-        }
-        for (int i = tid; i < A.max_len; i += blockDim.x) {
-            const uint32_t v = s_disc[m * A.max_len + i];
-            if (v) atomicAdd(&qd.disc[i], (unsigned long long)v);
-        }
-    }
+    qc_flush_cta(A.qc, s_acc, s_disc, A.max_len, tid, blockDim.x);
     for (int i = tid; i <= A.max_len; i += blockDim.x) {
         uint32_t v = s_ovh[i]; if (v) atomicAdd(&A.counters[AQC_C_OVERLAP_HIST + i], (unsigned long long)v);
         v = s_dih[i]; if (v) atomicAdd(&A.counters[AQC_C_DISTANCE_HIST + i], (unsigned long long)v);

@@ -361,43 +361,13 @@ __global__ void __launch_bounds__(STAT2_WARPS * 32) stat_lane_kernel(const __gri
         }
         __syncwarp();
         if (stat_since_flush + 32u > flush_limit) {              // packed shared accumulators: count field is 12 bits
-            for (int m = 0; m < 2; m++) {
-                const QcDev &qd = A.qc[m];
-                if (!qd.valid) continue;
-                for (int i = lane; i < QC_CLASSES * A.max_len; i += 32) {
-                    const uint32_t v = atomicExch(&s_acc[m * QC_CLASSES * A.max_len + i], 0u);
-                    if (v) {
-                        const int c = i / A.max_len, pos = i - c * A.max_len;
-                        atomicAdd(&qd.cls_cnt[c * AQC_MAX_LEN + pos], (unsigned long long)(v >> 20));
-                        atomicAdd(&qd.cls_qsum[c * AQC_MAX_LEN + pos], (unsigned long long)(v & 0xFFFFFu));
-                    }
-                }
-                for (int i = lane; i < A.max_len; i += 32) {
-                    const uint32_t v = atomicExch(&s_disc[m * A.max_len + i], 0u);
-                    if (v) atomicAdd(&qd.disc[i], (unsigned long long)v);
-                }
-            }
+            qc_flush_warp(A.qc, s_acc, s_disc, A.max_len, lane);
             stat_since_flush = 0;
         }
     }
 
     __syncthreads();
-    for (int m = 0; m < 2; m++) {
-        const QcDev &qd = A.qc[m];
-        if (!qd.valid) continue;
-        for (int i = tid; i < QC_CLASSES * A.max_len; i += blockDim.x) {
-            const uint32_t v = s_acc[m * QC_CLASSES * A.max_len + i];
-            if (v) {
-                const int c = i / A.max_len, pos = i - c * A.max_len;
-                atomicAdd(&qd.cls_cnt[c * AQC_MAX_LEN + pos], (unsigned long long)(v >> 20));
-                atomicAdd(&qd.cls_qsum[c * AQC_MAX_LEN + pos], (unsigned long long)(v & 0xFFFFFu));
-            }
-        }
-        for (int i = tid; i < A.max_len; i += blockDim.x) {
-            const uint32_t v = s_disc[m * A.max_len + i];
-            if (v) atomicAdd(&qd.disc[i], (unsigned long long)v);
-        }
-    }
+    qc_flush_cta(A.qc, s_acc, s_disc, A.max_len, tid, blockDim.x);
 }
 
 }  // namespace aqc
