@@ -9,6 +9,7 @@
 #include <vector>
 #include <algorithm>
 #include "aqc_kernel.cuh"
+#include "aqc_pack.hpp"
 #include "aqc_lane_kernel.cuh"
 #include "aqc_lane2_kernel.cuh"
 
@@ -29,6 +30,11 @@ struct Staging {     // device staging of one host chunk
     uint32_t *off[2] = {nullptr, nullptr};
     void *res = nullptr;
     size_t col_cap = 0, off_cap = 0, res_cap = 0;
+    // packed base transport (AQC_BATCH_PACK_BASES): page-locked host buffers the pool packs into, and their device copies
+    uint8_t *hp[2] = {nullptr, nullptr}, *dp[2] = {nullptr, nullptr};       // 2-bit bases of mate 1 / mate 2
+    uint32_t *hx_pos[2] = {nullptr, nullptr}, *dx_pos[2] = {nullptr, nullptr};   // exceptions: position in the staged column
+    uint8_t *hx_val[2] = {nullptr, nullptr}, *dx_val[2] = {nullptr, nullptr};    //             and the byte
+    size_t pk_cap = 0, x_cap = 0;
     cudaEvent_t h2d_done = nullptr, k_done = nullptr, d2h_done = nullptr;
 };
 
@@ -49,6 +55,7 @@ struct aqc_ctx {
     // lane-per-pair filter path (aqc_lane_kernel.cuh): hand-over list of the pairs that need the general kernel
     uint32_t *d_fb_list = nullptr, *d_fb_count = nullptr;
     size_t fb_cap = 0;
+    aqc_pack::Pool *pack_pool = nullptr;    // host threads of the packed base transport, created at first use
     int lane_mode = 0;             // 0 = warp-per-pair kernel only, 1 = lane-per-pair kernel for batches of short reads
     int stat_mode = 0;             // AQC_STAT_KERNEL=2: statRead with one lane per read when aqc_params.stat_kernel is 0
     Staging stg[2];
@@ -133,6 +140,8 @@ size_t smem_bytes_for(int P, int col_cap, int max_len) {
 #define AQC_KERNEL_HANDLE(...) ((const void *)(__VA_ARGS__))
 #else
 template <int MODE, bool PAIRED> void emu_pair_kernel(void **a) { pair_kernel<MODE, PAIRED>(*(const KArgs *)a[0]); }
+void emu_unpack_bases_kernel(void **a) { unpack_bases_kernel(*(const uint32_t **)a[0], *(uint4 **)a[1], *(uint32_t *)a[2]); }
+void emu_apply_exceptions_kernel(void **a) { apply_exceptions_kernel(*(const uint32_t **)a[0], *(const uint8_t **)a[1], *(uint32_t *)a[2], *(uint8_t **)a[3]); }
 void emu_maxlen_kernel(void **a) { maxlen_kernel(*(const uint32_t **)a[0], *(const uint32_t **)a[1], *(uint32_t *)a[2], *(uint32_t **)a[3]); }
 #define pair_kernel emu_pair_kernel
 #define AQC_KERNEL_HANDLE(...) ((const void *)(simt::Entry)(__VA_ARGS__))
@@ -477,6 +486,74 @@ int ensure_staging(aqc_ctx *ctx, Staging &s, size_t col_bytes, size_t off_entrie
     return 0;
 }
 
+int ensure_pack_staging(aqc_ctx *ctx, Staging &s, size_t col_bytes) {
+    if (!ctx->pack_pool) ctx->pack_pool = aqc_pack::pool_create(0);
+    const size_t need = col_bytes / 4 + 64;
+    if (need > s.pk_cap) {
+        const size_t cap = need + need / 4;
+        const size_t xcap = col_bytes / 16 + 1024;          // more exceptions than that: the chunk's column travels as bytes
+        for (int m = 0; m < 2; m++) {
+            cudaFreeHost(s.hp[m]); cudaFree(s.dp[m]); cudaFreeHost(s.hx_pos[m]); cudaFree(s.dx_pos[m]); cudaFreeHost(s.hx_val[m]); cudaFree(s.dx_val[m]);
+            s.hp[m] = s.dp[m] = s.hx_val[m] = s.dx_val[m] = nullptr; s.hx_pos[m] = s.dx_pos[m] = nullptr;
+        }
+        s.pk_cap = s.x_cap = 0;
+        for (int m = 0; m < 2; m++) {
+            CK(cudaHostAlloc((void **)&s.hp[m], cap, cudaHostAllocDefault));
+            CK(cudaMalloc(&s.dp[m], cap));
+            CK(cudaHostAlloc((void **)&s.hx_pos[m], (xcap + xcap / 4) * 4, cudaHostAllocDefault));
+            CK(cudaMalloc(&s.dx_pos[m], (xcap + xcap / 4) * 4));
+            CK(cudaHostAlloc((void **)&s.hx_val[m], xcap + xcap / 4, cudaHostAllocDefault));
+            CK(cudaMalloc(&s.dx_val[m], xcap + xcap / 4));
+        }
+        s.pk_cap = cap; s.x_cap = xcap + xcap / 4;
+    }
+    return 0;
+}
+
+// One base column of a chunk through the packed transport: pack on the host threads, copy a quarter of the bytes (+ the
+// exception list) on copy_in; *n_exc / *n_bytes tell unpack_column what to launch.  false = too many exceptions, copy bytes.
+bool pack_and_copy(aqc_ctx *ctx, Staging &s, int m, const uint8_t *src, size_t n, size_t *n_exc) {
+    const size_t max_exc = std::min(s.x_cap, n / 16 + 1024);
+    if (!aqc_pack::pack_bases(ctx->pack_pool, src, n, s.hp[m], s.hx_pos[m], s.hx_val[m], max_exc, n_exc)) return false;
+    if (cudaMemcpyAsync(s.dp[m], s.hp[m], (n + 3) / 4, cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) return false;
+    if (*n_exc) {
+        if (cudaMemcpyAsync(s.dx_pos[m], s.hx_pos[m], *n_exc * 4, cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) return false;
+        if (cudaMemcpyAsync(s.dx_val[m], s.hx_val[m], *n_exc, cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) return false;
+    }
+    return true;
+}
+
+// after the copies landed (compute waits on h2d_done): expand the packed bases into the staged byte column
+int unpack_column(aqc_ctx *ctx, Staging &s, int m, uint8_t *col, size_t n, size_t n_exc) {
+    const uint32_t *packed = reinterpret_cast<const uint32_t *>(s.dp[m]);
+    uint4 *out = reinterpret_cast<uint4 *>(col);
+    uint32_t n_words = (uint32_t)(((n + 3) / 4 + 3) / 4);
+    if (n_words) {
+        void *a[3] = {(void *)&packed, (void *)&out, (void *)&n_words};
+#ifndef AQC_EMU
+        const void *k = (const void *)unpack_bases_kernel;
+#else
+        const void *k = (const void *)(simt::Entry)emu_unpack_bases_kernel;
+#endif
+        CK(cudaLaunchKernel(k, dim3(std::min<uint32_t>((n_words + 255) / 256, (uint32_t)ctx->sm_count * 8u)), dim3(256), a, 0, ctx->compute));
+        ctx->launches++;
+    }
+    if (n_exc) {
+        const uint32_t *pos = s.dx_pos[m];
+        const uint8_t *val = s.dx_val[m];
+        uint32_t ne = (uint32_t)n_exc;
+        void *a[4] = {(void *)&pos, (void *)&val, (void *)&ne, (void *)&col};
+#ifndef AQC_EMU
+        const void *k = (const void *)apply_exceptions_kernel;
+#else
+        const void *k = (const void *)(simt::Entry)emu_apply_exceptions_kernel;
+#endif
+        CK(cudaLaunchKernel(k, dim3(std::min<uint32_t>((ne + 255) / 256, (uint32_t)ctx->sm_count * 8u)), dim3(256), a, 0, ctx->compute));
+        ctx->launches++;
+    }
+    return 0;
+}
+
 // host-resident batch: chunked, double-buffered H2D -> kernel -> D2H
 int run_host(aqc_ctx *ctx, const aqc_batch *b, const LaunchExtra &x0, void *out_host, size_t out_elem) {
     const bool paired = b->seq2 != nullptr;
@@ -500,7 +577,17 @@ int run_host(aqc_ctx *ctx, const aqc_batch *b, const LaunchExtra &x0, void *out_
         size_t cb = std::max<size_t>(e1 - g1, paired ? (size_t)(e2 - g2) : 0) + 64;
         int rc = ensure_staging(ctx, s, cb, (size_t)cn + 8, out_host ? (size_t)cn * out_elem : 0);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(s.col[0], b->seq1 + g1, e1 - g1, cudaMemcpyHostToDevice, ctx->copy_in));
+        // base columns: as bytes, or (AQC_BATCH_PACK_BASES) 2 bits per base packed by the host threads and expanded on the device
+        const bool pack = (b->flags & AQC_BATCH_PACK_BASES) != 0 && b->n >= 1;
+        bool packed[2] = {false, false};
+        size_t n_exc[2] = {0, 0};
+        if (pack) {
+            rc = ensure_pack_staging(ctx, s, cb);
+            if (rc) return rc;
+            packed[0] = pack_and_copy(ctx, s, 0, b->seq1 + g1, e1 - g1, &n_exc[0]);
+            if (paired) packed[1] = pack_and_copy(ctx, s, 1, b->seq2 + g2, e2 - g2, &n_exc[1]);
+        }
+        if (!packed[0]) CK(cudaMemcpyAsync(s.col[0], b->seq1 + g1, e1 - g1, cudaMemcpyHostToDevice, ctx->copy_in));
         CK(cudaMemcpyAsync(s.col[1], b->qual1 + g1, e1 - g1, cudaMemcpyHostToDevice, ctx->copy_in));
         CK(cudaMemcpyAsync(s.off[0], b->off1 + lo, (size_t)(cn + 1) * 4, cudaMemcpyHostToDevice, ctx->copy_in));
         // mate-2 qualities may stay in page-locked host memory when the lane-per-pair kernel runs (AQC_BATCH_QUAL2_IN_PLACE)
@@ -508,12 +595,14 @@ int run_host(aqc_ctx *ctx, const aqc_batch *b, const LaunchExtra &x0, void *out_
         if (paired && (b->flags & AQC_BATCH_QUAL2_IN_PLACE) && e2 > a2 && lane_path(ctx, x0.mode, maxl))
             q2_in_place = device_view_of_host(b->qual2, a2, e2 - 1);
         if (paired) {
-            CK(cudaMemcpyAsync(s.col[2], b->seq2 + g2, e2 - g2, cudaMemcpyHostToDevice, ctx->copy_in));
+            if (!packed[1]) CK(cudaMemcpyAsync(s.col[2], b->seq2 + g2, e2 - g2, cudaMemcpyHostToDevice, ctx->copy_in));
             if (!q2_in_place) CK(cudaMemcpyAsync(s.col[3], b->qual2 + g2, e2 - g2, cudaMemcpyHostToDevice, ctx->copy_in));
             CK(cudaMemcpyAsync(s.off[1], b->off2 + lo, (size_t)(cn + 1) * 4, cudaMemcpyHostToDevice, ctx->copy_in));
         }
         CK(cudaEventRecord(s.h2d_done, ctx->copy_in));
         CK(cudaStreamWaitEvent(ctx->compute, s.h2d_done, 0));
+        if (packed[0]) { rc = unpack_column(ctx, s, 0, s.col[0], e1 - g1, n_exc[0]); if (rc) return rc; }
+        if (packed[1]) { rc = unpack_column(ctx, s, 1, s.col[2], e2 - g2, n_exc[1]); if (rc) return rc; }
         DevBatch d;
         // virtual column bases so that the absolute offsets of the chunk index the staged bytes
         d.seq1 = s.col[0] - g1; d.qual1 = s.col[1] - g1;
@@ -673,6 +762,9 @@ void aqc_destroy(aqc_ctx *ctx) {
         for (int k = 0; k < 4; k++) cudaFree(st.col[k]);
         for (int k = 0; k < 2; k++) cudaFree(st.off[k]);
         cudaFree(st.res);
+        for (int m = 0; m < 2; m++) {
+            cudaFreeHost(st.hp[m]); cudaFree(st.dp[m]); cudaFreeHost(st.hx_pos[m]); cudaFree(st.dx_pos[m]); cudaFreeHost(st.hx_val[m]); cudaFree(st.dx_val[m]);
+        }
         if (st.h2d_done) { cudaEventDestroy(st.h2d_done); cudaEventDestroy(st.k_done); cudaEventDestroy(st.d2h_done); }
     }
     for (auto &ev : ctx->ev_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -681,6 +773,7 @@ void aqc_destroy(aqc_ctx *ctx) {
     if (ctx->own_compute) cudaStreamDestroy(ctx->own_compute);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    aqc_pack::pool_destroy(ctx->pack_pool);
     delete ctx;
 }
 

@@ -515,4 +515,26 @@ __global__ void maxlen_kernel(const uint32_t *off1, const uint32_t *off2, uint32
     if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
+// ---- packed base transport of the host-buffer entry (aqc_pack.hpp, AQC_BATCH_PACK_BASES) ----
+// 2 bits per base (A0 C1 T2 G3, base j of a packed byte in bits 2*(j & 3)) -> the byte column the kernels read.  One thread
+// expands one 32-bit word (16 bases) and stores 16 bytes; `out` is 16-byte aligned, both buffers carry slack for the tail.
+__global__ void unpack_bases_kernel(const uint32_t *packed, uint4 *out, uint32_t n_words) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) {
+        const uint32_t w = packed[i];
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t b = (w >> (8 * k)) & 0xFFu;
+            const uint32_t sel = (b & 3u) | ((b & 0xCu) << 2) | ((b & 0x30u) << 4) | ((b & 0xC0u) << 6);     // one code per selector nibble
+            o[k] = __byte_perm(0x47544341u, 0u, sel);                                                        // "ACTG"
+        }
+        out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// the bytes that are not A,C,G,T (N, lower case, anything else) travel as (position, byte)
+__global__ void apply_exceptions_kernel(const uint32_t *pos, const uint8_t *val, uint32_t n, uint8_t *out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[pos[i]] = val[i];
+}
+
 }  // namespace aqc

@@ -1,0 +1,192 @@
+// aqc_pack.cpp -- host side of the packed base transport (see aqc_pack.hpp).  No CUDA here.
+#include "aqc_pack.hpp"
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+namespace aqc_pack {
+
+struct Pool {
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable cv_go, cv_done;
+    std::function<void(int)> job;
+    uint64_t generation = 0;
+    int pending = 0;
+    bool stop = false;
+    int n = 1;
+    std::vector<std::vector<uint32_t>> exc_pos;      // per piece
+    std::vector<std::vector<uint8_t>> exc_val;
+};
+
+static void worker(Pool *p, int tid) {
+    uint64_t seen = 0;
+    for (;;) {
+        std::function<void(int)> job;
+        {
+            std::unique_lock<std::mutex> lk(p->m);
+            p->cv_go.wait(lk, [&] { return p->stop || p->generation != seen; });
+            if (p->stop) return;
+            seen = p->generation;
+            job = p->job;
+        }
+        job(tid);
+        {
+            std::lock_guard<std::mutex> lk(p->m);
+            if (--p->pending == 0) p->cv_done.notify_all();
+        }
+    }
+}
+
+Pool *pool_create(int threads) {
+    int n = threads;
+    if (const char *e = getenv("AQC_PACK_THREADS")) n = atoi(e);
+    if (n <= 0) {
+        n = (int)std::thread::hardware_concurrency();
+        n = n > 4 ? n / 2 : n;                   // leave cores to the caller's own threads (readers, writers)
+        n = std::max(1, std::min(n, 48));
+    }
+    Pool *p = new Pool;
+    p->n = n;
+    p->exc_pos.resize((size_t)n);
+    p->exc_val.resize((size_t)n);
+    for (int t = 1; t < n; t++) p->workers.emplace_back(worker, p, t);     // piece 0 runs on the calling thread
+    return p;
+}
+
+void pool_destroy(Pool *p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(p->m);
+        p->stop = true;
+    }
+    p->cv_go.notify_all();
+    for (auto &t : p->workers) t.join();
+    delete p;
+}
+
+int pool_threads(const Pool *p) { return p ? p->n : 0; }
+
+static void run_all(Pool *p, const std::function<void(int)> &f) {
+    if (p->n == 1) { f(0); return; }
+    {
+        std::lock_guard<std::mutex> lk(p->m);
+        p->job = f;
+        p->pending = p->n - 1;
+        p->generation++;
+    }
+    p->cv_go.notify_all();
+    f(0);
+    std::unique_lock<std::mutex> lk(p->m);
+    p->cv_done.wait(lk, [&] { return p->pending == 0; });
+}
+
+// ---- one piece: src[0..n) -> dst[0..(n+3)/4), exceptions appended with positions relative to `base` ----
+static inline bool is_acgt(uint8_t b) { return b == 'A' || b == 'C' || b == 'G' || b == 'T'; }
+
+static void pack_scalar(const uint8_t *src, size_t n, uint8_t *dst, size_t base, std::vector<uint32_t> &xp, std::vector<uint8_t> &xv, size_t cap) {
+    size_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        uint8_t o = 0;
+        for (int j = 0; j < 4; j++) {
+            const uint8_t b = src[i + j];
+            o |= (uint8_t)(((b >> 1) & 3u) << (2 * j));
+            if (!is_acgt(b)) { xp.push_back((uint32_t)(base + i + j)); xv.push_back(b); }
+        }
+        dst[i >> 2] = o;
+        if (xp.size() > cap) return;             // the caller gives up on this chunk anyway
+    }
+    if (i < n) {
+        uint8_t o = 0;
+        for (int j = 0; i + j < n; j++) {
+            const uint8_t b = src[i + j];
+            o |= (uint8_t)(((b >> 1) & 3u) << (2 * j));
+            if (!is_acgt(b)) { xp.push_back((uint32_t)(base + i + j)); xv.push_back(b); }
+        }
+        dst[i >> 2] = o;
+    }
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2")))
+static void pack_avx2(const uint8_t *src, size_t n, uint8_t *dst, size_t base, std::vector<uint32_t> &xp, std::vector<uint8_t> &xv, size_t cap) {
+    const __m256i three = _mm256_set1_epi8(3);
+    const __m256i table = _mm256_setr_epi8('A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 'A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i mul1 = _mm256_set1_epi16(0x0401);          // bytes 1, 4: c0 + 4 * c1
+    const __m256i mul2 = _mm256_set1_epi32(0x00100001);      // words 1, 16: t0 + 16 * t1
+    const __m256i pick = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+        const __m256i code = _mm256_and_si256(_mm256_srli_epi16(v, 1), three);
+        const uint32_t bad = ~(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_shuffle_epi8(table, code), v));
+        const __m256i t = _mm256_maddubs_epi16(code, mul1);
+        const __m256i u = _mm256_shuffle_epi8(_mm256_madd_epi16(t, mul2), pick);
+        const uint32_t lo = (uint32_t)_mm256_extract_epi32(u, 0), hi = (uint32_t)_mm256_extract_epi32(u, 4);
+        const uint64_t out = (uint64_t)lo | ((uint64_t)hi << 32);
+        memcpy(dst + (i >> 2), &out, 8);
+        if (__builtin_expect(bad != 0u, 0)) {
+            uint32_t m = bad;
+            while (m) {
+                const int j = __builtin_ctz(m);
+                m &= m - 1;
+                xp.push_back((uint32_t)(base + i + (size_t)j));
+                xv.push_back(src[i + (size_t)j]);
+            }
+            if (xp.size() > cap) return;         // the caller gives up on this chunk anyway
+        }
+    }
+    if (i < n) pack_scalar(src + i, n - i, dst + (i >> 2), base + i, xp, xv, cap);
+}
+#endif
+
+static void pack_piece(const uint8_t *src, size_t n, uint8_t *dst, size_t base, std::vector<uint32_t> &xp, std::vector<uint8_t> &xv, size_t cap) {
+#if defined(__x86_64__)
+    if (__builtin_cpu_supports("avx2") && !getenv("AQC_PACK_SCALAR")) { pack_avx2(src, n, dst, base, xp, xv, cap); return; }   // once per piece
+#endif
+    pack_scalar(src, n, dst, base, xp, xv, cap);
+}
+
+bool pack_bases(Pool *p, const uint8_t *src, size_t n, uint8_t *dst, uint32_t *exc_pos, uint8_t *exc_val, size_t max_exc, size_t *n_exc) {
+    *n_exc = 0;
+    if (n == 0) return true;
+    const int T = p->n;
+    // pieces of a multiple of 32 bases (whole packed bytes, whole vector iterations)
+    size_t per = ((n + (size_t)T - 1) / (size_t)T + 31) & ~(size_t)31;
+    if (per < 4096) per = 4096;
+    run_all(p, [&](int tid) {
+        std::vector<uint32_t> &xp = p->exc_pos[(size_t)tid];
+        std::vector<uint8_t> &xv = p->exc_val[(size_t)tid];
+        xp.clear(); xv.clear();
+        const size_t lo = (size_t)tid * per;
+        if (lo >= n) return;
+        const size_t hi = std::min(n, lo + per);
+        pack_piece(src + lo, hi - lo, dst + (lo >> 2), lo, xp, xv, max_exc);
+    });
+    size_t total = 0;
+    for (int t = 0; t < T; t++) total += p->exc_pos[(size_t)t].size();
+    if (total > max_exc) return false;
+    size_t w = 0;
+    for (int t = 0; t < T; t++) {
+        const size_t k = p->exc_pos[(size_t)t].size();
+        if (k) {
+            memcpy(exc_pos + w, p->exc_pos[(size_t)t].data(), k * sizeof(uint32_t));
+            memcpy(exc_val + w, p->exc_val[(size_t)t].data(), k);
+            w += k;
+        }
+    }
+    *n_exc = total;
+    return true;
+}
+
+}  // namespace aqc_pack

@@ -111,7 +111,7 @@ typedef struct aqc_batch {
     uint64_t first_index;
     uint32_t n;
     uint32_t flags;             /* bits 0-15: optional hint, the longest read of the batch (0 = unknown);
-                                   AQC_BATCH_QUAL2_IN_PLACE: see below; other bits 0 */
+                                   AQC_BATCH_QUAL2_IN_PLACE, AQC_BATCH_PACK_BASES: see below; other bits 0 */
     const uint8_t *seq1, *qual1;
     const uint32_t *off1;
     const uint8_t *seq2, *qual2;
@@ -125,6 +125,11 @@ typedef struct aqc_batch {
  * copying a quarter of the batch.  The engine checks the pointer (cudaPointerGetAttributes) and silently copies as usual when
  * the condition does not hold.  Results are identical either way. */
 #define AQC_BATCH_QUAL2_IN_PLACE (1u << 16)
+/* aqc_batch.flags, AQC_MEM_HOST batches (aqc_filter_pairs, aqc_stat_reads): the engine may pack the base columns to 2 bits per
+ * base on host threads before the copy (bytes other than A,C,G,T travel in an exception list) and expand them on the device --
+ * a quarter of the base bytes cross PCIe.  Transport only: lossless for any input, results identical.  The pool uses half
+ * of the hardware threads (at most 48; AQC_PACK_THREADS overrides). */
+#define AQC_BATCH_PACK_BASES (1u << 17)
 
 /* Per-pair outcome, 32 bytes.  start/len are the final coordinates into the ORIGINAL read after
  * front/tail trim and adapter cut (what the good/bad writer must emit).  edits are the byte

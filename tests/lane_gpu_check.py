@@ -7,6 +7,7 @@ round without GPU time left and had only been run under the SIMT emulator (tests
                                                  that kernel vs the warp-per-pair kernel on the bench workload
                                                  (HBM-resident entry); prints one JSON line with both kernel times;
                                                  *_st2 = with aqc_params.stat_kernel = 2 (also compares aqc_stat_reads)
+  python tests/lane_gpu_check.py pack            the 2-bit base transport of the host-buffer entry (AQC_BATCH_PACK_BASES) vs the oracle
 Exit code 0 = identical everywhere.
 """
 import json
@@ -171,6 +172,38 @@ def full(pairs, candidate="lane", try_in_place=True):
     print(json.dumps(out), flush=True)
 
 
+def pack():
+    """AQC_BATCH_PACK_BASES (2-bit base transport of the host-buffer entry) against the oracle: both filter kernels, the
+    prefilter statistics entry, many chunks, a batch whose bases are mostly exceptions (falls back to bytes)."""
+    import cases
+    import compare
+    from afterqc_b200 import _abi
+    from afterqc_b200.batch import PackedBatch
+    from afterqc_b200.engine import Engine
+    from oracle import oracle
+    oracle.build()
+    odd = PackedBatch.from_reads([("N" * 100, "I" * 100)] * 50 + [("ACGT" * 25, "I" * 100)] * 50, [("acgtn" * 20, "I" * 100)] * 100)
+    n_cases = 0
+    for bname, batch in (("adversarial", cases.adversarial_batch()), ("pe150", cases.synthetic("pe150", 20000)),
+                         ("pe150_jitter", cases.synthetic("pe150", 8000, len_jitter=60)), ("mostly_exceptions", odd), ("se100", cases.synthetic("se100", 20000))):
+        for cand in ("warp", "lane"):
+            fk, sk = kernel_ids(cand)
+            p = cases.make_params("default_f0", paired=batch.paired); p.filter_kernel = fk; p.stat_kernel = sk; p.qc_sample = batch.n // 2
+            orc, eng = oracle.Oracle(p), Engine(p)
+            a = orc.filter_pairs(batch)
+            b = eng.filter_pairs(batch, pack_bases=True)
+            what = "pack_bases %s/%s" % (bname, cand)
+            compare.assert_records_equal(batch, a, b, what)
+            slots = (_abi.QC_R1_POST, _abi.QC_R2_POST) if batch.paired else (_abi.QC_R1_POST,)
+            compare.compare_backends(orc, eng, slots, what)
+            for be, kw in ((orc, {}), (eng, {"pack_bases": True})):
+                be.stat_reads(batch, _abi.QC_R1_PRE, _abi.QC_R2_PRE if batch.paired else -1, stat_lo=10, stat_hi=batch.n - 3, order_base=0, **kw)
+            compare.compare_backends(orc, eng, (_abi.QC_R1_PRE, _abi.QC_R2_PRE) if batch.paired else (_abi.QC_R1_PRE,), what + " prefilter")
+            orc.close(); eng.close()
+            n_cases += 1
+    print("pack_bases parity ok: %d cases" % n_cases)
+
+
 def smoke():
     """lane_kernel and lane2_kernel against the oracle on two small batches (adversarial reads incl. foreign bytes -> list
     mode, synthetic PE150); called from __graft_entry__.smoke() in a child process."""
@@ -204,6 +237,8 @@ if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "parity"
     if mode == "smoke":
         smoke()
+    elif mode == "pack":
+        pack()
     elif mode == "parity":
         parity(sys.argv[2] if len(sys.argv) > 2 else "lane")
     else:

@@ -70,3 +70,11 @@ def test_stat2_equals_warp_statistics_at_bench_size(cand):
 def test_stat2_parity_vs_oracle():
     out = _run(["parity", "lane_st2"], 300)
     assert "lane_st2 kernel parity ok" in out
+
+
+@pytest.mark.xfail(reason="AQC_BATCH_PACK_BASES (host threads pack the bases to 2 bits, unpack_bases_kernel restores them) was written after the "
+                          "round's GPU budget was spent; emulator-verified", strict=False)
+def test_packed_base_transport_parity_vs_oracle(monkeypatch):
+    monkeypatch.setenv("AQC_CHUNK_PAIRS", "3000")       # several chunks per batch: both staging slots, aligned chunk origins
+    out = _run(["pack"], 300)
+    assert "pack_bases parity ok" in out
