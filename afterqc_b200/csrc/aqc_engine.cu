@@ -510,17 +510,23 @@ int ensure_pack_staging(aqc_ctx *ctx, Staging &s, size_t col_bytes) {
     return 0;
 }
 
-// One base column of a chunk through the packed transport: pack on the host threads, copy a quarter of the bytes (+ the
-// exception list) on copy_in; *n_exc / *n_bytes tell unpack_column what to launch.  false = too many exceptions, copy bytes.
-bool pack_and_copy(aqc_ctx *ctx, Staging &s, int m, const uint8_t *src, size_t n, size_t *n_exc) {
-    const size_t max_exc = std::min(s.x_cap, n / 16 + 1024);
-    if (!aqc_pack::pack_bases(ctx->pack_pool, src, n, s.hp[m], s.hx_pos[m], s.hx_val[m], max_exc, n_exc)) return false;
-    if (cudaMemcpyAsync(s.dp[m], s.hp[m], (n + 3) / 4, cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) return false;
-    if (*n_exc) {
-        if (cudaMemcpyAsync(s.dx_pos[m], s.hx_pos[m], *n_exc * 4, cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) return false;
-        if (cudaMemcpyAsync(s.dx_val[m], s.hx_val[m], *n_exc, cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) return false;
+// The base columns of a chunk through the packed transport: packed by the host threads in one dispatch of the pool, then a
+// quarter of the bytes (+ the exception lists) go out on copy_in.  packed[m] = false: too many exceptions, copy the bytes.
+void pack_and_copy(aqc_ctx *ctx, Staging &s, int n_cols, const uint8_t *const src[2], const size_t n[2], bool packed[2], size_t n_exc[2]) {
+    aqc_pack::Column cols[2];
+    for (int m = 0; m < n_cols; m++)
+        cols[m] = aqc_pack::Column{src[m], n[m], s.hp[m], s.hx_pos[m], s.hx_val[m], std::min(s.x_cap, n[m] / 16 + 1024), 0, true};
+    aqc_pack::pack_columns(ctx->pack_pool, cols, n_cols);
+    for (int m = 0; m < n_cols; m++) {
+        packed[m] = false; n_exc[m] = cols[m].n_exc;
+        if (!cols[m].ok) continue;
+        if (cudaMemcpyAsync(s.dp[m], s.hp[m], (n[m] + 3) / 4, cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) continue;
+        if (n_exc[m]) {
+            if (cudaMemcpyAsync(s.dx_pos[m], s.hx_pos[m], n_exc[m] * 4, cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) continue;
+            if (cudaMemcpyAsync(s.dx_val[m], s.hx_val[m], n_exc[m], cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) continue;
+        }
+        packed[m] = true;
     }
-    return true;
 }
 
 // after the copies landed (compute waits on h2d_done): expand the packed bases into the staged byte column
@@ -584,8 +590,9 @@ int run_host(aqc_ctx *ctx, const aqc_batch *b, const LaunchExtra &x0, void *out_
         if (pack) {
             rc = ensure_pack_staging(ctx, s, cb);
             if (rc) return rc;
-            packed[0] = pack_and_copy(ctx, s, 0, b->seq1 + g1, e1 - g1, &n_exc[0]);
-            if (paired) packed[1] = pack_and_copy(ctx, s, 1, b->seq2 + g2, e2 - g2, &n_exc[1]);
+            const uint8_t *const srcs[2] = {b->seq1 + g1, paired ? b->seq2 + g2 : nullptr};
+            const size_t lens[2] = {(size_t)(e1 - g1), (size_t)(e2 - g2)};
+            pack_and_copy(ctx, s, paired ? 2 : 1, srcs, lens, packed, n_exc);
         }
         if (!packed[0]) CK(cudaMemcpyAsync(s.col[0], b->seq1 + g1, e1 - g1, cudaMemcpyHostToDevice, ctx->copy_in));
         CK(cudaMemcpyAsync(s.col[1], b->qual1 + g1, e1 - g1, cudaMemcpyHostToDevice, ctx->copy_in));

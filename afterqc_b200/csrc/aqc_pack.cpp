@@ -25,7 +25,7 @@ struct Pool {
     int pending = 0;
     bool stop = false;
     int n = 1;
-    std::vector<std::vector<uint32_t>> exc_pos;      // per piece
+    std::vector<std::vector<uint32_t>> exc_pos;      // per column and thread
     std::vector<std::vector<uint8_t>> exc_val;
 };
 
@@ -58,8 +58,8 @@ Pool *pool_create(int threads) {
     }
     Pool *p = new Pool;
     p->n = n;
-    p->exc_pos.resize((size_t)n);
-    p->exc_val.resize((size_t)n);
+    p->exc_pos.resize((size_t)2 * n);          // [column][thread]
+    p->exc_val.resize((size_t)2 * n);
     for (int t = 1; t < n; t++) p->workers.emplace_back(worker, p, t);     // piece 0 runs on the calling thread
     return p;
 }
@@ -157,36 +157,50 @@ static void pack_piece(const uint8_t *src, size_t n, uint8_t *dst, size_t base, 
     pack_scalar(src, n, dst, base, xp, xv, cap);
 }
 
-bool pack_bases(Pool *p, const uint8_t *src, size_t n, uint8_t *dst, uint32_t *exc_pos, uint8_t *exc_val, size_t max_exc, size_t *n_exc) {
-    *n_exc = 0;
-    if (n == 0) return true;
+void pack_columns(Pool *p, Column *cols, int n_cols) {
     const int T = p->n;
-    // pieces of a multiple of 32 bases (whole packed bytes, whole vector iterations)
-    size_t per = ((n + (size_t)T - 1) / (size_t)T + 31) & ~(size_t)31;
-    if (per < 4096) per = 4096;
-    run_all(p, [&](int tid) {
-        std::vector<uint32_t> &xp = p->exc_pos[(size_t)tid];
-        std::vector<uint8_t> &xv = p->exc_val[(size_t)tid];
-        xp.clear(); xv.clear();
-        const size_t lo = (size_t)tid * per;
-        if (lo >= n) return;
-        const size_t hi = std::min(n, lo + per);
-        pack_piece(src + lo, hi - lo, dst + (lo >> 2), lo, xp, xv, max_exc);
-    });
-    size_t total = 0;
-    for (int t = 0; t < T; t++) total += p->exc_pos[(size_t)t].size();
-    if (total > max_exc) return false;
-    size_t w = 0;
-    for (int t = 0; t < T; t++) {
-        const size_t k = p->exc_pos[(size_t)t].size();
-        if (k) {
-            memcpy(exc_pos + w, p->exc_pos[(size_t)t].data(), k * sizeof(uint32_t));
-            memcpy(exc_val + w, p->exc_val[(size_t)t].data(), k);
-            w += k;
-        }
+    if (n_cols > 2) n_cols = 2;
+    // every thread takes one piece of every column: pieces of a multiple of 32 bases (whole packed bytes, whole vector iterations)
+    size_t per[2] = {0, 0};
+    for (int c = 0; c < n_cols; c++) {
+        per[c] = ((cols[c].n + (size_t)T - 1) / (size_t)T + 31) & ~(size_t)31;
+        if (per[c] < 4096) per[c] = 4096;
+        cols[c].n_exc = 0; cols[c].ok = true;
     }
-    *n_exc = total;
-    return true;
+    run_all(p, [&](int tid) {
+        for (int c = 0; c < n_cols; c++) {
+            std::vector<uint32_t> &xp = p->exc_pos[(size_t)(c * T + tid)];
+            std::vector<uint8_t> &xv = p->exc_val[(size_t)(c * T + tid)];
+            xp.clear(); xv.clear();
+            const size_t lo = (size_t)tid * per[c];
+            if (lo >= cols[c].n) continue;
+            const size_t hi = std::min(cols[c].n, lo + per[c]);
+            pack_piece(cols[c].src + lo, hi - lo, cols[c].dst + (lo >> 2), lo, xp, xv, cols[c].max_exc);
+        }
+    });
+    for (int c = 0; c < n_cols; c++) {
+        size_t total = 0;
+        for (int t = 0; t < T; t++) total += p->exc_pos[(size_t)(c * T + t)].size();
+        if (total > cols[c].max_exc) { cols[c].ok = false; continue; }
+        size_t w = 0;
+        for (int t = 0; t < T; t++) {
+            const std::vector<uint32_t> &xp = p->exc_pos[(size_t)(c * T + t)];
+            const size_t k = xp.size();
+            if (k) {
+                memcpy(cols[c].exc_pos + w, xp.data(), k * sizeof(uint32_t));
+                memcpy(cols[c].exc_val + w, p->exc_val[(size_t)(c * T + t)].data(), k);
+                w += k;
+            }
+        }
+        cols[c].n_exc = total;
+    }
+}
+
+bool pack_bases(Pool *p, const uint8_t *src, size_t n, uint8_t *dst, uint32_t *exc_pos, uint8_t *exc_val, size_t max_exc, size_t *n_exc) {
+    Column c{src, n, dst, exc_pos, exc_val, max_exc, 0, true};
+    pack_columns(p, &c, 1);
+    *n_exc = c.n_exc;
+    return c.ok;
 }
 
 }  // namespace aqc_pack

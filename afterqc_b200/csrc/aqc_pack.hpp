@@ -21,4 +21,12 @@ int pool_threads(const Pool *p);
 // Returns false (dst and the lists undefined) when more than max_exc bytes are not A,C,G,T.
 bool pack_bases(Pool *p, const uint8_t *src, size_t n, uint8_t *dst, uint32_t *exc_pos, uint8_t *exc_val, size_t max_exc, size_t *n_exc);
 
+// the same for up to two columns (both mates of a chunk) in ONE dispatch of the pool; ok[k] as pack_bases' return value
+struct Column {
+    const uint8_t *src; size_t n; uint8_t *dst;
+    uint32_t *exc_pos; uint8_t *exc_val; size_t max_exc;
+    size_t n_exc; bool ok;
+};
+void pack_columns(Pool *p, Column *cols, int n_cols);
+
 }  // namespace aqc_pack
