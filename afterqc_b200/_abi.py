@@ -24,6 +24,7 @@ KERNEL_DEFAULT, KERNEL_WARP, KERNEL_LANE, KERNEL_LANE2 = 0, 1, 2, 3     # aqc_pa
 STAT_DEFAULT, STAT_WARP, STAT_LANE = 0, 1, 2                            # aqc_params.stat_kernel
 BATCH_QUAL2_IN_PLACE = 1 << 16                         # aqc_batch.flags
 BATCH_PACK_BASES = 1 << 17                             # aqc_batch.flags: 2-bit base transport for host batches
+BATCH_PACK_QUALS = 1 << 18                             # aqc_batch.flags: 6-bit quality transport for host batches
 
 # pair classes, reference priority order (preprocesser.py:436-614)
 GOOD, BADTRIM1, BADTRIM2, BADLEN, BADPOL, BADLQC, BADNCT, BADDIFF, BADMISMATCH = range(9)

@@ -31,9 +31,9 @@ struct Staging {     // device staging of one host chunk
     void *res = nullptr;
     size_t col_cap = 0, off_cap = 0, res_cap = 0;
     // packed base transport (AQC_BATCH_PACK_BASES): page-locked host buffers the pool packs into, and their device copies
-    uint8_t *hp[2] = {nullptr, nullptr}, *dp[2] = {nullptr, nullptr};       // 2-bit bases of mate 1 / mate 2
-    uint32_t *hx_pos[2] = {nullptr, nullptr}, *dx_pos[2] = {nullptr, nullptr};   // exceptions: position in the staged column
-    uint8_t *hx_val[2] = {nullptr, nullptr}, *dx_val[2] = {nullptr, nullptr};    //             and the byte
+    uint8_t *hp[4] = {}, *dp[4] = {};               // packed column k (as col[k]: bases 1, qualities 1, bases 2, qualities 2)
+    uint32_t *hx_pos[4] = {}, *dx_pos[4] = {};      // exceptions: position in the staged column
+    uint8_t *hx_val[4] = {}, *dx_val[4] = {};       //             and the byte
     size_t pk_cap = 0, x_cap = 0;
     cudaEvent_t h2d_done = nullptr, k_done = nullptr, d2h_done = nullptr;
 };
@@ -141,6 +141,7 @@ size_t smem_bytes_for(int P, int col_cap, int max_len) {
 #else
 template <int MODE, bool PAIRED> void emu_pair_kernel(void **a) { pair_kernel<MODE, PAIRED>(*(const KArgs *)a[0]); }
 void emu_unpack_bases_kernel(void **a) { unpack_bases_kernel(*(const uint32_t **)a[0], *(uint4 **)a[1], *(uint32_t *)a[2]); }
+void emu_unpack_quals_kernel(void **a) { unpack_quals_kernel(*(const uint32_t **)a[0], *(uint4 **)a[1], *(uint32_t *)a[2]); }
 void emu_apply_exceptions_kernel(void **a) { apply_exceptions_kernel(*(const uint32_t **)a[0], *(const uint8_t **)a[1], *(uint32_t *)a[2], *(uint8_t **)a[3]); }
 void emu_maxlen_kernel(void **a) { maxlen_kernel(*(const uint32_t **)a[0], *(const uint32_t **)a[1], *(uint32_t *)a[2], *(uint32_t **)a[3]); }
 #define pair_kernel emu_pair_kernel
@@ -488,73 +489,82 @@ int ensure_staging(aqc_ctx *ctx, Staging &s, size_t col_bytes, size_t off_entrie
 
 int ensure_pack_staging(aqc_ctx *ctx, Staging &s, size_t col_bytes) {
     if (!ctx->pack_pool) ctx->pack_pool = aqc_pack::pool_create(0);
-    const size_t need = col_bytes / 4 + 64;
+    const size_t need = 3 * (col_bytes / 4 + 1) + 64;       // the larger of the two encodings (6-bit qualities)
     if (need > s.pk_cap) {
         const size_t cap = need + need / 4;
-        const size_t xcap = col_bytes / 16 + 1024;          // more exceptions than that: the chunk's column travels as bytes
-        for (int m = 0; m < 2; m++) {
-            cudaFreeHost(s.hp[m]); cudaFree(s.dp[m]); cudaFreeHost(s.hx_pos[m]); cudaFree(s.dx_pos[m]); cudaFreeHost(s.hx_val[m]); cudaFree(s.dx_val[m]);
-            s.hp[m] = s.dp[m] = s.hx_val[m] = s.dx_val[m] = nullptr; s.hx_pos[m] = s.dx_pos[m] = nullptr;
+        const size_t xcap = (col_bytes / 16 + 1024) * 5 / 4;       // more exceptions than 1/16: the chunk's column travels as bytes
+        for (int k = 0; k < 4; k++) {
+            cudaFreeHost(s.hp[k]); cudaFree(s.dp[k]); cudaFreeHost(s.hx_pos[k]); cudaFree(s.dx_pos[k]); cudaFreeHost(s.hx_val[k]); cudaFree(s.dx_val[k]);
+            s.hp[k] = s.dp[k] = s.hx_val[k] = s.dx_val[k] = nullptr; s.hx_pos[k] = s.dx_pos[k] = nullptr;
         }
         s.pk_cap = s.x_cap = 0;
-        for (int m = 0; m < 2; m++) {
-            CK(cudaHostAlloc((void **)&s.hp[m], cap, cudaHostAllocDefault));
-            CK(cudaMalloc(&s.dp[m], cap));
-            CK(cudaHostAlloc((void **)&s.hx_pos[m], (xcap + xcap / 4) * 4, cudaHostAllocDefault));
-            CK(cudaMalloc(&s.dx_pos[m], (xcap + xcap / 4) * 4));
-            CK(cudaHostAlloc((void **)&s.hx_val[m], xcap + xcap / 4, cudaHostAllocDefault));
-            CK(cudaMalloc(&s.dx_val[m], xcap + xcap / 4));
+        for (int k = 0; k < 4; k++) {
+            CK(cudaHostAlloc((void **)&s.hp[k], cap, cudaHostAllocDefault));
+            CK(cudaMalloc(&s.dp[k], cap));
+            CK(cudaHostAlloc((void **)&s.hx_pos[k], xcap * 4, cudaHostAllocDefault));
+            CK(cudaMalloc(&s.dx_pos[k], xcap * 4));
+            CK(cudaHostAlloc((void **)&s.hx_val[k], xcap, cudaHostAllocDefault));
+            CK(cudaMalloc(&s.dx_val[k], xcap));
         }
-        s.pk_cap = cap; s.x_cap = xcap + xcap / 4;
+        s.pk_cap = cap; s.x_cap = xcap;
     }
     return 0;
 }
 
-// The base columns of a chunk through the packed transport: packed by the host threads in one dispatch of the pool, then a
-// quarter of the bytes (+ the exception lists) go out on copy_in.  packed[m] = false: too many exceptions, copy the bytes.
-void pack_and_copy(aqc_ctx *ctx, Staging &s, int n_cols, const uint8_t *const src[2], const size_t n[2], bool packed[2], size_t n_exc[2]) {
-    aqc_pack::Column cols[2];
-    for (int m = 0; m < n_cols; m++)
-        cols[m] = aqc_pack::Column{src[m], n[m], s.hp[m], s.hx_pos[m], s.hx_val[m], std::min(s.x_cap, n[m] / 16 + 1024), 0, true};
-    aqc_pack::pack_columns(ctx->pack_pool, cols, n_cols);
-    for (int m = 0; m < n_cols; m++) {
-        packed[m] = false; n_exc[m] = cols[m].n_exc;
-        if (!cols[m].ok) continue;
-        if (cudaMemcpyAsync(s.dp[m], s.hp[m], (n[m] + 3) / 4, cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) continue;
-        if (n_exc[m]) {
-            if (cudaMemcpyAsync(s.dx_pos[m], s.hx_pos[m], n_exc[m] * 4, cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) continue;
-            if (cudaMemcpyAsync(s.dx_val[m], s.hx_val[m], n_exc[m], cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) continue;
+// Columns of a chunk through the packed transport (want[k]: column k as in Staging::col): packed by the host threads in one
+// dispatch of the pool, then the packed bytes (+ the exception lists) go out on copy_in.  packed[k] = false afterwards: not
+// wanted, or too many exceptions -- the caller copies the bytes.
+void pack_and_copy(aqc_ctx *ctx, Staging &s, const bool want[4], const uint8_t *const src[4], const size_t n[4], bool packed[4], size_t n_exc[4]) {
+    aqc_pack::Column cols[4];
+    int idx[4], nc = 0;
+    for (int k = 0; k < 4; k++) {
+        packed[k] = false; n_exc[k] = 0;
+        if (!want[k] || n[k] == 0) continue;
+        cols[nc] = aqc_pack::Column{(k & 1) ? aqc_pack::KIND_QUALS : aqc_pack::KIND_BASES, src[k], n[k], s.hp[k], s.hx_pos[k], s.hx_val[k],
+                                    std::min(s.x_cap, n[k] / 16 + 1024), 0, true};
+        idx[nc++] = k;
+    }
+    if (!nc) return;
+    aqc_pack::pack_columns(ctx->pack_pool, cols, nc);
+    for (int c = 0; c < nc; c++) {
+        const int k = idx[c];
+        if (!cols[c].ok) continue;
+        if (cudaMemcpyAsync(s.dp[k], s.hp[k], aqc_pack::packed_bytes(cols[c].kind, n[k]), cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) continue;
+        if (cols[c].n_exc) {
+            if (cudaMemcpyAsync(s.dx_pos[k], s.hx_pos[k], cols[c].n_exc * 4, cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) continue;
+            if (cudaMemcpyAsync(s.dx_val[k], s.hx_val[k], cols[c].n_exc, cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) continue;
         }
-        packed[m] = true;
+        n_exc[k] = cols[c].n_exc;
+        packed[k] = true;
     }
 }
 
-// after the copies landed (compute waits on h2d_done): expand the packed bases into the staged byte column
-int unpack_column(aqc_ctx *ctx, Staging &s, int m, uint8_t *col, size_t n, size_t n_exc) {
-    const uint32_t *packed = reinterpret_cast<const uint32_t *>(s.dp[m]);
+// after the copies landed (compute waits on h2d_done): expand packed column k into the staged byte column
+int unpack_column(aqc_ctx *ctx, Staging &s, int k, uint8_t *col, size_t n, size_t n_exc) {
+    const uint32_t *packed = reinterpret_cast<const uint32_t *>(s.dp[k]);
     uint4 *out = reinterpret_cast<uint4 *>(col);
-    uint32_t n_words = (uint32_t)(((n + 3) / 4 + 3) / 4);
-    if (n_words) {
-        void *a[3] = {(void *)&packed, (void *)&out, (void *)&n_words};
+    uint32_t n_units = (uint32_t)((n + 15) / 16);           // threads: 16 output bytes each
+    if (n_units) {
+        void *a[3] = {(void *)&packed, (void *)&out, (void *)&n_units};
 #ifndef AQC_EMU
-        const void *k = (const void *)unpack_bases_kernel;
+        const void *kern = (k & 1) ? (const void *)unpack_quals_kernel : (const void *)unpack_bases_kernel;
 #else
-        const void *k = (const void *)(simt::Entry)emu_unpack_bases_kernel;
+        const void *kern = (k & 1) ? (const void *)(simt::Entry)emu_unpack_quals_kernel : (const void *)(simt::Entry)emu_unpack_bases_kernel;
 #endif
-        CK(cudaLaunchKernel(k, dim3(std::min<uint32_t>((n_words + 255) / 256, (uint32_t)ctx->sm_count * 8u)), dim3(256), a, 0, ctx->compute));
+        CK(cudaLaunchKernel(kern, dim3(std::min<uint32_t>((n_units + 255) / 256, (uint32_t)ctx->sm_count * 8u)), dim3(256), a, 0, ctx->compute));
         ctx->launches++;
     }
     if (n_exc) {
-        const uint32_t *pos = s.dx_pos[m];
-        const uint8_t *val = s.dx_val[m];
+        const uint32_t *pos = s.dx_pos[k];
+        const uint8_t *val = s.dx_val[k];
         uint32_t ne = (uint32_t)n_exc;
         void *a[4] = {(void *)&pos, (void *)&val, (void *)&ne, (void *)&col};
 #ifndef AQC_EMU
-        const void *k = (const void *)apply_exceptions_kernel;
+        const void *kern = (const void *)apply_exceptions_kernel;
 #else
-        const void *k = (const void *)(simt::Entry)emu_apply_exceptions_kernel;
+        const void *kern = (const void *)(simt::Entry)emu_apply_exceptions_kernel;
 #endif
-        CK(cudaLaunchKernel(k, dim3(std::min<uint32_t>((ne + 255) / 256, (uint32_t)ctx->sm_count * 8u)), dim3(256), a, 0, ctx->compute));
+        CK(cudaLaunchKernel(kern, dim3(std::min<uint32_t>((ne + 255) / 256, (uint32_t)ctx->sm_count * 8u)), dim3(256), a, 0, ctx->compute));
         ctx->launches++;
     }
     return 0;
@@ -583,33 +593,35 @@ int run_host(aqc_ctx *ctx, const aqc_batch *b, const LaunchExtra &x0, void *out_
         size_t cb = std::max<size_t>(e1 - g1, paired ? (size_t)(e2 - g2) : 0) + 64;
         int rc = ensure_staging(ctx, s, cb, (size_t)cn + 8, out_host ? (size_t)cn * out_elem : 0);
         if (rc) return rc;
-        // base columns: as bytes, or (AQC_BATCH_PACK_BASES) 2 bits per base packed by the host threads and expanded on the device
-        const bool pack = (b->flags & AQC_BATCH_PACK_BASES) != 0 && b->n >= 1;
-        bool packed[2] = {false, false};
-        size_t n_exc[2] = {0, 0};
-        if (pack) {
-            rc = ensure_pack_staging(ctx, s, cb);
-            if (rc) return rc;
-            const uint8_t *const srcs[2] = {b->seq1 + g1, paired ? b->seq2 + g2 : nullptr};
-            const size_t lens[2] = {(size_t)(e1 - g1), (size_t)(e2 - g2)};
-            pack_and_copy(ctx, s, paired ? 2 : 1, srcs, lens, packed, n_exc);
-        }
-        if (!packed[0]) CK(cudaMemcpyAsync(s.col[0], b->seq1 + g1, e1 - g1, cudaMemcpyHostToDevice, ctx->copy_in));
-        CK(cudaMemcpyAsync(s.col[1], b->qual1 + g1, e1 - g1, cudaMemcpyHostToDevice, ctx->copy_in));
-        CK(cudaMemcpyAsync(s.off[0], b->off1 + lo, (size_t)(cn + 1) * 4, cudaMemcpyHostToDevice, ctx->copy_in));
         // mate-2 qualities may stay in page-locked host memory when the lane-per-pair kernel runs (AQC_BATCH_QUAL2_IN_PLACE)
         const uint8_t *q2_in_place = nullptr;
         if (paired && (b->flags & AQC_BATCH_QUAL2_IN_PLACE) && e2 > a2 && lane_path(ctx, x0.mode, maxl))
             q2_in_place = device_view_of_host(b->qual2, a2, e2 - 1);
+        // columns travel as bytes, or packed by the host threads and expanded on the device: bases at 2 bits
+        // (AQC_BATCH_PACK_BASES), qualities at 6 bits (AQC_BATCH_PACK_QUALS)
+        const bool pb = (b->flags & AQC_BATCH_PACK_BASES) != 0, pq = (b->flags & AQC_BATCH_PACK_QUALS) != 0;
+        const bool want[4] = {pb, pq, pb && paired, pq && paired && !q2_in_place};
+        const uint8_t *const srcs[4] = {b->seq1 + g1, b->qual1 + g1, paired ? b->seq2 + g2 : nullptr, paired ? b->qual2 + g2 : nullptr};
+        const size_t lens[4] = {(size_t)(e1 - g1), (size_t)(e1 - g1), (size_t)(e2 - g2), (size_t)(e2 - g2)};
+        bool packed[4] = {false, false, false, false};
+        size_t n_exc[4] = {0, 0, 0, 0};
+        if (pb || pq) {
+            rc = ensure_pack_staging(ctx, s, cb);
+            if (rc) return rc;
+            pack_and_copy(ctx, s, want, srcs, lens, packed, n_exc);
+        }
+        if (!packed[0]) CK(cudaMemcpyAsync(s.col[0], srcs[0], lens[0], cudaMemcpyHostToDevice, ctx->copy_in));
+        if (!packed[1]) CK(cudaMemcpyAsync(s.col[1], srcs[1], lens[1], cudaMemcpyHostToDevice, ctx->copy_in));
+        CK(cudaMemcpyAsync(s.off[0], b->off1 + lo, (size_t)(cn + 1) * 4, cudaMemcpyHostToDevice, ctx->copy_in));
         if (paired) {
-            if (!packed[1]) CK(cudaMemcpyAsync(s.col[2], b->seq2 + g2, e2 - g2, cudaMemcpyHostToDevice, ctx->copy_in));
-            if (!q2_in_place) CK(cudaMemcpyAsync(s.col[3], b->qual2 + g2, e2 - g2, cudaMemcpyHostToDevice, ctx->copy_in));
+            if (!packed[2]) CK(cudaMemcpyAsync(s.col[2], srcs[2], lens[2], cudaMemcpyHostToDevice, ctx->copy_in));
+            if (!q2_in_place && !packed[3]) CK(cudaMemcpyAsync(s.col[3], srcs[3], lens[3], cudaMemcpyHostToDevice, ctx->copy_in));
             CK(cudaMemcpyAsync(s.off[1], b->off2 + lo, (size_t)(cn + 1) * 4, cudaMemcpyHostToDevice, ctx->copy_in));
         }
         CK(cudaEventRecord(s.h2d_done, ctx->copy_in));
         CK(cudaStreamWaitEvent(ctx->compute, s.h2d_done, 0));
-        if (packed[0]) { rc = unpack_column(ctx, s, 0, s.col[0], e1 - g1, n_exc[0]); if (rc) return rc; }
-        if (packed[1]) { rc = unpack_column(ctx, s, 1, s.col[2], e2 - g2, n_exc[1]); if (rc) return rc; }
+        for (int k = 0; k < 4; k++)
+            if (packed[k]) { rc = unpack_column(ctx, s, k, s.col[k], lens[k], n_exc[k]); if (rc) return rc; }
         DevBatch d;
         // virtual column bases so that the absolute offsets of the chunk index the staged bytes
         d.seq1 = s.col[0] - g1; d.qual1 = s.col[1] - g1;
@@ -769,7 +781,7 @@ void aqc_destroy(aqc_ctx *ctx) {
         for (int k = 0; k < 4; k++) cudaFree(st.col[k]);
         for (int k = 0; k < 2; k++) cudaFree(st.off[k]);
         cudaFree(st.res);
-        for (int m = 0; m < 2; m++) {
+        for (int m = 0; m < 4; m++) {
             cudaFreeHost(st.hp[m]); cudaFree(st.dp[m]); cudaFreeHost(st.hx_pos[m]); cudaFree(st.dx_pos[m]); cudaFreeHost(st.hx_val[m]); cudaFree(st.dx_val[m]);
         }
         if (st.h2d_done) { cudaEventDestroy(st.h2d_done); cudaEventDestroy(st.k_done); cudaEventDestroy(st.d2h_done); }

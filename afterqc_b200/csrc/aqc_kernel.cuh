@@ -532,7 +532,21 @@ __global__ void unpack_bases_kernel(const uint32_t *packed, uint4 *out, uint32_t
     }
 }
 
-// the bytes that are not A,C,G,T (N, lower case, anything else) travel as (position, byte)
+// 6 bits per quality byte (code = byte - 33; four codes in three bytes, little endian) -> the byte column.  One thread expands
+// three 32-bit words (16 qualities) and stores 16 bytes.
+__global__ void unpack_quals_kernel(const uint32_t *packed, uint4 *out, uint32_t n_groups) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_groups; i += gridDim.x * blockDim.x) {
+        const uint32_t w0 = packed[3 * i], w1 = packed[3 * i + 1], w2 = packed[3 * i + 2];
+        const uint32_t v[4] = {w0 & 0xFFFFFFu, (w0 >> 24) | ((w1 & 0xFFFFu) << 8), (w1 >> 16) | ((w2 & 0xFFu) << 16), w2 >> 8};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            o[k] = ((v[k] & 0x3Fu) | ((v[k] & 0xFC0u) << 2) | ((v[k] & 0x3F000u) << 4) | ((v[k] & 0xFC0000u) << 6)) + 0x21212121u;
+        out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// the bytes that are not A,C,G,T (N, lower case, anything else) / not a quality in '!'..'`' travel as (position, byte)
 __global__ void apply_exceptions_kernel(const uint32_t *pos, const uint8_t *val, uint32_t n, uint8_t *out) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[pos[i]] = val[i];
 }

@@ -1,4 +1,4 @@
-// aqc_pack.hpp -- transport encoding of the base columns for the host-buffer entry (AQC_BATCH_PACK_BASES).
+// aqc_pack.hpp -- transport encoding of the columns for the host-buffer entry (AQC_BATCH_PACK_BASES, AQC_BATCH_PACK_QUALS).
 //
 // The host-buffer path of aqc_filter_pairs / aqc_stat_reads is PCIe bound: 4 x L bytes per pair cross
 // the bus.  Bases are two bits of information: host threads pack a chunk's base columns to 2 bits per base before the copy
@@ -21,8 +21,16 @@ int pool_threads(const Pool *p);
 // Returns false (dst and the lists undefined) when more than max_exc bytes are not A,C,G,T.
 bool pack_bases(Pool *p, const uint8_t *src, size_t n, uint8_t *dst, uint32_t *exc_pos, uint8_t *exc_val, size_t max_exc, size_t *n_exc);
 
-// the same for up to two columns (both mates of a chunk) in ONE dispatch of the pool; ok[k] as pack_bases' return value
+// Quality bytes, 6 bits each: code = byte - 33 ('!' .. '`', i.e. Phred+33 qualities 0..63); four codes a,b,c,d become the three
+// bytes of a | b << 6 | c << 12 | d << 18 (little endian).  dst holds 3 * ((n + 3) / 4) bytes.  Bytes outside that range are
+// exceptions, as for the bases.
+enum { KIND_BASES = 0, KIND_QUALS = 1 };
+constexpr int MAX_COLUMNS = 4;
+inline size_t packed_bytes(int kind, size_t n) { return kind == KIND_BASES ? (n + 3) / 4 : 3 * ((n + 3) / 4); }
+
+// up to four columns (bases and qualities of both mates of a chunk) in ONE dispatch of the pool; ok as pack_bases' return value
 struct Column {
+    int kind;
     const uint8_t *src; size_t n; uint8_t *dst;
     uint32_t *exc_pos; uint8_t *exc_val; size_t max_exc;
     size_t n_exc; bool ok;

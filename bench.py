@@ -630,7 +630,8 @@ def run_ours(args):
     # Run LAST: everything the JSON line needs exists by now, so an experimental mode that fails costs only itself.
     #   qual2_in_place (lane kernels, only if the child check saw it work on this GPU): mate-2 qualities stay in the pinned host
     #     column; the kernel fetches the bytes of the correction walk / sampled statRead over PCIe
-    #   pack_bases: host threads pack the base columns to 2 bits per base, unpack_bases_kernel restores the bytes in HBM
+    #   pack_bases / pack_quals: host threads pack the base columns to 2 bits per base (the quality columns to 6 bits per byte),
+    #     unpack_bases_kernel / unpack_quals_kernel restore the bytes in HBM
     if e2e is not None:
         try_in_place = use_lane and (args.filter_kernel in ("lane", "lane2") or bool((child or {}).get("in_place_ok")))
         if world > 1:
@@ -641,9 +642,11 @@ def run_ours(args):
         if try_in_place:
             modes.append(("qual2_in_place", _abi.BATCH_QUAL2_IN_PLACE))
         if not args.no_pack:
-            modes.append(("pack_bases", _abi.BATCH_PACK_BASES))
+            PB, PQ = _abi.BATCH_PACK_BASES, _abi.BATCH_PACK_QUALS
+            modes += [("pack_bases", PB), ("pack_bases+pack_quals", PB | PQ)]
             if try_in_place:
-                modes.append(("pack_bases+qual2_in_place", _abi.BATCH_PACK_BASES | _abi.BATCH_QUAL2_IN_PLACE))
+                modes += [("pack_bases+qual2_in_place", PB | _abi.BATCH_QUAL2_IN_PLACE),
+                          ("pack_bases+pack_quals+qual2_in_place", PB | PQ | _abi.BATCH_QUAL2_IN_PLACE)]
         variants = {"copy_all_columns": {"value": e2e["value"], "ms_per_step": e2e["ms_per_step"], "h2d_bytes_per_step": h2d}}
         best = ("copy_all_columns", e2e["value"])
         try:
@@ -651,10 +654,14 @@ def run_ours(args):
             base_bytes = int(off1[n] - off1[0]) + int(off2[n] - off2[0])
             n_edits = int(wb.results[:n * 32].view(-1, 32)[:, 1].sum().item())
             pulled = 32 * n_edits + min(n, QS) * READ_LEN      # one 32-byte sector per visited mismatch + the stat'd reads
-            n_exc = 0
-            for k in ("seq1", "seq2"):                          # bytes that travel in the exception list (5 bytes each)
-                c = wb.t[k][:int(wb.t["off1" if k == "seq1" else "off2"][n].item())]
-                n_exc += int(((c != 65) & (c != 67) & (c != 71) & (c != 84)).sum().item())
+            n_exc, q_exc = 0, {}
+            for k in ("seq1", "seq2", "qual1", "qual2"):        # bytes that travel in the exception lists (5 bytes each)
+                c = wb.t[k][:int(wb.t["off1" if k.endswith("1") else "off2"][n].item())]
+                if k.startswith("seq"):
+                    n_exc += int(((c != 65) & (c != 67) & (c != 71) & (c != 84)).sum().item())
+                else:
+                    q_exc[k] = int(((c < 33) | (c > 96)).sum().item())
+            q1_bytes = int(off1[n] - off1[0])
             for name, fl in modes:
                 xflags[0] = fl
                 res_host.zero_()
@@ -665,6 +672,10 @@ def run_ours(args):
                     hb += pulled - q2_bytes
                 if fl & _abi.BATCH_PACK_BASES:
                     hb += -base_bytes + (base_bytes + 3) // 4 + 5 * n_exc
+                if fl & _abi.BATCH_PACK_QUALS:
+                    hb += -(q1_bytes // 4) + 5 * q_exc["qual1"]
+                    if not (fl & _abi.BATCH_QUAL2_IN_PLACE):
+                        hb += -(q2_bytes // 4) + 5 * q_exc["qual2"]
                 variants[name] = {"value": world * n / (ms_v * 1e-3) / 1e6, "ms_per_step": ms_v, "results_match_resident": same_v,
                                   "h2d_bytes_per_step": hb}
                 if same_v and variants[name]["value"] > best[1]:
@@ -680,7 +691,8 @@ def run_ours(args):
                         "results_match_resident": v["results_match_resident"]})
             e2e["note"] += ("; mode %s: AQC_BATCH_QUAL2_IN_PLACE = the qual2 column is not copied, the kernel reads what the correction walk and "
                             "the sampled statRead need from the pinned column over PCIe (estimate in h2d_bytes_per_step); AQC_BATCH_PACK_BASES = "
-                            "host threads pack the bases to 2 bits before the copy (+ 5 bytes per byte that is not A,C,G,T)" % best[0])
+                            "host threads pack the bases to 2 bits before the copy (+ 5 bytes per byte that is not A,C,G,T); AQC_BATCH_PACK_QUALS = ... and "
+                            "the qualities to 6 bits" % best[0])
         if line is not None:
             line["e2e"] = e2e
         del host, res_host

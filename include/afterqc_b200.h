@@ -111,7 +111,7 @@ typedef struct aqc_batch {
     uint64_t first_index;
     uint32_t n;
     uint32_t flags;             /* bits 0-15: optional hint, the longest read of the batch (0 = unknown);
-                                   AQC_BATCH_QUAL2_IN_PLACE, AQC_BATCH_PACK_BASES: see below; other bits 0 */
+                                   AQC_BATCH_QUAL2_IN_PLACE, AQC_BATCH_PACK_BASES, AQC_BATCH_PACK_QUALS: see below; other bits 0 */
     const uint8_t *seq1, *qual1;
     const uint32_t *off1;
     const uint8_t *seq2, *qual2;
@@ -130,6 +130,9 @@ typedef struct aqc_batch {
  * a quarter of the base bytes cross PCIe.  Transport only: lossless for any input, results identical.  The pool uses half
  * of the hardware threads (at most 48; AQC_PACK_THREADS overrides). */
 #define AQC_BATCH_PACK_BASES (1u << 17)
+/* ... and the quality columns to 6 bits per byte (code = byte - 33, i.e. Phred+33 qualities 0..63; other bytes are exceptions):
+ * three quarters of the quality bytes cross PCIe.  A qual2 column left in place (AQC_BATCH_QUAL2_IN_PLACE) is not packed. */
+#define AQC_BATCH_PACK_QUALS (1u << 18)
 
 /* Per-pair outcome, 32 bytes.  start/len are the final coordinates into the ORIGINAL read after
  * front/tail trim and adapter cut (what the good/bad writer must emit).  edits are the byte

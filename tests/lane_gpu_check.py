@@ -191,12 +191,12 @@ def pack():
             p = cases.make_params("default_f0", paired=batch.paired); p.filter_kernel = fk; p.stat_kernel = sk; p.qc_sample = batch.n // 2
             orc, eng = oracle.Oracle(p), Engine(p)
             a = orc.filter_pairs(batch)
-            b = eng.filter_pairs(batch, pack_bases=True)
+            b = eng.filter_pairs(batch, pack_bases=True, pack_quals=(cand == "lane"))
             what = "pack_bases %s/%s" % (bname, cand)
             compare.assert_records_equal(batch, a, b, what)
             slots = (_abi.QC_R1_POST, _abi.QC_R2_POST) if batch.paired else (_abi.QC_R1_POST,)
             compare.compare_backends(orc, eng, slots, what)
-            for be, kw in ((orc, {}), (eng, {"pack_bases": True})):
+            for be, kw in ((orc, {}), (eng, {"pack_bases": True, "pack_quals": True})):
                 be.stat_reads(batch, _abi.QC_R1_PRE, _abi.QC_R2_PRE if batch.paired else -1, stat_lo=10, stat_hi=batch.n - 3, order_base=0, **kw)
             compare.compare_backends(orc, eng, (_abi.QC_R1_PRE, _abi.QC_R2_PRE) if batch.paired else (_abi.QC_R1_PRE,), what + " prefilter")
             orc.close(); eng.close()

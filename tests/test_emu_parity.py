@@ -251,9 +251,9 @@ def test_emu_host_path_many_chunks(backends, monkeypatch):
 
 
 def test_emu_packed_base_transport(backends, monkeypatch):
-    """AQC_BATCH_PACK_BASES: host threads pack the base columns of every chunk to 2 bits per base, bytes that are not A,C,G,T
-    travel in an exception list, unpack_bases_kernel / apply_exceptions_kernel restore the byte column; a chunk that is mostly
-    exceptions falls back to bytes.  Identical results through aqc_filter_pairs and aqc_stat_reads, alone and with qual2 in place."""
+    """AQC_BATCH_PACK_BASES / AQC_BATCH_PACK_QUALS: host threads pack the base columns of every chunk to 2 bits per base and
+    the quality columns to 6 bits per byte, bytes outside the code range travel in an exception list, unpack_*_kernel /
+    apply_exceptions_kernel restore the byte columns; a column that is mostly exceptions falls back to bytes.  Identical results through aqc_filter_pairs and aqc_stat_reads, alone and with qual2 in place."""
     if backends.stat2 or backends.kernel == "lane2":
         pytest.skip("transport only: one lane-per-pair kernel and the warp kernel cover it")
     from afterqc_b200.batch import PackedBatch
@@ -261,19 +261,25 @@ def test_emu_packed_base_transport(backends, monkeypatch):
     if backends.kernel == "warp":
         monkeypatch.setenv("AQC_PACK_SCALAR", "1")      # the portable packer; the other backend runs the AVX2 one where the CPU has it
     odd = PackedBatch.from_reads([("N" * 100, "I" * 100)] * 50 + [("ACGT" * 25, "I" * 100)] * 50, [("acgtn" * 20, "I" * 100)] * 100)
+    hiq = cases.synthetic("pe150", 1500)                  # qualities outside '!'..'`' (Phred+33 above 63): exceptions of the 6-bit code
+    rng = np.random.default_rng(3)
+    for col in (hiq.qual1, hiq.qual2):
+        idx = rng.choice(col.size - 64, size=col.size // 50, replace=False)
+        col[idx] = rng.integers(97, 127, size=idx.size).astype(np.uint8)
+    hiq.qual1[100:400] = 126                                # and a solid run of them
     for bname, batch in (("adversarial", cases.adversarial_batch()), ("pe150_jitter", cases.synthetic("pe150", 2000, len_jitter=60)),
-                         ("mostly_exceptions", odd), ("se100", cases.synthetic("se100", 2000))):
+                         ("mostly_exceptions", odd), ("high_qualities", hiq), ("se100", cases.synthetic("se100", 2000))):
         p = cases.make_params("default_f0", paired=batch.paired); p.qc_sample = 1500
         orc, eng = backends(p)
         a = orc.filter_pairs(batch)
         n0 = eng.launch_count()
-        b = eng.filter_pairs(batch, pack_bases=True, qual2_in_place=(backends.kernel == "lane" and batch.paired))
-        if bname == "mostly_exceptions":
-            assert eng.launch_count() - n0 <= 2, "the fall-back to bytes launches no unpack kernel"
+        b = eng.filter_pairs(batch, pack_bases=True, pack_quals=True, qual2_in_place=(backends.kernel == "lane" and batch.paired))
+        if bname == "mostly_exceptions":       # bases fall back to bytes; the qualities ('I') still travel packed
+            assert eng.launch_count() - n0 <= 4, "the fall-back to bytes launches no unpack kernel for the base columns"
         compare.assert_records_equal(batch, a, b, "emu pack %s" % bname)
         slots = (_abi.QC_R1_POST, _abi.QC_R2_POST) if batch.paired else (_abi.QC_R1_POST,)
         compare.compare_backends(orc, eng, slots, "emu pack %s" % bname)
-        for be, kw in ((orc, {}), (eng, {"pack_bases": True})):
+        for be, kw in ((orc, {}), (eng, {"pack_bases": True, "pack_quals": bname != "se100"})):
             be.stat_reads(batch, _abi.QC_R1_PRE, _abi.QC_R2_PRE if batch.paired else -1, stat_lo=10, stat_hi=batch.n - 3, order_base=0, **kw)
         compare.compare_backends(orc, eng, (_abi.QC_R1_PRE, _abi.QC_R2_PRE) if batch.paired else (_abi.QC_R1_PRE,), "emu pack stat %s" % bname)
         orc.close(); eng.close()
