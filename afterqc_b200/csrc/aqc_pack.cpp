@@ -13,6 +13,9 @@
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
+#if defined(__linux__)
+#include <sched.h>
+#endif
 
 namespace aqc_pack {
 
@@ -53,6 +56,11 @@ Pool *pool_create(int threads) {
     if (const char *e = getenv("AQC_PACK_THREADS")) n = atoi(e);
     if (n <= 0) {
         n = (int)std::thread::hardware_concurrency();
+#if defined(__linux__)
+        cpu_set_t set;                           // the CPUs this process may run on (containers, taskset, torchrun bindings)
+        CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) n = std::min(n > 0 ? n : 1 << 20, (int)CPU_COUNT(&set));
+#endif
         n = n > 4 ? n / 2 : n;                   // leave cores to the caller's own threads (readers, writers)
         n = std::max(1, std::min(n, 48));
     }
