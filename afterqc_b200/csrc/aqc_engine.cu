@@ -583,10 +583,12 @@ int run_host(aqc_ctx *ctx, const aqc_batch *b, const LaunchExtra &x0, void *out_
         uint32_t a1 = b->off1[lo], e1 = b->off1[hi], g1 = a1 & ~15u;
         uint32_t a2 = 0, e2 = 0, g2 = 0;
         if (paired) { a2 = b->off2[lo]; e2 = b->off2[hi]; g2 = a2 & ~15u; }
-        int maxl = 0;
-        for (uint32_t i = lo; i < hi; i++) {
-            maxl = std::max<int>(maxl, (int)(b->off1[i + 1] - b->off1[i]));
-            if (paired) maxl = std::max<int>(maxl, (int)(b->off2[i + 1] - b->off2[i]));
+        int maxl = (int)(b->flags & 0xFFFFu);               // the caller's hint (longest read of the batch), else look
+        if (maxl == 0) {
+            for (uint32_t i = lo; i < hi; i++) {
+                maxl = std::max<int>(maxl, (int)(b->off1[i + 1] - b->off1[i]));
+                if (paired) maxl = std::max<int>(maxl, (int)(b->off2[i + 1] - b->off2[i]));
+            }
         }
         Staging &s = ctx->stg[slot];
         if (used[slot]) CK(cudaEventSynchronize(s.d2h_done));    // slot free again

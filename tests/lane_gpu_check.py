@@ -230,6 +230,18 @@ def smoke():
             print("%s kernel smoke ok (bit-exact vs the oracle: adversarial + pe150)" % cand)
         except Exception as e:      # noqa: BLE001
             print("%s kernel smoke FAILED: %s" % (cand, str(e)[:300]))
+    try:        # the packed transport of the host-buffer entry (host threads + unpack kernels), several chunks
+        os.environ["AQC_CHUNK_PAIRS"] = "1000"
+        for bname, batch in (("adversarial", cases.adversarial_batch()), ("pe150", cases.synthetic("pe150", 4096))):
+            p = cases.make_params("default_f0"); p.qc_sample = 3000
+            orc, eng = oracle.Oracle(p), Engine(p)
+            a = orc.filter_pairs(batch); b = eng.filter_pairs(batch, pack_bases=True, pack_quals=True)
+            compare.assert_records_equal(batch, a, b, "pack smoke %s" % bname)
+            compare.compare_backends(orc, eng, (_abi.QC_R1_POST, _abi.QC_R2_POST), "pack smoke %s" % bname)
+            orc.close(); eng.close()
+        print("packed transport smoke ok (AQC_BATCH_PACK_BASES | AQC_BATCH_PACK_QUALS, bit-exact vs the oracle)")
+    except Exception as e:      # noqa: BLE001
+        print("packed transport smoke FAILED: %s" % str(e)[:300])
 
 
 if __name__ == "__main__":

@@ -283,3 +283,22 @@ def test_emu_packed_base_transport(backends, monkeypatch):
             be.stat_reads(batch, _abi.QC_R1_PRE, _abi.QC_R2_PRE if batch.paired else -1, stat_lo=10, stat_hi=batch.n - 3, order_base=0, **kw)
         compare.compare_backends(orc, eng, (_abi.QC_R1_PRE, _abi.QC_R2_PRE) if batch.paired else (_abi.QC_R1_PRE,), "emu pack stat %s" % bname)
         orc.close(); eng.close()
+
+
+def test_emu_host_path_with_length_hint(backends, monkeypatch):
+    """aqc_batch.flags bits 0-15 (the longest read of the batch) on a host batch: the engine takes the hint instead of scanning
+    the offsets of every chunk; same results"""
+    import ctypes as C
+    if backends.stat2:
+        pytest.skip("independent of the statistics kernel")
+    monkeypatch.setenv("AQC_CHUNK_PAIRS", "500")
+    batch = cases.synthetic("pe150", 1800, len_jitter=40)
+    orc, eng = backends(cases.make_params("default_f0"))
+    a = orc.filter_pairs(batch)
+    res = np.zeros(batch.n, dtype=_abi.RESULT_DTYPE)
+    b = batch.as_struct()
+    b.flags |= batch.max_len()
+    eng._check(eng._L.aqc_filter_pairs(eng._h, C.byref(b), _abi.MEM_HOST, res.ctypes.data))
+    compare.assert_records_equal(batch, a, res, "emu length hint")
+    compare.assert_counters_equal(orc.counters(), eng.counters(), "emu length hint")
+    orc.close(); eng.close()

@@ -15,6 +15,9 @@ echo "== lane2 kernel and the lane-per-read statistics (stat_kernel = 2): oracle
 for c in lane2 lane_st2; do timeout 600 python tests/lane_gpu_check.py parity $c > gpurun_out/parity_$c.log 2>&1; echo "$c parity exit $?"; tail -1 gpurun_out/parity_$c.log; done
 for c in lane2 warp_st2 lane_st2 lane2_st2; do timeout 300 python tests/lane_gpu_check.py full 2000000 $c > gpurun_out/full_$c.json 2> gpurun_out/full_$c.err; echo "$c full exit $?"; cat gpurun_out/full_$c.json; done
 
+echo "== packed transport of the host-buffer entry (AQC_BATCH_PACK_BASES / _QUALS) vs the oracle =="
+AQC_CHUNK_PAIRS=3000 timeout 300 python tests/lane_gpu_check.py pack > gpurun_out/pack_parity.log 2>&1; echo "pack parity exit $?"; tail -1 gpurun_out/pack_parity.log
+
 echo "== gpu test suite =="
 timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "exit $?" | tee -a gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log
 
