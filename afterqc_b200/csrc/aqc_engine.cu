@@ -57,7 +57,9 @@ struct aqc_ctx {
     size_t fb_cap = 0;
     aqc_pack::Pool *pack_pool = nullptr;    // host threads of the packed base transport, created at first use
     int lane_mode = 0;             // 0 = warp-per-pair kernel only, 1 = lane-per-pair kernel for batches of short reads
-    int stat_mode = 0;             // AQC_STAT_KERNEL=2: statRead with one lane per read when aqc_params.stat_kernel is 0
+    int stat_mode = 0;             // AQC_STAT_KERNEL=2|3: statRead with one lane per read when aqc_params.stat_kernel is 0
+    uint32_t *d_skip_bits = nullptr;   // stat_kernel 3: pairs of the launch that pair_kernel's list mode filtered (and stat'd)
+    size_t skip_cap = 0;               // words
     Staging stg[2];
     uint32_t chunk_pairs = 1u << 18;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -122,7 +124,7 @@ unsigned long long host_side_hash(unsigned long long k) {   // must match aqc::s
 int check_params(const aqc_params *p, char *err, size_t errn) {
     if (p->qc_kmer < 1 || p->qc_kmer > AQC_MAX_KMER) { snprintf(err, errn, "qc_kmer %d outside 1..%d", p->qc_kmer, AQC_MAX_KMER); return AQC_ERR_INVALID; }
     if (p->filter_kernel < 0 || p->filter_kernel > 3) { snprintf(err, errn, "filter_kernel %d outside 0..3", p->filter_kernel); return AQC_ERR_INVALID; }
-    if (p->stat_kernel < 0 || p->stat_kernel > 2) { snprintf(err, errn, "stat_kernel %d outside 0..2", p->stat_kernel); return AQC_ERR_INVALID; }
+    if (p->stat_kernel < 0 || p->stat_kernel > 3) { snprintf(err, errn, "stat_kernel %d outside 0..3", p->stat_kernel); return AQC_ERR_INVALID; }
     if (p->trim_front < 0 || p->trim_tail < 0 || p->trim_front2 < 0 || p->trim_tail2 < 0) { snprintf(err, errn, "negative trim value (resolve auto-trim on the host first)"); return AQC_ERR_INVALID; }
     return 0;
 }
@@ -156,47 +158,41 @@ const void *kernel_for(int mode, bool paired) {
 }
 #ifdef AQC_EMU
 #undef pair_kernel
-template <bool PAIRED, int NW, bool STAT2 = false> void emu_lane_kernel(void **a) { lane_kernel<PAIRED, NW, STAT2>(*(const LArgs *)a[0]); }
+template <bool PAIRED, int NW, int SMODE = 0> void emu_lane_kernel(void **a) { lane_kernel<PAIRED, NW, SMODE>(*(const LArgs *)a[0]); }
 #define lane_kernel emu_lane_kernel
 #endif
 
 // lane-per-pair filter kernel for mates of at most 32*NW bases
 int lane_words_for(int max_len) { return max_len <= 128 ? 4 : (max_len <= 160 ? 5 : (max_len <= 256 ? 8 : 0)); }
-const void *lane_kernel_for(bool paired, int nw, bool stat2) {     // stat2: sampled statRead with one lane per read (aqc_stat2.cuh)
-    if (stat2) {
-        if (nw == 4) return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 4, true>) : AQC_KERNEL_HANDLE(lane_kernel<false, 4, true>);
-        if (nw == 5) return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 5, true>) : AQC_KERNEL_HANDLE(lane_kernel<false, 5, true>);
-        return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 8, true>) : AQC_KERNEL_HANDLE(lane_kernel<false, 8, true>);
-    }
-    if (nw == 4) return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 4>) : AQC_KERNEL_HANDLE(lane_kernel<false, 4>);
-    if (nw == 5) return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 5>) : AQC_KERNEL_HANDLE(lane_kernel<false, 5>);
-    return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 8>) : AQC_KERNEL_HANDLE(lane_kernel<false, 8>);
+#define AQC_LANE_TABLE(KERNEL, SM)                                                                                             \
+    if (nw == 4) return paired ? AQC_KERNEL_HANDLE(KERNEL<true, 4, SM>) : AQC_KERNEL_HANDLE(KERNEL<false, 4, SM>);              \
+    if (nw == 5) return paired ? AQC_KERNEL_HANDLE(KERNEL<true, 5, SM>) : AQC_KERNEL_HANDLE(KERNEL<false, 5, SM>);              \
+    return paired ? AQC_KERNEL_HANDLE(KERNEL<true, 8, SM>) : AQC_KERNEL_HANDLE(KERNEL<false, 8, SM>);
+// smode: where the sampled postfilter statistics run (0 stat_read in the kernel, 1 stat_tile in the kernel, 2 stat_lane_kernel<POST> afterwards)
+const void *lane_kernel_for(bool paired, int nw, int smode) {
+    if (smode == 1) { AQC_LANE_TABLE(lane_kernel, 1) }
+    if (smode == 2) { AQC_LANE_TABLE(lane_kernel, 2) }
+    AQC_LANE_TABLE(lane_kernel, 0)
 }
 #ifdef AQC_EMU
 #undef lane_kernel
-template <bool PAIRED, int NW, bool STAT2 = false> void emu_lane2_kernel(void **a) { lane2_kernel<PAIRED, NW, STAT2>(*(const LArgs *)a[0]); }
+template <bool PAIRED, int NW, int SMODE = 0> void emu_lane2_kernel(void **a) { lane2_kernel<PAIRED, NW, SMODE>(*(const LArgs *)a[0]); }
 #define lane2_kernel emu_lane2_kernel
 #endif
-const void *lane2_kernel_for(bool paired, int nw, bool stat2) {
-    if (stat2) {
-        if (nw == 4) return paired ? AQC_KERNEL_HANDLE(lane2_kernel<true, 4, true>) : AQC_KERNEL_HANDLE(lane2_kernel<false, 4, true>);
-        if (nw == 5) return paired ? AQC_KERNEL_HANDLE(lane2_kernel<true, 5, true>) : AQC_KERNEL_HANDLE(lane2_kernel<false, 5, true>);
-        return paired ? AQC_KERNEL_HANDLE(lane2_kernel<true, 8, true>) : AQC_KERNEL_HANDLE(lane2_kernel<false, 8, true>);
-    }
-    if (nw == 4) return paired ? AQC_KERNEL_HANDLE(lane2_kernel<true, 4>) : AQC_KERNEL_HANDLE(lane2_kernel<false, 4>);
-    if (nw == 5) return paired ? AQC_KERNEL_HANDLE(lane2_kernel<true, 5>) : AQC_KERNEL_HANDLE(lane2_kernel<false, 5>);
-    return paired ? AQC_KERNEL_HANDLE(lane2_kernel<true, 8>) : AQC_KERNEL_HANDLE(lane2_kernel<false, 8>);
+const void *lane2_kernel_for(bool paired, int nw, int smode) {
+    if (smode == 1) { AQC_LANE_TABLE(lane2_kernel, 1) }
+    if (smode == 2) { AQC_LANE_TABLE(lane2_kernel, 2) }
+    AQC_LANE_TABLE(lane2_kernel, 0)
 }
 #ifdef AQC_EMU
 #undef lane2_kernel
-template <bool PAIRED, int NW> void emu_stat_lane_kernel(void **a) { stat_lane_kernel<PAIRED, NW>(*(const KArgs *)a[0]); }
+template <bool PAIRED, int NW, bool POST = false> void emu_stat_lane_kernel(void **a) { stat_lane_kernel<PAIRED, NW, POST>(*(const SArgs *)a[0]); }
 #define stat_lane_kernel emu_stat_lane_kernel
 #endif
-// prefilter statistics with one lane per read (aqc_params.stat_kernel = 2)
-const void *stat_lane_kernel_for(bool paired, int nw) {
-    if (nw == 4) return paired ? AQC_KERNEL_HANDLE(stat_lane_kernel<true, 4>) : AQC_KERNEL_HANDLE(stat_lane_kernel<false, 4>);
-    if (nw == 5) return paired ? AQC_KERNEL_HANDLE(stat_lane_kernel<true, 5>) : AQC_KERNEL_HANDLE(stat_lane_kernel<false, 5>);
-    return paired ? AQC_KERNEL_HANDLE(stat_lane_kernel<true, 8>) : AQC_KERNEL_HANDLE(stat_lane_kernel<false, 8>);
+// statistics with one lane per read: the prefilter window (aqc_stat_reads) / the sampled pairs of a filter launch (post)
+const void *stat_lane_kernel_for(bool paired, int nw, bool post) {
+    if (post) { AQC_LANE_TABLE(stat_lane_kernel, true) }
+    AQC_LANE_TABLE(stat_lane_kernel, false)
 }
 #ifdef AQC_EMU
 #undef stat_lane_kernel
@@ -300,7 +296,9 @@ size_t pair_tiling(aqc_ctx *ctx, KArgs &A, uint32_t n_tiles_of, int maxl, int ca
     return smem;
 }
 
-bool stat2_on(const aqc_ctx *ctx) { return ctx->p.stat_kernel == 2 || (ctx->p.stat_kernel == 0 && ctx->stat_mode); }
+// effective aqc_params.stat_kernel: 0/1 = stat_read (one warp per read), 2 / 3 = one lane per read (3: sampled statistics in their own launch)
+int stat_level(const aqc_ctx *ctx) { return ctx->p.stat_kernel ? ctx->p.stat_kernel : ctx->stat_mode; }
+bool stat2_on(const aqc_ctx *ctx) { return stat_level(ctx) >= 2; }
 
 bool lane_path(const aqc_ctx *ctx, int mode, int max_len) {
     const bool want_lane = ctx->p.filter_kernel == 2 || ctx->p.filter_kernel == 3 || (ctx->p.filter_kernel == 0 && ctx->lane_mode);
@@ -380,8 +378,18 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         L.tile_counter = ctx->d_fb_count + 1;
         const bool gen2 = ctx->p.filter_kernel == 3;
         const int ncols = (pe && !gen2) ? 3 : 2;
-        const bool stat2 = stat2_on(ctx);
-        const void *lk = gen2 ? lane2_kernel_for(pe, nw, stat2) : lane_kernel_for(pe, nw, stat2);
+        const int smode = stat_level(ctx) == 2 ? 1 : (stat_level(ctx) == 3 ? 2 : 0);
+        const void *lk = gen2 ? lane2_kernel_for(pe, nw, smode) : lane_kernel_for(pe, nw, smode);
+        if (smode == 2) {               // the sampled statistics get their own launch below; pairs handed to pair_kernel are marked
+            const size_t words = ((size_t)b.n + 31) / 32 + 1;
+            if (words > ctx->skip_cap) {
+                cudaFree(ctx->d_skip_bits); ctx->d_skip_bits = nullptr; ctx->skip_cap = 0;
+                CK(cudaMalloc(&ctx->d_skip_bits, (words + words / 4) * sizeof(uint32_t)));
+                ctx->skip_cap = words + words / 4;
+            }
+            CK(cudaMemsetAsync(ctx->d_skip_bits, 0, words * sizeof(uint32_t), stream));
+            L.skip_bits = ctx->d_skip_bits;
+        }
         int best_w = 0, best_occ = 0;
         for (int w = LANE_MAX_WARPS; w >= 1; w--) {           // most resident warps per SM; ties go to the larger CTA
             size_t sm = lane_smem_bytes(w, ncols, nw, L.lane_col_cap, maxl);
@@ -418,17 +426,44 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         void *kargs[1] = {(void *)&A};
         CK(cudaLaunchKernel(kern, dim3(grid), dim3(THREADS), kargs, smem, stream));
         CK(cudaGetLastError());
-        if (timed) CK(cudaEventRecord(e1, stream));
         ctx->launches++;
+        if (smode == 2) {
+            // ---- postfilter statistics of the sampled good pairs (preprocesser.py:624-627), one lane per read, from the records ----
+            uint64_t lim = b.n;                                  // pairs [0, lim) of this batch are inside the sample gate (quirk Q10)
+            if (ctx->p.qc_sample > 0) {
+                const uint64_t gate = (uint64_t)ctx->p.qc_sample - 1;      // global indices below this one are sampled
+                lim = gate > b.first_index ? std::min<uint64_t>(b.n, gate - b.first_index) : 0;
+            }
+            if (lim) {
+                SArgs P;
+                memset(&P, 0, sizeof P);
+                P.k = L.k;
+                P.k.num_tiles = (uint32_t)((lim + 31) / 32);
+                P.skip_bits = ctx->d_skip_bits;
+                const void *pk = stat_lane_kernel_for(pe, nw, true);
+                const size_t psmem = stat_lane_smem_bytes(STAT2_WARPS, nw, maxl);
+                int pocc = 1;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc, pk, STAT2_WARPS * 32, psmem));
+                if (pocc < 1) pocc = 1;
+                const uint32_t pwant = (P.k.num_tiles + STAT2_WARPS - 1) / STAT2_WARPS;
+                void *pargs[1] = {(void *)&P};
+                CK(cudaLaunchKernel(pk, dim3(std::min<uint32_t>(pwant, (uint32_t)(ctx->sm_count * pocc))), dim3(STAT2_WARPS * 32), pargs, psmem, stream));
+                CK(cudaGetLastError());
+                ctx->launches++;
+            }
+        }
+        if (timed) CK(cudaEventRecord(e1, stream));
         return 0;
     }
 
     if (x.mode == MODE_STAT && stat2_on(ctx) && lane_words_for(maxl) != 0) {
         // ---- prefilter statistics with one lane per read (aqc_stat2.cuh) ----
         const int snw = lane_words_for(maxl);
-        const void *sk = stat_lane_kernel_for(pe, snw);
+        const void *sk = stat_lane_kernel_for(pe, snw, false);
         A.tile_pairs = 32;
         A.num_tiles = (b.n + 31) / 32;
+        SArgs SA;
+        memset(&SA, 0, sizeof SA);
         const size_t ssmem = stat_lane_smem_bytes(STAT2_WARPS, snw, maxl);
         if (ssmem > 64 * 1024) return fail(ctx, AQC_ERR_INVALID, "statistics accumulators do not fit shared memory");
         int socc = 1;
@@ -437,7 +472,8 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         const uint32_t swant = (A.num_tiles + STAT2_WARPS - 1) / STAT2_WARPS;
         const uint32_t sgrid = std::min<uint32_t>(swant, (uint32_t)(ctx->sm_count * socc));
         if (timed) CK(cudaEventRecord(e0, stream));
-        void *sargs[1] = {(void *)&A};
+        SA.k = A;
+        void *sargs[1] = {(void *)&SA};
         CK(cudaLaunchKernel(sk, dim3(sgrid), dim3(STAT2_WARPS * 32), sargs, ssmem, stream));
         CK(cudaGetLastError());
         if (timed) CK(cudaEventRecord(e1, stream));
@@ -739,10 +775,11 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
         std::vector<const void *> lanes;
         for (int nw : {4, 5, 8})
             for (bool pe : {true, false}) {
-                for (bool st2 : {false, true}) { lanes.push_back(lane_kernel_for(pe, nw, st2)); lanes.push_back(lane2_kernel_for(pe, nw, st2)); }
+                for (int sm : {0, 1, 2}) { lanes.push_back(lane_kernel_for(pe, nw, sm)); lanes.push_back(lane2_kernel_for(pe, nw, sm)); }
                 // stat_lane_kernel: small accumulators only, and it re-reads each 32-byte sector of a read eight times (word loads
                 // per lane), so it keeps the default carve-out (a large L1)
-                CK(cudaFuncSetAttribute(stat_lane_kernel_for(pe, nw), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                for (bool post : {false, true})
+                    CK(cudaFuncSetAttribute(stat_lane_kernel_for(pe, nw, post), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             }
         for (const void *k : lanes) {
             cudaFuncAttributes fa;
@@ -760,7 +797,7 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
         }
         CK(cudaMalloc(&ctx->d_fb_count, 2 * sizeof(uint32_t)));
         if (const char *lm = getenv("AQC_LANE_KERNEL")) ctx->lane_mode = atoi(lm) != 0;
-        if (const char *sk = getenv("AQC_STAT_KERNEL")) ctx->stat_mode = atoi(sk) == 2;       // opt-in for callers that pass stat_kernel = 0
+        if (const char *sk = getenv("AQC_STAT_KERNEL")) { int v = atoi(sk); ctx->stat_mode = (v == 2 || v == 3) ? v : 0; }   // opt-in for callers that pass stat_kernel = 0
         if (const char *cp = getenv("AQC_CHUNK_PAIRS")) {          // host-path chunk size (tests exercise the multi-chunk pipeline with small batches)
             long v = atol(cp);
             if (v >= 4) ctx->chunk_pairs = (uint32_t)std::min<long>(v & ~3L, 1L << 24);
@@ -790,7 +827,7 @@ void aqc_destroy(aqc_ctx *ctx) {
     }
     for (auto &ev : ctx->ev_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     cudaFree(ctx->d_counters); cudaFree(ctx->d_luts); cudaFree(ctx->d_error); cudaFree(ctx->d_maxlen);
-    cudaFree(ctx->d_fb_list); cudaFree(ctx->d_fb_count);
+    cudaFree(ctx->d_fb_list); cudaFree(ctx->d_fb_count); cudaFree(ctx->d_skip_bits);
     if (ctx->own_compute) cudaStreamDestroy(ctx->own_compute);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);

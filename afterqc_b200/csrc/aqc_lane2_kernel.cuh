@@ -20,7 +20,9 @@ namespace aqc {
 //   [nwarps][ 4 * 32*NW ]                  per-warp scratch of the statistics hand-over
 //   luts (768 B)
 //   qc acc [2][5][max_len] u32, qc disc [2][max_len] u32, overlap_hist [max_len+1], distance_hist [max_len+1], err matrix [16]
-template <bool PAIRED, int NW, bool STAT2 = false>
+// SMODE: sampled postfilter statistics -- 0 = stat_read hand-over (one warp per read), 1 = stat_tile (one lane per read), both in this kernel;
+//        2 = none here: stat_lane_kernel<.., POST> runs after this kernel and pair_kernel's list mode (pairs handed over are marked in skip_bits)
+template <bool PAIRED, int NW, int SMODE = 0>
 __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane2_kernel(const __grid_constant__ LArgs L) {
     AQC_DYN_SMEM(smem_raw);
     __shared__ __align__(8) uint64_t full_bar[2 * LANE_MAX_WARPS];      // per warp: [0] bases landed, [1] qualities landed
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane2_k
                 if (lane == 0) base = atomicAdd(L.fb_count, (uint32_t)__popc(fb));
                 base = __shfl_sync(FULL, base, 0);
                 if (fallback) L.fb_list[base + (uint32_t)__popc(fb & lowmask(lane))] = pp;
+                if constexpr (SMODE == 2) { if (fallback) atomicOr(&L.skip_bits[pp >> 5], 1u << (pp & 31u)); }     // pair_kernel does their statistics
             }
         }
 
@@ -410,14 +413,14 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane2_k
 
         // ---- postfilter statistics of the sampled good pairs (:624-627): the warp rebuilds the trimmed, corrected reads
         //      in its scratch from the record and runs statRead on them ----
-        {
+        if constexpr (SMODE != 2) {
             const bool want = valid && cls == AQC_GOOD && (A.p.qc_sample <= 0 || gidx + 1 < (uint64_t)A.p.qc_sample);
             uint32_t sbm = __ballot_sync(FULL, want);
             if (__builtin_expect(sbm != 0u, 0)) {
                 stat_since_flush += (uint32_t)__popc(sbm);
                 uint8_t *sc_s1 = scratch, *sc_q1 = scratch + MAXB, *sc_s2 = scratch + 2 * MAXB, *sc_q2 = scratch + 3 * MAXB;
                 uint32_t need[2] = {sbm, sbm};                    // per mate: lanes whose read still needs stat_read
-                if constexpr (STAT2) {                            // one lane per read for everything made of A,C,G,T,N (aqc_stat2.cuh)
+                if constexpr (SMODE == 1) {                       // one lane per read for everything made of A,C,G,T,N (aqc_stat2.cuh)
 #pragma unroll 1
                     for (int m = 0; m < (paired ? 2 : 1); m++) {
                         MatePatches mp;
@@ -458,7 +461,7 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane2_k
                     __syncwarp();
 #pragma unroll 1
                     for (int m = 0; m < (paired ? 2 : 1); m++) {
-                        if constexpr (STAT2) { if (!((need[m] >> src) & 1u)) continue; }
+                        if constexpr (SMODE == 1) { if (!((need[m] >> src) & 1u)) continue; }
                         stat_read(m ? sc_s2 : sc_s1, m ? sc_q2 : sc_q1, m ? bl2 : bl1, m, bg, qsm, A.qc[m], lut1, lut2, lut3, A.p.qc_kmer, lane, A.error_flag);
                     }
                 }

@@ -298,8 +298,17 @@ __device__ __forceinline__ bool stat_tile(bool want, const uint8_t *s, const uin
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int STAT2_WARPS = 4;
 
-template <bool PAIRED, int NW>
-__global__ void __launch_bounds__(STAT2_WARPS * 32) stat_lane_kernel(const __grid_constant__ KArgs A) {
+struct SArgs {
+    KArgs k;
+    const uint32_t *skip_bits;    // POST: bit pp set = pair pp was filtered (and stat'd) by pair_kernel's list mode
+};
+
+// POST = false: the prefilter window [stat_lo, stat_hi) of raw reads (aqc_stat_reads).
+// POST = true : the postfilter statistics of a filter launch that ran with SMODE 2 (preprocesser.py:624-627): the sampled GOOD
+//               pairs of k.results, final slices and the correction walk's edits taken from the 32-byte records.
+template <bool PAIRED, int NW, bool POST = false>
+__global__ void __launch_bounds__(STAT2_WARPS * 32, (POST ? 4 : 5)) stat_lane_kernel(const __grid_constant__ SArgs S) {
+    const KArgs &A = S.k;
     AQC_DYN_SMEM(smem_raw);
     constexpr bool paired = PAIRED;
     constexpr int MAXB = 32 * NW;
@@ -327,19 +336,39 @@ __global__ void __launch_bounds__(STAT2_WARPS * 32) stat_lane_kernel(const __gri
     for (uint32_t t = blockIdx.x * (uint32_t)nwarps + (uint32_t)warp; t < A.num_tiles; t += W) {
         const uint32_t pp = t * 32u + (uint32_t)lane;
         const uint64_t gidx = A.first_index + pp;
-        const bool want = pp < A.n && gidx >= A.stat_lo && gidx < A.stat_hi;
+        bool want;
+        uint32_t rec[4] = {0, 0, 0, 0}, edits[4] = {0, 0, 0, 0};  // POST: the pair's record (class, slices | edits)
+        if constexpr (POST) {
+            want = pp < A.n && (A.p.qc_sample <= 0 || gidx + 1 < (uint64_t)A.p.qc_sample) && !((S.skip_bits[pp >> 5] >> (pp & 31u)) & 1u);
+            if (want) {
+                const uint4 *r = reinterpret_cast<const uint4 *>(A.results + pp);
+                const uint4 w0 = r[0], w1 = r[1];
+                rec[0] = w0.x; rec[1] = w0.y; rec[2] = w0.z;
+                edits[0] = w1.x; edits[1] = w1.y; edits[2] = w1.z; edits[3] = w1.w;
+                want = (rec[0] & 0xFFu) == (uint32_t)AQC_GOOD;
+            }
+        } else {
+            want = pp < A.n && gidx >= A.stat_lo && gidx < A.stat_hi;
+        }
         const uint32_t sbm = __ballot_sync(FULL, want);
         if (sbm == 0u) continue;
         stat_since_flush += (uint32_t)__popc(sbm);
-        const uint64_t order = A.order_base + (gidx - A.stat_lo);
+        const uint64_t order = POST ? gidx : A.order_base + (gidx - A.stat_lo);
         const uint32_t pc = min(pp, A.n), pq = min(pp + 1u, A.n);
+        const int n_edits = (int)((rec[0] >> 8) & 0xFFu);
+        const int start1 = (int)(rec[0] >> 16), start2 = (int)(rec[1] >> 16);
 #pragma unroll 1
         for (int m = 0; m < (paired ? 2 : 1); m++) {
             if (!A.qc[m].valid) continue;
             const uint32_t *off = m ? A.off2 : A.off1;
             const uint8_t *seq = m ? A.seq2 : A.seq1, *qual = m ? A.qual2 : A.qual1;
-            const uint32_t a = off[pc], e = off[pq];
-            const int len = (int)(e - a);
+            uint32_t a = off[pc];
+            int len = (int)(off[pq] - a);
+            if constexpr (POST) {                               // the final slice of the read (trim + adapter cut) and the walk's edits
+                a += (uint32_t)(m ? start2 : start1);
+                len = (int)((m ? rec[2] : rec[1]) & 0xFFFFu);
+                mate_patches(edits, n_edits, m, start1, start2, mp);
+            }
             bool handled = false;
             if (len > MAXB) {                                   // the host picks NW from the longest read; defensive
                 if (want) atomicExch(A.error_flag, AQC_ERR_TOO_LONG);
@@ -352,9 +381,20 @@ __global__ void __launch_bounds__(STAT2_WARPS * 32) stat_lane_kernel(const __gri
                 need &= need - 1;
                 const uint32_t ba = __shfl_sync(FULL, a, src);
                 const int bl = __shfl_sync(FULL, len, src);
-                const uint64_t bo = A.order_base + (A.first_index + t * 32u + (uint32_t)src - A.stat_lo);
+                const uint64_t bg = A.first_index + t * 32u + (uint32_t)src;
+                const uint64_t bo = POST ? bg : A.order_base + (bg - A.stat_lo);
                 __syncwarp();
                 for (int x = lane; x < bl; x += 32) { scratch[x] = seq[ba + x]; scratch[MAXB + x] = qual[ba + x]; }
+                if constexpr (POST) {
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {                // the source lane patches its own read
+                        if (lane == src && mp.pos[k] >= 0) {
+                            if (mp.base[k]) scratch[mp.pos[k]] = (uint8_t)mp.base[k];
+                            if (mp.qual[k]) scratch[MAXB + mp.pos[k]] = (uint8_t)mp.qual[k];
+                        }
+                    }
+                }
                 __syncwarp();
                 stat_read(scratch, scratch + MAXB, bl, m, bo, qsm, A.qc[m], lut1, lut2, lut3, A.p.qc_kmer, lane, A.error_flag);
             }

@@ -56,9 +56,10 @@ def parse_args():
     ap.add_argument("--filter-kernel", default="auto", choices=["auto", "warp", "lane", "lane2"],
                     help="filter kernel: warp = pair_kernel (one warp per pair), lane = lane_kernel (one lane per pair); auto = lane "
                          "only if it first proves bit-identical to warp on this GPU (child process with a timeout, then the full batch)")
-    ap.add_argument("--stat-kernel", default="auto", choices=["auto", "warp", "lane"],
+    ap.add_argument("--stat-kernel", default="auto", choices=["auto", "warp", "lane", "lane_post"],
                     help="statRead kernel (aqc_params.stat_kernel): warp = stat_read (one warp per read), lane = stat_tile / "
-                         "stat_lane_kernel (one lane per read); auto = lane only after the same two-stage identity check, and only if faster")
+                         "stat_lane_kernel (one lane per read), lane_post = the same with the sampled statistics in their own launch; "
+                         "auto = one of the lane forms only after the same two-stage identity check, and only if faster")
     ap.add_argument("--no-pack", action="store_true", help="do not try the packed base transport (AQC_BATCH_PACK_BASES) in the e2e measurement")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -364,7 +365,9 @@ def run_ours(args):
     KID = {"warp": _abi.KERNEL_WARP, "lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}
     selection = {"requested": args.filter_kernel}
     chosen = args.filter_kernel if args.filter_kernel != "auto" else "warp"
-    stat2 = args.stat_kernel == "lane"          # aqc_params.stat_kernel = 2 (statRead with one lane per read, aqc_stat2.cuh)
+    # aqc_params.stat_kernel: 0 = stat_read; 2 / 3 = statRead with one lane per read (aqc_stat2.cuh), inside the lane-per-pair filter
+    # kernel / in a launch of its own after it
+    stat2 = {"lane": _abi.STAT_LANE, "lane_post": _abi.STAT_LANE_POST}.get(args.stat_kernel, 0)
     child = None
     if args.filter_kernel == "auto":
         best_ms = None
@@ -379,16 +382,23 @@ def run_ours(args):
     if args.stat_kernel == "auto":
         # the statistics kernel: the chosen filter kernel with stat_kernel = 2 must be identical in a child process and
         # faster on filter + prefilter statistics together (written without GPU access, emulator-verified when committed)
-        c = lane_child_check(local_rank, min(n, 2_000_000), timeout_s=150, candidate=chosen + "_st2")
-        selection["child_check_" + chosen + "_st2"] = c
-        if c.get("ok"):
+        best_total = None
+        for suffix, level in (("_st3", _abi.STAT_LANE_POST), ("_st2", _abi.STAT_LANE)):
+            if chosen == "warp" and suffix == "_st3":
+                continue                # pair_kernel keeps its fused statistics: levels 2 and 3 are the same launches
+            c = lane_child_check(local_rank, min(n, 2_000_000), timeout_s=150, candidate=chosen + suffix)
+            selection["child_check_" + chosen + suffix] = c
+            if not c.get("ok"):
+                continue
             # the chosen filter kernel with stat_read: timed by its own child check, or the warp kernel of this one
             base_ms = child.get("lane_ms", 0) if child else (c.get("warp_ms", 0) if chosen == "warp" else None)
+            new_ms = c.get("lane_ms", 0) + c.get("stat_ms", 0)
             if base_ms is None:         # explicit --filter-kernel: only the prefilter launches are comparable
-                stat2 = 0 < c.get("stat_ms", 0) < c.get("stat_warp_ms", 0)
+                faster = 0 < c.get("stat_ms", 0) < c.get("stat_warp_ms", 0)
             else:
-                old_ms, new_ms = base_ms + c.get("stat_warp_ms", 0), c.get("lane_ms", 0) + c.get("stat_ms", 0)
-                stat2 = 0 < new_ms < old_ms
+                faster = 0 < new_ms < base_ms + c.get("stat_warp_ms", 0)
+            if faster and (best_total is None or new_ms < best_total):
+                best_total, stat2 = new_ms, level
     wb = make_device_workload(device, n, seed=20260927 + rank, first_index=first_index)
     # records of this shard inside the prefilter window [999, 999 + qc_sample) (global indices)
     w_lo_g, w_hi_g = STAT_LO, STAT_LO + QS
@@ -397,15 +407,15 @@ def run_ours(args):
     has_window = s_hi > s_lo
     s_lo_al = (s_lo // 4) * 4
     if (chosen != "warp" or stat2) and (args.filter_kernel == "auto" or args.stat_kernel == "auto"):
-        attempts = [(chosen, stat2)] + ([(chosen, False)] if (stat2 and chosen != "warp") else [])
-        chosen, stat2 = "warp", False
+        attempts = [(chosen, stat2)] + ([(chosen, 0)] if (stat2 and chosen != "warp") else [])
+        chosen, stat2 = "warp", 0
         for cand, st in attempts:       # a failing statistics kernel must not cost the filter kernel its place
             try:
-                ok, why = lane_full_size_check(wb, n, QS, local_rank, stream, KID[cand], _abi.STAT_LANE if st else _abi.STAT_DEFAULT,
+                ok, why = lane_full_size_check(wb, n, QS, local_rank, stream, KID[cand], st,
                                                (s_lo_al, s_hi, w_lo_g, w_hi_g) if has_window else None)
             except Exception as e:      # noqa: BLE001
                 ok, why = False, "full-size check raised %r" % (e,)
-            selection["full_size_check_%s%s" % (cand, "_st2" if st else "")] = why
+            selection["full_size_check_%s%s" % (cand, "_st%d" % st if st else "")] = why
             if ok:
                 chosen, stat2 = cand, st
                 break
@@ -421,20 +431,21 @@ def run_ours(args):
         else:
             agreed = _abi.KERNEL_LANE
         chosen = {v: k for k, v in KID.items()}[agreed]
-        sflag = torch.tensor([1 if stat2 else 0], dtype=torch.int32, device=device)
+        sflag = torch.tensor([stat2, -stat2], dtype=torch.int32, device=device)
         dist.all_reduce(sflag, op=dist.ReduceOp.MIN)
-        stat2 = bool(sflag.item())
+        stat2 = stat2 if int(sflag[0].item()) == -int(sflag[1].item()) else 0      # every rank the same level, else stat_read
     use_lane = chosen != "warp"
     selection["used"] = chosen
     selection["stat_kernel_requested"] = args.stat_kernel
-    selection["stat_kernel_used"] = "lane (stat_tile / stat_lane_kernel)" if stat2 else "warp (stat_read)"
+    selection["stat_kernel_used"] = {0: "warp (stat_read)", 2: "lane (stat_tile in the filter kernel / stat_lane_kernel)",
+                                     3: "lane_post (stat_lane_kernel, also for the sampled pairs of the filter launch)"}[stat2]
     kernel_label = {"warp": "aqc::pair_kernel (MODE_FILTER, one warp per pair)",
                     "lane": "aqc::lane_kernel (one lane per pair) + aqc::pair_kernel list mode",
                     "lane2": "aqc::lane2_kernel (one lane per pair, 2-column stage, dynamic tiles) + aqc::pair_kernel list mode"}[chosen]
 
     if world > 1:       # the packed base transport's host threads: the ranks of one box share its cores
         os.environ.setdefault("AQC_PACK_THREADS", str(max(2, (os.cpu_count() or 8) // (2 * world))))
-    params = _abi.Params.defaults(qc_sample=QS, filter_kernel=KID[chosen], stat_kernel=_abi.STAT_LANE if stat2 else _abi.STAT_DEFAULT)
+    params = _abi.Params.defaults(qc_sample=QS, filter_kernel=KID[chosen], stat_kernel=stat2)
     eng = Engine(params, device=local_rank)
     eng.set_stream(stream.cuda_stream)
     L = eng._L

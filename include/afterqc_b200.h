@@ -99,7 +99,9 @@ typedef struct aqc_params {
     int32_t stat_kernel;             /* how statRead (qualitycontrol.py:73-122) is executed: 0 / 1 = one warp per read (stat_read);
                                         2 = one lane per read with per-cycle warp reductions (stat_tile, aqc_stat2.cuh) in
                                         aqc_stat_reads and in the sampled statistics of the lane-per-pair filter kernels, for batches
-                                        whose reads are <= 256 bases (experimental, emulator-verified).  Results are identical. */
+                                        whose reads are <= 256 bases (experimental, emulator-verified); 3 = the same, but the lane-per-pair
+                                        filter kernels carry no statistics code and the sampled good pairs are stat'd from their result
+                                        records by one more launch of stat_lane_kernel.  Results are identical. */
     int32_t reserved[5];
 } aqc_params;
 

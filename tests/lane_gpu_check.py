@@ -25,13 +25,14 @@ import numpy as np  # noqa: E402
 
 
 def kernel_ids(candidate):
-    """'lane' | 'lane2' | 'warp', optionally with '_st2' (aqc_params.stat_kernel = 2: statRead with one lane per read)"""
+    """'lane' | 'lane2' | 'warp', optionally with '_st2' / '_st3' (aqc_params.stat_kernel = 2 / 3: statRead with one lane per read, in the
+    filter kernel / in its own launch after it)"""
     from afterqc_b200 import _abi
     base, _, st2 = candidate.partition("_")
     fk = {"warp": _abi.KERNEL_WARP, "lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}[base]
-    if st2 not in ("", "st2"):
+    if st2 not in ("", "st2", "st3"):
         raise SystemExit("unknown candidate %r" % candidate)
-    return fk, (_abi.STAT_LANE if st2 else _abi.STAT_DEFAULT)
+    return fk, {"": _abi.STAT_DEFAULT, "st2": _abi.STAT_LANE, "st3": _abi.STAT_LANE_POST}[st2]
 
 
 def parity(candidate="lane"):
@@ -213,7 +214,7 @@ def smoke():
     from afterqc_b200.engine import Engine
     from oracle import oracle
     oracle.build()
-    for cand in ("lane", "lane2", "lane_st2"):
+    for cand in ("lane", "lane2", "lane_st2", "lane_st3"):
         kid, sk = kernel_ids(cand)
         try:
             for bname, batch in (("adversarial", cases.adversarial_batch()), ("pe150", cases.synthetic("pe150", 4096))):

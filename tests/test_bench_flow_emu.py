@@ -15,9 +15,10 @@ KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "
 
 
 @pytest.mark.parametrize("fail,want_kernel,want_stat", [
-    ((), "lane", "lane"),                              # every candidate identical: fastest filter kernel + lane-per-read statistics
-    (("lane", "lane2"), "warp", "lane"),               # no lane-per-pair kernel: pair_kernel, prefilter statistics may still switch
-    (("lane2", "lane_st2"), "lane", "warp"),           # a failing statistics candidate does not cost the filter kernel its place
+    ((), "lane", "lane_post"),                         # every candidate identical: fastest filter kernel + statistics in their own launch
+    (("lane", "lane2"), "warp", "lane ("),             # no lane-per-pair kernel: pair_kernel, prefilter statistics may still switch
+    (("lane_st3",), "lane", "lane ("),                 # the deferred form fails: statistics with one lane per read inside the filter kernel
+    (("lane2", "lane_st2", "lane_st3"), "lane", "warp"),   # failing statistics candidates do not cost the filter kernel its place
 ])
 def test_bench_flow_on_emulator(oracle_lib, fail, want_kernel, want_stat):
     import bench_on_emulator

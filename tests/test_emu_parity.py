@@ -13,20 +13,21 @@ from afterqc_b200 import _abi
 KERNELS = {"warp": _abi.KERNEL_WARP, "lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}
 
 
-@pytest.fixture(scope="module", params=["warp", "lane", "lane2", "lane_st2", "lane2_st2"])
+@pytest.fixture(scope="module", params=["warp", "lane", "lane2", "lane_st2", "lane_st3", "lane2_st3"])
 def backends(oracle_lib, request):
     """warp = pair_kernel (one warp per pair); lane = lane_kernel (one lane per pair) + pair_kernel's list mode;
     lane2 = lane2_kernel (two staged columns per warp, dynamic tile claiming); *_st2 = the same with aqc_params.stat_kernel = 2
-    (statRead with one lane per read, aqc_stat2.cuh: stat_tile in the sampled statistics, stat_lane_kernel for aqc_stat_reads)"""
+    (statRead with one lane per read, aqc_stat2.cuh: stat_tile in the sampled statistics, stat_lane_kernel for aqc_stat_reads);
+    *_st3 = stat_kernel = 3 (the filter kernel carries no statistics, stat_lane_kernel<POST> stats the sampled pairs from the records)"""
     import emu
     name, _, st2 = request.param.partition("_")
 
     def make(params):
         params.filter_kernel = KERNELS[name]
-        params.stat_kernel = _abi.STAT_LANE if st2 else _abi.STAT_DEFAULT
+        params.stat_kernel = {"": _abi.STAT_DEFAULT, "st2": _abi.STAT_LANE, "st3": _abi.STAT_LANE_POST}[st2]
         return oracle_lib.Oracle(params), emu.EmuEngine(params)
     make.kernel = name
-    make.stat2 = bool(st2)
+    make.stat2 = st2              # "", "st2" or "st3"
     return make
 
 
@@ -69,7 +70,7 @@ def test_emu_filter_parity(backends, bname, pname):
 
 def test_emu_stat_parity(backends):
     """aqc_stat_reads: pair_kernel<MODE_STAT> (warp) and stat_lane_kernel (lane_st2: stat_kernel = 2)"""
-    if not (backends.kernel == "warp" or (backends.kernel == "lane" and backends.stat2)):
+    if not (backends.kernel == "warp" or (backends.kernel == "lane" and backends.stat2 == "st2")):
         pytest.skip("the prefilter statistics entry does not depend on the filter kernel")
     for bname, kmer in (("pe150_jitter", 8), ("pe150_jitter", 4), ("adversarial", 8), ("pe250", 8), ("long", 8), ("adversarial", 1)):
         if not backends.stat2 and bname != "pe150_jitter":
@@ -177,7 +178,7 @@ def test_emu_empty_mate_reaches_statread(backends):
     orc.close(); eng.close()
 
 
-@pytest.mark.parametrize("kernel", ["warp", "lane", "lane2", "lane_st2"])
+@pytest.mark.parametrize("kernel", ["warp", "lane", "lane2", "lane_st2", "lane2_st3"])
 @pytest.mark.parametrize("name", ["pe150_default", "pe150_err3_mask_overlap", "pe250_k5_strict", "se100_f0"])
 def test_emu_pipeline_matches_reference_golden(name, kernel, tmp_path):
     """the whole drop-in pipeline (readers, packed columns, engine calls, writers, JSON) on the emulated engine reproduces
@@ -189,7 +190,7 @@ def test_emu_pipeline_matches_reference_golden(name, kernel, tmp_path):
 
     def factory(p):
         p.filter_kernel = KERNELS[kernel.partition("_")[0]]
-        p.stat_kernel = _abi.STAT_LANE if kernel.endswith("_st2") else _abi.STAT_DEFAULT
+        p.stat_kernel = {"": _abi.STAT_DEFAULT, "st2": _abi.STAT_LANE, "st3": _abi.STAT_LANE_POST}[kernel.partition("_")[2]]
         return emu.EmuEngine(p)
     problems = golden_util.run_case(name, tmp_path, factory)
     assert not problems, problems

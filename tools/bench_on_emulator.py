@@ -84,6 +84,8 @@ def run(argv, fail=()):
             # no clock under the emulator: made-up times with lane < lane2 < warp, tile statistics faster than stat_read
             j.update({"warp_ms": 3.0, "lane_ms": 2.0 if candidate.startswith("lane2") else (1.0 if candidate.startswith("lane") else 3.0),
                       "stat_warp_ms": 1.0, "stat_ms": 0.5})
+            if candidate.endswith("_st3"):
+                j["lane_ms"] -= 0.1            # ... and the filter kernel without statistics code a little faster still
             return j
         saved["child"], saved["emit"] = bench.lane_child_check, bench.emit_json
         bench.lane_child_check = child

@@ -12,8 +12,8 @@ echo "== lane kernel: full oracle matrix ==" | tee gpurun_out/lane_parity.log
 timeout 900 python tests/lane_gpu_check.py parity >> gpurun_out/lane_parity.log 2>&1; echo "exit $?" | tee -a gpurun_out/lane_parity.log
 
 echo "== lane2 kernel and the lane-per-read statistics (stat_kernel = 2): oracle matrix, then 2 M pairs vs the warp kernels =="
-for c in lane2 lane_st2; do timeout 600 python tests/lane_gpu_check.py parity $c > gpurun_out/parity_$c.log 2>&1; echo "$c parity exit $?"; tail -1 gpurun_out/parity_$c.log; done
-for c in lane2 warp_st2 lane_st2 lane2_st2; do timeout 300 python tests/lane_gpu_check.py full 2000000 $c > gpurun_out/full_$c.json 2> gpurun_out/full_$c.err; echo "$c full exit $?"; cat gpurun_out/full_$c.json; done
+for c in lane2 lane_st2 lane_st3; do timeout 600 python tests/lane_gpu_check.py parity $c > gpurun_out/parity_$c.log 2>&1; echo "$c parity exit $?"; tail -1 gpurun_out/parity_$c.log; done
+for c in lane2 warp_st2 lane_st2 lane_st3 lane2_st3; do timeout 300 python tests/lane_gpu_check.py full 2000000 $c > gpurun_out/full_$c.json 2> gpurun_out/full_$c.err; echo "$c full exit $?"; cat gpurun_out/full_$c.json; done
 
 echo "== packed transport of the host-buffer entry (AQC_BATCH_PACK_BASES / _QUALS) vs the oracle =="
 AQC_CHUNK_PAIRS=3000 timeout 300 python tests/lane_gpu_check.py pack > gpurun_out/pack_parity.log 2>&1; echo "pack parity exit $?"; tail -1 gpurun_out/pack_parity.log
@@ -32,7 +32,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:lane
     python bench.py --filter-kernel lane --pairs 2000000 --qc-sample 40000 --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/lane_full_bench.log 2>&1
 ncu -i gpurun_out/lane_full.ncu-rep --page raw --csv > gpurun_out/lane_full_raw.csv 2>/dev/null
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:stat_lane_kernel -s 3 -c 1 -o gpurun_out/stat_lane_full \
-    python bench.py --filter-kernel lane --stat-kernel lane --pairs 2000000 --qc-sample 40000 --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/stat_lane_full_bench.log 2>&1
+    python bench.py --filter-kernel lane --stat-kernel lane_post --pairs 2000000 --qc-sample 40000 --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/stat_lane_full_bench.log 2>&1
 ncu -i gpurun_out/stat_lane_full.ncu-rep --page raw --csv > gpurun_out/stat_lane_full_raw.csv 2>/dev/null
 
 echo "== lane tuning variants (built here with nvcc, benchmarked with parity) =="

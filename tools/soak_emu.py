@@ -100,7 +100,7 @@ def one_case(rng, k):
     p = rand_params(rng, paired)
     results = {}
     # (filter kernel, statistics kernel): the lane-per-read statistics (stat_kernel = 2) ride on every filter kernel
-    for kern, sk in ((_abi.KERNEL_WARP, 0), (_abi.KERNEL_LANE, 0), (_abi.KERNEL_LANE2, 0), (_abi.KERNEL_WARP, 2), (_abi.KERNEL_LANE, 2), (_abi.KERNEL_LANE2, 2)):
+    for kern, sk in ((_abi.KERNEL_WARP, 0), (_abi.KERNEL_LANE, 0), (_abi.KERNEL_LANE2, 0), (_abi.KERNEL_WARP, 2), (_abi.KERNEL_LANE, 2), (_abi.KERNEL_LANE2, 2), (_abi.KERNEL_LANE, 3), (_abi.KERNEL_LANE2, 3)):
         p.filter_kernel = kern
         p.stat_kernel = sk
         orc, eng = oracle.Oracle(p), emu.EmuEngine(p)
