@@ -255,29 +255,33 @@ def cuda_tensor_view(ptr, n, torch_dtype, device):
     return torch.as_tensor(s, device=device)
 
 
-def lane_child_check(local_rank, pairs, timeout_s=300, candidate="lane"):
-    """tests/lane_gpu_check.py `full` in a child process with a timeout: both filter kernels on `pairs` pairs of the bench
-    workload, every output compared.  lane_kernel was committed without having run on hardware, so a hang or a mismatch
-    must not take the benchmark down: anything but a clean 'identical' keeps the warp-per-pair kernel."""
+def lane_child_check(local_rank, pairs, timeout_s=300, candidates="lane"):
+    """tests/lane_gpu_check.py `full` in a child process with a timeout: pair_kernel and every candidate of the comma-separated
+    list on `pairs` pairs of the bench workload, every output compared.  The candidates were committed without having run on
+    hardware, so a hang, a crash or a mismatch must not take the benchmark down: anything but a clean 'identical' keeps the
+    measured kernels.  Returns {candidate: verdict}; a verdict printed before a later crash or time-out of the child stands."""
+    names = [c for c in candidates.split(",") if c]
     env = dict(os.environ)
     ids = [x for x in env.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip() != ""]
     env["CUDA_VISIBLE_DEVICES"] = (ids[local_rank] if local_rank < len(ids) else ids[0]) if ids else str(local_rank)
-    cmd = [sys.executable, os.path.join(ROOT, "tests", "lane_gpu_check.py"), "full", str(pairs), candidate]
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "lane_gpu_check.py"), "full", str(pairs), ",".join(names)]
     t0 = time.time()
-    note = None
+    note, rc = None, 0
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
         stdout, stderr, rc = r.stdout or "", r.stderr or "", r.returncode
-    except subprocess.TimeoutExpired as e:      # the verdict on the resident kernels is printed before the optional experiments
+    except subprocess.TimeoutExpired as e:
         stdout, stderr, rc = e.stdout or "", e.stderr or "", None
         note = "child timed out after %d s" % timeout_s
     except Exception as e:      # noqa: BLE001
-        return {"ok": False, "why": "child could not run: %r" % (e,)}
+        return {c: {"ok": False, "why": "child could not run: %r" % (e,)} for c in names}
     if isinstance(stdout, bytes):
         stdout = stdout.decode("utf-8", "replace")
     if isinstance(stderr, bytes):
         stderr = stderr.decode("utf-8", "replace")
-    out = {"ok": False, "seconds": round(time.time() - t0, 1)}
+    if rc not in (0, None):
+        note = "child exit %d: %s" % (rc, (stderr or stdout)[-300:].replace("\n", " | "))
+    out = {c: {"ok": False} for c in names}
     for ln in stdout.splitlines():
         ln = ln.strip()
         if ln.startswith("{"):
@@ -285,16 +289,18 @@ def lane_child_check(local_rank, pairs, timeout_s=300, candidate="lane"):
                 j = json.loads(ln)
             except ValueError:
                 continue
-            out.update(j)
-            out["ok"] = bool(j.get("identical"))
-    if rc not in (0, None):
-        note = "child exit %d: %s" % (rc, (stderr or stdout)[-300:].replace("\n", " | "))
-    if note:
-        out["why" if not out["ok"] else "after_verdict"] = note
-    if rc is None:
-        out.pop("in_place_ok", None)
-    if not out["ok"]:
-        out.setdefault("why", "no verdict in the child's output")
+            c = j.get("candidate")
+            if c in out:
+                out[c] = dict(j, ok=bool(j.get("identical")))
+    seconds = round(time.time() - t0, 1)
+    for c in names:
+        out[c]["seconds_child"] = seconds
+        if note:
+            out[c]["after_verdict" if out[c]["ok"] else "why"] = note
+            if rc is None:
+                out[c].pop("in_place_ok", None)
+        if not out[c]["ok"]:
+            out[c].setdefault("why", "no verdict in the child's output")
     return out
 
 
@@ -371,8 +377,9 @@ def run_ours(args):
     child = None
     if args.filter_kernel == "auto":
         best_ms = None
+        verdicts = lane_child_check(local_rank, min(n, 2_000_000), timeout_s=300, candidates="lane,lane2")
         for cand in ("lane", "lane2"):
-            c = lane_child_check(local_rank, min(n, 2_000_000), timeout_s=240 if cand == "lane" else 150, candidate=cand)
+            c = verdicts[cand]
             selection["child_check_" + cand] = c
             if not c.get("ok"):
                 continue
@@ -383,10 +390,11 @@ def run_ours(args):
         # the statistics kernel: the chosen filter kernel with stat_kernel = 2 must be identical in a child process and
         # faster on filter + prefilter statistics together (written without GPU access, emulator-verified when committed)
         best_total = None
-        for suffix, level in (("_st3", _abi.STAT_LANE_POST), ("_st2", _abi.STAT_LANE)):
-            if chosen == "warp" and suffix == "_st3":
-                continue                # pair_kernel keeps its fused statistics: levels 2 and 3 are the same launches
-            c = lane_child_check(local_rank, min(n, 2_000_000), timeout_s=150, candidate=chosen + suffix)
+        # pair_kernel keeps its fused statistics: levels 2 and 3 are the same launches there
+        levels = (("_st2", _abi.STAT_LANE),) if chosen == "warp" else (("_st3", _abi.STAT_LANE_POST), ("_st2", _abi.STAT_LANE))
+        verdicts = lane_child_check(local_rank, min(n, 2_000_000), timeout_s=240, candidates=",".join(chosen + sfx for sfx, _ in levels))
+        for suffix, level in levels:
+            c = verdicts[chosen + suffix]
             selection["child_check_" + chosen + suffix] = c
             if not c.get("ok"):
                 continue

@@ -3,7 +3,7 @@
 round without GPU time left and had only been run under the SIMT emulator (tests/emu) when it was committed.
 
   python tests/lane_gpu_check.py parity          lane engine vs the CPU oracle, bit-exact, on the parity-test batches
-  python tests/lane_gpu_check.py full [pairs] [lane|lane2|warp_st2|lane_st2|lane2_st2] [noinplace]
+  python tests/lane_gpu_check.py full [pairs] [lane|lane2|warp_st2|lane_st2|lane_st3|...][,more] [noinplace]
                                                  that kernel vs the warp-per-pair kernel on the bench workload
                                                  (HBM-resident entry); prints one JSON line with both kernel times;
                                                  *_st2 = with aqc_params.stat_kernel = 2 (also compares aqc_stat_reads)
@@ -87,9 +87,10 @@ def parity(candidate="lane"):
     print("%s kernel parity ok: %d cases" % (candidate, n_cases))
 
 
-def full(pairs, candidate="lane", try_in_place=True):
-    """pair_kernel and a lane-per-pair kernel (lane / lane2) on the bench workload, resident in HBM: records, counters and
-    the postfilter QC slots must match."""
+def full(pairs, candidates="lane", try_in_place=True):
+    """pair_kernel (+ stat_read) once, then every candidate of the comma-separated list on the bench workload, resident in HBM:
+    records, counters, the postfilter QC slots and -- for the *_st2 / *_st3 candidates -- the prefilter slots after aqc_stat_reads
+    must match.  One JSON line per candidate as soon as its verdict is known (callers take the LAST line of a candidate)."""
     import torch
     from afterqc_b200 import _abi, synth
     from afterqc_b200.batch import PackedBatch
@@ -99,56 +100,60 @@ def full(pairs, candidate="lane", try_in_place=True):
                        t["seq2"].cpu().numpy(), t["qual2"].cpu().numpy(), t["off2"].cpu().numpy().astype(np.uint32))
     del t
     torch.cuda.empty_cache()
-    out = {}
-    ref = None
-    cand_id, cand_stat = kernel_ids(candidate)
-    out["candidate"] = candidate
-    sref = None
     s_lo, s_hi = 999, 999 + min(200000, max(1, pairs // 2))       # bench.py's prefilter window
-    for name, k, sk in (("warp", _abi.KERNEL_WARP, _abi.STAT_DEFAULT), ("lane", cand_id, cand_stat)):      # key "lane_ms" = the candidate's time
+    post = (_abi.QC_R1_POST, _abi.QC_R2_POST)
+    pre = (_abi.QC_R1_PRE, _abi.QC_R2_PRE)
+
+    def run(k, sk, with_stat):
         eng = Engine(_abi.Params.defaults(filter_kernel=k, stat_kernel=sk))
         d = eng.upload(host)
-        if cand_stat:                                        # aqc_stat_reads: pair_kernel<MODE_STAT> vs stat_lane_kernel
-            eng.stat_reads(d, _abi.QC_R1_PRE, _abi.QC_R2_PRE, s_lo, s_hi, 0); eng.sync()
+        r = {"eng": eng, "d": d}
+        if with_stat:                                        # aqc_stat_reads: pair_kernel<MODE_STAT> or stat_lane_kernel
+            eng.stat_reads(d, pre[0], pre[1], s_lo, s_hi, 0); eng.sync()
             eng.reset()
-            eng.stat_reads(d, _abi.QC_R1_PRE, _abi.QC_R2_PRE, s_lo, s_hi, 0); eng.sync()
-            out["stat_warp_ms" if name == "warp" else "stat_ms"] = round(eng.last_kernel_ms(), 4)
-            sgot = ([eng.qc(x) for x in (_abi.QC_R1_PRE, _abi.QC_R2_PRE)], [eng.kmers(x) for x in (_abi.QC_R1_PRE, _abi.QC_R2_PRE)])
-            if sref is None:
-                sref = sgot
-            else:
-                for a, b in zip(sgot[0], sref[0]):
-                    for f in a.dtype.names:
-                        assert np.array_equal(a[f], b[f]), "prefilter QC field %s differs between the statistics kernels" % f
-                for a, b in zip(sgot[1], sref[1]):
-                    for x, y in zip(a, b):
-                        assert np.array_equal(x, y), "prefilter k-mer tables differ between the statistics kernels"
+            eng.stat_reads(d, pre[0], pre[1], s_lo, s_hi, 0); eng.sync()
+            r["stat_ms"] = round(eng.last_kernel_ms(), 4)
+            r["pre"] = ([eng.qc(x) for x in pre], [eng.kmers(x) for x in pre])
         eng.filter_pairs(d); eng.sync()                      # warm-up
         eng.reset()
         eng.filter_pairs(d); eng.sync()
-        ms = eng.last_kernel_ms()
-        res = eng.fetch_results(d)
-        cnt = eng.counters()
-        qc = [eng.qc(s) for s in (_abi.QC_R1_POST, _abi.QC_R2_POST)]
-        km = [eng.kmers(s) for s in (_abi.QC_R1_POST, _abi.QC_R2_POST)]
-        out[name + "_ms"] = round(ms, 4)
-        if ref is None:
-            ref = (res, cnt, qc, km)
-        else:
-            assert res.tobytes() == ref[0].tobytes(), "records differ between the kernels"
-            assert np.array_equal(cnt, ref[1]), "counters differ between the kernels"
-            for a, b in zip(qc, ref[2]):
-                for f in a.dtype.names:
-                    assert np.array_equal(a[f], b[f]), "QC field %s differs between the kernels" % f
-            for a, b in zip(km, ref[3]):
-                for x, y in zip(a, b):
-                    assert np.array_equal(x, y), "k-mer tables differ between the kernels"
-        if name == "lane":
-            # the verdict on the resident kernels stands whatever happens below (callers take the LAST JSON line they can parse)
-            out["pairs"] = pairs
+        r["ms"] = round(eng.last_kernel_ms(), 4)
+        r["res"] = eng.fetch_results(d)
+        r["cnt"] = eng.counters()
+        r["post"] = ([eng.qc(x) for x in post], [eng.kmers(x) for x in post])
+        return r
+
+    def same_qc(a, b, what):
+        for x, y in zip(a[0], b[0]):
+            for f in x.dtype.names:
+                assert np.array_equal(x[f], y[f]), "%s QC field %s differs" % (what, f)
+        for x, y in zip(a[1], b[1]):
+            for u, v in zip(x, y):
+                assert np.array_equal(u, v), "%s k-mer tables differ" % what
+
+    ref = run(_abi.KERNEL_WARP, _abi.STAT_DEFAULT, True)
+    ref["d"].free(); ref["eng"].close()
+    for candidate in [c for c in candidates.split(",") if c]:
+        out = {"candidate": candidate, "pairs": pairs, "warp_ms": ref["ms"], "stat_warp_ms": ref["stat_ms"]}
+        cand_id, cand_stat = kernel_ids(candidate)
+        eng = d = None
+        try:
+            r = run(cand_id, cand_stat, bool(cand_stat))
+            eng, d = r["eng"], r["d"]
+            out["lane_ms"] = r["ms"]                         # key "lane_ms" = the candidate's filter launches
+            if cand_stat:
+                out["stat_ms"] = r["stat_ms"]
+                same_qc(r["pre"], ref["pre"], "prefilter")
+            assert r["res"].tobytes() == ref["res"].tobytes(), "records differ between the kernels"
+            assert np.array_equal(r["cnt"], ref["cnt"]), "counters differ between the kernels"
+            same_qc(r["post"], ref["post"], "postfilter")
             out["identical"] = True
-            print(json.dumps(out), flush=True)
-        if name == "lane" and cand_id != _abi.KERNEL_WARP and not cand_stat and try_in_place:
+        except AssertionError as e:
+            out["identical"] = False
+            out["why"] = str(e)[:200]
+        # the verdict on the resident kernels stands whatever happens below (callers take the LAST line of a candidate they can parse)
+        print(json.dumps(out), flush=True)
+        if out["identical"] and cand_id != _abi.KERNEL_WARP and not cand_stat and try_in_place:
             # host-buffer entry, mate-2 qualities copied vs left in page-locked host memory (AQC_BATCH_QUAL2_IN_PLACE)
             try:
                 import ctypes as C
@@ -160,17 +165,20 @@ def full(pairs, candidate="lane", try_in_place=True):
                 for key, kw in (("host_ms", {}), ("host_in_place_ms", {"qual2_in_place": True})):
                     eng.reset()
                     t0 = time.perf_counter()
-                    r = eng.filter_pairs(h2, **kw)
+                    rr = eng.filter_pairs(h2, **kw)
                     out[key] = round(1e3 * (time.perf_counter() - t0), 2)
-                    assert r.tobytes() == ref[0].tobytes(), "host path (%s): records differ" % key
-                    assert np.array_equal(eng.counters(), ref[1]), "host path (%s): counters differ" % key
+                    assert rr.tobytes() == ref["res"].tobytes(), "host path (%s): records differ" % key
+                    assert np.array_equal(eng.counters(), ref["cnt"]), "host path (%s): counters differ" % key
                 out["in_place_ok"] = True
                 eng._L.aqc_host_free(p)
             except Exception as e:      # noqa: BLE001  (the resident verdict stands; the in-place mode is simply not used)
                 out["in_place_ok"] = False
                 out["in_place_why"] = repr(e)[:200]
-        d.free(); eng.close()
-    print(json.dumps(out), flush=True)
+            print(json.dumps(out), flush=True)
+        if d is not None:
+            d.free()
+        if eng is not None:
+            eng.close()
 
 
 def pack():

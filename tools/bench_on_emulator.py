@@ -73,20 +73,25 @@ def run(argv, fail=()):
         import bench
         import lane_gpu_check
 
-        def child(local_rank, pairs, timeout_s=300, candidate="lane"):
-            if candidate in fail:
-                return {"ok": False, "why": "made to fail by the harness"}
-            buf = io.StringIO()
-            with contextlib.redirect_stdout(buf):
-                lane_gpu_check.full(pairs, candidate)
-            j = json.loads(buf.getvalue().strip().splitlines()[-1])
-            j["ok"] = bool(j.get("identical"))
-            # no clock under the emulator: made-up times with lane < lane2 < warp, tile statistics faster than stat_read
-            j.update({"warp_ms": 3.0, "lane_ms": 2.0 if candidate.startswith("lane2") else (1.0 if candidate.startswith("lane") else 3.0),
-                      "stat_warp_ms": 1.0, "stat_ms": 0.5})
-            if candidate.endswith("_st3"):
-                j["lane_ms"] -= 0.1            # ... and the filter kernel without statistics code a little faster still
-            return j
+        def child(local_rank, pairs, timeout_s=300, candidates="lane"):
+            names = [c for c in candidates.split(",") if c]
+            out = {c: {"ok": False, "why": "made to fail by the harness"} for c in names}
+            run = [c for c in names if c not in fail]
+            if run:
+                buf = io.StringIO()
+                with contextlib.redirect_stdout(buf):
+                    lane_gpu_check.full(pairs, ",".join(run))
+                for ln in buf.getvalue().splitlines():
+                    if ln.startswith("{"):
+                        j = json.loads(ln)
+                        j["ok"] = bool(j.get("identical"))
+                        out[j["candidate"]] = j
+            for c in run:       # no clock under the emulator: made-up times with lane < lane2 < warp, tile statistics faster than stat_read
+                out[c].update({"warp_ms": 3.0, "lane_ms": 2.0 if c.startswith("lane2") else (1.0 if c.startswith("lane") else 3.0),
+                               "stat_warp_ms": 1.0, "stat_ms": 0.5})
+                if c.endswith("_st3"):
+                    out[c]["lane_ms"] -= 0.1       # ... and the filter kernel without statistics code a little faster still
+            return out
         saved["child"], saved["emit"] = bench.lane_child_check, bench.emit_json
         bench.lane_child_check = child
         out = []
