@@ -44,10 +44,41 @@ def test_lane_kernel_host_path_with_qual2_in_place():
     assert '"in_place_ok": true' in out
 
 
-@pytest.mark.xfail(reason="lane2_kernel has not run on hardware yet (written after the round's GPU budget was spent); emulator-verified", strict=False)
-def test_lane2_kernel_equals_warp_kernel_at_bench_size():
-    out = _run(["full", "2000000", "lane2"], 240)
-    assert '"identical": true' in out
+_GROUP = {}
+GROUP_CANDIDATES = ["lane2", "warp_st2", "lane_st2", "lane_st3", "lane2_st3"]
+
+
+def _group_verdicts():
+    """ONE child process for all never-on-hardware candidates at bench size (one torch import, one workload, pair_kernel once);
+    a verdict line is printed per candidate as soon as it is known, so a later crash or hang costs only the candidates after it"""
+    import json
+    if not _GROUP:
+        _GROUP["ran"] = True
+        cmd = [sys.executable, os.path.join(HERE, "lane_gpu_check.py"), "full", "2000000", ",".join(GROUP_CANDIDATES), "noinplace"]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=480)
+            out = r.stdout or ""
+        except subprocess.TimeoutExpired as e:
+            out = e.stdout or ""
+            if isinstance(out, bytes):
+                out = out.decode("utf-8", "replace")
+        for ln in out.splitlines():
+            if ln.startswith("{"):
+                try:
+                    j = json.loads(ln)
+                except ValueError:
+                    continue
+                _GROUP[j.get("candidate")] = j
+    return _GROUP
+
+
+@pytest.mark.xfail(reason="lane2_kernel and the lane-per-read statistics (stat_kernel = 2 / 3) were written after the round's GPU budget was spent; "
+                          "emulator-verified", strict=False)
+@pytest.mark.parametrize("cand", GROUP_CANDIDATES)
+def test_candidate_equals_warp_kernel_at_bench_size(cand):
+    v = _group_verdicts().get(cand)
+    assert v is not None, "no verdict for %s (the child crashed or hung before it)" % cand
+    assert v.get("identical") is True, v
 
 
 @pytest.mark.xfail(reason="lane2_kernel has not run on hardware yet (written after the round's GPU budget was spent); emulator-verified", strict=False)
@@ -57,13 +88,6 @@ def test_lane2_kernel_parity_vs_oracle():
 
 
 ST2_REASON = "stat_tile / stat_lane_kernel (aqc_params.stat_kernel = 2 / 3) were written after the round's GPU budget was spent; emulator-verified"
-
-
-@pytest.mark.xfail(reason=ST2_REASON, strict=False)
-@pytest.mark.parametrize("cand", ["warp_st2", "lane_st2", "lane_st3"])
-def test_stat2_equals_warp_statistics_at_bench_size(cand):
-    out = _run(["full", "2000000", cand], 240)
-    assert '"identical": true' in out
 
 
 @pytest.mark.xfail(reason=ST2_REASON, strict=False)
