@@ -2,7 +2,9 @@
 """Randomised differential soak of the DEVICE code under the SIMT emulator (tests/emu) against the oracle.
 
 Random pairs (lengths 0..256 or up to 600, overlaps, adapters, N runs, foreign bytes, homopolymers, low-quality stretches,
-power-of-two lengths) x random parameter sets x both filter kernels.  Test infrastructure; needs no GPU.
+power-of-two lengths, qualities outside the 6-bit transport range) x random parameter sets x every filter kernel x every statistics
+kernel, with the packed transport (AQC_BATCH_PACK_BASES / _QUALS) and the in-place qual2 column switched on at random.  Test
+infrastructure; needs no GPU.
 
     python tools/soak_emu.py --cases 200 --seed 1
 """
@@ -32,6 +34,8 @@ def rand_qual(rng, n, style):
         return "".join(rng.choice("#$%5?ACEFGHI") for _ in range(n))
     if style == 2:
         return "".join(rng.choice("#I") for _ in range(n))
+    if style == 4:        # qualities above Phred 63 and below '!': exceptions of the 6-bit transport code (AQC_BATCH_PACK_QUALS)
+        return "".join(rng.choice("I5~}a{ \"") if rng.random() < 0.3 else "F" for _ in range(n))
     return rng.choice("#/05I") * n
 
 
@@ -62,7 +66,7 @@ def make_pair(rng, maxlen, alphabet):
     if rng.random() < 0.05 and L2 > 20:
         b = rng.choice("ACGTN"); st = rng.randint(0, L2 - 10); run = rng.randint(8, 50)
         r2 = (r2[:st] + b * run + r2[st + run:])[:L2]
-    s1, s2 = rng.randint(0, 3), rng.randint(0, 3)
+    s1, s2 = rng.randint(0, 4), rng.randint(0, 4)
     return (r1, rand_qual(rng, len(r1), s1)), (r2, rand_qual(rng, len(r2), s2))
 
 
@@ -111,7 +115,8 @@ def one_case(rng, k):
             except Exception as e:      # noqa: BLE001
                 err_o = getattr(e, "code", repr(e))
             try:
-                b = eng.filter_pairs(batch, qual2_in_place=rng.random() < 0.5); cb = eng.counters()
+                b = eng.filter_pairs(batch, qual2_in_place=rng.random() < 0.5, pack_bases=rng.random() < 0.5, pack_quals=rng.random() < 0.5)
+                cb = eng.counters()
             except Exception as e:      # noqa: BLE001
                 err_e = getattr(e, "code", repr(e))
             if err_o is not None or err_e is not None:
