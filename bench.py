@@ -450,6 +450,8 @@ def run_ours(args):
     kernel_label = {"warp": "aqc::pair_kernel (MODE_FILTER, one warp per pair)",
                     "lane": "aqc::lane_kernel (one lane per pair) + aqc::pair_kernel list mode",
                     "lane2": "aqc::lane2_kernel (one lane per pair, 2-column stage, dynamic tiles) + aqc::pair_kernel list mode"}[chosen]
+    if use_lane and stat2 == _abi.STAT_LANE_POST:
+        kernel_label += " + aqc::stat_lane_kernel<POST> (sampled statistics)"
 
     if world > 1:       # the packed base transport's host threads: the ranks of one box share its cores
         os.environ.setdefault("AQC_PACK_THREADS", str(max(2, (os.cpu_count() or 8) // (2 * world))))
