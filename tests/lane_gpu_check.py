@@ -100,7 +100,8 @@ def full(pairs, candidates="lane", try_in_place=True):
                        t["seq2"].cpu().numpy(), t["qual2"].cpu().numpy(), t["off2"].cpu().numpy().astype(np.uint32))
     del t
     torch.cuda.empty_cache()
-    s_lo, s_hi = 999, 999 + min(200000, max(1, pairs // 2))       # bench.py's prefilter window
+    s_lo, s_hi = 999, 999 + min(200000, max(1, pairs // 2))       # bench.py's prefilter window ...
+    window = host.slice((s_lo // 4) * 4, s_hi)                     # ... and, as there, a batch of just those records
     post = (_abi.QC_R1_POST, _abi.QC_R2_POST)
     pre = (_abi.QC_R1_PRE, _abi.QC_R2_PRE)
 
@@ -109,11 +110,13 @@ def full(pairs, candidates="lane", try_in_place=True):
         d = eng.upload(host)
         r = {"eng": eng, "d": d}
         if with_stat:                                        # aqc_stat_reads: pair_kernel<MODE_STAT> or stat_lane_kernel
-            eng.stat_reads(d, pre[0], pre[1], s_lo, s_hi, 0); eng.sync()
+            dw = eng.upload(window)
+            eng.stat_reads(dw, pre[0], pre[1], s_lo, s_hi, 0); eng.sync()
             eng.reset()
-            eng.stat_reads(d, pre[0], pre[1], s_lo, s_hi, 0); eng.sync()
+            eng.stat_reads(dw, pre[0], pre[1], s_lo, s_hi, 0); eng.sync()
             r["stat_ms"] = round(eng.last_kernel_ms(), 4)
             r["pre"] = ([eng.qc(x) for x in pre], [eng.kmers(x) for x in pre])
+            dw.free()
         eng.filter_pairs(d); eng.sync()                      # warm-up
         eng.reset()
         eng.filter_pairs(d); eng.sync()
