@@ -100,13 +100,14 @@ def full(pairs, candidates="lane", try_in_place=True):
                        t["seq2"].cpu().numpy(), t["qual2"].cpu().numpy(), t["off2"].cpu().numpy().astype(np.uint32))
     del t
     torch.cuda.empty_cache()
-    s_lo, s_hi = 999, 999 + min(200000, max(1, pairs // 2))       # bench.py's prefilter window ...
+    qs = max(1000, pairs // 50)                                     # bench.py's mix: --qc_sample 200000 on 10 M pairs = 2 %
+    s_lo, s_hi = 999, 999 + min(qs, max(1, pairs // 2))            # its prefilter window ...
     window = host.slice((s_lo // 4) * 4, s_hi)                     # ... and, as there, a batch of just those records
     post = (_abi.QC_R1_POST, _abi.QC_R2_POST)
     pre = (_abi.QC_R1_PRE, _abi.QC_R2_PRE)
 
     def run(k, sk, with_stat):
-        eng = Engine(_abi.Params.defaults(filter_kernel=k, stat_kernel=sk))
+        eng = Engine(_abi.Params.defaults(filter_kernel=k, stat_kernel=sk, qc_sample=qs))
         d = eng.upload(host)
         r = {"eng": eng, "d": d}
         if with_stat:                                        # aqc_stat_reads: pair_kernel<MODE_STAT> or stat_lane_kernel
