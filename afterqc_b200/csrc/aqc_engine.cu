@@ -634,7 +634,7 @@ int run_host(aqc_ctx *ctx, const aqc_batch *b, const LaunchExtra &x0, void *out_
         // mate-2 qualities may stay in page-locked host memory when the lane-per-pair kernel runs (AQC_BATCH_QUAL2_IN_PLACE)
         const uint8_t *q2_in_place = nullptr;
         if (paired && (b->flags & AQC_BATCH_QUAL2_IN_PLACE) && e2 > a2 && lane_path(ctx, x0.mode, maxl))
-            q2_in_place = device_view_of_host(b->qual2, a2, e2 - 1);
+            q2_in_place = device_view_of_host(b->qual2, a2, e2 - 1 + (stat2_on(ctx) ? 3 : 0));    // stat_tile reads whole words
         // columns travel as bytes, or packed by the host threads and expanded on the device: bases at 2 bits
         // (AQC_BATCH_PACK_BASES), qualities at 6 bits (AQC_BATCH_PACK_QUALS)
         const bool pb = (b->flags & AQC_BATCH_PACK_BASES) != 0, pq = (b->flags & AQC_BATCH_PACK_QUALS) != 0;

@@ -125,7 +125,8 @@ typedef struct aqc_batch {
  * walk (two bytes per visited mismatch, preprocesser.py:566-567) and in the sampled statRead (:624-627), so with the
  * lane-per-pair kernel the engine may leave that column where it is and let the kernel fetch those bytes over PCIe instead of
  * copying a quarter of the batch.  The engine checks the pointer (cudaPointerGetAttributes) and silently copies as usual when
- * the condition does not hold.  Results are identical either way. */
+ * the condition does not hold (with stat_kernel 2 / 3 the three bytes after the last quality must be addressable too: the
+ * usual 16 bytes of column slack cover it).  Results are identical either way. */
 #define AQC_BATCH_QUAL2_IN_PLACE (1u << 16)
 /* aqc_batch.flags, AQC_MEM_HOST batches (aqc_filter_pairs, aqc_stat_reads): the engine may pack the base columns to 2 bits per
  * base on host threads before the copy (bytes other than A,C,G,T travel in an exception list) and expand them on the device --
