@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_LEN = 1000          # qualitycontrol.py:23
 MAX_KMER = 8
 NUM_QC = 4
@@ -20,11 +20,9 @@ ERR_NAMES = {
 }
 
 MEM_HOST, MEM_DEVICE = 0, 1
-KERNEL_DEFAULT, KERNEL_WARP, KERNEL_LANE, KERNEL_LANE2 = 0, 1, 2, 3     # aqc_params.filter_kernel
-STAT_DEFAULT, STAT_WARP, STAT_LANE, STAT_LANE_POST = 0, 1, 2, 3            # aqc_params.stat_kernel
+KERNEL_DEFAULT, KERNEL_WARP, KERNEL_LANE = 0, 1, 2     # aqc_params.filter_kernel
+STAT_DEFAULT, STAT_WARP = 0, 1                          # aqc_params.stat_kernel
 BATCH_QUAL2_IN_PLACE = 1 << 16                         # aqc_batch.flags
-BATCH_PACK_BASES = 1 << 17                             # aqc_batch.flags: 2-bit base transport for host batches
-BATCH_PACK_QUALS = 1 << 18                             # aqc_batch.flags: 6-bit quality transport for host batches
 
 # pair classes, reference priority order (preprocesser.py:436-614)
 GOOD, BADTRIM1, BADTRIM2, BADLEN, BADPOL, BADLQC, BADNCT, BADDIFF, BADMISMATCH = range(9)

@@ -12,7 +12,7 @@ SYMBOLS = [
     "aqc_abi_version", "aqc_create", "aqc_destroy", "aqc_set_params", "aqc_reset", "aqc_reset_filter",
     "aqc_last_error", "aqc_host_alloc", "aqc_host_free", "aqc_device_alloc", "aqc_device_free",
     "aqc_memcpy_h2d", "aqc_memcpy_d2h", "aqc_stat_reads", "aqc_filter_pairs", "aqc_ops_pairs", "aqc_sync",
-    "aqc_get_counters", "aqc_add_counters", "aqc_get_qc", "aqc_get_kmer_dense", "aqc_get_kmer_side",
+    "aqc_get_counters", "aqc_add_counters", "aqc_get_qc", "aqc_get_kmer_dense", "aqc_get_kmer_side", "aqc_get_kmer_side_raw", "aqc_last_phase_ms",
     "aqc_launch_count", "aqc_last_kernel_ms", "aqc_set_stream", "aqc_device_ptr", "aqc_fastq_parse", "aqc_fastq_emit",
     "aqc_barcode_pairs", "aqc_gunzip_buffer", "aqc_gunzip_buffer_mt", "aqc_reader_open", "aqc_reader_next", "aqc_reader_release", "aqc_reader_error", "aqc_reader_close",
 ]
@@ -63,6 +63,7 @@ def bind(L):
         "aqc_get_qc": (i32, [vp, i32, vp]),
         "aqc_get_kmer_dense": (i32, [vp, i32, vp, vp]),
         "aqc_get_kmer_side": (i32, [vp, i32, vp, vp, vp, u32, C.POINTER(u32)]),
+        "aqc_get_kmer_side_raw": (i32, [vp, i32, vp, vp, vp, vp, u32, C.POINTER(u32)]),
         "aqc_set_stream": (i32, [vp, vp]),
         "aqc_device_ptr": (i32, [vp, i32, i32, C.POINTER(vp), C.POINTER(u64)]),
         "aqc_fastq_parse": (i32, [vp, u64, i32, u64, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), C.POINTER(u64), C.POINTER(i32), C.POINTER(u64)]),
@@ -77,6 +78,7 @@ def bind(L):
         "aqc_reader_close": (None, [vp]),
         "aqc_launch_count": (u64, [vp]),
         "aqc_last_kernel_ms": (C.c_float, [vp]),
+        "aqc_last_phase_ms": (C.c_float, [vp, i32]),
     }
     for name in SYMBOLS:
         fn = getattr(L, name)     # AttributeError if the library does not export it

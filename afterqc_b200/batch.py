@@ -20,6 +20,18 @@ def _as_bytes(s):
     return s.encode("latin-1")
 
 
+class _Pinned:
+    """page-locked allocations of a pinned PackedBatch, freed with it"""
+
+    def __init__(self, lib):
+        self.lib, self.ptrs = lib, []
+
+    def __del__(self):
+        for p in self.ptrs:
+            self.lib.aqc_host_free(p)
+        self.ptrs = []
+
+
 class PackedBatch:
     """Host-side packed batch.  seq2/qual2/off2 are None for single-end input."""
 
@@ -101,6 +113,27 @@ class PackedBatch:
             return PackedBatch(s1, q1, o1, first_index=self.first_index + lo)
         s2, q2, o2 = cut(self.seq2, self.qual2, self.off2)
         return PackedBatch(s1, q1, o1, s2, q2, o2, first_index=self.first_index + lo)
+
+    def pinned(self, engine):
+        """Copy of this batch whose columns live in page-locked host memory (aqc_host_alloc), as the host-buffer entry wants
+        them for asynchronous copies and for AQC_BATCH_QUAL2_IN_PLACE.  The memory is released with the returned object."""
+        lib = engine._L
+        owner = _Pinned(lib)
+
+        def pin(arr):
+            if arr is None:
+                return None
+            p = C.c_void_p()
+            rc = lib.aqc_host_alloc(max(1, arr.nbytes), C.byref(p))
+            if rc:
+                raise MemoryError("aqc_host_alloc(%d) failed" % arr.nbytes)
+            owner.ptrs.append(p)
+            view = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(1, arr.nbytes),))[:arr.nbytes].view(arr.dtype)
+            view[...] = arr
+            return view
+        out = PackedBatch(pin(self.seq1), pin(self.qual1), pin(self.off1), pin(self.seq2), pin(self.qual2), pin(self.off2), self.first_index)
+        out._owner = owner
+        return out
 
     # ---- views ---------------------------------------------------------------------------
     def read(self, mate, i):

@@ -7,8 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libafterqc_b200.so")
-SOURCES = ["aqc_engine.cu", "aqc_fastq.cpp", "aqc_stream.cpp", "aqc_inflate.cpp", "aqc_pinflate.cpp", "aqc_pack.cpp"]
-DEPS = ["aqc_stat2.cuh", "aqc_pack.cpp", "aqc_pack.hpp", "aqc_engine.cu", "aqc_fastq.cpp", "aqc_stream.cpp", "aqc_inflate.cpp", "aqc_inflate.hpp", "aqc_pinflate.cpp", "aqc_pinflate.hpp", "aqc_kernel.cuh", "aqc_device.cuh", "aqc_lane_kernel.cuh", "aqc_lane2_kernel.cuh", os.path.join("..", "..", "include", "afterqc_b200.h")]
+SOURCES = ["aqc_engine.cu", "aqc_fastq.cpp", "aqc_stream.cpp", "aqc_inflate.cpp", "aqc_pinflate.cpp"]
+DEPS = ["aqc_stat_kernel.cuh", "aqc_engine.cu", "aqc_fastq.cpp", "aqc_stream.cpp", "aqc_inflate.cpp", "aqc_inflate.hpp", "aqc_pinflate.cpp", "aqc_pinflate.hpp", "aqc_kernel.cuh", "aqc_device.cuh", "aqc_lane_kernel.cuh", os.path.join("..", "..", "include", "afterqc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -91,6 +91,7 @@ struct KArgs {
     // list mode (filter): tile i is the single pair list[i], i < *list_count -- the pairs lane_kernel hands over
     const uint32_t *list;
     const uint32_t *list_count;
+    int no_stats;         // filter modes: the postfilter statistics of this launch's good pairs are left to stat_kernel<.., POST>
 };
 
 // ------------------------------------------------------------------------------------------

@@ -1,4 +1,4 @@
-// aqc_engine.cu -- C-ABI of libafterqc_b200.so (include/afterqc_b200.h) on top of pair_kernel.
+// aqc_engine.cu -- C-ABI of libafterqc_b200.so (include/afterqc_b200.h) on top of lane_kernel / stat_kernel / pair_kernel.
 //
 // Host responsibilities only: context + device buffers, tile sizing, the chunked
 // H2D -> kernel -> D2H pipeline for host-resident batches, counter fetch/convert.
@@ -7,11 +7,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <array>
 #include <algorithm>
 #include "aqc_kernel.cuh"
-#include "aqc_pack.hpp"
 #include "aqc_lane_kernel.cuh"
-#include "aqc_lane2_kernel.cuh"
+#include "aqc_stat_kernel.cuh"
 
 using namespace aqc;
 
@@ -30,11 +30,6 @@ struct Staging {     // device staging of one host chunk
     uint32_t *off[2] = {nullptr, nullptr};
     void *res = nullptr;
     size_t col_cap = 0, off_cap = 0, res_cap = 0;
-    // packed base transport (AQC_BATCH_PACK_BASES): page-locked host buffers the pool packs into, and their device copies
-    uint8_t *hp[4] = {}, *dp[4] = {};               // packed column k (as col[k]: bases 1, qualities 1, bases 2, qualities 2)
-    uint32_t *hx_pos[4] = {}, *dx_pos[4] = {};      // exceptions: position in the staged column
-    uint8_t *hx_val[4] = {}, *dx_val[4] = {};       //             and the byte
-    size_t pk_cap = 0, x_cap = 0;
     cudaEvent_t h2d_done = nullptr, k_done = nullptr, d2h_done = nullptr;
 };
 
@@ -55,14 +50,10 @@ struct aqc_ctx {
     // lane-per-pair filter path (aqc_lane_kernel.cuh): hand-over list of the pairs that need the general kernel
     uint32_t *d_fb_list = nullptr, *d_fb_count = nullptr;
     size_t fb_cap = 0;
-    aqc_pack::Pool *pack_pool = nullptr;    // host threads of the packed base transport, created at first use
-    int lane_mode = 0;             // 0 = warp-per-pair kernel only, 1 = lane-per-pair kernel for batches of short reads
-    int stat_mode = 0;             // AQC_STAT_KERNEL=2|3: statRead with one lane per read when aqc_params.stat_kernel is 0
-    uint32_t *d_skip_bits = nullptr;   // stat_kernel 3: pairs of the launch that pair_kernel's list mode filtered (and stat'd)
-    size_t skip_cap = 0;               // words
+    uint32_t *d_kbits = nullptr;   // stat_kernel: "already stamped" bitmaps of the two mates of a launch (aqc_stat_kernel.cuh)
     Staging stg[2];
     uint32_t chunk_pairs = 1u << 18;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    std::vector<std::array<cudaEvent_t, 4>> ev_pool;    // per timed launch group: start | filter kernel done | list mode done | statistics done
     size_t ev_used = 0;
     uint64_t launches = 0;
     int sticky_err = 0;
@@ -123,8 +114,8 @@ unsigned long long host_side_hash(unsigned long long k) {   // must match aqc::s
 
 int check_params(const aqc_params *p, char *err, size_t errn) {
     if (p->qc_kmer < 1 || p->qc_kmer > AQC_MAX_KMER) { snprintf(err, errn, "qc_kmer %d outside 1..%d", p->qc_kmer, AQC_MAX_KMER); return AQC_ERR_INVALID; }
-    if (p->filter_kernel < 0 || p->filter_kernel > 3) { snprintf(err, errn, "filter_kernel %d outside 0..3", p->filter_kernel); return AQC_ERR_INVALID; }
-    if (p->stat_kernel < 0 || p->stat_kernel > 3) { snprintf(err, errn, "stat_kernel %d outside 0..3", p->stat_kernel); return AQC_ERR_INVALID; }
+    if (p->filter_kernel < 0 || p->filter_kernel > 2) { snprintf(err, errn, "filter_kernel %d outside 0..2", p->filter_kernel); return AQC_ERR_INVALID; }
+    if (p->stat_kernel < 0 || p->stat_kernel > 1) { snprintf(err, errn, "stat_kernel %d outside 0..1", p->stat_kernel); return AQC_ERR_INVALID; }
     if (p->trim_front < 0 || p->trim_tail < 0 || p->trim_front2 < 0 || p->trim_tail2 < 0) { snprintf(err, errn, "negative trim value (resolve auto-trim on the host first)"); return AQC_ERR_INVALID; }
     return 0;
 }
@@ -142,9 +133,6 @@ size_t smem_bytes_for(int P, int col_cap, int max_len) {
 #define AQC_KERNEL_HANDLE(...) ((const void *)(__VA_ARGS__))
 #else
 template <int MODE, bool PAIRED> void emu_pair_kernel(void **a) { pair_kernel<MODE, PAIRED>(*(const KArgs *)a[0]); }
-void emu_unpack_bases_kernel(void **a) { unpack_bases_kernel(*(const uint32_t **)a[0], *(uint4 **)a[1], *(uint32_t *)a[2]); }
-void emu_unpack_quals_kernel(void **a) { unpack_quals_kernel(*(const uint32_t **)a[0], *(uint4 **)a[1], *(uint32_t *)a[2]); }
-void emu_apply_exceptions_kernel(void **a) { apply_exceptions_kernel(*(const uint32_t **)a[0], *(const uint8_t **)a[1], *(uint32_t *)a[2], *(uint8_t **)a[3]); }
 void emu_maxlen_kernel(void **a) { maxlen_kernel(*(const uint32_t **)a[0], *(const uint32_t **)a[1], *(uint32_t *)a[2], *(uint32_t **)a[3]); }
 #define pair_kernel emu_pair_kernel
 #define AQC_KERNEL_HANDLE(...) ((const void *)(simt::Entry)(__VA_ARGS__))
@@ -158,53 +146,37 @@ const void *kernel_for(int mode, bool paired) {
 }
 #ifdef AQC_EMU
 #undef pair_kernel
-template <bool PAIRED, int NW, int SMODE = 0> void emu_lane_kernel(void **a) { lane_kernel<PAIRED, NW, SMODE>(*(const LArgs *)a[0]); }
+template <bool PAIRED, int NW> void emu_lane_kernel(void **a) { lane_kernel<PAIRED, NW>(*(const LArgs *)a[0]); }
+template <bool PAIRED, int NW, bool POST> void emu_stat_kernel(void **a) { stat_kernel<PAIRED, NW, POST>(*(const SKArgs *)a[0]); }
+void emu_stamp_bits_kernel(void **a) {
+    stamp_bits_kernel(*(const unsigned long long **)a[0], *(const unsigned long long **)a[1], *(uint32_t *)a[2], *(unsigned long long *)a[3],
+                      *(uint32_t **)a[4], *(uint32_t **)a[5]);
+}
 #define lane_kernel emu_lane_kernel
+#define stat_kernel emu_stat_kernel
 #endif
 
-// lane-per-pair filter kernel for mates of at most 32*NW bases
+// lane-per-pair filter kernel / warp-per-read statistics kernel for mates of at most 32*NW bases
 int lane_words_for(int max_len) { return max_len <= 128 ? 4 : (max_len <= 160 ? 5 : (max_len <= 256 ? 8 : 0)); }
-#define AQC_LANE_TABLE(KERNEL, SM)                                                                                             \
-    if (nw == 4) return paired ? AQC_KERNEL_HANDLE(KERNEL<true, 4, SM>) : AQC_KERNEL_HANDLE(KERNEL<false, 4, SM>);              \
-    if (nw == 5) return paired ? AQC_KERNEL_HANDLE(KERNEL<true, 5, SM>) : AQC_KERNEL_HANDLE(KERNEL<false, 5, SM>);              \
-    return paired ? AQC_KERNEL_HANDLE(KERNEL<true, 8, SM>) : AQC_KERNEL_HANDLE(KERNEL<false, 8, SM>);
-// smode: where the sampled postfilter statistics run (0 stat_read in the kernel, 1 stat_tile in the kernel, 2 stat_lane_kernel<POST> afterwards)
-const void *lane_kernel_for(bool paired, int nw, int smode) {
-    if (smode == 1) { AQC_LANE_TABLE(lane_kernel, 1) }
-    if (smode == 2) { AQC_LANE_TABLE(lane_kernel, 2) }
-    AQC_LANE_TABLE(lane_kernel, 0)
+const void *lane_kernel_for(bool paired, int nw) {
+    if (nw == 4) return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 4>) : AQC_KERNEL_HANDLE(lane_kernel<false, 4>);
+    if (nw == 5) return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 5>) : AQC_KERNEL_HANDLE(lane_kernel<false, 5>);
+    return paired ? AQC_KERNEL_HANDLE(lane_kernel<true, 8>) : AQC_KERNEL_HANDLE(lane_kernel<false, 8>);
+}
+// post: the sampled good pairs of a filter launch, from their records; else the prefilter window of aqc_stat_reads
+const void *stat_kernel_for(bool paired, int nw, bool post) {
+#define AQC_STAT_ROW(NWV)                                                                                                         \
+    if (nw == NWV) return paired ? (post ? AQC_KERNEL_HANDLE(stat_kernel<true, NWV, true>) : AQC_KERNEL_HANDLE(stat_kernel<true, NWV, false>)) \
+                                 : (post ? AQC_KERNEL_HANDLE(stat_kernel<false, NWV, true>) : AQC_KERNEL_HANDLE(stat_kernel<false, NWV, false>));
+    AQC_STAT_ROW(4) AQC_STAT_ROW(5)
+    return paired ? (post ? AQC_KERNEL_HANDLE(stat_kernel<true, 8, true>) : AQC_KERNEL_HANDLE(stat_kernel<true, 8, false>))
+                  : (post ? AQC_KERNEL_HANDLE(stat_kernel<false, 8, true>) : AQC_KERNEL_HANDLE(stat_kernel<false, 8, false>));
+#undef AQC_STAT_ROW
 }
 #ifdef AQC_EMU
 #undef lane_kernel
-template <bool PAIRED, int NW, int SMODE = 0> void emu_lane2_kernel(void **a) { lane2_kernel<PAIRED, NW, SMODE>(*(const LArgs *)a[0]); }
-#define lane2_kernel emu_lane2_kernel
+#undef stat_kernel
 #endif
-const void *lane2_kernel_for(bool paired, int nw, int smode) {
-    if (smode == 1) { AQC_LANE_TABLE(lane2_kernel, 1) }
-    if (smode == 2) { AQC_LANE_TABLE(lane2_kernel, 2) }
-    AQC_LANE_TABLE(lane2_kernel, 0)
-}
-#ifdef AQC_EMU
-#undef lane2_kernel
-template <bool PAIRED, int NW, bool POST = false> void emu_stat_lane_kernel(void **a) { stat_lane_kernel<PAIRED, NW, POST>(*(const SArgs *)a[0]); }
-#define stat_lane_kernel emu_stat_lane_kernel
-#endif
-// statistics with one lane per read: the prefilter window (aqc_stat_reads) / the sampled pairs of a filter launch (post)
-const void *stat_lane_kernel_for(bool paired, int nw, bool post) {
-    if (post) { AQC_LANE_TABLE(stat_lane_kernel, true) }
-    AQC_LANE_TABLE(stat_lane_kernel, false)
-}
-#ifdef AQC_EMU
-#undef stat_lane_kernel
-#endif
-size_t stat_lane_smem_bytes(int nwarps, int nw, int max_len) {
-    return (size_t)nwarps * 2 * 32 * (size_t)nw + 768 + (size_t)(2 * QC_CLASSES * max_len + 2 * max_len) * 4 + 64;
-}
-
-size_t lane_smem_bytes(int nwarps, int ncols, int nw, int col_cap, int max_len) {
-    size_t acc = (size_t)(2 * QC_CLASSES * max_len + 2 * max_len + 2 * (max_len + 1) + 16) * 4;
-    return (size_t)nwarps * (ncols * (size_t)col_cap + 4 * 32 * (size_t)nw) + 768 + acc + 64;
-}
 
 int alloc_qc(aqc_ctx *ctx, QcHost &q) {
     q.dense_n = (size_t)1 << (2 * ctx->p.qc_kmer);
@@ -296,13 +268,13 @@ size_t pair_tiling(aqc_ctx *ctx, KArgs &A, uint32_t n_tiles_of, int maxl, int ca
     return smem;
 }
 
-// effective aqc_params.stat_kernel: 0/1 = stat_read (one warp per read), 2 / 3 = one lane per read (3: sampled statistics in their own launch)
-int stat_level(const aqc_ctx *ctx) { return ctx->p.stat_kernel ? ctx->p.stat_kernel : ctx->stat_mode; }
-bool stat2_on(const aqc_ctx *ctx) { return stat_level(ctx) >= 2; }
-
+// aqc_params.filter_kernel: 0 / 2 = lane-per-pair kernel for batches of short reads (pair_kernel otherwise), 1 = pair_kernel always
 bool lane_path(const aqc_ctx *ctx, int mode, int max_len) {
-    const bool want_lane = ctx->p.filter_kernel == 2 || ctx->p.filter_kernel == 3 || (ctx->p.filter_kernel == 0 && ctx->lane_mode);
-    return mode == MODE_FILTER && want_lane && lane_words_for(std::max(max_len, 8)) != 0;
+    return mode == MODE_FILTER && ctx->p.filter_kernel != 1 && lane_words_for(std::max(max_len, 8)) != 0;
+}
+// aqc_params.stat_kernel: 0 = stat_kernel (shared-memory histograms) for batches of short reads, 1 = stat_read inside pair_kernel always
+bool stat_path(const aqc_ctx *ctx, int max_len) {
+    return ctx->p.stat_kernel != 1 && lane_words_for(std::max(max_len, 8)) != 0;
 }
 
 // device-side address of a page-locked host range, or nullptr when the device cannot address all of it
@@ -348,26 +320,81 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
     const bool pe = b.seq2 != nullptr;
     const int nw = lane_path(ctx, x.mode, maxl) ? lane_words_for(maxl) : 0;
 
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (timed) {
         if (ctx->ev_used == ctx->ev_pool.size()) {
-            cudaEvent_t a, c;
-            CK(cudaEventCreate(&a)); CK(cudaEventCreate(&c));
-            ctx->ev_pool.push_back({a, c});
+            std::array<cudaEvent_t, 4> a;
+            for (auto &e : a) CK(cudaEventCreate(&e));
+            ctx->ev_pool.push_back(a);
         }
-        e0 = ctx->ev_pool[ctx->ev_used].first; e1 = ctx->ev_pool[ctx->ev_used].second;
+        for (int i = 0; i < 4; i++) ev[i] = ctx->ev_pool[ctx->ev_used][i];
         ctx->ev_used++;
     }
+    auto mark = [&](int i) -> int { if (timed) CK(cudaEventRecord(ev[i], stream)); return 0; };
+
+    // statRead over records [lo, hi) of the batch with stat_kernel (aqc_stat_kernel.cuh): the "already stamped" bitmaps of both
+    // mates are rebuilt for the launch's lowest possible stamp; a large range is split into a short head and the rest, so that
+    // the rest finds (nearly) every dense k-mer stamped and never touches the stamp table in HBM.
+    auto stat_launches = [&](const KArgs &K0, bool post, uint32_t lo, uint32_t hi) -> int {
+        if (hi <= lo) return 0;
+        const int snw = lane_words_for(maxl);
+        const void *sk = stat_kernel_for(pe, snw, post);
+        const size_t ssmem = stat_smem_bytes(ctx->p.qc_kmer, snw, STAT_WARPS);
+        if (ssmem > ctx->max_dyn_smem) return fail(ctx, AQC_ERR_INVALID, "statistics tables do not fit shared memory");
+        const bool both = pe && K0.qc[0].valid && K0.qc[1].valid;
+        const uint32_t n_dense = 1u << (2 * ctx->p.qc_kmer), bw = stat_kbit_words(ctx->p.qc_kmer);
+        constexpr uint32_t HEAD = 8192;
+        uint32_t cuts[3] = {lo, hi, hi};
+        int n_parts = 1;
+        if (hi - lo > 4 * HEAD) { cuts[1] = lo + HEAD; n_parts = 2; }
+        for (int part = 0; part < n_parts; part++) {
+            const uint32_t plo = cuts[part], phi = cuts[part + 1];
+            // lowest stamp a record of [plo, phi) can produce: order << 11 (see stat_read)
+            unsigned long long min_order;
+            if (post) min_order = K0.first_index + plo;
+            else {
+                const unsigned long long g = std::max<unsigned long long>(K0.first_index + plo, K0.stat_lo);
+                min_order = K0.order_base + (g - K0.stat_lo);
+            }
+            unsigned long long min_when = min_order << 11;
+            const unsigned long long *f0 = K0.qc[0].valid ? K0.qc[0].kfirst : nullptr, *f1 = (pe && K0.qc[1].valid) ? K0.qc[1].kfirst : nullptr;
+            uint32_t *o0 = ctx->d_kbits, *o1 = ctx->d_kbits + bw;
+            uint32_t nd = n_dense;
+            void *bargs[6] = {(void *)&f0, (void *)&f1, (void *)&nd, (void *)&min_when, (void *)&o0, (void *)&o1};
+#ifndef AQC_EMU
+            const void *bk = (const void *)stamp_bits_kernel;
+#else
+            const void *bk = (const void *)(simt::Entry)emu_stamp_bits_kernel;
+#endif
+            CK(cudaLaunchKernel(bk, dim3(std::max<uint32_t>(1u, std::min<uint32_t>((n_dense + 255) / 256, 64u))), dim3(256), bargs, 0, stream));
+            CK(cudaGetLastError());
+            ctx->launches++;
+            SKArgs SA;
+            memset(&SA, 0, sizeof SA);
+            SA.k = K0;
+            SA.kbits[0] = o0; SA.kbits[1] = o1;
+            SA.lo = plo; SA.hi = phi;
+            const uint32_t per_mate = std::max<uint32_t>(1u, std::min<uint32_t>((phi - plo + STAT_WARPS - 1) / STAT_WARPS,
+                                                                               both ? std::max(1, ctx->sm_count / 2) : ctx->sm_count));
+            const uint32_t sgrid = both ? 2 * per_mate : per_mate;
+            void *sargs[1] = {(void *)&SA};
+            CK(cudaLaunchKernel(sk, dim3(sgrid), dim3(STAT_WARPS * 32), sargs, ssmem, stream));
+            CK(cudaGetLastError());
+            ctx->launches++;
+        }
+        return 0;
+    };
 
     if (nw) {
-        // ---- lane-per-pair kernel over the whole batch, then pair_kernel (list mode) over the pairs it handed over ----
+        // ---- lane-per-pair kernel over the whole batch, pair_kernel (list mode) over the pairs it handed over, then the
+        //      postfilter statistics of the sampled good pairs from the records both wrote ----
         if (b.n > ctx->fb_cap) {
             cudaFree(ctx->d_fb_list); ctx->d_fb_list = nullptr; ctx->fb_cap = 0;
             size_t cap = (size_t)b.n + (size_t)b.n / 4 + 1024;
             CK(cudaMalloc(&ctx->d_fb_list, cap * sizeof(uint32_t)));
             ctx->fb_cap = cap;
         }
-        CK(cudaMemsetAsync(ctx->d_fb_count, 0, 2 * sizeof(uint32_t), stream));      // [0] hand-over count, [1] tile counter
+        CK(cudaMemsetAsync(ctx->d_fb_count, 0, sizeof(uint32_t), stream));
         LArgs L;
         memset(&L, 0, sizeof L);
         L.k = A;
@@ -375,24 +402,10 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         L.k.num_tiles = (b.n + 31) / 32;
         L.fb_list = ctx->d_fb_list; L.fb_count = ctx->d_fb_count;
         L.lane_col_cap = (32 * maxl + 96 + 15) & ~15;
-        L.tile_counter = ctx->d_fb_count + 1;
-        const bool gen2 = ctx->p.filter_kernel == 3;
-        const int ncols = (pe && !gen2) ? 3 : 2;
-        const int smode = stat_level(ctx) == 2 ? 1 : (stat_level(ctx) == 3 ? 2 : 0);
-        const void *lk = gen2 ? lane2_kernel_for(pe, nw, smode) : lane_kernel_for(pe, nw, smode);
-        if (smode == 2) {               // the sampled statistics get their own launch below; pairs handed to pair_kernel are marked
-            const size_t words = ((size_t)b.n + 31) / 32 + 1;
-            if (words > ctx->skip_cap) {
-                cudaFree(ctx->d_skip_bits); ctx->d_skip_bits = nullptr; ctx->skip_cap = 0;
-                CK(cudaMalloc(&ctx->d_skip_bits, (words + words / 4) * sizeof(uint32_t)));
-                ctx->skip_cap = words + words / 4;
-            }
-            CK(cudaMemsetAsync(ctx->d_skip_bits, 0, words * sizeof(uint32_t), stream));
-            L.skip_bits = ctx->d_skip_bits;
-        }
+        const void *lk = lane_kernel_for(pe, nw);
         int best_w = 0, best_occ = 0;
         for (int w = LANE_MAX_WARPS; w >= 1; w--) {           // most resident warps per SM; ties go to the larger CTA
-            size_t sm = lane_smem_bytes(w, ncols, nw, L.lane_col_cap, maxl);
+            size_t sm = lane_smem_bytes(w, L.lane_col_cap, maxl);
             if (sm > ctx->max_dyn_smem) continue;
             int occ = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lk, w * 32, sm));
@@ -400,84 +413,56 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         }
         if (const char *fw = getenv("AQC_LANE_WARPS")) {        // tuning knob
             int w = std::max(1, std::min(LANE_MAX_WARPS, atoi(fw)));
-            size_t sm = lane_smem_bytes(w, ncols, nw, L.lane_col_cap, maxl);
+            size_t sm = lane_smem_bytes(w, L.lane_col_cap, maxl);
             int occ = 0;
             if (sm <= ctx->max_dyn_smem) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lk, w * 32, sm)); if (occ > 0) { best_w = w; best_occ = occ; } }
         }
         if (best_w == 0) return fail(ctx, AQC_ERR_INVALID, "lane kernel stage does not fit shared memory");
-        const size_t lsmem = lane_smem_bytes(best_w, ncols, nw, L.lane_col_cap, maxl);
+        const size_t lsmem = lane_smem_bytes(best_w, L.lane_col_cap, maxl);
         uint32_t want = (L.k.num_tiles + best_w - 1) / best_w;
         uint32_t lgrid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * best_occ));
-        if (timed) CK(cudaEventRecord(e0, stream));
+        if (mark(0)) return AQC_ERR_CUDA;
         void *largs[1] = {(void *)&L};
         CK(cudaLaunchKernel(lk, dim3(lgrid), dim3(best_w * 32), largs, lsmem, stream));
         CK(cudaGetLastError());
         ctx->launches++;
-        // general kernel over the hand-over list (usually empty: the count lives in device memory)
-        A.list = ctx->d_fb_list; A.list_count = ctx->d_fb_count;
-        size_t smem = pair_tiling(ctx, A, b.n, maxl, 1);
+        if (mark(1)) return AQC_ERR_CUDA;
+        // general kernel over the hand-over list (usually empty: the count lives in device memory); no statistics there either
+        KArgs G = A;
+        G.list = ctx->d_fb_list; G.list_count = ctx->d_fb_count;
+        G.no_stats = 1;
+        size_t smem = pair_tiling(ctx, G, b.n, maxl, 1);
         if (smem > ctx->max_dyn_smem) return fail(ctx, AQC_ERR_INVALID, "tile does not fit shared memory");
         const void *kern = kernel_for(MODE_LIST, pe);
-        A.mode = MODE_LIST;
+        G.mode = MODE_LIST;
         int occ = 1;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
         if (occ < 1) occ = 1;
         uint32_t grid = std::min<uint32_t>(b.n, (uint32_t)(ctx->sm_count * occ));
-        void *kargs[1] = {(void *)&A};
+        void *kargs[1] = {(void *)&G};
         CK(cudaLaunchKernel(kern, dim3(grid), dim3(THREADS), kargs, smem, stream));
         CK(cudaGetLastError());
         ctx->launches++;
-        if (smode == 2) {
-            // ---- postfilter statistics of the sampled good pairs (preprocesser.py:624-627), one lane per read, from the records ----
-            uint64_t lim = b.n;                                  // pairs [0, lim) of this batch are inside the sample gate (quirk Q10)
-            if (ctx->p.qc_sample > 0) {
-                const uint64_t gate = (uint64_t)ctx->p.qc_sample - 1;      // global indices below this one are sampled
-                lim = gate > b.first_index ? std::min<uint64_t>(b.n, gate - b.first_index) : 0;
-            }
-            if (lim) {
-                SArgs P;
-                memset(&P, 0, sizeof P);
-                P.k = L.k;
-                P.k.num_tiles = (uint32_t)((lim + 31) / 32);
-                P.skip_bits = ctx->d_skip_bits;
-                const void *pk = stat_lane_kernel_for(pe, nw, true);
-                const size_t psmem = stat_lane_smem_bytes(STAT2_WARPS, nw, maxl);
-                int pocc = 1;
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc, pk, STAT2_WARPS * 32, psmem));
-                if (pocc < 1) pocc = 1;
-                const uint32_t pwant = (P.k.num_tiles + STAT2_WARPS - 1) / STAT2_WARPS;
-                void *pargs[1] = {(void *)&P};
-                CK(cudaLaunchKernel(pk, dim3(std::min<uint32_t>(pwant, (uint32_t)(ctx->sm_count * pocc))), dim3(STAT2_WARPS * 32), pargs, psmem, stream));
-                CK(cudaGetLastError());
-                ctx->launches++;
-            }
+        if (mark(2)) return AQC_ERR_CUDA;
+        // ---- postfilter statistics of the sampled good pairs (preprocesser.py:624-627) ----
+        uint64_t lim = b.n;                                  // pairs [0, lim) of this batch are inside the sample gate (quirk Q10)
+        if (ctx->p.qc_sample > 0) {
+            const uint64_t gate = (uint64_t)ctx->p.qc_sample - 1;      // global indices below this one are sampled
+            lim = gate > b.first_index ? std::min<uint64_t>(b.n, gate - b.first_index) : 0;
         }
-        if (timed) CK(cudaEventRecord(e1, stream));
+        int rc = stat_launches(L.k, true, 0, (uint32_t)lim);
+        if (rc) return rc;
+        if (mark(3)) return AQC_ERR_CUDA;
         return 0;
     }
 
-    if (x.mode == MODE_STAT && stat2_on(ctx) && lane_words_for(maxl) != 0) {
-        // ---- prefilter statistics with one lane per read (aqc_stat2.cuh) ----
-        const int snw = lane_words_for(maxl);
-        const void *sk = stat_lane_kernel_for(pe, snw, false);
-        A.tile_pairs = 32;
-        A.num_tiles = (b.n + 31) / 32;
-        SArgs SA;
-        memset(&SA, 0, sizeof SA);
-        const size_t ssmem = stat_lane_smem_bytes(STAT2_WARPS, snw, maxl);
-        if (ssmem > 64 * 1024) return fail(ctx, AQC_ERR_INVALID, "statistics accumulators do not fit shared memory");
-        int socc = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&socc, sk, STAT2_WARPS * 32, ssmem));
-        if (socc < 1) socc = 1;
-        const uint32_t swant = (A.num_tiles + STAT2_WARPS - 1) / STAT2_WARPS;
-        const uint32_t sgrid = std::min<uint32_t>(swant, (uint32_t)(ctx->sm_count * socc));
-        if (timed) CK(cudaEventRecord(e0, stream));
-        SA.k = A;
-        void *sargs[1] = {(void *)&SA};
-        CK(cudaLaunchKernel(sk, dim3(sgrid), dim3(STAT2_WARPS * 32), sargs, ssmem, stream));
-        CK(cudaGetLastError());
-        if (timed) CK(cudaEventRecord(e1, stream));
-        ctx->launches++;
+    if (x.mode == MODE_STAT && stat_path(ctx, maxl)) {
+        // ---- prefilter statistics: only the records inside the window [stat_lo, stat_hi) are walked ----
+        uint64_t lo = x.stat_lo > b.first_index ? x.stat_lo - b.first_index : 0;
+        uint64_t hi = x.stat_hi > b.first_index ? std::min<uint64_t>(b.n, x.stat_hi - b.first_index) : 0;
+        if (mark(0) || mark(1) || mark(2)) return AQC_ERR_CUDA;
+        if (lo < hi) { int rc = stat_launches(A, false, (uint32_t)lo, (uint32_t)hi); if (rc) return rc; }
+        if (mark(3)) return AQC_ERR_CUDA;
         return 0;
     }
 
@@ -488,11 +473,13 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
     if (occ < 1) occ = 1;
     uint32_t grid = std::min<uint32_t>(A.num_tiles, (uint32_t)(ctx->sm_count * occ));
-    if (timed) CK(cudaEventRecord(e0, stream));
+    // pair_kernel does everything of its mode in one launch: reported as phase 0 (filter / ops) or phase 2 (MODE_STAT)
+    const bool as_stat = x.mode == MODE_STAT;
+    if (mark(0) || (as_stat && (mark(1) || mark(2)))) return AQC_ERR_CUDA;
     void *kargs[1] = {(void *)&A};
     CK(cudaLaunchKernel(kern, dim3(grid), dim3(THREADS), kargs, smem, stream));
     CK(cudaGetLastError());
-    if (timed) CK(cudaEventRecord(e1, stream));
+    if ((!as_stat && (mark(1) || mark(2))) || mark(3)) return AQC_ERR_CUDA;
     ctx->launches++;
     return 0;
 }
@@ -519,89 +506,6 @@ int ensure_staging(aqc_ctx *ctx, Staging &s, size_t col_bytes, size_t off_entrie
         cudaFree(s.res); s.res = nullptr;
         CK(cudaMalloc(&s.res, res_bytes + 256));
         s.res_cap = res_bytes;
-    }
-    return 0;
-}
-
-int ensure_pack_staging(aqc_ctx *ctx, Staging &s, size_t col_bytes) {
-    if (!ctx->pack_pool) ctx->pack_pool = aqc_pack::pool_create(0);
-    const size_t need = 3 * (col_bytes / 4 + 1) + 64;       // the larger of the two encodings (6-bit qualities)
-    if (need > s.pk_cap) {
-        const size_t cap = need + need / 4;
-        const size_t xcap = (col_bytes / 16 + 1024) * 5 / 4;       // more exceptions than 1/16: the chunk's column travels as bytes
-        for (int k = 0; k < 4; k++) {
-            cudaFreeHost(s.hp[k]); cudaFree(s.dp[k]); cudaFreeHost(s.hx_pos[k]); cudaFree(s.dx_pos[k]); cudaFreeHost(s.hx_val[k]); cudaFree(s.dx_val[k]);
-            s.hp[k] = s.dp[k] = s.hx_val[k] = s.dx_val[k] = nullptr; s.hx_pos[k] = s.dx_pos[k] = nullptr;
-        }
-        s.pk_cap = s.x_cap = 0;
-        for (int k = 0; k < 4; k++) {
-            CK(cudaHostAlloc((void **)&s.hp[k], cap, cudaHostAllocDefault));
-            CK(cudaMalloc(&s.dp[k], cap));
-            CK(cudaHostAlloc((void **)&s.hx_pos[k], xcap * 4, cudaHostAllocDefault));
-            CK(cudaMalloc(&s.dx_pos[k], xcap * 4));
-            CK(cudaHostAlloc((void **)&s.hx_val[k], xcap, cudaHostAllocDefault));
-            CK(cudaMalloc(&s.dx_val[k], xcap));
-        }
-        s.pk_cap = cap; s.x_cap = xcap;
-    }
-    return 0;
-}
-
-// Columns of a chunk through the packed transport (want[k]: column k as in Staging::col): packed by the host threads in one
-// dispatch of the pool, then the packed bytes (+ the exception lists) go out on copy_in.  packed[k] = false afterwards: not
-// wanted, or too many exceptions -- the caller copies the bytes.
-void pack_and_copy(aqc_ctx *ctx, Staging &s, const bool want[4], const uint8_t *const src[4], const size_t n[4], bool packed[4], size_t n_exc[4]) {
-    aqc_pack::Column cols[4];
-    int idx[4], nc = 0;
-    for (int k = 0; k < 4; k++) {
-        packed[k] = false; n_exc[k] = 0;
-        if (!want[k] || n[k] == 0) continue;
-        cols[nc] = aqc_pack::Column{(k & 1) ? aqc_pack::KIND_QUALS : aqc_pack::KIND_BASES, src[k], n[k], s.hp[k], s.hx_pos[k], s.hx_val[k],
-                                    std::min(s.x_cap, n[k] / 16 + 1024), 0, true};
-        idx[nc++] = k;
-    }
-    if (!nc) return;
-    aqc_pack::pack_columns(ctx->pack_pool, cols, nc);
-    for (int c = 0; c < nc; c++) {
-        const int k = idx[c];
-        if (!cols[c].ok) continue;
-        if (cudaMemcpyAsync(s.dp[k], s.hp[k], aqc_pack::packed_bytes(cols[c].kind, n[k]), cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) continue;
-        if (cols[c].n_exc) {
-            if (cudaMemcpyAsync(s.dx_pos[k], s.hx_pos[k], cols[c].n_exc * 4, cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) continue;
-            if (cudaMemcpyAsync(s.dx_val[k], s.hx_val[k], cols[c].n_exc, cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess) continue;
-        }
-        n_exc[k] = cols[c].n_exc;
-        packed[k] = true;
-    }
-}
-
-// after the copies landed (compute waits on h2d_done): expand packed column k into the staged byte column
-int unpack_column(aqc_ctx *ctx, Staging &s, int k, uint8_t *col, size_t n, size_t n_exc) {
-    const uint32_t *packed = reinterpret_cast<const uint32_t *>(s.dp[k]);
-    uint4 *out = reinterpret_cast<uint4 *>(col);
-    uint32_t n_units = (uint32_t)((n + 15) / 16);           // threads: 16 output bytes each
-    if (n_units) {
-        void *a[3] = {(void *)&packed, (void *)&out, (void *)&n_units};
-#ifndef AQC_EMU
-        const void *kern = (k & 1) ? (const void *)unpack_quals_kernel : (const void *)unpack_bases_kernel;
-#else
-        const void *kern = (k & 1) ? (const void *)(simt::Entry)emu_unpack_quals_kernel : (const void *)(simt::Entry)emu_unpack_bases_kernel;
-#endif
-        CK(cudaLaunchKernel(kern, dim3(std::min<uint32_t>((n_units + 255) / 256, (uint32_t)ctx->sm_count * 8u)), dim3(256), a, 0, ctx->compute));
-        ctx->launches++;
-    }
-    if (n_exc) {
-        const uint32_t *pos = s.dx_pos[k];
-        const uint8_t *val = s.dx_val[k];
-        uint32_t ne = (uint32_t)n_exc;
-        void *a[4] = {(void *)&pos, (void *)&val, (void *)&ne, (void *)&col};
-#ifndef AQC_EMU
-        const void *kern = (const void *)apply_exceptions_kernel;
-#else
-        const void *kern = (const void *)(simt::Entry)emu_apply_exceptions_kernel;
-#endif
-        CK(cudaLaunchKernel(kern, dim3(std::min<uint32_t>((ne + 255) / 256, (uint32_t)ctx->sm_count * 8u)), dim3(256), a, 0, ctx->compute));
-        ctx->launches++;
     }
     return 0;
 }
@@ -634,32 +538,19 @@ int run_host(aqc_ctx *ctx, const aqc_batch *b, const LaunchExtra &x0, void *out_
         // mate-2 qualities may stay in page-locked host memory when the lane-per-pair kernel runs (AQC_BATCH_QUAL2_IN_PLACE)
         const uint8_t *q2_in_place = nullptr;
         if (paired && (b->flags & AQC_BATCH_QUAL2_IN_PLACE) && e2 > a2 && lane_path(ctx, x0.mode, maxl))
-            q2_in_place = device_view_of_host(b->qual2, a2, e2 - 1 + (stat2_on(ctx) ? 3 : 0));    // stat_tile reads whole words
-        // columns travel as bytes, or packed by the host threads and expanded on the device: bases at 2 bits
-        // (AQC_BATCH_PACK_BASES), qualities at 6 bits (AQC_BATCH_PACK_QUALS)
-        const bool pb = (b->flags & AQC_BATCH_PACK_BASES) != 0, pq = (b->flags & AQC_BATCH_PACK_QUALS) != 0;
-        const bool want[4] = {pb, pq, pb && paired, pq && paired && !q2_in_place};
+            q2_in_place = device_view_of_host(b->qual2, a2, e2 - 1);
         const uint8_t *const srcs[4] = {b->seq1 + g1, b->qual1 + g1, paired ? b->seq2 + g2 : nullptr, paired ? b->qual2 + g2 : nullptr};
         const size_t lens[4] = {(size_t)(e1 - g1), (size_t)(e1 - g1), (size_t)(e2 - g2), (size_t)(e2 - g2)};
-        bool packed[4] = {false, false, false, false};
-        size_t n_exc[4] = {0, 0, 0, 0};
-        if (pb || pq) {
-            rc = ensure_pack_staging(ctx, s, cb);
-            if (rc) return rc;
-            pack_and_copy(ctx, s, want, srcs, lens, packed, n_exc);
-        }
-        if (!packed[0]) CK(cudaMemcpyAsync(s.col[0], srcs[0], lens[0], cudaMemcpyHostToDevice, ctx->copy_in));
-        if (!packed[1]) CK(cudaMemcpyAsync(s.col[1], srcs[1], lens[1], cudaMemcpyHostToDevice, ctx->copy_in));
+        CK(cudaMemcpyAsync(s.col[0], srcs[0], lens[0], cudaMemcpyHostToDevice, ctx->copy_in));
+        CK(cudaMemcpyAsync(s.col[1], srcs[1], lens[1], cudaMemcpyHostToDevice, ctx->copy_in));
         CK(cudaMemcpyAsync(s.off[0], b->off1 + lo, (size_t)(cn + 1) * 4, cudaMemcpyHostToDevice, ctx->copy_in));
         if (paired) {
-            if (!packed[2]) CK(cudaMemcpyAsync(s.col[2], srcs[2], lens[2], cudaMemcpyHostToDevice, ctx->copy_in));
-            if (!q2_in_place && !packed[3]) CK(cudaMemcpyAsync(s.col[3], srcs[3], lens[3], cudaMemcpyHostToDevice, ctx->copy_in));
+            CK(cudaMemcpyAsync(s.col[2], srcs[2], lens[2], cudaMemcpyHostToDevice, ctx->copy_in));
+            if (!q2_in_place) CK(cudaMemcpyAsync(s.col[3], srcs[3], lens[3], cudaMemcpyHostToDevice, ctx->copy_in));
             CK(cudaMemcpyAsync(s.off[1], b->off2 + lo, (size_t)(cn + 1) * 4, cudaMemcpyHostToDevice, ctx->copy_in));
         }
         CK(cudaEventRecord(s.h2d_done, ctx->copy_in));
         CK(cudaStreamWaitEvent(ctx->compute, s.h2d_done, 0));
-        for (int k = 0; k < 4; k++)
-            if (packed[k]) { rc = unpack_column(ctx, s, k, s.col[k], lens[k], n_exc[k]); if (rc) return rc; }
         DevBatch d;
         // virtual column bases so that the absolute offsets of the chunk index the staged bytes
         d.seq1 = s.col[0] - g1; d.qual1 = s.col[1] - g1;
@@ -775,11 +666,8 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
         std::vector<const void *> lanes;
         for (int nw : {4, 5, 8})
             for (bool pe : {true, false}) {
-                for (int sm : {0, 1, 2}) { lanes.push_back(lane_kernel_for(pe, nw, sm)); lanes.push_back(lane2_kernel_for(pe, nw, sm)); }
-                // stat_lane_kernel: small accumulators only, and it re-reads each 32-byte sector of a read eight times (word loads
-                // per lane), so it keeps the default carve-out (a large L1)
-                for (bool post : {false, true})
-                    CK(cudaFuncSetAttribute(stat_lane_kernel_for(pe, nw, post), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                lanes.push_back(lane_kernel_for(pe, nw));
+                for (bool post : {false, true}) lanes.push_back(stat_kernel_for(pe, nw, post));
             }
         for (const void *k : lanes) {
             cudaFuncAttributes fa;
@@ -796,8 +684,7 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
             CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
         CK(cudaMalloc(&ctx->d_fb_count, 2 * sizeof(uint32_t)));
-        if (const char *lm = getenv("AQC_LANE_KERNEL")) ctx->lane_mode = atoi(lm) != 0;
-        if (const char *sk = getenv("AQC_STAT_KERNEL")) { int v = atoi(sk); ctx->stat_mode = (v == 2 || v == 3) ? v : 0; }   // opt-in for callers that pass stat_kernel = 0
+        CK(cudaMalloc(&ctx->d_kbits, 2 * (size_t)stat_kbit_words(ctx->p.qc_kmer) * sizeof(uint32_t)));
         if (const char *cp = getenv("AQC_CHUNK_PAIRS")) {          // host-path chunk size (tests exercise the multi-chunk pipeline with small batches)
             long v = atol(cp);
             if (v >= 4) ctx->chunk_pairs = (uint32_t)std::min<long>(v & ~3L, 1L << 24);
@@ -820,18 +707,14 @@ void aqc_destroy(aqc_ctx *ctx) {
         for (int k = 0; k < 4; k++) cudaFree(st.col[k]);
         for (int k = 0; k < 2; k++) cudaFree(st.off[k]);
         cudaFree(st.res);
-        for (int m = 0; m < 4; m++) {
-            cudaFreeHost(st.hp[m]); cudaFree(st.dp[m]); cudaFreeHost(st.hx_pos[m]); cudaFree(st.dx_pos[m]); cudaFreeHost(st.hx_val[m]); cudaFree(st.dx_val[m]);
-        }
         if (st.h2d_done) { cudaEventDestroy(st.h2d_done); cudaEventDestroy(st.k_done); cudaEventDestroy(st.d2h_done); }
     }
-    for (auto &ev : ctx->ev_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto &ev : ctx->ev_pool) for (auto e : ev) cudaEventDestroy(e);
     cudaFree(ctx->d_counters); cudaFree(ctx->d_luts); cudaFree(ctx->d_error); cudaFree(ctx->d_maxlen);
-    cudaFree(ctx->d_fb_list); cudaFree(ctx->d_fb_count); cudaFree(ctx->d_skip_bits);
+    cudaFree(ctx->d_fb_list); cudaFree(ctx->d_fb_count); cudaFree(ctx->d_kbits);
     if (ctx->own_compute) cudaStreamDestroy(ctx->own_compute);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
-    aqc_pack::pool_destroy(ctx->pack_pool);
     delete ctx;
 }
 
@@ -1091,17 +974,41 @@ int aqc_get_kmer_side(aqc_ctx *ctx, int slot, uint64_t *keys, uint64_t *counts, 
     return rc;
 }
 
+int aqc_get_kmer_side_raw(aqc_ctx *ctx, int slot, uint64_t *keys, uint64_t *counts, uint64_t *first_direct, uint64_t *first_seed,
+                          uint32_t cap, uint32_t *n_out) {
+    if (!ctx || !n_out || slot < 0 || slot >= AQC_NUM_QC) return AQC_ERR_INVALID;
+    int rc = aqc_sync(ctx);
+    QcHost &q = ctx->qc[slot];
+    std::vector<unsigned long long> k(q.side_cap), c(q.side_cap), d(q.side_cap), sf(q.side_cap);
+    CK(cudaMemcpy(k.data(), q.d.skeys, (size_t)q.side_cap * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(c.data(), q.d.scnt, (size_t)q.side_cap * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(d.data(), q.d.sfirst, (size_t)q.side_cap * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(sf.data(), q.d.sseed, (size_t)q.side_cap * 8, cudaMemcpyDeviceToHost));
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < q.side_cap; i++) n += k[i] != AQC_KMER_NEVER;
+    *n_out = n;
+    if (cap == 0 && !keys) return rc;
+    if (cap < n || !keys || !counts || !first_direct || !first_seed) return fail(ctx, AQC_ERR_INVALID, "side-table output too small");
+    uint32_t o = 0;
+    for (uint32_t i = 0; i < q.side_cap; i++)
+        if (k[i] != AQC_KMER_NEVER) { keys[o] = k[i]; counts[o] = c[i]; first_direct[o] = d[i]; first_seed[o] = sf[i]; o++; }
+    return rc;
+}
+
 uint64_t aqc_launch_count(const aqc_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-float aqc_last_kernel_ms(const aqc_ctx *ctx) {
-    if (!ctx) return 0.f;
+float aqc_last_phase_ms(const aqc_ctx *ctx, int phase) {
+    if (!ctx || phase < -1 || phase > 2) return 0.f;
+    const int a = phase < 0 ? 0 : phase, b = phase < 0 ? 3 : phase + 1;
     float total = 0.f;
     for (size_t i = 0; i < ctx->ev_used; i++) {
         float ms = 0.f;
-        if (cudaEventSynchronize(ctx->ev_pool[i].second) == cudaSuccess &&
-            cudaEventElapsedTime(&ms, ctx->ev_pool[i].first, ctx->ev_pool[i].second) == cudaSuccess) total += ms;
+        if (cudaEventSynchronize(ctx->ev_pool[i][3]) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, ctx->ev_pool[i][a], ctx->ev_pool[i][b]) == cudaSuccess) total += ms;
     }
     return total;
 }
+
+float aqc_last_kernel_ms(const aqc_ctx *ctx) { return aqc_last_phase_ms(ctx, -1); }
 
 }  // extern "C"

@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(THREADS, AQC_MIN_BLOCKS) pair_kernel(const __g
                 bump(AQC_C_GOOD_BASES_R1, (unsigned long long)len1);
                 bump(AQC_C_GOOD_BASES_R2, (unsigned long long)len2);
                 const uint64_t total_reads = gidx + 1;
-                if (__builtin_expect(A.p.qc_sample <= 0 || total_reads < (uint64_t)A.p.qc_sample, 0)) {       // :624
+                if (__builtin_expect(!A.no_stats && (A.p.qc_sample <= 0 || total_reads < (uint64_t)A.p.qc_sample), 0)) {       // :624
 #pragma unroll 1
                     for (int m = 0; m < (paired ? 2 : 1); m++)      // one inlined copy of statRead for both mates
                         stat_read(m ? S2 + start2 : S1 + start1, m ? Q2 + start2 : Q1 + start1, m ? len2 : len1, m, gidx, qsm, A.qc[m],
@@ -513,42 +513,6 @@ __global__ void maxlen_kernel(const uint32_t *off1, const uint32_t *off2, uint32
     }
     m = __reduce_max_sync(FULL, m);
     if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
-}
-
-// ---- packed base transport of the host-buffer entry (aqc_pack.hpp, AQC_BATCH_PACK_BASES) ----
-// 2 bits per base (A0 C1 T2 G3, base j of a packed byte in bits 2*(j & 3)) -> the byte column the kernels read.  One thread
-// expands one 32-bit word (16 bases) and stores 16 bytes; `out` is 16-byte aligned, both buffers carry slack for the tail.
-__global__ void unpack_bases_kernel(const uint32_t *packed, uint4 *out, uint32_t n_words) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) {
-        const uint32_t w = packed[i];
-        uint32_t o[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t b = (w >> (8 * k)) & 0xFFu;
-            const uint32_t sel = (b & 3u) | ((b & 0xCu) << 2) | ((b & 0x30u) << 4) | ((b & 0xC0u) << 6);     // one code per selector nibble
-            o[k] = __byte_perm(0x47544341u, 0u, sel);                                                        // "ACTG"
-        }
-        out[i] = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-}
-
-// 6 bits per quality byte (code = byte - 33; four codes in three bytes, little endian) -> the byte column.  One thread expands
-// three 32-bit words (16 qualities) and stores 16 bytes.
-__global__ void unpack_quals_kernel(const uint32_t *packed, uint4 *out, uint32_t n_groups) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_groups; i += gridDim.x * blockDim.x) {
-        const uint32_t w0 = packed[3 * i], w1 = packed[3 * i + 1], w2 = packed[3 * i + 2];
-        const uint32_t v[4] = {w0 & 0xFFFFFFu, (w0 >> 24) | ((w1 & 0xFFFFu) << 8), (w1 >> 16) | ((w2 & 0xFFu) << 16), w2 >> 8};
-        uint32_t o[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            o[k] = ((v[k] & 0x3Fu) | ((v[k] & 0xFC0u) << 2) | ((v[k] & 0x3F000u) << 4) | ((v[k] & 0xFC0000u) << 6)) + 0x21212121u;
-        out[i] = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-}
-
-// the bytes that are not A,C,G,T (N, lower case, anything else) / not a quality in '!'..'`' travel as (position, byte)
-__global__ void apply_exceptions_kernel(const uint32_t *pos, const uint8_t *val, uint32_t n, uint8_t *out) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[pos[i]] = val[i];
 }
 
 }  // namespace aqc

@@ -4,22 +4,25 @@
 // only 5 of the 32 lanes of a plane set and every piece of per-pair bookkeeping is executed 32 times.  For Illumina
 // lengths the planes of both mates fit in registers (2 x NW words per plane), so here a warp takes a tile of 32 pairs
 // and every lane runs the whole reference loop body (preprocesser.py:455-631) for its own pair:
-//   * the warp's private shared-memory stage receives the tile's three byte columns (bases 1, qualities 1, bases 2;
-//     qualities 2 are only ever touched by the correction walk and the statistics) with 1-D TMA bulk copies; the lane
-//     converts its own reads to bit-planes (SWAR, 4 bases per 32-bit word: codes from the ASCII bits, re-encoding
-//     check for foreign bytes, multiply-gather of the code bits) and counts low qualities; after that the stage is
+//   * the warp's private shared-memory stage has TWO columns: bases 1 and bases 2 arrive first (1-D TMA bulk copies);
+//     as soon as the lane has converted mate 1 to bit-planes (SWAR, 4 bases per 32-bit word: codes from the ASCII bits,
+//     re-encoding check for foreign bytes, multiply-gather of the code bits) the qualities of mate 1 are copied over
+//     its bases and that copy overlaps the conversion of mate 2.  Qualities of mate 2 are only ever touched by the
+//     correction walk (two bytes per visited mismatch) and are never staged.  After the low-quality count the stage is
 //     free and the next tile's copy overlaps the rest of the work;
-//   * util.overlap_hm (util.py:158-212): per 32 candidate offsets the lane funnel-shifts two plane words, XORs them with
-//     the fixed mate's first word and keeps the offsets with < 3 mismatches in the first 32 positions as a bit mask
+//   * util.overlap_hm (util.py:158-212): per 32 candidate offsets the lane funnel-shifts one code-bit plane, XORs it with
+//     the fixed mate's first word and keeps the offsets with < 3 differing bits in the first 32 positions as a bit mask
 //     (a necessary condition of the acceptance rule); the lanes then evaluate their candidates exactly, in scan order,
 //     in lock step; the scanned mate's words are rotated one register per round so that the code does not depend on
 //     the round;
 //   * hasPolyX is screened by a multi-word run-length test per lane; adapter cut, rescan, correction walk and the
 //     classifier are per-lane code on registers, reading the few bytes the walk needs from HBM (L2);
-//   * rare work that is better done by a whole warp is handed over by ballot: exact hasPolyX of screened reads,
-//     statRead of the sampled good pairs (the trimmed, corrected reads are rebuilt in a per-warp scratch from the
-//     result record), and pairs holding a byte outside A,C,G,T,N, which are appended to a list that pair_kernel
-//     processes in its list mode right after this kernel.
+//   * work that suits a whole warp is handed over by ballot: exact hasPolyX of screened reads, and pairs holding a byte
+//     outside A,C,G,T,N, which are appended to a list that pair_kernel processes in its list mode right after this kernel;
+//   * the kernel carries NO statistics code: the sampled good pairs are stat'd from their 32-byte records by
+//     stat_kernel<.., POST> (aqc_stat_kernel.cuh) in the next launch -- instruction-cache misses were the first stall
+//     reason of the previous generation (profiles/r02_lane2_kernel_ncu_full.txt), the fused statRead hand-over a
+//     seventh of its instructions.
 // Counters: per-tile packed warp reductions into lane-owned 64-bit registers; histograms and the error matrix are
 // shared-memory atomics.  Results are bit-identical to pair_kernel and the oracle.
 #pragma once
@@ -34,8 +37,6 @@ struct LArgs {
     uint32_t *fb_list;            // pairs that need the general (warp-per-pair) path
     uint32_t *fb_count;
     int lane_col_cap;             // bytes reserved per column in a warp's stage
-    uint32_t *tile_counter;       // lane2_kernel: next unclaimed tile (zeroed before the launch)
-    uint32_t *skip_bits;          // SMODE 2: bit pp set = pair pp went to pair_kernel's list mode (which also does its statistics)
 };
 
 template <int NW> struct LanePlanes {
@@ -87,11 +88,7 @@ __device__ __forceinline__ void lane_convert(const uint8_t *s, int len, LanePlan
     exotic = false;
     n_count = 0;
     uint32_t prev = len > 0 ? lds_u32(w) : 0u;
-#ifdef AQC_LANE_UNROLL_CONVERT
-#pragma unroll
-#else
 #pragma unroll 1
-#endif
     for (int c = 0; c < NW; c++) {
         uint32_t p0 = 0, p1 = 0, pn = 0;
         const int nvalid = len - 32 * c;
@@ -103,18 +100,21 @@ __device__ __forceinline__ void lane_convert(const uint8_t *s, int len, LanePlan
                 v[j] = __funnelshift_r(prev, cur, sh);
                 prev = cur;
             }
-            uint32_t rlo = 0, rhi = 0, bad = 0;
+            uint32_t rlo = 0, rhi = 0, nlo = 0, nhi = 0, bad = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const uint32_t t = v[j] & 0x06060606u;
-                const uint32_t tt = t >> 1;                                                     // 2-bit codes
-                // codes -> ASCII: the four codes of the word become the four selector nibbles of a table lookup
-                const uint32_t e = prmt_raw(0x47544341u, 0u, prmt_raw(tt + (tt >> 4), 0u, 0x4420u));
-                bad |= e ^ v[j];
-                const uint32_t z = ((t << 2) + tt) & 0x11111111u;                               // bit0 = code bit 0, bit4 = code bit 1
+                // bits 1..3 of the ASCII byte: A 000, C 001, T 010, G 011, N 111 -- 2-bit code + "is N"
+                const uint32_t tt = (v[j] & 0x0E0E0E0Eu) >> 1;
+                // codes -> ASCII: the four 3-bit values become the selector nibbles of an 8-entry table lookup
+                // (entries 4..6 hold 0, which no byte with those bits re-encodes to)
+                const uint32_t e = prmt_raw(0x47544341u, 0x4E000000u, prmt_raw(tt + (tt >> 4), 0u, 0x4420u));
+                bad |= e ^ v[j];                                                                // non-zero: a byte outside A,C,G,T,N
+                const uint32_t z = (tt + (tt << 3)) & 0x11111111u;                              // bit0 = code bit 0, bit4 = code bit 1
                 const uint32_t r = z * 0x01020408u;                     // byte 3 = nibble of plane 0 | nibble of plane 1 << 4
+                const uint32_t rn = (tt & 0x04040404u) * 0x00408102u;   // byte 3 = nibble of the N plane
                 constexpr uint32_t sel[4] = {0x3217u, 0x3270u, 0x3710u, 0x7210u};               // byte 3 of r -> byte j of the accumulator
-                if (j < 4) rlo = __byte_perm(rlo, r, sel[j & 3]); else rhi = __byte_perm(rhi, r, sel[j & 3]);
+                if (j < 4) { rlo = __byte_perm(rlo, r, sel[j & 3]); nlo = __byte_perm(nlo, rn, sel[j & 3]); }
+                else { rhi = __byte_perm(rhi, r, sel[j & 3]); nhi = __byte_perm(nhi, rn, sel[j & 3]); }
             }
             // de-interleave the nibbles: bytes of rlo/rhi hold (p1 nibble << 4 | p0 nibble) of 4 bases each
             {
@@ -122,40 +122,32 @@ __device__ __forceinline__ void lane_convert(const uint8_t *s, int len, LanePlan
                 const uint32_t l1 = (rlo >> 4) & 0x0F0F0F0Fu, h1 = (rhi >> 4) & 0x0F0F0F0Fu;
                 const uint32_t a0 = (l0 | (l0 >> 4)) & 0x00FF00FFu, b0 = (h0 | (h0 >> 4)) & 0x00FF00FFu;
                 const uint32_t a1 = (l1 | (l1 >> 4)) & 0x00FF00FFu, b1 = (h1 | (h1 >> 4)) & 0x00FF00FFu;
+                const uint32_t an = (nlo | (nlo >> 4)) & 0x00FF00FFu, bn = (nhi | (nhi >> 4)) & 0x00FF00FFu;
                 p0 = __byte_perm(a0, b0, 0x6420);
                 p1 = __byte_perm(a1, b1, 0x6420);
+                pn = __byte_perm(an, bn, 0x6420);
             }
             const uint32_t vm = lowmask(nvalid);
-            p0 &= vm; p1 &= vm;
-            if (__builtin_expect(bad != 0u, 0)) {           // some byte of the 32 is not A,C,G,T (maybe beyond the read)
-                uint32_t nb = 0, xb = 0;
+            pn &= vm;
+            p0 &= vm & ~pn; p1 &= vm & ~pn;                     // 'N' keeps its own plane, its code bits are cleared
+            n_count += __popc(pn);
+            if (__builtin_expect(bad != 0u, 0)) {               // a byte outside A,C,G,T,N among the 32 (maybe beyond the read)
+                uint32_t xb = 0;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const uint32_t t = v[j] & 0x06060606u;
-                    const uint32_t tt = t >> 1;
-                    const uint32_t e = __byte_perm(0x47544341u, 0u, __byte_perm(tt | (tt >> 4), 0u, 0x4420));
-                    const uint32_t isn = ~hibit_nonzero(v[j] ^ 0x4E4E4E4Eu) & 0x80808080u;
-                    const uint32_t isbad = hibit_nonzero(e ^ v[j]);
-                    nb |= gather4(isn >> 7) << (4 * j);
-                    xb |= gather4((isbad & ~isn) >> 7) << (4 * j);
+                    const uint32_t tt = (v[j] & 0x0E0E0E0Eu) >> 1;
+                    const uint32_t e = __byte_perm(0x47544341u, 0x4E000000u, __byte_perm(tt | (tt >> 4), 0u, 0x4420));
+                    xb |= gather4(hibit_nonzero(e ^ v[j]) >> 7) << (4 * j);
                 }
-                nb &= vm; xb &= vm;
-                if (xb) exotic = true;
-                pn = nb;
-                p0 &= ~nb; p1 &= ~nb;
-                n_count += __popc(nb);
+                if (xb & vm) exotic = true;
             }
         }
-#ifdef AQC_LANE_UNROLL_CONVERT
-        P.p0[c] = p0; P.p1[c] = p1; P.pn[c] = pn;
-#else
 #pragma unroll
         for (int i = 0; i < NW; i++) {
             P.p0[i] = (i + 1 < NW) ? P.p0[i + 1 < NW ? i + 1 : 0] : p0;
             P.p1[i] = (i + 1 < NW) ? P.p1[i + 1 < NW ? i + 1 : 0] : p1;
             P.pn[i] = (i + 1 < NW) ? P.pn[i + 1 < NW ? i + 1 : 0] : pn;
         }
-#endif
     }
 }
 
@@ -222,9 +214,6 @@ __device__ __forceinline__ bool lane_scan_dir(uint32_t (&S0)[NW], uint32_t (&S1)
     const int rounds = (maxOff + 31) >> 5;
     const bool slow = lenF < 32;                                // first window shorter than 32: every offset is evaluated exactly
     const uint32_t f0 = F0[0];
-#ifdef AQC_LANE_TWO_PLANE_FILTER
-    const uint32_t f1 = F1[0];
-#endif
     bool found = false;
 #pragma unroll 1
     for (int r = 0; r < rounds; r++) {
@@ -233,21 +222,13 @@ __device__ __forceinline__ bool lane_scan_dir(uint32_t (&S0)[NW], uint32_t (&S1)
         uint32_t cm = 0;
         if (!found && rem > 0) {
             if (!slow) {
+                // one code bit is enough for a necessary condition: equal bases have equal bits, and 32 random positions
+                // differ in fewer than 3 of them with probability 1.2e-7.  The verdicts are shifted into the mask through the
+                // sign of popc - 3 (offset 31 first, so offset b ends up in bit b).
 #pragma unroll
-                for (int b = 0; b < 32; b++) {
-#ifdef AQC_LANE_TWO_PLANE_FILTER
-                    const uint32_t x = (__funnelshift_r(S0[0], S0[1], b) ^ f0) | (__funnelshift_r(S1[0], S1[1], b) ^ f1);
-#else
-                    // one code bit is enough for a necessary condition: equal bases have equal bits, and 32 random positions
-                    // differ in fewer than 3 of them with probability 1.2e-7
-#ifdef AQC_LANE_IMAD_SHIFT
-                    // tuning variant: the window as two multiplies (FMA pipe) instead of one funnel shift (ALU pipe, the busy one)
-                    const uint32_t x = (b == 0 ? S0[0] : __umulhi(S0[0], 1u << ((32 - b) & 31)) + S0[1] * (1u << ((32 - b) & 31))) ^ f0;
-#else
+                for (int b = 31; b >= 0; b--) {
                     const uint32_t x = __funnelshift_r(S0[0], S0[1], b) ^ f0;
-#endif
-#endif
-                    if (__popc(x) < 3) cm |= 1u << b;
+                    cm = __funnelshift_l((uint32_t)(__popc(x) - 3), cm, 1);
                 }
                 cm &= lowmask(rem);
                 if (rem <= 32) cm |= 1u << (rem - 1);           // offset lenS-31 sees only 31 positions: always evaluated exactly
@@ -314,59 +295,46 @@ __device__ __forceinline__ void lane_overlap(const LanePlanes<NW> &P1, const Lan
     }
 }
 
-}  // namespace aqc
-#include "aqc_stat2.cuh"      // stat_tile: statRead with one lane per read (needs LanePlanes / shr_bits above)
-namespace aqc {
-
 // dynamic shared memory of one CTA:
-//   [nwarps][ 3 * lane_col_cap ]           per-warp stage: bases 1 | qualities 1 | bases 2 (TMA destinations)
-//   [nwarps][ 4 * 32*NW ]                  per-warp scratch of the statistics hand-over
-//   luts (768 B)
-//   qc acc [2][5][max_len] u32, qc disc [2][max_len] u32, overlap_hist [max_len+1], distance_hist [max_len+1], err matrix [16]
-// SMODE: sampled postfilter statistics -- 0 = stat_read hand-over (one warp per read), 1 = stat_tile (one lane per read), both in this kernel;
-//        2 = none here: stat_lane_kernel<.., POST> runs after this kernel and pair_kernel's list mode (pairs handed over are marked in skip_bits)
-template <bool PAIRED, int NW, int SMODE = 0>
-__global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_kernel(const __grid_constant__ LArgs L) {
+//   [nwarps][ 2 * lane_col_cap ]     per-warp stage: column 0 = bases 1, later qualities 1 | column 1 = bases 2 (or qualities 1, single-end)
+//   luts (768 B) | overlap_hist [max_len+1] | distance_hist [max_len+1] | err matrix [16]
+__host__ __device__ __forceinline__ size_t lane_smem_bytes(int nwarps, int col_cap, int max_len) {
+    return (size_t)nwarps * 2 * (size_t)col_cap + 768 + (size_t)(2 * (max_len + 1) + 16) * 4 + 64;
+}
+
+template <bool PAIRED, int NW>
+__global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 5)) lane_kernel(const __grid_constant__ LArgs L) {
     AQC_DYN_SMEM(smem_raw);
-    __shared__ __align__(8) uint64_t full_bar[LANE_MAX_WARPS];
+    __shared__ __align__(8) uint64_t full_bar[2 * LANE_MAX_WARPS];      // per warp: [0] bases landed, [1] qualities landed
     const KArgs &A = L.k;
     constexpr bool paired = PAIRED;
     constexpr int MAXB = 32 * NW;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
     const int col_cap = L.lane_col_cap;
-    const int ncols = paired ? 3 : 2;
 
-    uint8_t *stage = smem_raw + (size_t)warp * ncols * col_cap;
-    uint8_t *scratch = smem_raw + (size_t)nwarps * ncols * col_cap + (size_t)warp * 4 * MAXB;
-    uint8_t *lutbase = smem_raw + (size_t)nwarps * (ncols * col_cap + 4 * MAXB);
-    const uint8_t *lut1 = lutbase, *lut2 = lutbase + 256, *lut3 = lutbase + 512;
-    uint32_t *s_acc = reinterpret_cast<uint32_t *>(lutbase + 768);
-    uint32_t *s_disc = s_acc + 2 * QC_CLASSES * A.max_len;
-    uint32_t *s_ovh = s_disc + 2 * A.max_len;
+    uint8_t *stage = smem_raw + (size_t)warp * 2 * col_cap;
+    uint8_t *lutbase = smem_raw + (size_t)nwarps * 2 * col_cap;
+    const uint8_t *lut2 = lutbase + 256, *lut3 = lutbase + 512;
+    uint32_t *s_ovh = reinterpret_cast<uint32_t *>(lutbase + 768);
     uint32_t *s_dih = s_ovh + (A.max_len + 1);
     uint32_t *s_em = s_dih + (A.max_len + 1);
-    const int n_qc_words = 2 * QC_CLASSES * A.max_len + 2 * A.max_len;
-    const int n_acc_words = n_qc_words + 2 * (A.max_len + 1) + 16;
+    const int n_acc_words = 2 * (A.max_len + 1) + 16;
 
     for (int i = tid; i < 768; i += blockDim.x) lutbase[i] = reinterpret_cast<const uint8_t *>(A.luts)[i];
-    for (int i = tid; i < n_acc_words; i += blockDim.x) s_acc[i] = 0;
+    for (int i = tid; i < n_acc_words; i += blockDim.x) s_ovh[i] = 0;
     if (tid == 0) {
-        for (int s = 0; s < nwarps; s++) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < 2 * nwarps; s++) mbar_init(&full_bar[s], 1);
         fence_mbar_init();
     }
     __syncthreads();
 
-    QcSmem qsm; qsm.acc = s_acc; qsm.disc = s_disc; qsm.max_len = A.max_len;
-    const uint32_t flush_limit = QC_FLUSH_READS / (uint32_t)nwarps;
-    uint32_t stat_since_flush = 0;
-
     // lane i owns scalar counter i
     unsigned long long wc0 = 0;
 
+    uint64_t *bar = &full_bar[2 * warp], *qbar = &full_bar[2 * warp + 1];
     const uint32_t gw = blockIdx.x * (uint32_t)nwarps + (uint32_t)warp;
     const uint32_t W = gridDim.x * (uint32_t)nwarps;
-    uint64_t *bar = &full_bar[warp];
 
     // offsets of the lane's pair in tile t (pairs beyond n: empty records at the end of the columns)
     auto load_offsets = [&](uint32_t t, uint32_t &a1, uint32_t &e1, uint32_t &a2, uint32_t &e2) {
@@ -375,19 +343,28 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_ke
         a2 = 0; e2 = 0;
         if (paired) { a2 = A.off2[pp]; e2 = A.off2[pq]; }
     };
-    // producer (whole warp computes, lane 0 issues): bulk copies of the tile's columns into the warp's stage
+    // producer (whole warp computes, lane 0 issues).  Paired input: the bases of both mates first; the qualities of mate 1
+    // follow into column 0 once mate 1 has been converted (issue_quals).  Single-end input: bases and qualities together.
     auto issue_tile = [&](uint32_t a1, uint32_t e1, uint32_t a2, uint32_t e2) {
         const uint32_t f1 = __shfl_sync(FULL, a1, 0), l1 = __shfl_sync(FULL, e1, 31);
         const uint32_t f2 = __shfl_sync(FULL, a2, 0), l2 = __shfl_sync(FULL, e2, 31);
         if (lane == 0) {
             const uint32_t g1 = f1 & ~15u, bytes1 = (l1 - g1 + 15u) & ~15u;
             const uint32_t g2 = f2 & ~15u, bytes2 = paired ? ((l2 - g2 + 15u) & ~15u) : 0u;
-            mbar_expect_tx(bar, 2 * bytes1 + bytes2);
+            mbar_expect_tx(bar, paired ? bytes1 + bytes2 : 2 * bytes1);
             if (bytes1) {
                 bulk_g2s(stage, A.seq1 + g1, bytes1, bar);
-                bulk_g2s(stage + col_cap, A.qual1 + g1, bytes1, bar);
+                if (!paired) bulk_g2s(stage + col_cap, A.qual1 + g1, bytes1, bar);
             }
-            if (paired && bytes2) bulk_g2s(stage + 2 * col_cap, A.seq2 + g2, bytes2, bar);
+            if (paired && bytes2) bulk_g2s(stage + col_cap, A.seq2 + g2, bytes2, bar);
+        }
+    };
+    auto issue_quals = [&](uint32_t a1, uint32_t e1) {          // paired only: qualities of mate 1 over the bases of mate 1
+        const uint32_t f1 = __shfl_sync(FULL, a1, 0), l1 = __shfl_sync(FULL, e1, 31);
+        if (lane == 0) {
+            const uint32_t g1 = f1 & ~15u, bytes1 = (l1 - g1 + 15u) & ~15u;
+            mbar_expect_tx(qbar, bytes1);
+            if (bytes1) bulk_g2s(stage, A.qual1 + g1, bytes1, qbar);
         }
     };
 
@@ -397,7 +374,7 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_ke
         load_offsets(t, a1, e1, a2, e2);
         issue_tile(a1, e1, a2, e2);
     }
-    uint32_t parity = 0;
+    uint32_t parity = 0, qparity = 0;
 
 #pragma unroll 1
     for (; t < A.num_tiles; t += W) {
@@ -410,7 +387,6 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_ke
 
         const uint32_t pp = t * 32u + (uint32_t)lane;
         const bool valid = pp < A.n;
-        const uint64_t gidx = A.first_index + pp;
         const uint32_t g1 = __shfl_sync(FULL, a1, 0) & ~15u;
         const uint32_t g2 = __shfl_sync(FULL, a2, 0) & ~15u;
         const int olen1 = (int)(e1 - a1), olen2 = paired ? (int)(e2 - a2) : 0;
@@ -444,35 +420,46 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_ke
             }
             if (live && len1 < A.p.seq_len_req) { cls = AQC_BADLEN; live = false; }   // :476-479 (R2 never checked, quirk Q3)
         }
-        if (live) {
+        const bool want_lowq = A.p.unqualified_base_limit > 0;     // warp-uniform
+        {
             bool ex = false;
 #pragma unroll 1
             for (int m = 0; m < (paired ? 2 : 1); m++) {              // one copy of the conversion + screen code for both mates
-                const uint8_t *r = m ? stage + 2 * col_cap + (a2 - g2) + start2 : stage + (a1 - g1) + start1;
-                const int len = m ? len2 : len1;
-                LanePlanes<NW> F;
+                if (live) {
+                    const uint8_t *r = m ? stage + col_cap + (a2 - g2) + start2 : stage + (a1 - g1) + start1;
+                    const int len = m ? len2 : len1;
+                    LanePlanes<NW> F;
 #pragma unroll
-                for (int i = 0; i < NW; i++) F.p0[i] = F.p1[i] = F.pn[i] = 0;
-                bool exm = false; int nn = 0;
-                lane_convert<NW>(r, len, F, exm, nn);
-                ex |= exm;
-                const bool cand = A.p.poly_size_limit > 0 && lane_polyx_screen<NW>(F.p0, F.p1, F.pn, len, A.p.poly_size_limit, A.poly_m);
-                if (m == 0) {
-                    n1 = nn; cand1 = cand;
+                    for (int i = 0; i < NW; i++) F.p0[i] = F.p1[i] = F.pn[i] = 0;
+                    bool exm = false; int nn = 0;
+                    lane_convert<NW>(r, len, F, exm, nn);
+                    ex |= exm;
+                    const bool cand = A.p.poly_size_limit > 0 && lane_polyx_screen<NW>(F.p0, F.p1, F.pn, len, A.p.poly_size_limit, A.poly_m);
+                    if (m == 0) {
+                        n1 = nn; cand1 = cand;
 #pragma unroll
-                    for (int i = 0; i < NW; i++) { P1.p0[i] = F.p0[i]; P1.p1[i] = F.p1[i]; P1.pn[i] = F.pn[i]; }
-                } else {
-                    n2 = nn; cand2 = cand;
-                    // reverseComplement (util.py:42-51): reverse the 32*NW-bit strings, shift the read down to bit 0, flip plane 1
+                        for (int i = 0; i < NW; i++) { P1.p0[i] = F.p0[i]; P1.p1[i] = F.p1[i]; P1.pn[i] = F.pn[i]; }
+                    } else {
+                        n2 = nn; cand2 = cand;
+                        // reverseComplement (util.py:42-51): reverse the 32*NW-bit strings, shift the read down to bit 0, flip plane 1
 #pragma unroll
-                    for (int i = 0; i < NW; i++) { RC.p0[i] = __brev(F.p0[NW - 1 - i]); RC.p1[i] = __brev(F.p1[NW - 1 - i]); RC.pn[i] = __brev(F.pn[NW - 1 - i]); }
-                    shr_bits<NW>(RC.p0, MAXB - len2); shr_bits<NW>(RC.p1, MAXB - len2); shr_bits<NW>(RC.pn, MAXB - len2);
+                        for (int i = 0; i < NW; i++) { RC.p0[i] = __brev(F.p0[NW - 1 - i]); RC.p1[i] = __brev(F.p1[NW - 1 - i]); RC.pn[i] = __brev(F.pn[NW - 1 - i]); }
+                        shr_bits<NW>(RC.p0, MAXB - len2); shr_bits<NW>(RC.p1, MAXB - len2); shr_bits<NW>(RC.pn, MAXB - len2);
 #pragma unroll
-                    for (int i = 0; i < NW; i++) RC.p1[i] ^= lowmask(len2 - 32 * i) & ~RC.pn[i];
+                        for (int i = 0; i < NW; i++) RC.p1[i] ^= lowmask(len2 - 32 * i) & ~RC.pn[i];
+                    }
+                }
+                if (paired && m == 0 && want_lowq) {     // the bases of mate 1 are in registers: their column takes the qualities
+                    fence_proxy_async();
+                    __syncwarp();
+                    issue_quals(a1, e1);
                 }
             }
-            if (A.p.unqualified_base_limit > 0) lowq1 = lane_lowq(stage + col_cap + (a1 - g1) + start1, len1, A.p.qualified_quality_phred + 33);
-            if (ex) { fallback = true; live = false; cls = AQC_NUM_CLASSES; }
+            if (want_lowq) {
+                if (paired) { mbar_wait(qbar, qparity); qparity ^= 1u; }
+                if (live) lowq1 = lane_lowq(stage + (paired ? 0 : col_cap) + (a1 - g1) + start1, len1, A.p.qualified_quality_phred + 33);
+            }
+            if (live && ex) { fallback = true; live = false; cls = AQC_NUM_CLASSES; }
         }
 
         // ---- the stage is free: prefetch the next tile while the registers are worked on ----
@@ -488,7 +475,6 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_ke
                 if (lane == 0) base = atomicAdd(L.fb_count, (uint32_t)__popc(fb));
                 base = __shfl_sync(FULL, base, 0);
                 if (fallback) L.fb_list[base + (uint32_t)__popc(fb & lowmask(lane))] = pp;
-                if constexpr (SMODE == 2) { if (fallback) atomicOr(&L.skip_bits[pp >> 5], 1u << (pp & 31u)); }     // pair_kernel does their statistics
             }
         }
 
@@ -551,6 +537,12 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_ke
                         if (len1 < A.p.seq_len_req) {                                    // :529-532
                             ov_off = offset; ov_len = ol; ov_diff = distance;
                             cls = AQC_BADLEN; live = false;
+                        } else if (sh == -offset) {
+                            // The rescan (:534) starts with forward offset 0 on the cut mates: r1[i] against rc(r2[0:ol])[i], i < ol.
+                            // When the cut dropped exactly the -offset leading bases of rc(r2) (always for mates of equal
+                            // length) that is the alignment just accepted -- same positions, same mismatches, same rule --
+                            // so the rescan returns (0, ol, distance) without being run.
+                            offset = 0;
                         } else again = true;
                     }
                 }
@@ -573,57 +565,72 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_ke
                     uint32_t xx[NW];
 #pragma unroll
                     for (int i = 0; i < NW; i++) xx[i] = ((X0[i] ^ RC.p0[i]) | (X1[i] ^ RC.p1[i]) | (XN[i] ^ RC.pn[i])) & lowmask(ol - 32 * i);
+                    // the first `distance` (<= 3) mismatches of the walk; their four bytes each are fetched together so that
+                    // the walk waits for HBM (or, with AQC_BATCH_QUAL2_IN_PLACE, for PCIe) once, not once per mismatch
+                    int wo[3] = {-1, -1, -1};
+                    uint32_t wb[3] = {0, 0, 0};          // b1 | r2 byte << 8 | qa << 16 | qb << 24
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        if (k < distance) {
+                            int o = -1;
+#pragma unroll
+                            for (int i = 0; i < NW; i++) {
+                                if (o < 0 && xx[i]) { o = 32 * i + __ffs(xx[i]) - 1; xx[i] &= xx[i] - 1; }
+                            }
+                            wo[k] = o;
+                            if (o >= 0) {
+                                const int p1 = len1 - ol + o, p2 = len2 - 1 - o;
+                                wb[k] = (uint32_t)G1[p1] | ((uint32_t)G2[p2] << 8) | ((uint32_t)G1q[p1] << 16) | ((uint32_t)G2q[p2] << 24);
+                            }
+                        }
+                    }
                     int corrected = 0, masked = 0, skipped = 0;
                     int em_cell[3] = {-1, -1, -1};
                     int done = 0;
-#pragma unroll 1
-                    while (done < distance) {
-                        int o = -1;
 #pragma unroll
-                        for (int i = 0; i < NW; i++) {
-                            if (o < 0 && xx[i]) { o = 32 * i + __ffs(xx[i]) - 1; xx[i] &= xx[i] - 1; }
+                    for (int k = 0; k < 3; k++) {
+                        if (k < distance && wo[k] >= 0) {
+                            const int o = wo[k];
+                            const int p1 = len1 - ol + o, p2 = len2 - 1 - o;
+                            const uint8_t b1 = (uint8_t)wb[k];                            // :564
+                            const uint8_t b2 = lut3[(wb[k] >> 8) & 0xFFu];                // :565 util.complement
+                            const uint8_t qa = (uint8_t)(wb[k] >> 16), qb = (uint8_t)(wb[k] >> 24);   // :566-567
+                            const int Qa = (int)qa - 33, Qb = (int)qb - 33;
+                            bool fixed = false;
+                            uint32_t e = 0;
+                            int cell = -1;
+                            if (Qa >= 30 && Qb <= 14) {                                // :571
+                                if (b1 != 'N' && b2 != 'N') {
+                                    const uint32_t la = lut2[lut3[b1]], lc = lut2[lut3[b2]];
+                                    if ((la & 0x40u) && (lc & 0x40u)) cell = (int)((la & 7u) * 4u + (lc & 7u));   // :573
+                                }
+                                if (!A.p.no_correction) {                              // :574-578
+                                    const uint8_t nb = lut3[b1];
+                                    corrected++; fixed = true;
+                                    e = (uint32_t)(start2 + p2) | (1u << 10) | ((uint32_t)nb << 16) | ((uint32_t)qa << 24);
+                                }
+                            } else if (Qb >= 30 && Qa <= 14) {                         // :579
+                                if (b1 != 'N' && b2 != 'N') {
+                                    const uint32_t la = lut2[b2], lc = lut2[b1];
+                                    if ((la & 0x40u) && (lc & 0x40u)) cell = (int)((la & 7u) * 4u + (lc & 7u));   // :581
+                                }
+                                if (!A.p.no_correction) {                              // :582-586
+                                    corrected++; fixed = true;
+                                    e = (uint32_t)(start1 + p1) | (0u << 10) | ((uint32_t)b2 << 16) | ((uint32_t)qb << 24);
+                                }
+                            }
+                            if (!fixed) {                                              // :587-595
+                                if (A.p.mask_mismatch) {
+                                    masked++;
+                                    e = (uint32_t)(start1 + p1) | (2u << 10) | ((uint32_t)(start2 + p2) << 16);
+                                } else {
+                                    skipped++;
+                                    e = (uint32_t)(start1 + p1) | (3u << 10) | ((uint32_t)(start2 + p2) << 16);
+                                }
+                            }
+                            edits[k] = e; em_cell[k] = cell;
+                            done++;
                         }
-                        if (o < 0) break;
-                        const int p1 = len1 - ol + o, p2 = len2 - 1 - o;
-                        const uint8_t b1 = G1[p1];                                 // :564
-                        const uint8_t b2 = lut3[G2[p2]];                           // :565 util.complement
-                        const uint8_t qa = G1q[p1], qb = G2q[p2];                  // :566-567
-                        const int Qa = (int)qa - 33, Qb = (int)qb - 33;
-                        bool fixed = false;
-                        uint32_t e = 0;
-                        int cell = -1;
-                        if (Qa >= 30 && Qb <= 14) {                                // :571
-                            if (b1 != 'N' && b2 != 'N') {
-                                const uint32_t la = lut2[lut3[b1]], lc = lut2[lut3[b2]];
-                                if ((la & 0x40u) && (lc & 0x40u)) cell = (int)((la & 7u) * 4u + (lc & 7u));   // :573
-                            }
-                            if (!A.p.no_correction) {                              // :574-578
-                                const uint8_t nb = lut3[b1];
-                                corrected++; fixed = true;
-                                e = (uint32_t)(start2 + p2) | (1u << 10) | ((uint32_t)nb << 16) | ((uint32_t)qa << 24);
-                            }
-                        } else if (Qb >= 30 && Qa <= 14) {                         // :579
-                            if (b1 != 'N' && b2 != 'N') {
-                                const uint32_t la = lut2[b2], lc = lut2[b1];
-                                if ((la & 0x40u) && (lc & 0x40u)) cell = (int)((la & 7u) * 4u + (lc & 7u));   // :581
-                            }
-                            if (!A.p.no_correction) {                              // :582-586
-                                corrected++; fixed = true;
-                                e = (uint32_t)(start1 + p1) | (0u << 10) | ((uint32_t)b2 << 16) | ((uint32_t)qb << 24);
-                            }
-                        }
-                        if (!fixed) {                                              // :587-595
-                            if (A.p.mask_mismatch) {
-                                masked++;
-                                e = (uint32_t)(start1 + p1) | (2u << 10) | ((uint32_t)(start2 + p2) << 16);
-                            } else {
-                                skipped++;
-                                e = (uint32_t)(start1 + p1) | (3u << 10) | ((uint32_t)(start2 + p2) << 16);
-                            }
-                        }
-#pragma unroll
-                        for (int k = 0; k < 3; k++) if (k == done) { edits[k] = e; em_cell[k] = cell; }   // distance <= 3 here
-                        done++;
                     }
                     n_edits = done;
                     if (corrected + masked + skipped == distance) {               // :603-610
@@ -688,104 +695,11 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 4)) lane_ke
             wc0 += add;
         }
 
-        // ---- postfilter statistics of the sampled good pairs (:624-627): the warp rebuilds the trimmed, corrected reads
-        //      in its scratch from the record and runs statRead on them ----
-        if constexpr (SMODE != 2) {
-            const bool want = valid && cls == AQC_GOOD && (A.p.qc_sample <= 0 || gidx + 1 < (uint64_t)A.p.qc_sample);
-            uint32_t sbm = __ballot_sync(FULL, want);
-            if (__builtin_expect(sbm != 0u, 0)) {
-                stat_since_flush += (uint32_t)__popc(sbm);
-                uint8_t *sc_s1 = scratch, *sc_q1 = scratch + MAXB, *sc_s2 = scratch + 2 * MAXB, *sc_q2 = scratch + 3 * MAXB;
-                uint32_t need[2] = {sbm, sbm};                    // per mate: lanes whose read still needs stat_read
-                if constexpr (SMODE == 1) {                       // one lane per read for everything made of A,C,G,T,N (aqc_stat2.cuh)
-#pragma unroll 1
-                    for (int m = 0; m < (paired ? 2 : 1); m++) {
-                        MatePatches mp;
-                        mate_patches(edits, n_edits, m, start1, start2, mp);
-                        const uint8_t *gs = m ? A.seq2 + a2 + start2 : A.seq1 + a1 + start1;
-                        const uint8_t *gq = m ? A.qual2 + a2 + start2 : A.qual1 + a1 + start1;
-                        const bool done = stat_tile<NW>(want, gs, gq, m ? len2 : len1, gidx, m, mp, qsm, A.qc[m], A.p.qc_kmer, lane, A.error_flag);
-                        need[m] = __ballot_sync(FULL, want && !done);
-                    }
-                    sbm = need[0] | (paired ? need[1] : 0u);
-                }
-                while (sbm) {
-                    const int src = __ffs(sbm) - 1;
-                    sbm &= sbm - 1;
-                    const uint32_t ba1 = __shfl_sync(FULL, a1, src), ba2 = __shfl_sync(FULL, a2, src);
-                    const int bs1 = __shfl_sync(FULL, start1, src), bs2 = __shfl_sync(FULL, start2, src);
-                    const int bl1 = __shfl_sync(FULL, len1, src), bl2 = __shfl_sync(FULL, len2, src);
-                    const int bne = __shfl_sync(FULL, n_edits, src);
-                    const uint32_t be0 = __shfl_sync(FULL, edits[0], src), be1 = __shfl_sync(FULL, edits[1], src);
-                    const uint32_t be2 = __shfl_sync(FULL, edits[2], src), be3 = __shfl_sync(FULL, edits[3], src);
-                    const uint64_t bg = A.first_index + t * 32u + (uint32_t)src;
-                    __syncwarp();
-                    for (int x = lane; x < bl1; x += 32) { sc_s1[x] = A.seq1[ba1 + bs1 + x]; sc_q1[x] = A.qual1[ba1 + bs1 + x]; }
-                    if (paired)
-                        for (int x = lane; x < bl2; x += 32) { sc_s2[x] = A.seq2[ba2 + bs2 + x]; sc_q2[x] = A.qual2[ba2 + bs2 + x]; }
-                    __syncwarp();
-                    if (lane == 0) {
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            if (k >= bne) break;
-                            const uint32_t e = k == 0 ? be0 : (k == 1 ? be1 : (k == 2 ? be2 : be3));
-                            const int kind = (int)AQC_EDIT_KIND(e), pos = (int)AQC_EDIT_POS(e);
-                            if (kind == 0) { sc_s1[pos - bs1] = (uint8_t)AQC_EDIT_BASE(e); sc_q1[pos - bs1] = (uint8_t)AQC_EDIT_QUAL(e); }
-                            else if (kind == 1) { sc_s2[pos - bs2] = (uint8_t)AQC_EDIT_BASE(e); sc_q2[pos - bs2] = (uint8_t)AQC_EDIT_QUAL(e); }
-                            else if (kind == 2) { sc_q1[pos - bs1] = '!'; sc_q2[(int)AQC_EDIT_POS2(e) - bs2] = '!'; }
-                        }
-                    }
-                    __syncwarp();
-#pragma unroll 1
-                    for (int m = 0; m < (paired ? 2 : 1); m++) {
-                        if constexpr (SMODE == 1) { if (!((need[m] >> src) & 1u)) continue; }
-                        stat_read(m ? sc_s2 : sc_s1, m ? sc_q2 : sc_q1, m ? bl2 : bl1, m, bg, qsm, A.qc[m], lut1, lut2, lut3, A.p.qc_kmer, lane, A.error_flag);
-                    }
-                }
-                __syncwarp();
-                if (stat_since_flush + 32u > flush_limit) {      // packed shared accumulators: count field is 12 bits
-                    for (int m = 0; m < 2; m++) {
-                        const QcDev &qd = A.qc[m];
-                        if (!qd.valid) continue;
-                        for (int i = lane; i < QC_CLASSES * A.max_len; i += 32) {
-                            const uint32_t v = atomicExch(&s_acc[m * QC_CLASSES * A.max_len + i], 0u);
-                            if (v) {
-                                const int c = i / A.max_len, pos = i - c * A.max_len;
-                                atomicAdd(&qd.cls_cnt[c * AQC_MAX_LEN + pos], (unsigned long long)(v >> 20));
-                                atomicAdd(&qd.cls_qsum[c * AQC_MAX_LEN + pos], (unsigned long long)(v & 0xFFFFFu));
-                            }
-                        }
-                        for (int i = lane; i < A.max_len; i += 32) {
-                            const uint32_t v = atomicExch(&s_disc[m * A.max_len + i], 0u);
-                            if (v) atomicAdd(&qd.disc[i], (unsigned long long)v);
-                        }
-                    }
-                    stat_since_flush = 0;
-                }
-            }
-        }
-
         a1 = na1; e1 = ne1; a2 = na2; e2 = ne2;
     }
 
     // ---- epilogue: flush everything this CTA accumulated ----
     __syncthreads();
-    for (int m = 0; m < 2; m++) {
-        const QcDev &qd = A.qc[m];
-        if (!qd.valid) continue;
-        for (int i = tid; i < QC_CLASSES * A.max_len; i += blockDim.x) {
-            const uint32_t v = s_acc[m * QC_CLASSES * A.max_len + i];
-            if (v) {
-                const int c = i / A.max_len, pos = i - c * A.max_len;
-                atomicAdd(&qd.cls_cnt[c * AQC_MAX_LEN + pos], (unsigned long long)(v >> 20));
-                atomicAdd(&qd.cls_qsum[c * AQC_MAX_LEN + pos], (unsigned long long)(v & 0xFFFFFu));
-            }
-        }
-        for (int i = tid; i < A.max_len; i += blockDim.x) {
-            const uint32_t v = s_disc[m * A.max_len + i];
-            if (v) atomicAdd(&qd.disc[i], (unsigned long long)v);
-        }
-    }
     for (int i = tid; i <= A.max_len; i += blockDim.x) {
         uint32_t v = s_ovh[i]; if (v) atomicAdd(&A.counters[AQC_C_OVERLAP_HIST + i], (unsigned long long)v);
         v = s_dih[i]; if (v) atomicAdd(&A.counters[AQC_C_DISTANCE_HIST + i], (unsigned long long)v);

@@ -114,14 +114,12 @@ class Engine:
         return DeviceBatch(self, host_batch)
 
     # ---- hot path --------------------------------------------------------------------------
-    def stat_reads(self, batch, qc1, qc2, stat_lo=0, stat_hi=(1 << 63), order_base=0, pack_bases=False, pack_quals=False):
+    def stat_reads(self, batch, qc1, qc2, stat_lo=0, stat_hi=(1 << 63), order_base=0):
         mem = _abi.MEM_DEVICE if isinstance(batch, DeviceBatch) else _abi.MEM_HOST
         b = batch.as_struct()
-        if mem == _abi.MEM_HOST:
-            b.flags |= (_abi.BATCH_PACK_BASES if pack_bases else 0) | (_abi.BATCH_PACK_QUALS if pack_quals else 0)
         self._check(self._L.aqc_stat_reads(self._h, C.byref(b), mem, qc1, qc2, stat_lo, stat_hi, order_base))
 
-    def filter_pairs(self, batch, out=None, qual2_in_place=False, pack_bases=False, pack_quals=False):
+    def filter_pairs(self, batch, out=None, qual2_in_place=False):
         """Host batch: returns the result records (copies inside).  DeviceBatch: asynchronous, results stay in HBM.
         qual2_in_place: the host batch's qual2 column is page-locked (aqc_host_alloc / cudaHostAlloc): with the lane-per-pair
         kernel the engine may read it in place over PCIe instead of copying it (AQC_BATCH_QUAL2_IN_PLACE)."""
@@ -133,10 +131,6 @@ class Engine:
         b = batch.as_struct()
         if qual2_in_place:
             b.flags |= _abi.BATCH_QUAL2_IN_PLACE
-        if pack_bases:      # host threads pack the bases to 2 bits before the copy (AQC_BATCH_PACK_BASES); results identical
-            b.flags |= _abi.BATCH_PACK_BASES
-        if pack_quals:      # ... and the qualities to 6 bits (AQC_BATCH_PACK_QUALS)
-            b.flags |= _abi.BATCH_PACK_QUALS
         self._check(self._L.aqc_filter_pairs(self._h, C.byref(b), _abi.MEM_HOST, res.ctypes.data))
         return res
 
@@ -184,6 +178,19 @@ class Engine:
 
     def launch_count(self):
         return int(self._L.aqc_launch_count(self._h))
+
+    def kmer_side_raw(self, slot):
+        """(keys, counts, first_direct, first_seed) of the side table as the device holds it (aqc_get_kmer_side_raw)"""
+        n = C.c_uint32(0)
+        self._check(self._L.aqc_get_kmer_side_raw(self._h, slot, None, None, None, None, 0, C.byref(n)))
+        arrs = [np.zeros(n.value, dtype=np.uint64) for _ in range(4)]
+        if n.value:
+            self._check(self._L.aqc_get_kmer_side_raw(self._h, slot, *[a.ctypes.data for a in arrs], n.value, C.byref(n)))
+        return tuple(arrs)
+
+    def last_phase_ms(self, phase):
+        """device time of the last call's kernels by phase: 0 filter kernel, 1 list mode, 2 statistics launches, -1 all"""
+        return float(self._L.aqc_last_phase_ms(self._h, phase))
 
     def last_kernel_ms(self):
         return float(self._L.aqc_last_kernel_ms(self._h))

@@ -69,9 +69,26 @@ class DistBackend:
         # shift into the signed range first
         bias = np.uint64(1) << np.uint64(63)
         f = self._allreduce((first ^ bias), "min").view(np.uint64) ^ bias
-        # side tables (non-ACGT k-mers): gather and merge by key (sum counts, min stamps)
+        # side tables (k-mers with a byte outside A,C,G,T): gathered and merged by key
         world = self.dist.get_world_size(group=self.group)
         gathered = [None] * world
+        if hasattr(self.local, "kmer_side_raw"):
+            # the engine's unresolved table: counts add, direct sightings and foreign-byte seedings take the minimum, and the
+            # insertion rule is applied to the merged table -- exact for every byte (quirk Q12)
+            self.dist.all_gather_object(gathered, self.local.kmer_side_raw(slot), group=self.group)
+            keys = np.concatenate([g[0] for g in gathered])
+            if not len(keys):
+                return cnt, f, skeys, scnt, sfirst
+            never = np.iinfo(np.uint64).max
+            uk, inv = np.unique(keys, return_inverse=True)
+            c2 = np.zeros(len(uk), dtype=np.uint64); np.add.at(c2, inv, np.concatenate([g[1] for g in gathered]))
+            d2 = np.full(len(uk), never, dtype=np.uint64); np.minimum.at(d2, inv, np.concatenate([g[2] for g in gathered]))
+            s2 = np.full(len(uk), never, dtype=np.uint64); np.minimum.at(s2, inv, np.concatenate([g[3] for g in gathered]))
+            stamp = resolve_side(uk, d2, s2, self.params.qc_kmer)
+            keep = stamp != never
+            return cnt, f, uk[keep], c2[keep], stamp[keep]
+        # a backend that only exposes resolved stamps (the oracle in the CPU tests): minimum of the resolved stamps, exact for
+        # k-mers over util.COMP's alphabet
         self.dist.all_gather_object(gathered, (skeys, scnt, sfirst), group=self.group)
         keys = np.concatenate([g[0] for g in gathered])
         if len(keys):
@@ -81,6 +98,36 @@ class DistBackend:
             f2 = np.full(len(uk), np.iinfo(np.uint64).max, dtype=np.uint64); np.minimum.at(f2, inv, fs)
             return cnt, f, uk, c2, f2
         return cnt, f, skeys, scnt, sfirst
+
+
+_COMP = {65: 84, 84: 65, 67: 71, 71: 67, 97: 116, 116: 97, 99: 103, 103: 99, 78: 78, 10: 10}      # util.py:27 as bytes
+
+
+def resolve_side(keys, direct, seed, k):
+    """Insertion stamps of the side-table k-mers from their first direct sighting and their first seeding by a k-mer that
+    holds a byte outside util.COMP -- the rule of aqc_get_kmer_side (csrc/aqc_engine.cu; derivation above stat_read in
+    csrc/aqc_device.cuh), here on a table merged over shards.  keys: sorted, unique, k raw bytes big-endian."""
+    never = int(np.iinfo(np.uint64).max)
+    pos = {int(x): i for i, x in enumerate(keys)}
+    out = np.full(len(keys), never, dtype=np.uint64)
+    for i, key in enumerate(keys):
+        key = int(key)
+        bs = [(key >> (8 * (k - 1 - j))) & 0xFF for j in range(k)]
+        foreign = any(b not in _COMP for b in bs)
+        di, si = int(direct[i]), int(seed[i])
+        if foreign:                                   # no pre-image under reverseComplement: present from its first sighting
+            p = di
+        else:
+            p = min(di, si)
+            rkey = 0
+            for j, b in enumerate(bs):
+                rkey |= _COMP[b] << (8 * j)
+            if rkey != key:
+                jx = pos.get(rkey)
+                if jx is not None and int(direct[jx]) < di and int(direct[jx]) < int(seed[jx]):
+                    p = min(p, int(direct[jx]) | 1)   # the partner was sighted first and newly inserted: it seeded this one
+        out[i] = p
+    return out
 
 
 def shard_range(n, rank, world):

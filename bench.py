@@ -1,24 +1,31 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200 AfterQC hot path (BASELINE.json metric).
+"""bench.py -- the B200 AfterQC hot path on the BASELINE.json configs (metric: M read-pairs/s; achieved HBM GB/s vs peak).
 
-Workload (config.workload): BASELINE.json configs[2] = synthetic PE150, 10 M read pairs per GPU,
-reference defaults + `-f 0 -t 0` (so qc_sample = 200000: prefilter statistics over records
-999..200998 of both mates, postfilter statistics over the good pairs with index < 200000, and
-filter + overlap scan + adapter trim + correction over every pair).  One "step" = one full pass
-of that path over the batch:  aqc_stat_reads(window) + aqc_filter_pairs(all pairs).
+  --config pe150        (default) BASELINE configs[2]: synthetic PE150, 10 M pairs per GPU, reference defaults + `-f 0 -t 0`
+                        (qc_sample 200000: prefilter statistics over records 999..200998, postfilter statistics over the good
+                        pairs with index < 199999, filter + overlap scan + adapter trim + correction over every pair)
+  --config se100        configs[1]: synthetic SE100, 10 M reads, quality + polyX + N filters (no mate, no overlap),
+                        `-f 0 -t 0 --qc_sample 0`: every read is stat'd before and, if good, after the filter
+  --config pe250_full   configs[3]: synthetic PE250, 2.5 M pairs per GPU (20 M over 8), the FULL pipeline: `--qc_sample 0`,
+                        prefilter statistics of every read, autoTrim resolved on the host from them (qualitycontrol.py:359-408),
+                        filter with those trims, postfilter statistics of every good pair
+  --config pe150_err3   configs[4]: synthetic PE150 with 3 % injected error, 25 M pairs per GPU (200 M over 8), defaults + `-f 0 -t 0`
 
-  value      whole-job M read-pairs/s with the batch resident in HBM (CUDA events on the launching stream)
-  e2e        the same pass through the host-buffer C-ABI entry (pinned host columns -> H2D -> kernels -> D2H of
-             the 32-byte records), copies inside the timed region
-  roofline   algorithmic bytes of the dominant kernel launch (pair_kernel, filter mode) / its event-timed
-             duration vs the measured HBM peak (MEASURED_PEAKS.json)
-  cpu_baseline  the CPU oracle (C restatement of the reference algorithm, kind "port") on a bounded sample
-             of the same workload with all host threads
+One "step" = one full pass of that path over the batch:  aqc_stat_reads(prefilter window) [+ autoTrim] + aqc_filter_pairs(all).
 
-N > 1 (torchrun): weak scaling, one process per GPU, each rank filters its own contiguous shard of
-10 M pairs (global record indices rank*n ..), no data-path collective; every step ends with the NCCL
-all-reduce of the counter blocks (the only exchange the path has).
-`--impl reference` times the CPU arm alone (rank 0 only).
+  value         whole-job M read-pairs/s (reads/s for se100) with the batch resident in HBM (CUDA events on the launching stream)
+  e2e           the same pass through the host-buffer C-ABI entry (pinned host columns -> H2D -> kernels -> D2H of the 32-byte
+                records), copies inside the timed region
+  roofline      algorithmic bytes of the dominant launch / its event-timed duration vs the measured HBM peak
+                (MEASURED_PEAKS.json); `phases` lists every launch group of the step the same way
+  cpu_baseline  the CPU oracle (C restatement of the reference algorithm, kind "port") on a bounded sample of the same
+                workload with all host threads (rank 0, N = 1 only); cpu_baseline_python = the reference's own Python under
+                CPython 3.12, timed in the build container (profiles/r02_reference_python_timing.json; it cannot run on the box)
+
+N > 1 (torchrun): weak scaling, one process per GPU, each rank filters its own contiguous shard (global record indices
+rank*n ..), no data-path collective; every step ends with the NCCL all-reduce of the counter blocks (the only exchange the
+path has).  Before timing, a 200 k-pair slice is run sharded + all-reduced and compared with one engine over the whole
+slice (`shard_parity`).  `--impl reference` times the CPU arm alone (rank 0 only) on the same config, steps and warm-up.
 """
 import argparse
 import ctypes as C
@@ -35,12 +42,28 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-PAIRS_PER_GPU = 10_000_000
-READ_LEN = 150
-QC_SAMPLE = 200_000
-STAT_LO = 999
-ALGO_BYTES_PER_PAIR = 4 * READ_LEN + 32 + 8          # 2 mates x (bases + quals) + result record + 2 offsets
-WORKLOAD = "synthetic PE150 10M pairs/GPU, overlap correction + adapter trim, defaults -f 0 -t 0 (BASELINE configs[2])"
+STAT_LO = 999           # statFile sets the first 999 records aside (qualitycontrol.py:333-341)
+E2E_MAX_PAIRS = 10_000_000      # pinned host columns of the e2e leg are capped at this many records per GPU
+
+CONFIGS = {
+    "pe150": dict(synth="pe150", paired=True, L=150, units=10_000_000, qc_sample=200_000, autotrim=False, unit="M read-pairs/s",
+                  metric="read-pairs/s PE150 (filter + overlap correction + adapter trim + per-cycle QC)",
+                  workload="synthetic PE150 10M pairs/GPU, overlap correction + adapter trim, defaults -f 0 -t 0 (BASELINE configs[2])"),
+    "se100": dict(synth="se100", paired=False, L=100, units=10_000_000, qc_sample=0, autotrim=False, unit="M reads/s",
+                  metric="reads/s SE100 (quality + polyX + N filters + per-cycle QC of every read)",
+                  workload="synthetic SE100 10M reads/GPU, quality+polyX filter only, -f 0 -t 0 --qc_sample 0 (BASELINE configs[1])"),
+    "pe250_full": dict(synth="pe250", paired=True, L=250, units=2_500_000, qc_sample=0, autotrim=True, unit="M read-pairs/s",
+                       metric="read-pairs/s PE250 (full pipeline: prefilter QC of every read, autoTrim, filter + overlap correction, postfilter QC)",
+                       workload="synthetic PE250 2.5M pairs/GPU (20M over 8), full pipeline --qc_sample 0 + autoTrim (BASELINE configs[3])"),
+    "pe150_err3": dict(synth="pe150_err3", paired=True, L=150, units=25_000_000, qc_sample=200_000, autotrim=False, unit="M read-pairs/s",
+                       metric="read-pairs/s PE150 3% error (filter + overlap correction stress + adapter trim + per-cycle QC)",
+                       workload="synthetic PE150 3% injected error 25M pairs/GPU (200M over 8), defaults -f 0 -t 0 (BASELINE configs[4])"),
+}
+
+
+def algo_bytes_per_unit(cfg):
+    """every base / quality byte once, one result record, the offsets: 4L + 32 + 8 per pair, 2L + 16 + 4 per SE read"""
+    return 4 * cfg["L"] + 40 if cfg["paired"] else 2 * cfg["L"] + 20
 
 
 def parse_args():
@@ -49,20 +72,37 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU (default = BASELINE config)")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU sample (0 = auto)")
-    ap.add_argument("--qc-sample", type=int, default=QC_SAMPLE, help="--qc_sample of the workload (profiling runs on fewer pairs scale it to keep the 2%% mix)")
+    ap.add_argument("--config", default="pe150", choices=list(CONFIGS))
+    ap.add_argument("--pairs", type=int, default=0, help="records per GPU (default = the config's)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="records in the CPU sample (0 = auto)")
+    ap.add_argument("--qc-sample", type=int, default=-1, help="--qc_sample of the workload (profiling runs on fewer pairs scale it to keep the mix)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--filter-kernel", default="auto", choices=["auto", "warp", "lane", "lane2"],
-                    help="filter kernel: warp = pair_kernel (one warp per pair), lane = lane_kernel (one lane per pair); auto = lane "
-                         "only if it first proves bit-identical to warp on this GPU (child process with a timeout, then the full batch)")
-    ap.add_argument("--stat-kernel", default="auto", choices=["auto", "warp", "lane", "lane_post"],
-                    help="statRead kernel (aqc_params.stat_kernel): warp = stat_read (one warp per read), lane = stat_tile / "
-                         "stat_lane_kernel (one lane per read), lane_post = the same with the sampled statistics in their own launch; "
-                         "auto = one of the lane forms only after the same two-stage identity check, and only if faster")
-    ap.add_argument("--no-pack", action="store_true", help="do not try the packed base transport (AQC_BATCH_PACK_BASES) in the e2e measurement")
+    ap.add_argument("--filter-kernel", default="default", choices=["default", "warp"],
+                    help="default = the engine as shipped (lane_kernel + list mode + stat_kernel); warp = pair_kernel with the fused stat_read "
+                         "everywhere (aqc_params.filter_kernel = stat_kernel = 1), the round-1 path, for comparison")
     ap.add_argument("--no-cpu", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    a.cfg = dict(CONFIGS[a.config])
+    a.n = a.pairs or a.cfg["units"]
+    a.qs = a.cfg["qc_sample"] if a.qc_sample < 0 else a.qc_sample
+    return a
+
+
+def workload_config(args, world):
+    cfg = args.cfg
+    return {"workload": cfg["workload"], "config": args.config, "units_per_gpu": args.n, "read_len": cfg["L"], "qc_sample": args.qs,
+            "autotrim": cfg["autotrim"], "parallelism": ("read-sharded x%d, NCCL all-reduce of the counter blocks per step" % world) if world > 1 else "1 GPU"}
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side autoTrim of the full pipeline (qualitycontrol.py:359-408 on the prefilter counters; preprocesser.py:260-280)
+# ------------------------------------------------------------------------------------------------
+def resolve_autotrim(backend, paired, qs, kmer=8):
+    from afterqc_b200 import _abi
+    from afterqc_b200.qc import QualityControl
+    q = QualityControl(qs, kmer).load(backend.qc(_abi.QC_R1_PRE), None)
+    q.calcReadLen(); q.calcPercents(); q.calcQualities()
+    return q.autoTrim()           # trim_pair_same (default true) copies R1's values to R2
 
 
 # ------------------------------------------------------------------------------------------------
@@ -75,33 +115,40 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-CPU_SAMPLE_CAP = 2_000_000
+def cpu_sample_size(args, threads):
+    if args.cpu_sample:
+        return args.cpu_sample
+    per_thread = {"pe150": 100_000, "se100": 60_000, "pe250_full": 12_000, "pe150_err3": 100_000}[args.config]
+    return min(args.n, per_thread * threads, 2_000_000)
 
 
-def cpu_sample_size(pairs, threads, requested):
-    return requested or min(pairs, 100_000 * threads, CPU_SAMPLE_CAP)
-
-
-def cpu_arm(batch, threads, steps=1, warmup=0):
-    """Oracle throughput on the PackedBatch `batch` (a prefix of the workload), split over `threads` host threads.
-    The sample keeps the workload's mix: the QC window is scaled to the same 2 % of the pairs."""
+def cpu_arm(args, batch, threads, steps=1, warmup=0):
+    """Oracle throughput on the PackedBatch `batch` (a prefix of the workload), split over `threads` host threads (each thread
+    runs the whole path on its slice).  The sample keeps the workload's mix: a finite QC window is scaled with the sample."""
     from afterqc_b200 import _abi
     from oracle import oracle as orc_mod
     orc_mod.build()
-    sample_pairs = batch.n
-    qs = max(1000, sample_pairs * QC_SAMPLE // PAIRS_PER_GPU)
-    params = _abi.Params.defaults(qc_sample=qs)
-    per = (sample_pairs + threads - 1) // threads
-    parts = [batch.slice(i * per, min(sample_pairs, (i + 1) * per)) for i in range(threads) if i * per < sample_pairs]
+    cfg = args.cfg
+    sample = batch.n
+    qs = args.qs if args.qs <= 0 else max(1000, sample * args.qs // cfg["units"])
+    params = _abi.Params.defaults(qc_sample=qs, paired=1 if cfg["paired"] else 0)
+    per = (sample + threads - 1) // threads
+    parts = [batch.slice(i * per, min(sample, (i + 1) * per)) for i in range(threads) if i * per < sample]     # global record indices kept
 
     def work(part, out, k):
-        o = orc_mod.Oracle(params)
-        lo = min(STAT_LO, max(0, part.n - 1))
-        o.stat_reads(part, _abi.QC_R1_PRE, _abi.QC_R2_PRE, stat_lo=lo, stat_hi=lo + qs)
+        o = orc_mod.Oracle(_abi.Params.defaults(qc_sample=qs, paired=1 if cfg["paired"] else 0))
+        lo = min(STAT_LO, max(0, sample - 1))
+        hi = (1 << 62) if qs <= 0 else lo + qs
+        o.stat_reads(part, _abi.QC_R1_PRE, _abi.QC_R2_PRE if cfg["paired"] else -1, stat_lo=lo, stat_hi=hi)
+        if cfg["autotrim"]:
+            f, t = resolve_autotrim(o, cfg["paired"], qs)
+            p2 = _abi.Params.defaults(qc_sample=qs, paired=1 if cfg["paired"] else 0, trim_front=f, trim_tail=t, trim_front2=f, trim_tail2=t)
+            o.set_params(p2)
         res = o.filter_pairs(part)
         out[k] = int((res["cls"] == 0).sum())
         o.close()
 
+    del params
     times = []
     for it in range(warmup + steps):
         out = [0] * len(parts)
@@ -115,11 +162,11 @@ def cpu_arm(batch, threads, steps=1, warmup=0):
         if it >= warmup:
             times.append(dt)
     total = sum(times)
-    return {"pairs_per_s": sample_pairs * len(times) / total, "seconds": total, "threads": len(parts),
-            "sample_pairs": sample_pairs, "qc_sample_scaled": qs, "ms_per_step": 1e3 * total / len(times)}
+    return {"units_per_s": sample * len(times) / total, "seconds": total, "threads": len(parts),
+            "sample": sample, "qc_sample_scaled": qs, "ms_per_step": 1e3 * total / len(times)}
 
 
-def host_sample(pairs, threads):
+def host_sample(args, units, threads):
     """CPU-generated prefix of the workload (reference arm: no GPU work at all)."""
     import torch
     from afterqc_b200 import synth
@@ -127,7 +174,23 @@ def host_sample(pairs, threads):
         torch.set_num_threads(max(1, min(threads, 32)))     # torchrun exports OMP_NUM_THREADS=1
     except Exception:
         pass
-    return synth.generate("pe150", pairs)
+    return synth.generate(args.cfg["synth"], units)
+
+
+def cpu_sample_text(args, r):
+    return ("%d records of the same %s workload per step (%s), %.1f s of wall time on %d threads; C oracle oracle/aqc_oracle.c, one "
+            "context per host thread" % (r["sample"], args.config,
+                                         "QC window scaled to %d reads, the same mix" % r["qc_sample_scaled"] if r["qc_sample_scaled"] > 0 else "--qc_sample 0: every read stat'd",
+                                         r["seconds"], r["threads"]))
+
+
+def python_reference_timing(config):
+    p = os.path.join(ROOT, "profiles", "r02_reference_python_timing.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(config)
+    except Exception:
+        return None
 
 
 def run_reference_arm(args):
@@ -135,21 +198,20 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = host_threads()
-    sample = cpu_sample_size(args.pairs, threads, args.cpu_sample)
-    r = cpu_arm(host_sample(sample, threads), threads, steps=args.steps, warmup=min(args.warmup, 1))
-    mps = r["pairs_per_s"] / 1e6
+    sample = cpu_sample_size(args, threads)
+    r = cpu_arm(args, host_sample(args, sample, threads), threads, steps=args.steps, warmup=args.warmup)
+    ups = r["units_per_s"] / 1e6
+    cfg = args.cfg
     line = {
         "impl": "reference",
-        "metric": "read-pairs/s PE150 (filter + overlap correction + adapter trim + per-cycle QC)",
-        "value": mps, "unit": "M read-pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "metric": cfg["metric"], "value": ups, "unit": cfg["unit"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_pairs_per_step": sample},
-        "cpu_baseline": {"value": mps, "unit": "M read-pairs/s", "cores": r["threads"], "kind": "port",
-                         "sample": "%d pairs of the PE150 workload per step, QC window scaled to %d reads (same 2%% mix); "
-                                   "C oracle (oracle/aqc_oracle.c), one context per host thread; the reference itself is "
-                                   "Python 2 and cannot run on the GPU box" % (sample, r["qc_sample_scaled"])},
-        "e2e": {"value": mps, "unit": "M read-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": workload_config(args, 1 if args.gpus <= 1 else args.gpus),
+        "cpu_baseline": {"value": ups, "unit": cfg["unit"], "cores": r["threads"], "kind": "port",
+                         "sample": cpu_sample_text(args, r) + "; the reference itself is Python 2 and cannot run on the GPU box"},
+        "cpu_baseline_python": python_reference_timing(args.config),
+        "e2e": {"value": ups, "unit": cfg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit_json(line)
@@ -210,12 +272,13 @@ class ClockSampler:
 class TorchBatch:
     """HBM-resident batch backed by torch tensors (plumbing only: memory + RNG)."""
 
-    def __init__(self, t, first_index, n, max_len):
+    def __init__(self, t, first_index, n, max_len, paired):
         import torch
         self.t = t
         self.n = n
         self.first_index = first_index
         self.max_len = max_len
+        self.paired = paired
         self.results = torch.empty(max(1, n) * 32, dtype=torch.uint8, device=t["seq1"].device)
 
     def struct(self, lo=0, hi=None):
@@ -228,23 +291,27 @@ class TorchBatch:
         b.n = hi - lo
         b.flags = self.max_len
         b.seq1 = self.t["seq1"].data_ptr(); b.qual1 = self.t["qual1"].data_ptr(); b.off1 = self.t["off1"].data_ptr() + 4 * lo
-        b.seq2 = self.t["seq2"].data_ptr(); b.qual2 = self.t["qual2"].data_ptr(); b.off2 = self.t["off2"].data_ptr() + 4 * lo
+        if self.paired:
+            b.seq2 = self.t["seq2"].data_ptr(); b.qual2 = self.t["qual2"].data_ptr(); b.off2 = self.t["off2"].data_ptr() + 4 * lo
+        else:
+            b.seq2 = None; b.qual2 = None; b.off2 = None
         return b
 
 
-def make_device_workload(device, n, seed, first_index):
+def make_device_workload(cfg, device, n, seed, first_index):
     import torch
     from afterqc_b200 import synth
-    t = synth.generate_device("pe150", n, device=device, seed=seed)
+    t = synth.generate_device(cfg["synth"], n, device=device, seed=seed)
     for k in ("off1", "off2"):
-        last = t[k][-1:].to(torch.int32)
-        t[k] = torch.cat([t[k].to(torch.int32), last.expand(8)])   # slack entries for the 16-byte granular copies
+        if k in t:
+            last = t[k][-1:].to(torch.int32)
+            t[k] = torch.cat([t[k].to(torch.int32), last.expand(8)])   # slack entries for the 16-byte granular copies
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
-    return TorchBatch(t, first_index, n, READ_LEN)
+    return TorchBatch(t, first_index, n, cfg["L"], cfg["paired"])
 
 
-def cuda_tensor_view(ptr, n, torch_dtype, device):
+def cuda_tensor_view(ptr, n, device):
     """torch tensor aliasing `n` 64-bit elements at device address `ptr` (for in-place NCCL reductions)."""
     import torch
 
@@ -255,99 +322,149 @@ def cuda_tensor_view(ptr, n, torch_dtype, device):
     return torch.as_tensor(s, device=device)
 
 
-def lane_child_check(local_rank, pairs, timeout_s=300, candidates="lane"):
-    """tests/lane_gpu_check.py `full` in a child process with a timeout: pair_kernel and every candidate of the comma-separated
-    list on `pairs` pairs of the bench workload, every output compared.  The candidates were committed without having run on
-    hardware, so a hang, a crash or a mismatch must not take the benchmark down: anything but a clean 'identical' keeps the
-    measured kernels.  Returns {candidate: verdict}; a verdict printed before a later crash or time-out of the child stands."""
-    names = [c for c in candidates.split(",") if c]
-    env = dict(os.environ)
-    ids = [x for x in env.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip() != ""]
-    env["CUDA_VISIBLE_DEVICES"] = (ids[local_rank] if local_rank < len(ids) else ids[0]) if ids else str(local_rank)
-    cmd = [sys.executable, os.path.join(ROOT, "tests", "lane_gpu_check.py"), "full", str(pairs), ",".join(names)]
-    t0 = time.time()
-    note, rc = None, 0
-    try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
-        stdout, stderr, rc = r.stdout or "", r.stderr or "", r.returncode
-    except subprocess.TimeoutExpired as e:
-        stdout, stderr, rc = e.stdout or "", e.stderr or "", None
-        note = "child timed out after %d s" % timeout_s
-    except Exception as e:      # noqa: BLE001
-        return {c: {"ok": False, "why": "child could not run: %r" % (e,)} for c in names}
-    if isinstance(stdout, bytes):
-        stdout = stdout.decode("utf-8", "replace")
-    if isinstance(stderr, bytes):
-        stderr = stderr.decode("utf-8", "replace")
-    if rc not in (0, None):
-        note = "child exit %d: %s" % (rc, (stderr or stdout)[-300:].replace("\n", " | "))
-    out = {c: {"ok": False} for c in names}
-    for ln in stdout.splitlines():
-        ln = ln.strip()
-        if ln.startswith("{"):
-            try:
-                j = json.loads(ln)
-            except ValueError:
-                continue
-            c = j.get("candidate")
-            if c in out:
-                out[c] = dict(j, ok=bool(j.get("identical")))
-    seconds = round(time.time() - t0, 1)
-    for c in names:
-        out[c]["seconds_child"] = seconds
-        if note:
-            out[c]["after_verdict" if out[c]["ok"] else "why"] = note
-            if rc is None:
-                out[c].pop("in_place_ok", None)
-        if not out[c]["ok"]:
-            out[c].setdefault("why", "no verdict in the child's output")
-    return out
+class Runner:
+    """one engine + its workload: the resident step, the host-buffer step, the reductions of the N > 1 runs"""
+
+    def __init__(self, args, wb, device, local_rank, stream, world, dist):
+        from afterqc_b200 import _abi
+        from afterqc_b200.engine import Engine
+        self.abi, self.args, self.wb, self.device, self.world, self.dist, self.stream = _abi, args, wb, device, world, dist, stream
+        cfg = args.cfg
+        self.cfg = cfg
+        self.paired = cfg["paired"]
+        kw = dict(qc_sample=args.qs, paired=1 if self.paired else 0)
+        if args.filter_kernel == "warp":
+            kw.update(filter_kernel=_abi.KERNEL_WARP, stat_kernel=_abi.STAT_WARP)
+        self.base_kw = kw
+        self.eng = Engine(_abi.Params.defaults(**kw), device=local_rank)
+        self.eng.set_stream(stream.cuda_stream)
+        self.L = self.eng._L
+        self.qc2 = _abi.QC_R2_PRE if self.paired else -1
+        # records of this shard inside the prefilter window [999, 999 + qc_sample) -- all from 999 on with --qc_sample 0
+        n, fi = wb.n, wb.first_index
+        self.w_lo_g = STAT_LO
+        self.w_hi_g = (STAT_LO + args.qs) if args.qs > 0 else (1 << 62)
+        self.s_lo = max(self.w_lo_g, fi) - fi
+        self.s_hi = min(self.w_hi_g, fi + n) - fi
+        self.has_window = self.s_hi > self.s_lo
+        self.s_lo_al = (max(self.s_lo, 0) // 4) * 4
+        self.trims = None
+        self.phase_ms = None
+        self.sum_views, self.min_views = [], []
+        if world > 1:
+            import torch  # noqa: F401
+            p, cnt = self.eng.device_ptr(0)
+            self.sum_views.append(cuda_tensor_view(p, cnt, device))
+            for slot in range(4):
+                for what in (1, 2, 3, 4, 5, 6):
+                    p, cnt = self.eng.device_ptr(what, slot)
+                    self.sum_views.append(cuda_tensor_view(p, cnt, device))
+                p, cnt = self.eng.device_ptr(7, slot)
+                self.min_views.append(cuda_tensor_view(p, cnt, device))
+
+    def allreduce_counters(self):
+        """the path's only exchange: reduce (copies of) the counter blocks over NVLink -- one SUM, one MIN"""
+        import torch
+        for op, views in ((self.dist.ReduceOp.SUM, self.sum_views), (self.dist.ReduceOp.MIN, self.min_views)):
+            c = torch.cat(views)
+            self.dist.all_reduce(c, op=op)
+        return c
+
+    def _autotrim(self):
+        """full pipeline: trims from the prefilter statistics (device -> host fetch of one QC slot, host float code, new params)"""
+        f, t = resolve_autotrim(self.eng, self.paired, self.args.qs)
+        self.trims = (f, t)
+        self.eng.set_params(self.abi.Params.defaults(trim_front=f, trim_tail=t, trim_front2=f, trim_tail2=t, **self.base_kw))
+
+    def step_resident(self, record_phases=False):
+        eng, L, wb, abi = self.eng, self.L, self.wb, self.abi
+        ph = [0.0, 0.0, 0.0, 0.0]          # prefilter statistics | filter kernel | list mode | postfilter statistics
+        if self.has_window:
+            b = wb.struct(self.s_lo_al, self.s_hi)
+            eng._check(L.aqc_stat_reads(eng._h, C.byref(b), abi.MEM_DEVICE, abi.QC_R1_PRE, self.qc2, self.w_lo_g, self.w_hi_g, 0))
+            if record_phases:
+                ph[0] = eng.last_phase_ms(-1)
+        if self.cfg["autotrim"]:
+            self._autotrim()
+        b = wb.struct()
+        eng._check(L.aqc_filter_pairs(eng._h, C.byref(b), abi.MEM_DEVICE, wb.results.data_ptr()))
+        if record_phases:
+            ph[1], ph[2], ph[3] = eng.last_phase_ms(0), eng.last_phase_ms(1), eng.last_phase_ms(2)
+            self.phase_ms = ph
+        if self.world > 1:
+            self.allreduce_counters()
+
+    def close(self):
+        try:
+            self.eng.close()
+        except Exception:       # noqa: BLE001
+            pass
 
 
-def lane_full_size_check(wb, n, qs, local_rank, stream, cand_kernel, cand_stat=0, window=None):
-    """Both kernels once over the resident full-size batch in this process: records, scalar counters, histograms, error
-    matrix, per-cycle statistics and k-mer tables must be identical (with a candidate statistics kernel: also the prefilter
-    slots after aqc_stat_reads over `window` = (first record, end record, global lo, global hi))."""
+def shard_parity_check(args, device, local_rank, stream, world, rank, dist):
+    """N > 1: a 200 k-record slice (the same on every rank) is run sharded + all-reduced, and rank 0 compares counters, per-cycle
+    arrays and dense k-mer tables with ONE engine over the whole slice (the exact merge of the side tables is covered by
+    tests/test_multigpu_gloo.py)."""
     import torch
     from afterqc_b200 import _abi
-    from afterqc_b200.engine import Engine
-    ref = None
-    slots = (_abi.QC_R1_POST, _abi.QC_R2_POST) + ((_abi.QC_R1_PRE, _abi.QC_R2_PRE) if (cand_stat and window) else ())
-    for k, sk in ((_abi.KERNEL_WARP, _abi.STAT_DEFAULT), (cand_kernel, cand_stat)):
-        e = Engine(_abi.Params.defaults(qc_sample=qs, filter_kernel=k, stat_kernel=sk), device=local_rank)
-        e.set_stream(stream.cuda_stream)
-        res = torch.empty(max(1, n) * 32, dtype=torch.uint8, device=wb.results.device)
-        if cand_stat and window:
-            b = wb.struct(window[0], window[1])
-            e._check(e._L.aqc_stat_reads(e._h, C.byref(b), _abi.MEM_DEVICE, _abi.QC_R1_PRE, _abi.QC_R2_PRE, window[2], window[3], 0))
-        b = wb.struct()
+    n = 200_000
+    cfg = args.cfg
+    full = make_device_workload(cfg, device, n, seed=777, first_index=0)
+    lo, hi = (n * rank // world) // 4 * 4, (n if rank == world - 1 else (n * (rank + 1) // world) // 4 * 4)
+    a2 = argparse.Namespace(**vars(args)); a2.qs = 50_000 if args.qs > 0 else 0
+    part = TorchBatch(full.t, 0, n, cfg["L"], cfg["paired"])
+    r = Runner(a2, part, device, local_rank, stream, world, dist)
+    eng = r.eng
+
+    def run(e, lo_, hi_):
+        s_lo, s_hi = max(STAT_LO, lo_), min(hi_, (STAT_LO + a2.qs) if a2.qs > 0 else hi_)
+        if s_hi > s_lo:
+            b = part.struct(s_lo // 4 * 4, s_hi)
+            e._check(e._L.aqc_stat_reads(e._h, C.byref(b), _abi.MEM_DEVICE, _abi.QC_R1_PRE, r.qc2, STAT_LO, (STAT_LO + a2.qs) if a2.qs > 0 else (1 << 62), 0))
+        b = part.struct(lo_, hi_)
+        res = torch.empty(max(1, hi_ - lo_) * 32, dtype=torch.uint8, device=device)
         e._check(e._L.aqc_filter_pairs(e._h, C.byref(b), _abi.MEM_DEVICE, res.data_ptr()))
         e.sync()
-        got = (res, e.counters(), [e.qc(s) for s in slots], [e.kmers(s) for s in slots])
-        e.close()
-        if ref is None:
-            ref = got
-            continue
-        if not bool(torch.equal(ref[0], got[0])):
-            return False, "records differ"
-        if not np.array_equal(ref[1], got[1]):
-            return False, "counters differ"
-        for a, c in zip(ref[2], got[2]):
+    run(eng, lo, hi)
+    # reduce in place so that rank 0's fetches return the merged blocks
+    for v in r.sum_views:
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+    for v in r.min_views:
+        dist.all_reduce(v, op=dist.ReduceOp.MIN)
+    torch.cuda.synchronize()
+    ok = True
+    why = "identical"
+    if rank == 0:
+        from afterqc_b200.engine import Engine
+        one = Engine(_abi.Params.defaults(**r.base_kw), device=local_rank)
+        one.set_stream(stream.cuda_stream)
+        run(one, 0, n)
+        if not np.array_equal(one.counters(), eng.counters()):
+            ok, why = False, "counters differ"
+        slots = (0, 1, 2, 3) if cfg["paired"] else (0, 2)
+        for s in slots:
+            if not ok:
+                break
+            a, b = one.qc(s), eng.qc(s)
             for f in a.dtype.names:
-                if not np.array_equal(a[f], c[f]):
-                    return False, "QC field %s differs" % f
-        for a, c in zip(ref[3], got[3]):
-            for x, y in zip(a, c):
-                if not np.array_equal(x, y):
-                    return False, "k-mer tables differ"
-    return True, "identical"
+                if not np.array_equal(a[f], b[f]):
+                    ok, why = False, "QC slot %d field %s differs" % (s, f)
+            ka, kb = one.kmers(s), eng.kmers(s)
+            if ok and not (np.array_equal(ka[0], kb[0]) and np.array_equal(ka[1], kb[1])):
+                ok, why = False, "dense k-mer table of slot %d differs" % s
+        one.close()
+    r.close()
+    del full, part
+    torch.cuda.empty_cache()
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item()), why
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from afterqc_b200 import _abi
-    from afterqc_b200.engine import Engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -358,132 +475,22 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    n = args.pairs
-    QS = args.qc_sample
+    cfg = args.cfg
+    n, QS = args.n, args.qs
     stream = torch.cuda.Stream(device)          # the launching stream of every kernel below (torch events time it)
     torch.cuda.set_stream(stream)
     first_index = rank * n
 
-    # ---------------- which filter kernel ----------------
-    # warp = pair_kernel (measured since the first GPU session); lane = lane_kernel; lane2 = lane2_kernel (never on hardware when
-    # committed).  "auto": each candidate must prove identical to pair_kernel in a child process (a hang or crash there costs a
-    # timeout, not the benchmark), the fastest identical one is then compared once more on the full-size batch in this process.
-    KID = {"warp": _abi.KERNEL_WARP, "lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}
-    selection = {"requested": args.filter_kernel}
-    chosen = args.filter_kernel if args.filter_kernel != "auto" else "warp"
-    # aqc_params.stat_kernel: 0 = stat_read; 2 / 3 = statRead with one lane per read (aqc_stat2.cuh), inside the lane-per-pair filter
-    # kernel / in a launch of its own after it
-    stat2 = {"lane": _abi.STAT_LANE, "lane_post": _abi.STAT_LANE_POST}.get(args.stat_kernel, 0)
-    child = None
-    if args.filter_kernel == "auto":
-        best_ms = None
-        verdicts = lane_child_check(local_rank, min(n, 2_000_000), timeout_s=300, candidates="lane,lane2")
-        for cand in ("lane", "lane2"):
-            c = verdicts[cand]
-            selection["child_check_" + cand] = c
-            if not c.get("ok"):
-                continue
-            ms, wms = c.get("lane_ms", 0), c.get("warp_ms", 0)
-            if ms > 0 and ms < wms and (best_ms is None or ms < best_ms):
-                best_ms, chosen, child = ms, cand, c
-    if args.stat_kernel == "auto":
-        # the statistics kernel: the chosen filter kernel with stat_kernel = 2 must be identical in a child process and
-        # faster on filter + prefilter statistics together (written without GPU access, emulator-verified when committed)
-        best_total = None
-        # pair_kernel keeps its fused statistics: levels 2 and 3 are the same launches there
-        levels = (("_st2", _abi.STAT_LANE),) if chosen == "warp" else (("_st3", _abi.STAT_LANE_POST), ("_st2", _abi.STAT_LANE))
-        verdicts = lane_child_check(local_rank, min(n, 2_000_000), timeout_s=240, candidates=",".join(chosen + sfx for sfx, _ in levels))
-        for suffix, level in levels:
-            c = verdicts[chosen + suffix]
-            selection["child_check_" + chosen + suffix] = c
-            if not c.get("ok"):
-                continue
-            # the chosen filter kernel with stat_read: timed by its own child check, or the warp kernel of this one
-            base_ms = child.get("lane_ms", 0) if child else (c.get("warp_ms", 0) if chosen == "warp" else None)
-            new_ms = c.get("lane_ms", 0) + c.get("stat_ms", 0)
-            if base_ms is None:         # explicit --filter-kernel: only the prefilter launches are comparable
-                faster = 0 < c.get("stat_ms", 0) < c.get("stat_warp_ms", 0)
-            else:
-                faster = 0 < new_ms < base_ms + c.get("stat_warp_ms", 0)
-            if faster and (best_total is None or new_ms < best_total):
-                best_total, stat2 = new_ms, level
-    wb = make_device_workload(device, n, seed=20260927 + rank, first_index=first_index)
-    # records of this shard inside the prefilter window [999, 999 + qc_sample) (global indices)
-    w_lo_g, w_hi_g = STAT_LO, STAT_LO + QS
-    s_lo = max(w_lo_g, first_index) - first_index
-    s_hi = min(w_hi_g, first_index + n) - first_index
-    has_window = s_hi > s_lo
-    s_lo_al = (s_lo // 4) * 4
-    if (chosen != "warp" or stat2) and (args.filter_kernel == "auto" or args.stat_kernel == "auto"):
-        attempts = [(chosen, stat2)] + ([(chosen, 0)] if (stat2 and chosen != "warp") else [])
-        chosen, stat2 = "warp", 0
-        for cand, st in attempts:       # a failing statistics kernel must not cost the filter kernel its place
-            try:
-                ok, why = lane_full_size_check(wb, n, QS, local_rank, stream, KID[cand], st,
-                                               (s_lo_al, s_hi, w_lo_g, w_hi_g) if has_window else None)
-            except Exception as e:      # noqa: BLE001
-                ok, why = False, "full-size check raised %r" % (e,)
-            selection["full_size_check_%s%s" % (cand, "_st%d" % st if st else "")] = why
-            if ok:
-                chosen, stat2 = cand, st
-                break
-    if world > 1:       # every rank runs the same kernel: the most conservative choice any rank made
-        flag = torch.tensor([KID[chosen]], dtype=torch.int32, device=device)
-        flags = [torch.zeros_like(flag) for _ in range(world)]
-        dist.all_gather(flags, flag)
-        ids = [int(f.item()) for f in flags]
-        if len(set(ids)) == 1:
-            agreed = ids[0]
-        elif _abi.KERNEL_WARP in ids:
-            agreed = _abi.KERNEL_WARP
-        else:
-            agreed = _abi.KERNEL_LANE
-        chosen = {v: k for k, v in KID.items()}[agreed]
-        sflag = torch.tensor([stat2, -stat2], dtype=torch.int32, device=device)
-        dist.all_reduce(sflag, op=dist.ReduceOp.MIN)
-        stat2 = stat2 if int(sflag[0].item()) == -int(sflag[1].item()) else 0      # every rank the same level, else stat_read
-    use_lane = chosen != "warp"
-    selection["used"] = chosen
-    selection["stat_kernel_requested"] = args.stat_kernel
-    selection["stat_kernel_used"] = {0: "warp (stat_read)", 2: "lane (stat_tile in the filter kernel / stat_lane_kernel)",
-                                     3: "lane_post (stat_lane_kernel, also for the sampled pairs of the filter launch)"}[stat2]
-    kernel_label = {"warp": "aqc::pair_kernel (MODE_FILTER, one warp per pair)",
-                    "lane": "aqc::lane_kernel (one lane per pair) + aqc::pair_kernel list mode",
-                    "lane2": "aqc::lane2_kernel (one lane per pair, 2-column stage, dynamic tiles) + aqc::pair_kernel list mode"}[chosen]
-    if use_lane and stat2 == _abi.STAT_LANE_POST:
-        kernel_label += " + aqc::stat_lane_kernel<POST> (sampled statistics)"
-
-    if world > 1:       # the packed base transport's host threads: the ranks of one box share its cores
-        os.environ.setdefault("AQC_PACK_THREADS", str(max(2, (os.cpu_count() or 8) // (2 * world))))
-    params = _abi.Params.defaults(qc_sample=QS, filter_kernel=KID[chosen], stat_kernel=stat2)
-    eng = Engine(params, device=local_rank)
-    eng.set_stream(stream.cuda_stream)
-    L = eng._L
-
-    reduce_views = []
+    shard_parity = None
     if world > 1:
-        p, cnt = eng.device_ptr(0)
-        reduce_views.append(("sum", cuda_tensor_view(p, cnt, torch.int64, device)))
-        for slot in range(4):
-            for what in (1, 2, 3, 4, 5, 6):
-                p, cnt = eng.device_ptr(what, slot)
-                reduce_views.append(("sum", cuda_tensor_view(p, cnt, torch.int64, device)))
-            p, cnt = eng.device_ptr(7, slot)
-            reduce_views.append(("min", cuda_tensor_view(p, cnt, torch.int64, device)))
+        try:
+            shard_parity = shard_parity_check(args, device, local_rank, stream, world, rank, dist)
+        except Exception as e:      # noqa: BLE001
+            shard_parity = (False, "check raised %r" % (e,))
 
-    sum_views = [v for op, v in reduce_views if op == "sum"]
-    min_views = [v for op, v in reduce_views if op == "min"]
-
-    def step_resident():
-        if has_window:
-            b = wb.struct(s_lo_al, s_hi)
-            eng._check(L.aqc_stat_reads(eng._h, C.byref(b), _abi.MEM_DEVICE, _abi.QC_R1_PRE, _abi.QC_R2_PRE, w_lo_g, w_hi_g, 0))
-        b = wb.struct()
-        eng._check(L.aqc_filter_pairs(eng._h, C.byref(b), _abi.MEM_DEVICE, wb.results.data_ptr()))
-        if world > 1:   # the path's only exchange: reduce (copies of) the counter blocks over NVLink -- one SUM, one MIN
-            for op, views in (("sum", sum_views), ("min", min_views)):
-                c = torch.cat(views)
-                dist.all_reduce(c, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MIN)
+    wb = make_device_workload(cfg, device, n, seed=20260927 + rank, first_index=first_index)
+    R = Runner(args, wb, device, local_rank, stream, world, dist)
+    eng, L = R.eng, R.L
 
     def barrier():
         torch.cuda.synchronize()
@@ -492,8 +499,9 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- resident (kernel-side) number ----------------
-    for _ in range(max(3, args.warmup)):
-        step_resident()
+    warm = max(3, args.warmup)
+    for _ in range(warm):
+        R.step_resident()
     barrier()
     launches0 = eng.launch_count()
     sampler = ClockSampler(local_rank)
@@ -501,22 +509,19 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    filter_ms = []
     for _ in range(args.steps):
-        step_resident()
-        filter_ms.append(None)
+        R.step_resident()
     e1.record(stream)
     barrier()
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     launches = eng.launch_count() - launches0
-    # duration of the dominant kernel (filter-mode pair_kernel): events on its launching stream, one more launch
-    kms = []
+    # durations of the step's launch groups (CUDA events recorded by the engine on the launching stream), three more steps
+    phases = []
     for _ in range(3):
-        b = wb.struct()
-        eng._check(L.aqc_filter_pairs(eng._h, C.byref(b), _abi.MEM_DEVICE, wb.results.data_ptr()))
-        kms.append(eng.last_kernel_ms())
-    kernel_ms = float(np.mean(kms))
+        R.step_resident(record_phases=True)
+        phases.append(R.phase_ms)
+    phase_ms = [float(np.mean([p[i] for p in phases])) for i in range(4)]
     t = torch.tensor([ms_total], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -527,37 +532,54 @@ def run_ours(args):
     # ---------------- end-to-end through the host-buffer C-ABI ----------------
     e2e = None
     if not args.no_e2e:
+        ne = min(n, E2E_MAX_PAIRS)
+        cols = ("seq1", "qual1", "off1") + (("seq2", "qual2", "off2") if cfg["paired"] else ())
+        ends = {"seq1": "off1", "qual1": "off1", "seq2": "off2", "qual2": "off2"}
         host = {}
-        for k in ("seq1", "qual1", "seq2", "qual2", "off1", "off2"):
-            h = torch.empty(wb.t[k].shape, dtype=wb.t[k].dtype, pin_memory=True)
-            h.copy_(wb.t[k])
+        for k in cols:
+            src = wb.t[k][:ne + 9] if k.startswith("off") else wb.t[k][:int(wb.t[ends[k]][ne].item()) + 16]
+            h = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            h.copy_(src)
             host[k] = h
-        res_host = torch.empty(n * 32, dtype=torch.uint8, pin_memory=True)
+        res_host = torch.empty(ne * 32, dtype=torch.uint8, pin_memory=True)
         torch.cuda.synchronize()
-
-        xflags = [0]            # transport flags of the calls: AQC_BATCH_QUAL2_IN_PLACE (lane kernels only) | AQC_BATCH_PACK_BASES
+        xflags = [0]
+        e_lo, e_hi = R.s_lo, min(R.s_hi, ne)
+        e_window = e_hi > e_lo
 
         def hstruct(lo, hi):
             b = _abi.Batch()
             b.first_index = first_index + lo
             b.n = hi - lo
-            b.flags = xflags[0] | READ_LEN                  # bits 0-15: the longest read (saves the engine a pass over the offsets)
+            b.flags = xflags[0] | cfg["L"]                  # bits 0-15: the longest read (saves the engine a pass over the offsets)
             b.seq1 = host["seq1"].data_ptr(); b.qual1 = host["qual1"].data_ptr(); b.off1 = host["off1"].data_ptr() + 4 * lo
-            b.seq2 = host["seq2"].data_ptr(); b.qual2 = host["qual2"].data_ptr(); b.off2 = host["off2"].data_ptr() + 4 * lo
+            if cfg["paired"]:
+                b.seq2 = host["seq2"].data_ptr(); b.qual2 = host["qual2"].data_ptr(); b.off2 = host["off2"].data_ptr() + 4 * lo
+            else:
+                b.seq2 = None; b.qual2 = None; b.off2 = None
             return b
 
-        off1 = host["off1"].numpy(); off2 = host["off2"].numpy()
-        h2d = 2 * int(off1[n] - off1[0]) + 2 * int(off2[n] - off2[0]) + 8 * (n + 1)
-        if has_window:
-            h2d += 2 * int(off1[s_hi] - off1[s_lo]) + 2 * int(off2[s_hi] - off2[s_lo]) + 8 * (s_hi - s_lo + 1)
-        d2h = 32 * n
+        off1 = host["off1"].numpy()
+        off2 = host["off2"].numpy() if cfg["paired"] else None
+        nm = 2 if cfg["paired"] else 1
+
+        def col_bytes(lo, hi):
+            return 2 * int(off1[hi] - off1[lo]) + (2 * int(off2[hi] - off2[lo]) if cfg["paired"] else 0)
+        h2d_all = col_bytes(0, ne) + 4 * nm * (ne + 1)
+        if e_window:
+            h2d_all += col_bytes(e_lo, e_hi) + 4 * nm * (e_hi - e_lo + 1)
+        d2h = 32 * ne
 
         def step_e2e():
-            if has_window:
-                b = hstruct(s_lo, s_hi)
-                eng._check(L.aqc_stat_reads(eng._h, C.byref(b), _abi.MEM_HOST, _abi.QC_R1_PRE, _abi.QC_R2_PRE, w_lo_g, w_hi_g, 0))
-            b = hstruct(0, n)
+            if e_window:
+                b = hstruct(e_lo, e_hi)
+                eng._check(L.aqc_stat_reads(eng._h, C.byref(b), _abi.MEM_HOST, _abi.QC_R1_PRE, R.qc2, R.w_lo_g, R.w_hi_g, 0))
+            if cfg["autotrim"]:
+                R._autotrim()
+            b = hstruct(0, ne)
             eng._check(L.aqc_filter_pairs(eng._h, C.byref(b), _abi.MEM_HOST, res_host.data_ptr()))
+            if world > 1:
+                R.allreduce_counters()
 
         e_steps = max(1, min(args.steps, 5))
 
@@ -571,22 +593,52 @@ def run_ours(args):
                 step_e2e()
             a1.record(stream)
             barrier()
-            t = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=device)
+            tt = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=device)
             if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            try:        # same pairs, same parameters: the host-buffer path must return the records of the resident path
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            try:        # same records, same parameters: the host-buffer path must return the records of the resident path
                 torch.cuda.synchronize()
-                same = bool(torch.equal(res_host.to(device, non_blocking=False), wb.results[:n * 32]))
+                same = bool(torch.equal(res_host.to(device, non_blocking=False), wb.results[:ne * 32]))
             except Exception:
                 same = None
-            return float(t.item()) / e_steps, same
+            return float(tt.item()) / e_steps, same
 
-        ms_e2e, same = time_e2e()
-        e2e = {"value": world * n / (ms_e2e * 1e-3) / 1e6, "unit": "M read-pairs/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e_steps, "results_match_resident": same,
-               "note": "aqc_stat_reads + aqc_filter_pairs with AQC_MEM_HOST on pinned host columns; chunked H2D/kernels/D2H pipeline inside"}
+        variants = {}
+        modes = [("copy_all_columns", 0)] + ([("qual2_in_place", _abi.BATCH_QUAL2_IN_PLACE)] if cfg["paired"] and args.filter_kernel == "default" else [])
+        best = None
+        for name, fl in modes:
+            xflags[0] = fl
+            res_host.zero_()
+            try:
+                ms_v, same_v = time_e2e()
+            except Exception as ex:      # noqa: BLE001
+                variants[name] = {"error": repr(ex)[:200]}
+                continue
+            hb = h2d_all
+            if fl & _abi.BATCH_QUAL2_IN_PLACE:
+                # counted from the tensors that are copied: the qual2 column stays in pinned memory; the kernels pull one 32-byte
+                # sector per byte pair of the correction walk and the mate-2 qualities of the sampled pairs over PCIe
+                n_edits = int(wb.results[:ne * 32].view(-1, 32)[:, 1].sum().item())
+                sampled = ne if QS <= 0 else min(ne, max(0, QS - 1 - first_index))
+                hb += -int(off2[ne] - off2[0]) + 32 * n_edits + sampled * cfg["L"]
+            variants[name] = {"value": world * ne / (ms_v * 1e-3) / 1e6, "ms_per_step": ms_v, "results_match_resident": same_v, "h2d_bytes_per_step": hb}
+            if same_v and (best is None or variants[name]["value"] > variants[best]["value"]):
+                best = name
+        xflags[0] = 0
+        if best is not None:
+            v = variants[best]
+            e2e = {"value": v["value"], "unit": cfg["unit"], "h2d_bytes_per_step": v["h2d_bytes_per_step"], "d2h_bytes_per_step": d2h,
+                   "ms_per_step": v["ms_per_step"], "steps": e_steps, "results_match_resident": v["results_match_resident"], "mode": best,
+                   "records_per_gpu": ne, "per_gpu_h2d_GBps": v["h2d_bytes_per_step"] / (v["ms_per_step"] * 1e-3) / 1e9,
+                   "variants": variants,
+                   "note": "aqc_stat_reads + aqc_filter_pairs with AQC_MEM_HOST on pinned host columns; chunked H2D / kernels / D2H pipeline inside; "
+                           "qual2_in_place = AQC_BATCH_QUAL2_IN_PLACE, the mate-2 quality column is not copied (the filter never reads it "
+                           "outside the correction walk and the sampled statistics)"}
+        else:
+            e2e = {"value": None, "unit": cfg["unit"], "variants": variants}
+        del host, res_host
 
-    # ---------------- roofline of the dominant kernel ----------------
+    # ---------------- roofline: every launch group of the step, the dominant one on top ----------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         with open(peaks_path) as f:
@@ -594,133 +646,82 @@ def run_ours(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    off1 = wb.t["off1"]; off2 = wb.t["off2"]
-    col_bytes = 2 * int(off1[n].item() - off1[0].item()) + 2 * int(off2[n].item() - off2[0].item())
-    algo_bytes = col_bytes + 32 * n + 8 * n
-    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_filter_kernel_dram_bytes.json")     # ncu capture of pair_kernel
-    if os.path.exists(tp) and not use_lane:
-        try:
-            with open(tp) as f:
-                tj = json.load(f)
-            traffic = tj["dram_bytes_per_pair"] * n     # ncu capture was taken on a smaller launch; per-pair traffic x pairs/launch
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "%s, %d pairs/launch" % (kernel_label, n), "kernel_ms": kernel_ms,
-                "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
-                "note": "integer ALU-bound kernel: see DESIGN.md (instruction budget per pair vs HBM budget)"}
+    off1d = wb.t["off1"]
+    b1 = int(off1d[n].item() - off1d[0].item())
+    b2 = int(wb.t["off2"][n].item() - wb.t["off2"][0].item()) if cfg["paired"] else 0
+    nm = 2 if cfg["paired"] else 1
+    lane = args.filter_kernel == "default"
+    n_pre = max(0, R.s_hi - R.s_lo) if R.has_window else 0
+    n_post = n if QS <= 0 else min(n, max(0, QS - 1 - first_index))
+    per_rec = (b1 + b2) / max(1, n)          # bases of one record (both mates)
+    groups = [
+        ("prefilter statistics: " + ("aqc::stamp_bits_kernel + aqc::stat_kernel (one warp per read, histograms in shared memory)" if lane
+                                     else "aqc::pair_kernel<MODE_STAT> (stat_read)"), phase_ms[0], 2 * per_rec * n_pre, n_pre, "stat_pre"),
+        ("filter: " + ("aqc::lane_kernel (one lane per pair, no statistics)" if lane else "aqc::pair_kernel<MODE_FILTER> (one warp per pair, fused stat_read)"),
+         phase_ms[1], 2 * (b1 + b2) + 32 * n + 4 * nm * n, n, "filter"),
+        ("list mode: aqc::pair_kernel<MODE_LIST> over the pairs lane_kernel handed over (bytes outside A,C,G,T,N)", phase_ms[2], 0, 0, "list"),
+        ("postfilter statistics: aqc::stamp_bits_kernel + aqc::stat_kernel<POST> over the sampled good pairs' records", phase_ms[3],
+         (2 * per_rec + 32) * n_post, n_post, "stat_post"),
+    ]
+    traffic_tab = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_dram_bytes.json")) as f:
+            traffic_tab = json.load(f)
+    except Exception:
+        traffic_tab = {}
+    ph_out = []
+    for name, ms, ab, units, key in groups:
+        if ms <= 0:
+            continue
+        tr = traffic_tab.get(args.config, {}).get(key) if lane else None
+        ph_out.append({"launches": name, "ms": ms, "algorithmic_bytes": ab, "achieved_GBps": ab / (ms * 1e-3) / 1e9,
+                       "frac": ab / (ms * 1e-3) / 1e9 / peak, "units": units,
+                       "traffic": (tr["dram_bytes_per_unit"] * units) if tr else None})
+    dom = max(ph_out, key=lambda p: p["ms"]) if ph_out else None
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "achieved": dom["achieved_GBps"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": dom["traffic"],
+                    "kernel": "%s, %d records/launch" % (dom["launches"], dom["units"]), "kernel_ms": dom["ms"],
+                    "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "peak_source": peak_src,
+                    "whole_step": {"algorithmic_bytes": algo_bytes_per_unit(cfg) * n, "ms": ms_per_step if world == 1 else None,
+                                   "achieved_GBps": algo_bytes_per_unit(cfg) * n / (ms_per_step * 1e-3) / 1e9 if world == 1 else None},
+                    "phases": ph_out,
+                    "note": "integer-issue bound filter kernel, shared-memory-atomic bound statistics kernel: DESIGN.md section 3"}
 
     line = None
     if rank == 0:
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:
             threads = host_threads()
-            sample = cpu_sample_size(n, threads, args.cpu_sample)
-            # the first `sample` pairs of the resident batch, copied back to the host
+            sample = cpu_sample_size(args, threads)
             from afterqc_b200.batch import PackedBatch, SLACK
-            o1 = wb.t["off1"][:sample + 1].cpu().numpy().astype(np.uint32); o2 = wb.t["off2"][:sample + 1].cpu().numpy().astype(np.uint32)
 
             def hostcol(name, end):
                 a = np.zeros(end + SLACK, dtype=np.uint8)
                 a[:end] = wb.t[name][:end].cpu().numpy()
                 return a
-            hb = PackedBatch(hostcol("seq1", int(o1[-1])), hostcol("qual1", int(o1[-1])), o1,
-                             hostcol("seq2", int(o2[-1])), hostcol("qual2", int(o2[-1])), o2)
-            r = cpu_arm(hb, threads)
-            cpu = {"value": r["pairs_per_s"] / 1e6, "unit": "M read-pairs/s", "cores": r["threads"], "kind": "port",
-                   "sample": "%d pairs of the same PE150 workload (QC window scaled to %d reads, the same 2%% mix), %.1f s of wall time on %d threads; "
-                             "C oracle oracle/aqc_oracle.c" % (sample, r["qc_sample_scaled"], r["seconds"], r["threads"])}
+            o1 = wb.t["off1"][:sample + 1].cpu().numpy().astype(np.uint32)
+            if cfg["paired"]:
+                o2 = wb.t["off2"][:sample + 1].cpu().numpy().astype(np.uint32)
+                hb = PackedBatch(hostcol("seq1", int(o1[-1])), hostcol("qual1", int(o1[-1])), o1,
+                                 hostcol("seq2", int(o2[-1])), hostcol("qual2", int(o2[-1])), o2)
+            else:
+                hb = PackedBatch(hostcol("seq1", int(o1[-1])), hostcol("qual1", int(o1[-1])), o1)
+            r = cpu_arm(args, hb, threads)
+            cpu = {"value": r["units_per_s"] / 1e6, "unit": cfg["unit"], "cores": r["threads"], "kind": "port", "sample": cpu_sample_text(args, r)}
+        confd = workload_config(args, world)
+        confd.update({"filter_kernel": args.filter_kernel, "autotrim_resolved": list(R.trims) if R.trims else None,
+                      "l2": "inputs (%.1f GB/GPU) exceed the 126 MB L2; no explicit flush" % (2 * (b1 + b2) / 1e9)})
         line = {
-            "metric": "read-pairs/s PE150 (filter + overlap correction + adapter trim + per-cycle QC)",
-            "value": value, "unit": "M read-pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu": n, "read_len": READ_LEN, "qc_sample": QS,
-                       "filter_kernel": selection,
-                       "l2": "inputs (%.1f GB/GPU) exceed the 126 MB L2; no explicit flush" % (col_bytes / 1e9),
-                       "parallelism": "read-sharded x%d, NCCL all-reduce of the counter blocks per step" % world if world > 1 else "1 GPU"},
-            "clocks": clocks,
-            "e2e": e2e,
-            "gpu_launches": launches,
-            "roofline": roofline,
-            "cpu_baseline": cpu,
+            "dtype": "u8", "data": "synthetic", "config": confd, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_python": python_reference_timing(args.config),
         }
-    # ---------------- other transport modes of the same host-buffer calls (identical results, fewer PCIe bytes) ----------------
-    # Run LAST: everything the JSON line needs exists by now, so an experimental mode that fails costs only itself.
-    #   qual2_in_place (lane kernels, only if the child check saw it work on this GPU): mate-2 qualities stay in the pinned host
-    #     column; the kernel fetches the bytes of the correction walk / sampled statRead over PCIe
-    #   pack_bases / pack_quals: host threads pack the base columns to 2 bits per base (the quality columns to 6 bits per byte),
-    #     unpack_bases_kernel / unpack_quals_kernel restore the bytes in HBM
-    if e2e is not None:
-        try_in_place = use_lane and (args.filter_kernel in ("lane", "lane2") or bool((child or {}).get("in_place_ok")))
-        if world > 1:
-            flag = torch.tensor([1 if try_in_place else 0], dtype=torch.int32, device=device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            try_in_place = bool(flag.item())
-        modes = []
-        if try_in_place:
-            modes.append(("qual2_in_place", _abi.BATCH_QUAL2_IN_PLACE))
-        if not args.no_pack:
-            PB, PQ = _abi.BATCH_PACK_BASES, _abi.BATCH_PACK_QUALS
-            modes += [("pack_bases", PB), ("pack_bases+pack_quals", PB | PQ)]
-            if try_in_place:
-                modes += [("pack_bases+qual2_in_place", PB | _abi.BATCH_QUAL2_IN_PLACE),
-                          ("pack_bases+pack_quals+qual2_in_place", PB | PQ | _abi.BATCH_QUAL2_IN_PLACE)]
-        variants = {"copy_all_columns": {"value": e2e["value"], "ms_per_step": e2e["ms_per_step"], "h2d_bytes_per_step": h2d}}
-        best = ("copy_all_columns", e2e["value"])
-        try:
-            q2_bytes = int(off2[n] - off2[0])
-            base_bytes = int(off1[n] - off1[0]) + int(off2[n] - off2[0])
-            n_edits = int(wb.results[:n * 32].view(-1, 32)[:, 1].sum().item())
-            pulled = 32 * n_edits + min(n, QS) * READ_LEN      # one 32-byte sector per visited mismatch + the stat'd reads
-            n_exc, q_exc = 0, {}
-            for k in ("seq1", "seq2", "qual1", "qual2"):        # bytes that travel in the exception lists (5 bytes each)
-                c = wb.t[k][:int(wb.t["off1" if k.endswith("1") else "off2"][n].item())]
-                if k.startswith("seq"):
-                    n_exc += int(((c != 65) & (c != 67) & (c != 71) & (c != 84)).sum().item())
-                else:
-                    q_exc[k] = int(((c < 33) | (c > 96)).sum().item())
-            q1_bytes = int(off1[n] - off1[0])
-            for name, fl in modes:
-                xflags[0] = fl
-                res_host.zero_()
-                ms_v, same_v = time_e2e()
-                xflags[0] = 0
-                hb = h2d
-                if fl & _abi.BATCH_QUAL2_IN_PLACE:
-                    hb += pulled - q2_bytes
-                if fl & _abi.BATCH_PACK_BASES:
-                    hb += -base_bytes + (base_bytes + 3) // 4 + 5 * n_exc
-                if fl & _abi.BATCH_PACK_QUALS:
-                    hb += -(q1_bytes // 4) + 5 * q_exc["qual1"]
-                    if not (fl & _abi.BATCH_QUAL2_IN_PLACE):
-                        hb += -(q2_bytes // 4) + 5 * q_exc["qual2"]
-                variants[name] = {"value": world * n / (ms_v * 1e-3) / 1e6, "ms_per_step": ms_v, "results_match_resident": same_v,
-                                  "h2d_bytes_per_step": hb}
-                if same_v and variants[name]["value"] > best[1]:
-                    best = (name, variants[name]["value"])
-        except Exception as ex:      # noqa: BLE001
-            xflags[0] = 0
-            variants["error"] = repr(ex)[:300]
-        e2e["variants"] = variants
-        e2e["mode"] = best[0]
-        if best[0] != "copy_all_columns":
-            v = variants[best[0]]
-            e2e.update({"value": v["value"], "ms_per_step": v["ms_per_step"], "h2d_bytes_per_step": v["h2d_bytes_per_step"],
-                        "results_match_resident": v["results_match_resident"]})
-            e2e["note"] += ("; mode %s: AQC_BATCH_QUAL2_IN_PLACE = the qual2 column is not copied, the kernel reads what the correction walk and "
-                            "the sampled statRead need from the pinned column over PCIe (estimate in h2d_bytes_per_step); AQC_BATCH_PACK_BASES = "
-                            "host threads pack the bases to 2 bits before the copy (+ 5 bytes per byte that is not A,C,G,T); AQC_BATCH_PACK_QUALS = ... and "
-                            "the qualities to 6 bits" % best[0])
-        if line is not None:
-            line["e2e"] = e2e
-        del host, res_host
-    try:
-        eng.close()
-    except Exception:       # noqa: BLE001
-        pass
+        if shard_parity is not None:
+            line["shard_parity"] = shard_parity[0]
+            line["shard_parity_note"] = shard_parity[1]
+    R.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define AQC_ABI_VERSION 1
+#define AQC_ABI_VERSION 2
 #define AQC_MAX_LEN 1000      /* qualitycontrol.py:23  MAX_LEN; longer reads raise IndexError there */
 #define AQC_MAX_KMER 8        /* dense 4^k table + 64-bit raw-byte keys for non-ACGT k-mers; --qc_kmer outside 1..8 is rejected */
 #define AQC_NUM_QC 4          /* r1 prefilter, r2 prefilter, r1 postfilter, r2 postfilter */
@@ -91,17 +91,14 @@ typedef struct aqc_params {
     int32_t qc_sample;               /* --qc_sample 200000 (postfilter gate, preprocesser.py:624) */
     int32_t qc_kmer;                 /* --qc_kmer 8 */
     int32_t kmer_side_log2;          /* log2 capacity of the non-ACGT k-mer side table (0 = default 20) */
-    int32_t filter_kernel;           /* which kernel aqc_filter_pairs launches: 0 = engine default (environment AQC_LANE_KERNEL,
-                                        else 1), 1 = warp-per-pair (pair_kernel, any read length), 2 = lane-per-pair
-                                        (lane_kernel) for batches whose reads are <= 256 bases, pair_kernel otherwise; 3 = lane2_kernel, the
-                                        same with two staged columns per warp and dynamic tile claiming (experimental).
-                                        Results are identical; this is a performance knob. */
-    int32_t stat_kernel;             /* how statRead (qualitycontrol.py:73-122) is executed: 0 / 1 = one warp per read (stat_read);
-                                        2 = one lane per read with per-cycle warp reductions (stat_tile, aqc_stat2.cuh) in
-                                        aqc_stat_reads and in the sampled statistics of the lane-per-pair filter kernels, for batches
-                                        whose reads are <= 256 bases (experimental, emulator-verified); 3 = the same, but the lane-per-pair
-                                        filter kernels carry no statistics code and the sampled good pairs are stat'd from their result
-                                        records by one more launch of stat_lane_kernel.  Results are identical. */
+    int32_t filter_kernel;           /* which kernel aqc_filter_pairs launches: 0 = default and 2 = lane-per-pair (lane_kernel, then
+                                        pair_kernel's list mode for pairs holding a byte outside A,C,G,T,N, then stat_kernel for the
+                                        sampled statistics) for batches whose reads are <= 256 bases, pair_kernel otherwise;
+                                        1 = warp-per-pair (pair_kernel) for every batch.  Results are identical; a performance knob. */
+    int32_t stat_kernel;             /* how statRead (qualitycontrol.py:73-122) is executed in aqc_stat_reads (and after lane_kernel):
+                                        0 = stat_kernel (one warp per read, every histogram in shared memory, aqc_stat_kernel.cuh) for
+                                        batches whose reads are <= 256 bases, stat_read inside pair_kernel otherwise; 1 = stat_read
+                                        always (with filter_kernel = 1 this is the whole round-1 path).  Results are identical. */
     int32_t reserved[5];
 } aqc_params;
 
@@ -113,7 +110,7 @@ typedef struct aqc_batch {
     uint64_t first_index;
     uint32_t n;
     uint32_t flags;             /* bits 0-15: optional hint, the longest read of the batch (0 = unknown);
-                                   AQC_BATCH_QUAL2_IN_PLACE, AQC_BATCH_PACK_BASES, AQC_BATCH_PACK_QUALS: see below; other bits 0 */
+                                   AQC_BATCH_QUAL2_IN_PLACE: see below; other bits 0 */
     const uint8_t *seq1, *qual1;
     const uint32_t *off1;
     const uint8_t *seq2, *qual2;
@@ -125,18 +122,8 @@ typedef struct aqc_batch {
  * walk (two bytes per visited mismatch, preprocesser.py:566-567) and in the sampled statRead (:624-627), so with the
  * lane-per-pair kernel the engine may leave that column where it is and let the kernel fetch those bytes over PCIe instead of
  * copying a quarter of the batch.  The engine checks the pointer (cudaPointerGetAttributes) and silently copies as usual when
- * the condition does not hold (with stat_kernel 2 / 3 the three bytes after the last quality must be addressable too: the
- * usual 16 bytes of column slack cover it).  Results are identical either way. */
+ * the condition does not hold.  Results are identical either way. */
 #define AQC_BATCH_QUAL2_IN_PLACE (1u << 16)
-/* aqc_batch.flags, AQC_MEM_HOST batches (aqc_filter_pairs, aqc_stat_reads): the engine may pack the base columns to 2 bits per
- * base on host threads before the copy (bytes other than A,C,G,T travel in an exception list) and expand them on the device --
- * a quarter of the base bytes cross PCIe.  Transport only: lossless for any input, results identical.  The pool uses half
- * of the hardware threads (at most 48; AQC_PACK_THREADS overrides). */
-#define AQC_BATCH_PACK_BASES (1u << 17)
-/* ... and the quality columns to 6 bits per byte (code = byte - 33, i.e. Phred+33 qualities 0..63; other bytes are exceptions):
- * three quarters of the quality bytes cross PCIe.  A qual2 column left in place (AQC_BATCH_QUAL2_IN_PLACE) is not packed. */
-#define AQC_BATCH_PACK_QUALS (1u << 18)
-
 /* Per-pair outcome, 32 bytes.  start/len are the final coordinates into the ORIGINAL read after
  * front/tail trim and adapter cut (what the good/bad writer must emit).  edits are the byte
  * changes of the correction walk (preprocesser.py:563-598), applied in order:
@@ -278,6 +265,13 @@ int aqc_get_kmer_dense(aqc_ctx *ctx, int slot, uint64_t *counts, uint64_t *first
 int aqc_get_kmer_side(aqc_ctx *ctx, int slot, uint64_t *keys, uint64_t *counts, uint64_t *first,
                       uint32_t cap, uint32_t *n_out);
 
+/* The side table as the device holds it, unresolved: per key the count, the first DIRECT sighting and the first seeding by a
+ * k-mer that holds a byte outside util.COMP (AQC_KMER_NEVER = none).  Shards merge these by key (sum, min, min) and then apply
+ * the insertion rule of aqc_get_kmer_side on the merged table (afterqc_b200/multigpu.py: resolve_side), which makes the
+ * first-seen order of sharded runs exact for every byte (quirk Q12).  Entries include keys that were only ever seeded. */
+int aqc_get_kmer_side_raw(aqc_ctx *ctx, int slot, uint64_t *keys, uint64_t *counts, uint64_t *first_direct, uint64_t *first_seed,
+                          uint32_t cap, uint32_t *n_out);
+
 /* ---- host-side FASTQ ingest / egress on the packed columns (no GPU work; replaces fastq.py:17-104) ---- */
 /* Parse complete 4-line records of buf[0..n): lines are rstrip()'d, the first empty line ends the file (its record is
  * dropped), a trailing partial record stays unconsumed unless `final`.  Column k (0 names, 1 bases, 2 '+' lines,
@@ -351,6 +345,9 @@ void aqc_reader_close(aqc_reader *r);
  * time in ms of the last filter/stat call's kernels (CUDA events on the launching stream) */
 uint64_t aqc_launch_count(const aqc_ctx *ctx);
 float aqc_last_kernel_ms(const aqc_ctx *ctx);
+/* ... split by phase: 0 = the filter kernel (lane_kernel or pair_kernel; aqc_ops_pairs), 1 = pair_kernel's list mode after
+ * lane_kernel, 2 = the statistics launches (stamp_bits_kernel + stat_kernel, or pair_kernel in stat mode); -1 = all */
+float aqc_last_phase_ms(const aqc_ctx *ctx, int phase);
 
 #ifdef __cplusplus
 }

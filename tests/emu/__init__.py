@@ -17,7 +17,7 @@ CSRC = os.path.join(ROOT, "afterqc_b200", "csrc")
 _DEFINES = [d for d in os.environ.get("AQC_EMU_DEFINES", "").split(",") if d]
 _TAG = ("_" + "".join(c if c.isalnum() else "_" for c in "".join(_DEFINES))) if _DEFINES else ""
 OUT = os.path.join(HERE, "_build", "libafterqc_b200_emu%s.so" % _TAG)
-SOURCES = ["aqc_engine.cu", "aqc_fastq.cpp", "aqc_stream.cpp", "aqc_inflate.cpp", "aqc_pinflate.cpp", "aqc_pack.cpp"]
+SOURCES = ["aqc_engine.cu", "aqc_fastq.cpp", "aqc_stream.cpp", "aqc_inflate.cpp", "aqc_pinflate.cpp"]
 
 _lib = None
 

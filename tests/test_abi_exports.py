@@ -26,7 +26,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, s), "missing export " + s
     assert sorted(_native.SYMBOLS) == syms, (set(syms) ^ set(_native.SYMBOLS))
     L = _native.lib()
-    assert L.aqc_abi_version() == 1
+    assert L.aqc_abi_version() == 2
 
 
 def test_product_never_imports_the_oracle():

@@ -10,24 +10,21 @@ import compare
 from afterqc_b200 import _abi
 
 
-KERNELS = {"warp": _abi.KERNEL_WARP, "lane": _abi.KERNEL_LANE, "lane2": _abi.KERNEL_LANE2}
+KERNELS = {"warp": (_abi.KERNEL_WARP, _abi.STAT_WARP), "lane": (_abi.KERNEL_DEFAULT, _abi.STAT_DEFAULT)}
 
 
-@pytest.fixture(scope="module", params=["warp", "lane", "lane2", "lane_st2", "lane_st3", "lane2_st3"])
+@pytest.fixture(scope="module", params=["warp", "lane"])
 def backends(oracle_lib, request):
-    """warp = pair_kernel (one warp per pair); lane = lane_kernel (one lane per pair) + pair_kernel's list mode;
-    lane2 = lane2_kernel (two staged columns per warp, dynamic tile claiming); *_st2 = the same with aqc_params.stat_kernel = 2
-    (statRead with one lane per read, aqc_stat2.cuh: stat_tile in the sampled statistics, stat_lane_kernel for aqc_stat_reads);
-    *_st3 = stat_kernel = 3 (the filter kernel carries no statistics, stat_lane_kernel<POST> stats the sampled pairs from the records)"""
+    """warp = pair_kernel everywhere (one warp per pair, fused stat_read: aqc_params.filter_kernel = stat_kernel = 1);
+    lane = the engine's default path: lane_kernel (one lane per pair) + pair_kernel's list mode + stat_kernel (shared-memory
+    histograms; also aqc_stat_reads) for batches of short reads"""
     import emu
-    name, _, st2 = request.param.partition("_")
+    name = request.param
 
     def make(params):
-        params.filter_kernel = KERNELS[name]
-        params.stat_kernel = {"": _abi.STAT_DEFAULT, "st2": _abi.STAT_LANE, "st3": _abi.STAT_LANE_POST}[st2]
+        params.filter_kernel, params.stat_kernel = KERNELS[name]
         return oracle_lib.Oracle(params), emu.EmuEngine(params)
     make.kernel = name
-    make.stat2 = st2              # "", "st2" or "st3"
     return make
 
 
@@ -57,8 +54,6 @@ def test_emu_ops_parity(backends, bname, pname):
 def test_emu_filter_parity(backends, bname, pname):
     if bname not in ("adversarial", "pe150") and pname not in ("default_f0", "trim", "strict"):
         pytest.skip("reduced matrix on the emulator")
-    if backends.stat2 and (pname not in ("default_f0", "trim", "mask", "nocorr_mask") or (backends.kernel == "lane2" and bname not in ("adversarial", "pe250"))):
-        pytest.skip("reduced matrix for the stat_kernel = 2 variants (the filter part is the base kernel's)")
     batch = BATCHES[bname]()
     orc, eng = backends(cases.make_params(pname))
     a = orc.filter_pairs(batch)
@@ -69,18 +64,18 @@ def test_emu_filter_parity(backends, bname, pname):
 
 
 def test_emu_stat_parity(backends):
-    """aqc_stat_reads: pair_kernel<MODE_STAT> (warp) and stat_lane_kernel (lane_st2: stat_kernel = 2)"""
-    if not (backends.kernel == "warp" or (backends.kernel == "lane" and backends.stat2 == "st2")):
-        pytest.skip("the prefilter statistics entry does not depend on the filter kernel")
-    for bname, kmer in (("pe150_jitter", 8), ("pe150_jitter", 4), ("adversarial", 8), ("pe250", 8), ("long", 8), ("adversarial", 1)):
-        if not backends.stat2 and bname != "pe150_jitter":
-            continue
+    """aqc_stat_reads: pair_kernel<MODE_STAT> (warp) and stat_kernel (lane); reads > 256 bases take pair_kernel on both"""
+    for bname, kmer in (("pe150_jitter", 8), ("pe150_jitter", 4), ("adversarial", 8), ("pe250", 8), ("long", 8), ("adversarial", 1), ("pe150", 2)):
         batch = BATCHES[bname]()
         orc, eng = backends(_abi.Params.defaults(qc_kmer=kmer))
         lo, hi = batch.n // 10, batch.n - batch.n // 7
         for be in (orc, eng):
             be.stat_reads(batch, _abi.QC_R1_PRE, _abi.QC_R2_PRE, stat_lo=lo, stat_hi=hi, order_base=0)
         compare.compare_backends(orc, eng, (_abi.QC_R1_PRE, _abi.QC_R2_PRE), "emu stat %s k=%d" % (bname, kmer))
+        # a second call on top (the stamp bitmap of the second launch is built from the first one's stamps), one mate only
+        for be in (orc, eng):
+            be.stat_reads(batch, -1, _abi.QC_R2_PRE, stat_lo=0, stat_hi=lo, order_base=hi - lo)
+        compare.compare_backends(orc, eng, (_abi.QC_R1_PRE, _abi.QC_R2_PRE), "emu stat twice %s k=%d" % (bname, kmer))
         orc.close(); eng.close()
 
 
@@ -178,7 +173,7 @@ def test_emu_empty_mate_reaches_statread(backends):
     orc.close(); eng.close()
 
 
-@pytest.mark.parametrize("kernel", ["warp", "lane", "lane2", "lane_st2", "lane2_st3"])
+@pytest.mark.parametrize("kernel", ["warp", "lane"])
 @pytest.mark.parametrize("name", ["pe150_default", "pe150_err3_mask_overlap", "pe250_k5_strict", "se100_f0"])
 def test_emu_pipeline_matches_reference_golden(name, kernel, tmp_path):
     """the whole drop-in pipeline (readers, packed columns, engine calls, writers, JSON) on the emulated engine reproduces
@@ -189,8 +184,7 @@ def test_emu_pipeline_matches_reference_golden(name, kernel, tmp_path):
         pytest.skip("golden case %s not present" % name)
 
     def factory(p):
-        p.filter_kernel = KERNELS[kernel.partition("_")[0]]
-        p.stat_kernel = {"": _abi.STAT_DEFAULT, "st2": _abi.STAT_LANE, "st3": _abi.STAT_LANE_POST}[kernel.partition("_")[2]]
+        p.filter_kernel, p.stat_kernel = KERNELS[kernel]
         return emu.EmuEngine(p)
     problems = golden_util.run_case(name, tmp_path, factory)
     assert not problems, problems
@@ -251,47 +245,10 @@ def test_emu_host_path_many_chunks(backends, monkeypatch):
         orc.close(); eng.close()
 
 
-def test_emu_packed_base_transport(backends, monkeypatch):
-    """AQC_BATCH_PACK_BASES / AQC_BATCH_PACK_QUALS: host threads pack the base columns of every chunk to 2 bits per base and
-    the quality columns to 6 bits per byte, bytes outside the code range travel in an exception list, unpack_*_kernel /
-    apply_exceptions_kernel restore the byte columns; a column that is mostly exceptions falls back to bytes.  Identical results through aqc_filter_pairs and aqc_stat_reads, alone and with qual2 in place."""
-    if backends.stat2 or backends.kernel == "lane2":
-        pytest.skip("transport only: one lane-per-pair kernel and the warp kernel cover it")
-    from afterqc_b200.batch import PackedBatch
-    monkeypatch.setenv("AQC_CHUNK_PAIRS", "700")
-    if backends.kernel == "warp":
-        monkeypatch.setenv("AQC_PACK_SCALAR", "1")      # the portable packer; the other backend runs the AVX2 one where the CPU has it
-    odd = PackedBatch.from_reads([("N" * 100, "I" * 100)] * 50 + [("ACGT" * 25, "I" * 100)] * 50, [("acgtn" * 20, "I" * 100)] * 100)
-    hiq = cases.synthetic("pe150", 1500)                  # qualities outside '!'..'`' (Phred+33 above 63): exceptions of the 6-bit code
-    rng = np.random.default_rng(3)
-    for col in (hiq.qual1, hiq.qual2):
-        idx = rng.choice(col.size - 64, size=col.size // 50, replace=False)
-        col[idx] = rng.integers(97, 127, size=idx.size).astype(np.uint8)
-    hiq.qual1[100:400] = 126                                # and a solid run of them
-    for bname, batch in (("adversarial", cases.adversarial_batch()), ("pe150_jitter", cases.synthetic("pe150", 2000, len_jitter=60)),
-                         ("mostly_exceptions", odd), ("high_qualities", hiq), ("se100", cases.synthetic("se100", 2000))):
-        p = cases.make_params("default_f0", paired=batch.paired); p.qc_sample = 1500
-        orc, eng = backends(p)
-        a = orc.filter_pairs(batch)
-        n0 = eng.launch_count()
-        b = eng.filter_pairs(batch, pack_bases=True, pack_quals=True, qual2_in_place=(backends.kernel == "lane" and batch.paired))
-        if bname == "mostly_exceptions":       # bases fall back to bytes; the qualities ('I') still travel packed
-            assert eng.launch_count() - n0 <= 4, "the fall-back to bytes launches no unpack kernel for the base columns"
-        compare.assert_records_equal(batch, a, b, "emu pack %s" % bname)
-        slots = (_abi.QC_R1_POST, _abi.QC_R2_POST) if batch.paired else (_abi.QC_R1_POST,)
-        compare.compare_backends(orc, eng, slots, "emu pack %s" % bname)
-        for be, kw in ((orc, {}), (eng, {"pack_bases": True, "pack_quals": bname != "se100"})):
-            be.stat_reads(batch, _abi.QC_R1_PRE, _abi.QC_R2_PRE if batch.paired else -1, stat_lo=10, stat_hi=batch.n - 3, order_base=0, **kw)
-        compare.compare_backends(orc, eng, (_abi.QC_R1_PRE, _abi.QC_R2_PRE) if batch.paired else (_abi.QC_R1_PRE,), "emu pack stat %s" % bname)
-        orc.close(); eng.close()
-
-
 def test_emu_host_path_with_length_hint(backends, monkeypatch):
     """aqc_batch.flags bits 0-15 (the longest read of the batch) on a host batch: the engine takes the hint instead of scanning
     the offsets of every chunk; same results"""
     import ctypes as C
-    if backends.stat2:
-        pytest.skip("independent of the statistics kernel")
     monkeypatch.setenv("AQC_CHUNK_PAIRS", "500")
     batch = cases.synthetic("pe150", 1800, len_jitter=40)
     orc, eng = backends(cases.make_params("default_f0"))

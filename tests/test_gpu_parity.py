@@ -9,12 +9,17 @@ from afterqc_b200 import _abi
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def backends(oracle_lib):
+@pytest.fixture(scope="module", params=["default", "warp"])
+def backends(oracle_lib, request):
+    """default = the engine as shipped (lane_kernel + pair_kernel's list mode + stat_kernel for batches of short reads);
+    warp = aqc_params.filter_kernel = stat_kernel = 1: pair_kernel with the fused stat_read everywhere"""
     from afterqc_b200.engine import Engine
 
     def make(params):
+        if request.param == "warp":
+            params.filter_kernel, params.stat_kernel = _abi.KERNEL_WARP, _abi.STAT_WARP
         return oracle_lib.Oracle(params), Engine(params)
+    make.kernel = request.param
     return make
 
 
@@ -31,6 +36,8 @@ BATCHES = {
 @pytest.mark.parametrize("bname", list(BATCHES))
 @pytest.mark.parametrize("pname", ["default_f0", "trim", "strict", "poly_wide"])
 def test_ops_parity(backends, bname, pname):
+    if backends.kernel == "warp":
+        pytest.skip("the operator entry always runs pair_kernel")
     batch = BATCHES[bname]()
     orc, eng = backends(cases.make_params(pname))
     a = orc.ops_pairs(batch)

@@ -1,15 +1,13 @@
 """TEST INFRASTRUCTURE: bench.py's `run_ours` on a machine without a GPU.
 
-torch.cuda is stubbed (streams, events, pinned memory -> plain host memory), the engine is the SIMT-emulated library
-(tests/emu) and the child-process kernel checks run tests/lane_gpu_check.py in-process.  Nothing here measures anything:
-the emulator has no clock, so the child checks are given made-up kernel times.  What it checks is the CONTROL FLOW of
-the benchmark -- kernel auto-selection, the fall-backs when a candidate fails, the resident and host-buffer steps, the
-identity checks between them and the one JSON line -- which otherwise only runs on the GPU box at round end.
+torch.cuda is stubbed (streams, events, pinned memory -> plain host memory) and the engine is the SIMT-emulated library
+(tests/emu).  Nothing here measures anything: the emulator has no clock, so the engine's event times are made up.  What it
+checks is the CONTROL FLOW of the benchmark -- every --config, the resident and host-buffer steps (autoTrim between the two
+engine calls of the full pipeline), the identity check between them, the roofline bookkeeping and the one JSON line --
+which otherwise only runs on the GPU box at round end.
 
-  python tools/bench_on_emulator.py [--fail lane,lane2,lane_st2,...] [bench.py options]
+  python tools/bench_on_emulator.py [bench.py options]
 prints the JSON line bench.py would print.  Used by tests/test_bench_flow_emu.py."""
-import contextlib
-import io
 import json
 import os
 import sys
@@ -21,7 +19,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
-def run(argv, fail=()):
+def run(argv):
     import torch
     import emu
     import afterqc_b200.engine as E
@@ -35,7 +33,8 @@ def run(argv, fail=()):
                 e = emu.EmuEngine(p)
             finally:
                 E.Engine = Shim
-            e.last_kernel_ms = lambda: 1.0
+            e.last_kernel_ms = lambda: 3.0
+            e.last_phase_ms = lambda ph: 3.0 if ph < 0 else 1.0
             return e
 
     class Stream:
@@ -71,29 +70,7 @@ def run(argv, fail=()):
         torch.empty = empty
         synth.generate_device = lambda name, n, device="cuda", **kw: real_gen(name, n, device="cpu", **kw)
         import bench
-        import lane_gpu_check
-
-        def child(local_rank, pairs, timeout_s=300, candidates="lane"):
-            names = [c for c in candidates.split(",") if c]
-            out = {c: {"ok": False, "why": "made to fail by the harness"} for c in names}
-            run = [c for c in names if c not in fail]
-            if run:
-                buf = io.StringIO()
-                with contextlib.redirect_stdout(buf):
-                    lane_gpu_check.full(pairs, ",".join(run))
-                for ln in buf.getvalue().splitlines():
-                    if ln.startswith("{"):
-                        j = json.loads(ln)
-                        j["ok"] = bool(j.get("identical"))
-                        out[j["candidate"]] = j
-            for c in run:       # no clock under the emulator: made-up times with lane < lane2 < warp, tile statistics faster than stat_read
-                out[c].update({"warp_ms": 3.0, "lane_ms": 2.0 if c.startswith("lane2") else (1.0 if c.startswith("lane") else 3.0),
-                               "stat_warp_ms": 1.0, "stat_ms": 0.5})
-                if c.endswith("_st3"):
-                    out[c]["lane_ms"] -= 0.1       # ... and the filter kernel without statistics code a little faster still
-            return out
-        saved["child"], saved["emit"] = bench.lane_child_check, bench.emit_json
-        bench.lane_child_check = child
+        saved["emit"] = bench.emit_json
         out = []
         bench.emit_json = out.append
         old_argv = sys.argv
@@ -107,7 +84,7 @@ def run(argv, fail=()):
             bench.run_ours(args)
         finally:
             torch.device = real_device
-            bench.lane_child_check, bench.emit_json = saved["child"], saved["emit"]
+            bench.emit_json = saved["emit"]
         return out[0] if out else None
     finally:
         E.Engine = saved["Engine"]
@@ -119,11 +96,6 @@ def run(argv, fail=()):
 
 if __name__ == "__main__":
     av = sys.argv[1:]
-    fail = ()
-    if "--fail" in av:
-        i = av.index("--fail")
-        fail = tuple(av[i + 1].split(","))
-        del av[i:i + 2]
     if not any(a == "--pairs" for a in av):
         av = ["--pairs", "3000", "--qc-sample", "1500", "--steps", "2", "--warmup", "1", "--cpu-sample", "2000"] + av
-    print(json.dumps(run(av, fail)))
+    print(json.dumps(run(av)))

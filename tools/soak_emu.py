@@ -3,7 +3,7 @@
 
 Random pairs (lengths 0..256 or up to 600, overlaps, adapters, N runs, foreign bytes, homopolymers, low-quality stretches,
 power-of-two lengths, qualities outside the 6-bit transport range) x random parameter sets x every filter kernel x every statistics
-kernel, with the packed transport (AQC_BATCH_PACK_BASES / _QUALS) and the in-place qual2 column switched on at random.  Test
+kernel path, with the in-place qual2 column switched on at random.  Test
 infrastructure; needs no GPU.
 
     python tools/soak_emu.py --cases 200 --seed 1
@@ -34,7 +34,7 @@ def rand_qual(rng, n, style):
         return "".join(rng.choice("#$%5?ACEFGHI") for _ in range(n))
     if style == 2:
         return "".join(rng.choice("#I") for _ in range(n))
-    if style == 4:        # qualities above Phred 63 and below '!': exceptions of the 6-bit transport code (AQC_BATCH_PACK_QUALS)
+    if style == 4:        # qualities above Phred 63 and below '!': odd bytes in the quality columns
         return "".join(rng.choice("I5~}a{ \"") if rng.random() < 0.3 else "F" for _ in range(n))
     return rng.choice("#/05I") * n
 
@@ -103,8 +103,8 @@ def one_case(rng, k):
     batch = PackedBatch.from_reads([p[0] for p in pairs], [p[1] for p in pairs] if paired else None, first_index=rng.choice([0, 0, 17, 199990]))
     p = rand_params(rng, paired)
     results = {}
-    # (filter kernel, statistics kernel): the lane-per-read statistics (stat_kernel = 2) ride on every filter kernel
-    for kern, sk in ((_abi.KERNEL_WARP, 0), (_abi.KERNEL_LANE, 0), (_abi.KERNEL_LANE2, 0), (_abi.KERNEL_WARP, 2), (_abi.KERNEL_LANE, 2), (_abi.KERNEL_LANE2, 2), (_abi.KERNEL_LANE, 3), (_abi.KERNEL_LANE2, 3)):
+    # (filter kernel, statistics kernel): the round-1 path, the shipped default, and the two mixed forms
+    for kern, sk in ((_abi.KERNEL_WARP, _abi.STAT_WARP), (_abi.KERNEL_DEFAULT, _abi.STAT_DEFAULT), (_abi.KERNEL_WARP, _abi.STAT_DEFAULT), (_abi.KERNEL_LANE, _abi.STAT_WARP)):
         p.filter_kernel = kern
         p.stat_kernel = sk
         orc, eng = oracle.Oracle(p), emu.EmuEngine(p)
@@ -115,7 +115,7 @@ def one_case(rng, k):
             except Exception as e:      # noqa: BLE001
                 err_o = getattr(e, "code", repr(e))
             try:
-                b = eng.filter_pairs(batch, qual2_in_place=rng.random() < 0.5, pack_bases=rng.random() < 0.5, pack_quals=rng.random() < 0.5)
+                b = eng.filter_pairs(batch, qual2_in_place=rng.random() < 0.5)
                 cb = eng.counters()
             except Exception as e:      # noqa: BLE001
                 err_e = getattr(e, "code", repr(e))
@@ -128,7 +128,7 @@ def one_case(rng, k):
             slots = (_abi.QC_R1_POST, _abi.QC_R2_POST) if paired else (_abi.QC_R1_POST,)
             compare.compare_backends(orc, eng, slots, what)
             results[(kern, sk)] = "ok"
-            if kern == _abi.KERNEL_WARP:        # the operator and prefilter-statistics entries (pair_kernel; stat_lane_kernel with stat_kernel = 2)
+            if kern == _abi.KERNEL_WARP:        # the operator and prefilter-statistics entries (pair_kernel; stat_kernel with stat_kernel = 0)
                 compare.assert_records_equal(batch, orc.ops_pairs(batch), eng.ops_pairs(batch), what + " ops")
                 lo = batch.first_index + rng.randint(0, max(0, batch.n - 1)); hi = lo + rng.randint(0, batch.n)
                 errs = []
