@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get("AQC_LIB_PATH") or os.path.join(_HERE, "libafterqc_b20
 
 # every symbol include/afterqc_b200.h declares
 SYMBOLS = [
-    "aqc_abi_version", "aqc_create", "aqc_destroy", "aqc_set_params", "aqc_reset", "aqc_reset_filter",
+    "aqc_abi_version", "aqc_device_count", "aqc_create", "aqc_destroy", "aqc_set_params", "aqc_reset", "aqc_reset_filter",
     "aqc_last_error", "aqc_host_alloc", "aqc_host_free", "aqc_device_alloc", "aqc_device_free",
     "aqc_memcpy_h2d", "aqc_memcpy_d2h", "aqc_stat_reads", "aqc_filter_pairs", "aqc_ops_pairs", "aqc_sync",
     "aqc_get_counters", "aqc_add_counters", "aqc_get_qc", "aqc_get_kmer_dense", "aqc_get_kmer_side", "aqc_get_kmer_side_raw", "aqc_last_phase_ms",
@@ -42,6 +42,7 @@ def bind(L):
     PB, PP = C.POINTER(_abi.Batch), C.POINTER(_abi.Params)
     sig = {
         "aqc_abi_version": (i32, []),
+        "aqc_device_count": (i32, []),
         "aqc_create": (i32, [i32, PP, C.POINTER(vp)]),
         "aqc_destroy": (None, [vp]),
         "aqc_set_params": (i32, [vp, PP]),

@@ -103,7 +103,24 @@ def processOptions(options):
     if gpus > 1:
         from .multigpu import run_sharded
         return run_sharded(options, gpus)
-    seqFilter(options).run()
+    device = getattr(options, "device", -1)
+    if device is None or device < 0:
+        return seqFilter(options).run()
+    from .engine import Engine
+    seqFilter(options, backend_factory=lambda p: Engine(p, device=device)).run()
+
+
+def device_count():
+    """CUDA devices visible to the jobs (0 when the library or the driver is missing).  Asked in a child process: the jobs are
+    forked (after.py:168-171) and CUDA must not have been initialised in the parent before a fork."""
+    import subprocess
+    code = "from afterqc_b200 import _native; print(_native.lib().aqc_device_count())"
+    try:
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        return max(0, int(r.stdout.strip().splitlines()[-1]))
+    except Exception:       # noqa: BLE001
+        return 0
 
 
 def processDir(folder, options):
@@ -136,11 +153,22 @@ def processDir(folder, options):
         print("no read files to run with, do you call the program correctly?")
         print("see -h for help")
         return
+    if (getattr(options, "gpus", 1) or 1) > 1:
+        # every job is sharded over the box's GPUs by itself: one after the other, not all at once
+        for o in jobs:
+            processOptions(o)
+        return
+    # the reference starts one process per R1 file (after.py:168-171); here job i runs on GPU i mod (GPUs of the box)
+    ngpu = device_count()
+    for i, o in enumerate(jobs):
+        o.device = (i % ngpu) if ngpu > 0 else -1
     procs = [Process(target=processOptions, args=(o,)) for o in jobs]
     for p in procs:
         p.start()
     for p in procs:
         p.join()
+    if any(p.exitcode != 0 for p in procs):
+        raise RuntimeError("a directory-mode job failed")
 
 
 def main(argv=None):

@@ -339,7 +339,7 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         if (hi <= lo) return 0;
         const int snw = lane_words_for(maxl);
         const void *sk = stat_kernel_for(pe, snw, post);
-        const size_t ssmem = stat_smem_bytes(ctx->p.qc_kmer, snw, STAT_WARPS);
+        const size_t ssmem = stat_smem_bytes(ctx->p.qc_kmer, snw);
         if (ssmem > ctx->max_dyn_smem) return fail(ctx, AQC_ERR_INVALID, "statistics tables do not fit shared memory");
         const bool both = pe && K0.qc[0].valid && K0.qc[1].valid;
         const uint32_t n_dense = 1u << (2 * ctx->p.qc_kmer), bw = stat_kbit_words(ctx->p.qc_kmer);
@@ -621,6 +621,12 @@ int check_batch(aqc_ctx *ctx, const aqc_batch *b, int mem) {
 extern "C" {
 
 int aqc_abi_version(void) { return AQC_ABI_VERSION; }
+
+int aqc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 const char *aqc_last_error(const aqc_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
 

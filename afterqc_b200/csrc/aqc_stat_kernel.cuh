@@ -1,21 +1,27 @@
 // aqc_stat_kernel.cuh -- QualityControl.statRead (qualitycontrol.py:73-122) for batches whose reads are <= 256 bases.
 //
-// One WARP per read, lane = cycle (position), one CTA of 32 warps per SM, and EVERY histogram of statRead lives in that
-// CTA's shared memory until the kernel ends:
-//   * the dense k-mer table (4^k counters, k <= 8) is 128 KB of packed 16-bit counters.  Measured on a B200
-//     (tools/ubench_atomics.cu, profiles/r02_ubench_atomics.jsonl): a random increment costs 1/161 ns as a global
-//     reduction (REDG, bound by the L2 atomic units whatever the grid), 1/3200 ns as a shared-memory atomic and 1/1400 ns
-//     as a shared-memory atomic whose old value is inspected -- the k-mer loop, 142 increments per 150-base read, is what
-//     bounded stat_read (aqc_device.cuh) at ~110 G k-mers/s.  A 16-bit half never overflows: the lane whose increment
-//     takes a half from 0x3FFF to 0x4000 (exactly one lane sees that old value) moves 0x4000 counts to the 64-bit global
-//     table; a half would have to collect another 49 151 increments before that lane's next instruction to be damaged.
-//   * per-cycle counts and quality sums, discontinuity and the GC histogram: 32-bit shared-memory atomics, lane = cycle,
-//     so a warp instruction touches 32 consecutive words (no bank conflicts, no per-read flush: 32 bits hold any launch).
+// One LANE per read, one CTA of 32 warps per SM, and EVERY histogram of statRead lives in that CTA's shared memory until
+// the kernel ends.  A warp takes 32 consecutive records of one mate; each lane streams its own read from HBM in aligned
+// 16-byte pieces (bases and qualities) and walks it byte by byte with a few registers of rolling state:
+//   * per-cycle counts and quality sums (:76-96): two shared-memory atomics per base into [class][cycle] tables; lanes sit
+//     at different cycles (every lane starts at its own 16-byte boundary) and the class stride is odd, so the 32 lanes of
+//     an instruction spread over the banks;
+//   * discontinuity (:97-108): a 4-bit history of "differs from the previous base"; cycle p-2 is settled when base p
+//     arrives, the clamped windows at both ends reuse the first / last complete window;
+//   * k-mers (:113-122): the dense index (two K-bit plane windows) and the number of consecutive A,C,G,T bases are rolling
+//     registers; a complete k-mer is one shared-memory atomic on a packed 16-bit counter of the CTA's 4^k table (128 KB for
+//     k = 8).  Measured on a B200 (tools/ubench_atomics.cu, profiles/r02_ubench_atomics.jsonl): a random increment costs
+//     1/161 ns as a global reduction (REDG, bound by the L2 atomic units whatever the grid), 1/3200 ns as a shared-memory
+//     atomic and 1/1400 ns as a shared-memory atomic whose old value is inspected.  A 16-bit half never overflows: the lane
+//     whose increment takes a half from 0x3FFF to 0x4000 (exactly one lane sees that old value) moves 0x4000 counts to the
+//     64-bit global table; a half would need another 49 151 increments before that lane's next instruction to be damaged;
 //   * first-seen stamps (quirk Q12: ties of sortKmer resolve by insertion order): the engine hands the kernel a bitmap
 //     "k-mer already stamped by an earlier, lower-ordered launch" (stamp_bits_kernel); it is copied to shared memory, a
 //     set bit costs one shared load, and only k-mers without it take the global path (load, rare atomicMin).  The engine
-//     splits a large launch into a short head and the rest, so that the rest runs with a nearly full bitmap.
-//   * k-mers with a byte outside A,C,G,T take stat_read's side-table path unchanged.
+//     splits a large launch into a short head and the rest, so that the rest runs with a nearly full bitmap;
+//   * k-mers with a byte outside A,C,G,T take stat_read's side-table path (the last eight raw bytes are a rolling register).
+// The first form of this kernel gave a warp to one read (lane = cycle, ballots for the k-mer planes): 1050 warp-instructions
+// per 150-base read, ~0.5 G reads/s (profiles/r02_v1_stat_kernel_ncu_full.txt).  Lane-per-read needs no cross-lane work at all.
 // Two entry forms: the prefilter window of raw reads (aqc_stat_reads; statFile, qualitycontrol.py:331-357) and, POST,
 // the sampled GOOD pairs of a filter launch taken from their 32-byte records (final slices + the correction walk's
 // edits; preprocesser.py:624-627) -- the lane-per-pair filter kernel itself carries no statistics code.
@@ -48,12 +54,45 @@ __global__ void stamp_bits_kernel(const unsigned long long *first0, const unsign
     }
 }
 
-// dynamic shared memory of one CTA (MAXB = 32*NW):
-//   ktab [stat_ktab_words] u32 | kbits [stat_kbit_words] u32 | cnt [5][MAXB] | qsum [5][MAXB] | disc [MAXB] | gch [MAXB+1 .. pad 4]
-//   | luts (768 B) | scratch [nwarps][MAXB] bytes (reads that hold a k-mer with a foreign byte)
-__host__ __device__ __forceinline__ size_t stat_smem_bytes(int K, int nw, int nwarps) {
+// dynamic shared memory of one CTA (MAXB = 32*NW, class stride CS = MAXB + 1):
+//   ktab [stat_ktab_words] u32 | kbits [stat_kbit_words] u32 | cnt [5][CS] | qsum [5][CS] | disc [MAXB] | gch [MAXB + 1] | pad
+__host__ __device__ __forceinline__ size_t stat_smem_bytes(int K, int nw) {
     const size_t maxb = 32 * (size_t)nw;
-    return ((size_t)stat_ktab_words(K) + stat_kbit_words(K) + 2 * QC_CLASSES * maxb + maxb + maxb + 4) * 4 + 768 + (size_t)nwarps * maxb;
+    return ((size_t)stat_ktab_words(K) + stat_kbit_words(K) + 2 * QC_CLASSES * (maxb + 1) + maxb + maxb + 1 + 5) * 4;
+}
+
+// COMP (util.py:27) and "byte outside COMP" without tables: the side-table path is rare, the bytes few
+__device__ __forceinline__ uint32_t comp_byte(uint32_t b) {
+    switch (b) {
+        case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C';
+        case 'a': return 't'; case 't': return 'a'; case 'c': return 'g'; case 'g': return 'c';
+        case 'N': return 'N'; case '\n': return '\n';
+        default: return 'N';
+    }
+}
+__device__ __forceinline__ bool outside_comp(uint32_t b) {
+    return !(b == 'A' || b == 'T' || b == 'C' || b == 'G' || b == 'a' || b == 't' || b == 'c' || b == 'g' || b == 'N' || b == '\n');
+}
+
+// A k-mer that holds a byte outside A,C,G,T: count + first direct sighting in the side table, and the seeding of its reverse
+// complement when it holds a byte outside util.COMP (see the comment above stat_read, aqc_device.cuh).  key = the K raw bytes,
+// first base most significant.  One out-of-line copy: the path is rare and would otherwise be inlined at every base of the
+// unrolled walk (instruction cache).
+__device__ __noinline__ void side_kmer(const QcDev &qd, unsigned long long key, unsigned long long when, int K, int *error_flag) {
+    unsigned long long rkey = 0;
+    bool foreign = false;
+    for (int j = 0; j < K; j++) {
+        const uint32_t bj = (uint32_t)(key >> (8 * (K - 1 - j))) & 0xFFu;
+        rkey |= (unsigned long long)comp_byte(bj) << (8 * j);
+        foreign |= outside_comp(bj);
+    }
+    if (key == AQC_KMER_NEVER || rkey == AQC_KMER_NEVER) { atomicExch(error_flag, AQC_ERR_INVALID); return; }
+    const int h = side_slot(qd, key);
+    const int hr = side_slot(qd, rkey);
+    if (h < 0 || hr < 0) { atomicExch(error_flag, AQC_ERR_KMER_TABLE_FULL); return; }
+    atomicAdd(&qd.scnt[h], 1ULL);
+    first_min(&qd.sfirst[h], when);
+    if (foreign) first_min(&qd.sseed[hr], when | 1ULL);
 }
 
 template <bool PAIRED, int NW, bool POST>
@@ -61,6 +100,7 @@ __global__ void __launch_bounds__(STAT_WARPS * 32, 1) stat_kernel(const __grid_c
     const KArgs &A = S.k;
     AQC_DYN_SMEM(smem_raw);
     constexpr int MAXB = 32 * NW;
+    constexpr int CS = MAXB + 1;                             // odd class stride: the five classes of a cycle sit in five banks
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = blockDim.x >> 5;
     const int K = A.p.qc_kmer;
@@ -69,205 +109,220 @@ __global__ void __launch_bounds__(STAT_WARPS * 32, 1) stat_kernel(const __grid_c
     uint32_t *ktab = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *kbits = ktab + TW;
     uint32_t *s_cnt = kbits + BW;
-    uint32_t *s_qs = s_cnt + QC_CLASSES * MAXB;
-    uint32_t *s_disc = s_qs + QC_CLASSES * MAXB;
+    uint32_t *s_qs = s_cnt + QC_CLASSES * CS;
+    uint32_t *s_disc = s_qs + QC_CLASSES * CS;
     uint32_t *s_gch = s_disc + MAXB;
-    uint8_t *lutbase = reinterpret_cast<uint8_t *>(s_gch + MAXB + 4);
-    const uint8_t *lut1 = lutbase, *lut2 = lutbase + 256, *lut3 = lutbase + 512;
-    uint8_t *scratch = lutbase + 768 + (size_t)warp * MAXB;
 
     // which mate this CTA works on: both mates wanted -> even CTAs mate 1, odd CTAs mate 2 (the host launches an even grid)
     const bool both = PAIRED && A.qc[0].valid && A.qc[1].valid;
     const int mate = both ? (int)(blockIdx.x & 1u) : ((PAIRED && !A.qc[0].valid) ? 1 : 0);
     const uint32_t cta = both ? blockIdx.x >> 1 : blockIdx.x, nctas = both ? gridDim.x >> 1 : gridDim.x;
     const QcDev &qd = A.qc[mate];
-    if (!qd.valid) return;                                   // uniform for the CTA: nothing to do (single-end launch of mate 2, ...)
+    if (!qd.valid) return;                                   // uniform for the CTA: nothing to do
 
     for (uint32_t i = tid; i < TW; i += blockDim.x) ktab[i] = 0;
     {
         const uint32_t *gb = S.kbits[mate];
         for (uint32_t i = tid; i < BW; i += blockDim.x) kbits[i] = gb ? gb[i] : 0u;
     }
-    for (int i = tid; i < 2 * QC_CLASSES * MAXB + 2 * MAXB + 4; i += blockDim.x) s_cnt[i] = 0;
-    for (int i = tid; i < 768; i += blockDim.x) lutbase[i] = reinterpret_cast<const uint8_t *>(A.luts)[i];
+    for (int i = tid; i < 2 * QC_CLASSES * CS + 2 * MAXB + 1; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
 
     const uint8_t *seq = mate ? A.seq2 : A.seq1, *qual = mate ? A.qual2 : A.qual1;
     const uint32_t *off = mate ? A.off2 : A.off1;
     const uint32_t km = (1u << K) - 1u;                      // K <= AQC_MAX_KMER (8)
-    unsigned long long n_kmers = 0, n_reads = 0;             // warp-uniform, added to the QC object at the end
+    const uint32_t ktop = 1u << (K - 1);
+    const unsigned long long keymask = K >= 8 ? ~0ULL : ((1ULL << (8 * K)) - 1ULL);
+    unsigned long long n_kmers = 0, n_reads = 0;             // per lane, reduced at the end
     unsigned long long *const kfirst = qd.kfirst, *const kcnt = qd.kcnt;
 
+    const uint32_t tiles = (S.hi - S.lo + 31u) >> 5;
     const uint32_t stride = nctas * (uint32_t)nwarps;
 #pragma unroll 1
-    for (uint32_t p = S.lo + cta * (uint32_t)nwarps + (uint32_t)warp; p < S.hi; p += stride) {
+    for (uint32_t t = cta * (uint32_t)nwarps + (uint32_t)warp; t < tiles; t += stride) {
+        const uint32_t p = S.lo + t * 32u + (uint32_t)lane;
         const uint64_t gidx = A.first_index + p;
-        uint32_t a = off[p];
-        int len = (int)(off[p + 1] - a);
-        uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+        bool want = p < S.hi;
+        uint32_t a = 0;
+        int len = 0;
+        uint32_t e0 = 0, e1 = 0, e2 = 0;
         int n_edits = 0, start1 = 0, start2 = 0;
-        uint64_t order;
+        uint64_t order = 0;
+        if (want) {
+            a = off[p];
+            len = (int)(off[p + 1] - a);
+            if constexpr (POST) {
+                want = A.p.qc_sample <= 0 || gidx + 1 < (uint64_t)A.p.qc_sample;                  // preprocesser.py:624 (quirk Q10)
+                if (want) {
+                    const uint4 *r = reinterpret_cast<const uint4 *>(A.results + p);
+                    const uint4 w0 = r[0];
+                    want = (w0.x & 0xFFu) == (uint32_t)AQC_GOOD;
+                    n_edits = (int)((w0.x >> 8) & 0xFFu);
+                    start1 = (int)(w0.x >> 16); start2 = (int)(w0.y >> 16);
+                    a += (uint32_t)(mate ? start2 : start1);                                       // the final slice: trim + adapter cut
+                    len = (int)((mate ? w0.z : w0.y) & 0xFFFFu);
+                    if (want && n_edits) { const uint4 w1 = r[1]; e0 = w1.x; e1 = w1.y; e2 = w1.z; }
+                }
+                order = gidx;
+            } else {
+                want = gidx >= A.stat_lo && gidx < A.stat_hi;
+                order = A.order_base + (gidx - A.stat_lo);
+            }
+        }
+        if (want) {
+            if (len <= 0) {          // an empty read runs no loop of statRead but is still counted: gcHistogram[0] += 1 (:112)
+                atomicAdd(&s_gch[0], 1u);
+                n_reads++;
+                want = false;
+            } else if (len < 5) { atomicExch(A.error_flag, AQC_ERR_TOO_SHORT_STAT); want = false; }  // reference: IndexError (:97-108)
+            else if (len > MAXB) { atomicExch(A.error_flag, AQC_ERR_TOO_LONG); want = false; }      // the host picks NW; defensive
+        }
+        if (!want) len = 0;
+        // the edits of the correction walk that touch this mate (preprocesser.py:575-592): position in the read, new base (0 =
+        // unchanged), new quality.  The walk visits at most three mismatches (distance <= 3).
+        int ep[3] = {-1, -1, -1};
+        uint32_t eb[3] = {0, 0, 0}, eq[3] = {0, 0, 0};
         if constexpr (POST) {
-            if (!(A.p.qc_sample <= 0 || gidx + 1 < (uint64_t)A.p.qc_sample)) continue;       // preprocesser.py:624 (quirk Q10)
-            const uint4 *r = reinterpret_cast<const uint4 *>(A.results + p);
-            const uint4 w0 = r[0];
-            if ((w0.x & 0xFFu) != (uint32_t)AQC_GOOD) continue;
-            n_edits = (int)((w0.x >> 8) & 0xFFu);
-            start1 = (int)(w0.x >> 16); start2 = (int)(w0.y >> 16);
-            a += (uint32_t)(mate ? start2 : start1);                                          // the final slice: trim + adapter cut
-            len = (int)((mate ? w0.z : w0.y) & 0xFFFFu);
-            if (n_edits) { const uint4 w1 = r[1]; e0 = w1.x; e1 = w1.y; e2 = w1.z; e3 = w1.w; }
-            order = gidx;
-        } else {
-            if (gidx < A.stat_lo || gidx >= A.stat_hi) continue;
-            order = A.order_base + (gidx - A.stat_lo);
-        }
-        if (len <= 0) {          // an empty read runs no loop of statRead but is still counted: gcHistogram[0] += 1 (:112)
-            if (lane == 0) atomicAdd(&s_gch[0], 1u);
-            n_reads++;
-            continue;
-        }
-        if (len < 5) { if (lane == 0) atomicExch(A.error_flag, AQC_ERR_TOO_SHORT_STAT); continue; }     // reference: IndexError (:97-108)
-        if (len > MAXB) { if (lane == 0) atomicExch(A.error_flag, AQC_ERR_TOO_LONG); continue; }        // the host picks NW; defensive
-        const int chunks = (len + 31) >> 5;
-        const int nk = len - K;                              // k-mers start at i < len - K (quirk Q11)
-
-        // ---- the read's bytes: lane l of chunk w holds cycle 32w + l ----
-        uint32_t b[NW], q[NW];
-        {
-            const uint8_t *s = seq + a, *qp = qual + a;
 #pragma unroll
-            for (int w = 0; w < NW; w++) {
-                const int pos = 32 * w + lane;
-                b[w] = 0; q[w] = 0;
-                if (pos < len) { b[w] = s[pos]; q[w] = qp[pos]; }
-            }
-        }
-        if constexpr (POST) {
-            if (n_edits) {                                   // bytes rewritten by the correction walk (preprocesser.py:575-592)
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (k < n_edits) {
-                        const uint32_t e = k == 0 ? e0 : (k == 1 ? e1 : (k == 2 ? e2 : e3));
-                        const int kind = (int)AQC_EDIT_KIND(e);
-                        int pos = -1;
-                        uint32_t nb = 0, nq = 0;
-                        if (kind == 0 && mate == 0) { pos = (int)AQC_EDIT_POS(e) - start1; nb = AQC_EDIT_BASE(e); nq = AQC_EDIT_QUAL(e); }
-                        else if (kind == 1 && mate == 1) { pos = (int)AQC_EDIT_POS(e) - start2; nb = AQC_EDIT_BASE(e); nq = AQC_EDIT_QUAL(e); }
-                        else if (kind == 2) { pos = mate == 0 ? (int)AQC_EDIT_POS(e) - start1 : (int)AQC_EDIT_POS2(e) - start2; nq = '!'; }
-                        if (pos >= 0 && pos < len && (pos & 31) == lane) {
-#pragma unroll
-                            for (int w = 0; w < NW; w++)
-                                if ((pos >> 5) == w) { if (kind != 2) b[w] = nb; q[w] = nq; }
-                        }
-                    }
+            for (int k = 0; k < 3; k++) {
+                if (k < n_edits && want) {
+                    const uint32_t e = k == 0 ? e0 : (k == 1 ? e1 : e2);
+                    const int kind = (int)AQC_EDIT_KIND(e);
+                    if (kind == 0 && mate == 0) { ep[k] = (int)AQC_EDIT_POS(e) - start1; eb[k] = AQC_EDIT_BASE(e); eq[k] = AQC_EDIT_QUAL(e); }
+                    else if (kind == 1 && mate == 1) { ep[k] = (int)AQC_EDIT_POS(e) - start2; eb[k] = AQC_EDIT_BASE(e); eq[k] = AQC_EDIT_QUAL(e); }
+                    else if (kind == 2) { ep[k] = mate == 0 ? (int)AQC_EDIT_POS(e) - start1 : (int)AQC_EDIT_POS2(e) - start2; eq[k] = '!'; }
                 }
             }
         }
 
-        // ---- per-cycle counters (:76-96), G/C count (:93-94), plane ballots for the k-mers, "differs from the next base" ----
-        uint32_t k0[NW + 1], k1[NW + 1], kv[NW + 1], nq[NW + 1];
-        int gc = 0;
-        bool foreign_kmer = false;
-#pragma unroll
-        for (int w = 0; w < NW; w++) {
-            k0[w] = k1[w] = kv[w] = nq[w] = 0;
-            if (w < chunks) {                                // warp-uniform
-                const int pos = 32 * w + lane;
-                const bool valid = pos < len;
-                const uint32_t l2 = valid ? lut2[b[w]] : 4u;
-                if (valid) {
-                    const uint32_t cls = l2 & 7u;
-                    atomicAdd(&s_cnt[cls * MAXB + pos], 1u);
-                    atomicAdd(&s_qs[cls * MAXB + pos], q[w]);
-                }
-                gc += __popc(__ballot_sync(FULL, valid && (l2 & 8u)));
-                k0[w] = __ballot_sync(FULL, valid && (l2 & 0x10u));
-                k1[w] = __ballot_sync(FULL, valid && (l2 & 0x20u));
-                kv[w] = __ballot_sync(FULL, valid && (l2 & 0x40u));
-                if (kv[w] != lowmask(len - 32 * w)) foreign_kmer = true;
-                uint32_t nx = __shfl_down_sync(FULL, b[w], 1);
-                const uint32_t first_of_next = __shfl_sync(FULL, b[w + 1 < NW ? w + 1 : w], 0);
-                if (lane == 31) nx = (w + 1 < NW) ? first_of_next : 0u;
-                nq[w] = __ballot_sync(FULL, pos + 1 < len && b[w] != nx);
-            }
-        }
-        k0[NW] = k1[NW] = kv[NW] = nq[NW] = 0;
-
-        // ---- discontinuity (:97-108): unequal neighbours inside the 5-base window around the cycle, clamped at both ends ----
-#pragma unroll
-        for (int w = 0; w < NW; w++) {
-            if (w < chunks) {
-                const int pos = 32 * w + lane;
-                if (pos < len) {
-                    int left = pos - 2;
-                    if (left < 0) left = 0;
-                    else if (pos + 3 >= len) left = len - 5;
-                    const bool prev = (left >> 5) < w;       // the window starts in chunk w-1 (never earlier) or in chunk w
-                    const uint32_t lo_w = prev ? nq[w > 0 ? w - 1 : 0] : nq[w];
-                    const uint32_t hi_w = prev ? nq[w] : nq[w + 1];
-                    const uint32_t d = (uint32_t)__popc(__funnelshift_r(lo_w, hi_w, (uint32_t)left & 31u) & 0xFu);
-                    if (d) atomicAdd(&s_disc[pos], d);
-                }
-            }
-        }
-
-        // ---- k-mers (:113-122): the K-bit windows of the plane ballots are the dense table index ----
-        if (__builtin_expect(foreign_kmer, 0)) {             // warp-uniform: the side-table path reads the bytes of the k-mer
-            __syncwarp();
-#pragma unroll
-            for (int w = 0; w < NW; w++) { const int pos = 32 * w + lane; if (pos < len) scratch[pos] = (uint8_t)b[w]; }
-            __syncwarp();
-        }
+        // the lane walks bytes [0, lead + len) from the 16-byte boundary below its read; cycle = byte index - lead
+        const uintptr_t sa = reinterpret_cast<uintptr_t>(seq + a), qa = reinterpret_cast<uintptr_t>(qual + a);
+        const int lead = (int)(sa & 15);                      // bases and qualities share the offsets: the same lead when the columns
+        const int qlead = (int)(qa & 15);                     // are equally aligned; handled separately when they are not
+        const uint4 *sp = reinterpret_cast<const uint4 *>(sa & ~(uintptr_t)15);
+        const int end = lead + len;                           // byte index (from the boundary) one past the last base
+        const int nch = len > 0 ? (end + 15) >> 4 : 0;
+        const int maxch = (int)__reduce_max_sync(FULL, (unsigned)nch);
+        const bool same_lead = __all_sync(FULL, lead == qlead);
+        const int nk = len - K;                               // k-mers start at i < len - K (quirk Q11)
         const unsigned long long when0 = order << 11;
+
+        // rolling state
+        uint32_t w0 = 0, w1 = 0;                              // plane windows of the last K bases: bit K-1 = newest
+        int vrun = 0;                                         // consecutive A,C,G,T bases ending here (saturates at K)
+        uint32_t prevb = 0, hist = 0;                         // previous base; bit j = "base p-j differs from base p-j-1"
+        unsigned long long raw = 0;                           // the last eight raw bytes, newest in the low byte
+        int gc = 0;
+
+        uint4 cb = make_uint4(0, 0, 0, 0), cq = make_uint4(0, 0, 0, 0);
+        if (0 < nch) {
+            cb = sp[0];
+            if (same_lead) cq = reinterpret_cast<const uint4 *>(qa & ~(uintptr_t)15)[0];
+        }
+#pragma unroll 1
+        for (int c = 0; c < maxch; c++) {
+            uint4 nb = make_uint4(0, 0, 0, 0), nq = make_uint4(0, 0, 0, 0);
+            if (c + 1 < nch) {                                // the next piece is on its way while this one is walked
+                nb = sp[c + 1];
+                if (same_lead) nq = reinterpret_cast<const uint4 *>(qa & ~(uintptr_t)15)[c + 1];
+            }
+            uint32_t bw[4] = {cb.x, cb.y, cb.z, cb.w}, qw[4] = {cq.x, cq.y, cq.z, cq.w};
+            if (!same_lead && c < nch) {                      // rare layout: quality bytes one by one
 #pragma unroll
-        for (int w = 0; w < NW; w++) {
-            if (32 * w < nk) {                               // warp-uniform
-                const int i = 32 * w + lane;
-                if (i < nk) {
-                    const uint32_t w0 = __funnelshift_r(k0[w], k0[w + 1], lane) & km;
-                    const uint32_t w1 = __funnelshift_r(k1[w], k1[w + 1], lane) & km;
-                    const uint32_t wv = __funnelshift_r(kv[w], kv[w + 1], lane) & km;
-                    const unsigned long long when = when0 | ((unsigned long long)i << 1);
-                    if (__builtin_expect(wv == km, 1)) {
-                        const uint32_t idx = (w1 << K) | w0;
-                        const uint32_t sh = (idx & 1u) << 4;
-                        const uint32_t old = atomicAdd(&ktab[idx >> 1], 1u << sh);
-                        if (__builtin_expect(((old >> sh) & 0xFFFFu) == KTAB_SPILL - 1u, 0)) {
-                            atomicSub(&ktab[idx >> 1], KTAB_SPILL << sh);
-                            atomicAdd(&kcnt[idx], (unsigned long long)KTAB_SPILL);
-                        }
-                        // only the DIRECT first sighting is tracked on the device (see stat_read)
-                        if (__builtin_expect(!((kbits[idx >> 5] >> (idx & 31u)) & 1u), 0)) {
-                            if (__ldcg(&kfirst[idx]) > when) atomicMin(&kfirst[idx], when);
-                        }
-                    } else {                                 // a byte outside A,C,G,T in the k-mer: side table, keyed by its bytes
-                        unsigned long long key = 0, rkey = 0;
-                        bool foreign = false;
-                        for (int j = 0; j < K; j++) {
-                            const unsigned long long bj = scratch[i + j];
-                            key = (key << 8) | bj;
-                            rkey |= (unsigned long long)lut3[bj] << (8 * j);
-                            foreign |= (lut1[bj] & 15u) == 15u;
-                        }
-                        if (key == AQC_KMER_NEVER || rkey == AQC_KMER_NEVER) atomicExch(A.error_flag, AQC_ERR_INVALID);
-                        else {
-                            const int h = side_slot(qd, key);
-                            const int hr = side_slot(qd, rkey);
-                            if (h < 0 || hr < 0) atomicExch(A.error_flag, AQC_ERR_KMER_TABLE_FULL);
-                            else {
-                                atomicAdd(&qd.scnt[h], 1ULL);
-                                first_min(&qd.sfirst[h], when);
-                                if (foreign) first_min(&qd.sseed[hr], when | 1ULL);
+                for (int w = 0; w < 4; w++) {
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int tt = 0; tt < 4; tt++) {
+                        const int pos = 16 * c + 4 * w + tt - lead;
+                        if (pos >= 0 && pos < len) v |= (uint32_t)qual[a + pos] << (8 * tt);
+                    }
+                    qw[w] = v;
+                }
+            }
+            if constexpr (POST) {
+                if (n_edits) {
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const int bi = ep[k] + lead - 16 * c;         // byte index inside this piece
+                        if (ep[k] >= 0 && bi >= 0 && bi < 16) {
+                            const uint32_t sh = 8u * (uint32_t)(bi & 3), m = 0xFFu << sh;
+#pragma unroll
+                            for (int w = 0; w < 4; w++) {
+                                if ((bi >> 2) == w) {
+                                    if (eb[k]) bw[w] = (bw[w] & ~m) | (eb[k] << sh);
+                                    qw[w] = (qw[w] & ~m) | (eq[k] << sh);
+                                }
                             }
                         }
                     }
                 }
             }
+#pragma unroll 1
+            for (int w = 0; w < 4; w++) {                             // rolled: four copies of the per-base code, not sixteen
+                const uint32_t wb_ = bw[0], wq_ = qw[0];
+                bw[0] = bw[1]; bw[1] = bw[2]; bw[2] = bw[3];
+                qw[0] = qw[1]; qw[1] = qw[2]; qw[2] = qw[3];
+#pragma unroll
+                for (int tt = 0; tt < 4; tt++) {
+                    const int pos = 16 * c + 4 * w + tt - lead;       // the lane's cycle
+                    if (pos >= 0 && pos < len) {
+                        const uint32_t b = (wb_ >> (8 * tt)) & 0xFFu, q = (wq_ >> (8 * tt)) & 0xFFu;
+                        // A 0x41, C 0x43, T 0x54, G 0x47: bits 1..2 are a 2-bit code (A0 C1 T2 G3); the byte is one of the four
+                        // iff it re-encodes to itself
+                        const uint32_t code = (b >> 1) & 3u;
+                        const bool acgt = ((0x47544341u >> (8 * code)) & 0xFFu) == b;
+                        // ALL_BASES order (qualitycontrol.py:24): A0 T1 C2 G3, anything else 4
+                        const uint32_t cls = acgt ? (((code & 1u) << 1) | (code >> 1)) : 4u;
+                        atomicAdd(&s_cnt[cls * CS + pos], 1u);
+                        atomicAdd(&s_qs[cls * CS + pos], q);
+                        gc += (acgt && (code & 1u)) ? 1 : 0;          // C and G have code bit 0 set (:93-94)
+                        // discontinuity: window of cycle pos-2 is complete now; the clamped windows at the ends reuse it
+                        hist = ((hist << 1) | ((pos > 0 && b != prevb) ? 1u : 0u)) & 0xFu;
+                        prevb = b;
+                        if (pos >= 4) {
+                            const uint32_t d = (uint32_t)__popc(hist);
+                            if (d) {
+                                atomicAdd(&s_disc[pos - 2], d);
+                                if (pos == 4) { atomicAdd(&s_disc[0], d); atomicAdd(&s_disc[1], d); }
+                                if (pos == len - 1) { atomicAdd(&s_disc[pos - 1], d); atomicAdd(&s_disc[pos], d); }
+                            }
+                        }
+                        // k-mer ending here: internal dense index (plane 1 bits << K) | plane 0 bits, bit t = base t of the k-mer,
+                        // k-mer codes A0 C1 G2 T3 (lut2 of the warp-per-read path): bit 0 = C or T, bit 1 = G or T
+                        const uint32_t k0 = (code ^ (code >> 1)) & 1u, k1 = code >> 1;
+                        w0 = (w0 >> 1) | (k0 ? ktop : 0u);
+                        w1 = (w1 >> 1) | (k1 ? ktop : 0u);
+                        vrun = acgt ? min(vrun + 1, K) : 0;
+                        raw = (raw << 8) | b;
+                        const int i = pos - K + 1;                     // its first base
+                        if (i >= 0 && i < nk) {
+                            const unsigned long long when = when0 | ((unsigned long long)i << 1);
+                            if (__builtin_expect(vrun == K, 1)) {
+                                const uint32_t idx = (w1 << K) | w0;
+                                const uint32_t sh = (idx & 1u) << 4;
+                                const uint32_t old = atomicAdd(&ktab[idx >> 1], 1u << sh);
+                                if (__builtin_expect(((old >> sh) & 0xFFFFu) == KTAB_SPILL - 1u, 0)) {
+                                    atomicSub(&ktab[idx >> 1], KTAB_SPILL << sh);
+                                    atomicAdd(&kcnt[idx], (unsigned long long)KTAB_SPILL);
+                                }
+                                // only the DIRECT first sighting is tracked on the device (see stat_read)
+                                if (__builtin_expect(!((kbits[idx >> 5] >> (idx & 31u)) & 1u), 0)) {
+                                    if (__ldcg(&kfirst[idx]) > when) atomicMin(&kfirst[idx], when);
+                                }
+                            } else {                                   // a byte outside A,C,G,T in the k-mer: side table, keyed by its bytes
+                                side_kmer(qd, raw & keymask, when, K, A.error_flag);
+                            }
+                        }
+                    }
+                }
+            }
+            cb = nb; cq = nq;
         }
-        if (lane == 0) atomicAdd(&s_gch[gc], 1u);            // :112
-        if (nk > 0) n_kmers += (unsigned long long)nk;       // totalKmer :114
-        n_reads++;
+        if (want) {
+            atomicAdd(&s_gch[gc], 1u);                        // :112
+            if (nk > 0) n_kmers += (unsigned long long)nk;    // totalKmer :114
+            n_reads++;
+        }
     }
 
     // ---- epilogue: the CTA's histograms go to the QC object ----
@@ -279,16 +334,14 @@ __global__ void __launch_bounds__(STAT_WARPS * 32, 1) stat_kernel(const __grid_c
     }
     for (int i = tid; i < QC_CLASSES * MAXB; i += blockDim.x) {
         const int c = i / MAXB, pos = i - c * MAXB;
-        const uint32_t n = s_cnt[i], qs = s_qs[i];
+        const uint32_t n = s_cnt[c * CS + pos], qs = s_qs[c * CS + pos];
         if (n) atomicAdd(&qd.cls_cnt[c * AQC_MAX_LEN + pos], (unsigned long long)n);
         if (qs) atomicAdd(&qd.cls_qsum[c * AQC_MAX_LEN + pos], (unsigned long long)qs);
     }
     for (int i = tid; i < MAXB; i += blockDim.x) { const uint32_t v = s_disc[i]; if (v) atomicAdd(&qd.disc[i], (unsigned long long)v); }
     for (int i = tid; i <= MAXB; i += blockDim.x) { const uint32_t v = s_gch[i]; if (v) atomicAdd(&qd.gchist[i], (unsigned long long)v); }
-    if (lane == 0) {
-        if (n_kmers) atomicAdd(&qd.scal[0], n_kmers);
-        if (n_reads) atomicAdd(&qd.scal[1], n_reads);
-    }
+    if (n_kmers) atomicAdd(&qd.scal[0], n_kmers);
+    if (n_reads) atomicAdd(&qd.scal[1], n_reads);
 }
 
 }  // namespace aqc

@@ -5,6 +5,7 @@ pipeline uses; overlap()/hasPolyX()/lowQualityNum()/nNumber() are the per-read o
 util.py:88 and preprocesser.py:30,61,70 routed through the GPU (for operator-level parity tests).
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -70,6 +71,8 @@ class Engine:
         rc = self._L.aqc_create(device, C.byref(params), C.byref(self._h))
         if rc:
             raise EngineError(rc, self._L.aqc_last_error(None).decode())
+        if os.environ.get("AQC_TRACE_DEVICE"):
+            print("[afterqc_b200] engine on device %d" % device, flush=True)
 
     # ---- lifecycle -----------------------------------------------------------------------
     def close(self):

@@ -153,11 +153,13 @@ def _worker(rank, world, options, port, backend_name, result_q, local_factory=No
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    import datetime
+    tmo = datetime.timedelta(seconds=int(os.environ.get("AQC_DIST_TIMEOUT", "1800")))
     if backend_name == "nccl":
         torch.cuda.set_device(rank)
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank), timeout=tmo)
     else:
-        dist.init_process_group("gloo", rank=rank, world_size=world)
+        dist.init_process_group("gloo", rank=rank, world_size=world, timeout=tmo)
     from .pipeline import seqFilter, default_backend
 
     def factory(params):
@@ -175,15 +177,36 @@ def _worker(rank, world, options, port, backend_name, result_q, local_factory=No
         result_q.put(True)
 
 
-def run_sharded(options, gpus, port=None):
-    """after.py --gpus N: one process per GPU of this box."""
+def free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def run_sharded(options, gpus, port=None, timeout_s=None):
+    """after.py --gpus N: one process per GPU of this box.  The rendezvous port is probed (directory mode may run several
+    sharded jobs one after another); when one shard process dies the others are terminated instead of waiting in a
+    collective for ever."""
+    import time
     import torch.multiprocessing as mp
-    port = port or (29500 + os.getpid() % 2000)
+    port = port or free_port()
     ctx = mp.get_context("spawn")
     procs = [ctx.Process(target=_worker, args=(r, gpus, options, port, "nccl", None)) for r in range(gpus)]
     for p in procs:
         p.start()
+    t0 = time.time()
+    failed = False
+    while any(p.is_alive() for p in procs):
+        if any((not p.is_alive()) and p.exitcode != 0 for p in procs) or (timeout_s and time.time() - t0 > timeout_s):
+            failed = True
+            break
+        time.sleep(0.05)
+    if failed:
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
     for p in procs:
         p.join()
-    if any(p.exitcode != 0 for p in procs):
+    if failed or any(p.exitcode != 0 for p in procs):
         raise RuntimeError("a shard process failed")

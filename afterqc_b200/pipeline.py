@@ -159,31 +159,26 @@ class seqFilter:
             if opt.barcode_length < 1:
                 raise ValueError("barcode_length=%d is outside the supported domain" % opt.barcode_length)
             opt.trim_front = 0            # no front trim if the sequence is barcoded (preprocesser.py:241-243)
-        # One GPU: stream the files in bounded memory (two passes, like the reference).  Shards: every rank parses the
-        # files and takes its contiguous record range.
-        streaming = world == 1
+        # The files are streamed in bounded memory (two passes, like the reference).  Shards: one counting pass gives the number
+        # of complete records n (the loop ends at the shortest file); rank r then statistics its slice of the prefilter window
+        # and filters records [n*r/W, n*(r+1)/W), skipping the rest of the stream without holding it.
         # index reads (-7 / -5) are carried along untouched (preprocesser.py:358-371,422-431)
         idx_files = [(k, getattr(opt, k)) for k in ("index1_file", "index2_file") if getattr(opt, k) is not None]
-        rec1 = rec2 = None
-        idx_recs = {}
-        if not streaming:
-            rec1 = fastq_io.read_all(opt.read1_file)
-            rec2 = fastq_io.read_all(opt.read2_file) if self.paired else None
-            idx_recs = {k: fastq_io.read_all(f) for k, f in idx_files}
+        self._n_total = None
+        self._extra = 0
+        if world > 1:
+            if opt.qc_only:
+                raise NotImplementedError("--qc_only stops at a data-dependent record; run it on one GPU")
+            self._n_total, self._extra = self._count_records(idx_files)
 
         params = params_from_options(opt, self.paired)
         be = self.backend_factory(params)
         self.backend = be
 
         # ---- prefilter QC (preprocesser.py:247-251) ----
-        if streaming:
-            self._prefilter_stream(be, opt.read1_file, _abi.QC_R1_PRE)
-            if self.paired:
-                self._prefilter_stream(be, opt.read2_file, _abi.QC_R2_PRE)
-        else:
-            prefilter_stat(be, rec1, _abi.QC_R1_PRE, opt.qc_sample, self.batch_records, self.shard)
-            if self.paired:
-                prefilter_stat(be, rec2, _abi.QC_R2_PRE, opt.qc_sample, self.batch_records, self.shard)
+        self._prefilter_stream(be, opt.read1_file, _abi.QC_R1_PRE)
+        if self.paired:
+            self._prefilter_stream(be, opt.read2_file, _abi.QC_R2_PRE)
         self.r1qc_prefilter = QualityControl(opt.qc_sample, opt.qc_kmer).load(be.qc(_abi.QC_R1_PRE), be.kmers(_abi.QC_R1_PRE))
         self.r1qc_prefilter.qc()
         self.r2qc_prefilter = QualityControl(opt.qc_sample, opt.qc_kmer)
@@ -263,28 +258,15 @@ class seqFilter:
         # ---- the per-read loop, in batches (preprocesser.py:411-631) ----
         params = params_from_options(opt, self.paired)
         be.set_params(params)
-        extra = 0
-        if streaming:
+        if world == 1:
             extra = self._filter_stream(be, writers, idx_files)
         else:
-            n = min([rec1.n] + ([rec2.n] if self.paired else []) + [r.n for r in idx_recs.values()])   # loop ends at the shortest file
-            if opt.qc_only:
-                raise NotImplementedError("--qc_only stops at a data-dependent record; run it on one GPU")
+            n = self._n_total
             if opt.index2_file is not None and not self.paired and n > 0:
                 raise TypeError("'NoneType' object is not subscriptable")       # preprocesser.py:426-431 without a read2 file
-            s_lo, s_hi = (n * rank) // world, (n * (rank + 1)) // world
-            for a in range(s_lo, s_hi, self.batch_records):
-                b = min(s_hi, a + self.batch_records)
-                batch = fastq_io.to_batch(rec1, rec2, a, b)
-                res = be.filter_pairs(batch)
-                self._write(writers, rec1, rec2, a, res)
-                for k, r in idx_recs.items():
-                    writers["good_" + k].write(fastq_io.emit(r, 0, 0, a, res))
-                    writers["bad_" + k].write(fastq_io.emit(r, 0, 1, a, res))
-                    if "ov_" + k in writers:
-                        writers["ov_" + k].write(fastq_io.emit(r, 0, 2, a, res))
+            self._filter_stream(be, writers, idx_files, (n * rank) // world, (n * (rank + 1)) // world)
             # the R1 record read just before a shorter mate/index file ran out is still counted (preprocesser.py:416-431)
-            extra = int(rec1.lengths()[n]) if rec1.n > n else 0
+            extra = self._extra
         for w in writers.values():
             w.close()
         if world > 1 and not opt.qc_only:
@@ -364,14 +346,53 @@ class seqFilter:
         figs += read_figs
         report.write_html(path, stat, getattr(opt, "version", "0.9.6"), figs)
 
+    def _count_records(self, idx_files):
+        """Sharded runs: the number of records the per-read loop will see (it ends at the shortest input,
+        preprocesser.py:411-431) and the length of the R1 record the reference reads -- and counts in total_bases -- just
+        before a shorter mate / index file runs out.  One streaming pass per file, nothing is kept."""
+        opt = self.options
+
+        def count(path, want_len_at=None):
+            stream = fastq_io.open_stream(path, self.batch_records, slots=2)
+            n, extra = 0, 0
+            try:
+                while True:
+                    k = stream.available(self.batch_records)
+                    if k == 0:
+                        break
+                    rec = stream.take(k)
+                    if want_len_at is not None and n <= want_len_at < n + rec.n:
+                        extra = int(rec.lengths()[want_len_at - n])
+                    n += rec.n
+                    rec.done()
+            finally:
+                stream.close()
+            self.__dict__.setdefault("_n_cache", {})[path] = n
+            return n, extra
+        others = ([opt.read2_file] if self.paired else []) + [f for _k, f in idx_files]
+        n_other = min([count(f)[0] for f in others]) if others else None
+        n1, extra = count(opt.read1_file, n_other)
+        if n_other is None or n1 <= n_other:
+            return n1, 0
+        return n_other, extra
+
     def _prefilter_stream(self, be, path, slot):
         """QualityControl.statFile (qualitycontrol.py:331-357) on a stream: window = records [999, 999+limit) (all when
         limit <= 0); reading stops one record past the window (that is all statFile's counter needs); if fewer than
-        1000 records were counted in the window loop the first 999 are stat'd afterwards."""
+        1000 records were counted in the window loop the first 999 are stat'd afterwards.  Sharded runs: every rank streams
+        the window and statistics an equal slice of it (counters add up in the all-reduce, k-mer stamps carry global order)."""
         opt = self.options
+        rank, world = self.shard
         limit = opt.qc_sample
         lo = READ_TO_SKIP - 1
         hi = lo + limit if limit > 0 else None
+        # this rank's share [m_lo, m_hi) of the window [lo, w_end) and of the head [0, lo)
+        if world > 1:
+            w_end = min(self._n_file(path), hi) if hi is not None else self._n_file(path)
+            w_end = max(w_end, lo)
+            m_lo, m_hi = lo + ((w_end - lo) * rank) // world, lo + ((w_end - lo) * (rank + 1)) // world
+        else:
+            m_lo, m_hi = lo, None
         stream = fastq_io.open_stream(path, self.batch_records, slots=2)      # the window is short: little read-ahead
         g = 0
         head = []
@@ -384,7 +405,9 @@ class seqFilter:
                 a, b = g, g + rec.n
                 if a < lo:
                     head.append(rec.slice(0, min(rec.n, lo - a)))
-                wa, wb = max(a, lo), (b if hi is None else min(b, hi))
+                wa, wb = max(a, lo, m_lo), (b if hi is None else min(b, hi))
+                if m_hi is not None:
+                    wb = min(wb, m_hi)
                 if wb > wa:
                     batch = fastq_io.to_batch(rec, None, wa - a, wb - a, first_index=wa)
                     be.stat_reads(batch, slot, -1, stat_lo=lo, stat_hi=(hi if hi is not None else 1 << 62), order_base=0)
@@ -397,13 +420,35 @@ class seqFilter:
         stat_reads_num = min(max(g - lo, 0), limit + 1) if limit > 0 else max(g - lo, 0)
         if stat_reads_num < READ_TO_SKIP and head:
             hrec = fastq_io.FastqRecords.concat(head)
-            batch = fastq_io.to_batch(hrec, None, 0, hrec.n, first_index=0)
-            be.stat_reads(batch, slot, -1, stat_lo=0, stat_hi=hrec.n, order_base=HEAD_ORDER_BASE)
+            h_lo, h_hi = (hrec.n * rank) // world, (hrec.n * (rank + 1)) // world
+            if h_hi > h_lo:
+                batch = fastq_io.to_batch(hrec, None, h_lo, h_hi, first_index=h_lo)
+                be.stat_reads(batch, slot, -1, stat_lo=0, stat_hi=hrec.n, order_base=HEAD_ORDER_BASE)
 
-    def _filter_stream(self, be, writers, idx_files):
+    def _n_file(self, path):
+        """records of one input file (sharded runs; cached)"""
+        cache = self.__dict__.setdefault("_n_cache", {})
+        if path not in cache:
+            stream = fastq_io.open_stream(path, self.batch_records, slots=2)
+            n = 0
+            try:
+                while True:
+                    k = stream.available(self.batch_records)
+                    if k == 0:
+                        break
+                    rec = stream.take(k)
+                    n += rec.n
+                    rec.done()
+            finally:
+                stream.close()
+            cache[path] = n
+        return cache[path]
+
+    def _filter_stream(self, be, writers, idx_files, lo=0, hi=None):
         """The per-read loop over lock-stepped streams of R1 [, R2] [, I1] [, I2]; ends at the shortest file
         (preprocesser.py:411-431).  Returns the bases of the R1 record that the reference reads (and counts) just before
         another file runs out.  --qc_only: stop after the first GOOD pair whose TOTAL_READS >= qc_sample (:630-631).
+        Sharded runs pass their record range [lo, hi): records before it are skipped in the streams, the loop stops at hi.
 
         Three stages overlap: the native readers parse the next batches on their own threads, this thread runs the
         device call, and every output file formats + (deflates +) writes its text on its own lane, in batch order."""
@@ -425,10 +470,21 @@ class seqFilter:
                 r.done()
 
         try:
+            while g < lo:                                   # skip to this rank's first record
+                k = min(s.available(min(self.batch_records, lo - g)) for s in streams)
+                if k == 0:
+                    break
+                for s_ in streams:
+                    s_.take(k).done()
+                g += k
             while not stopped:
                 want = self.batch_records
                 if opt.qc_only:
                     want = 1 if g + 1 >= qs else min(want, qs - 1 - g)    # single pairs once the stop rule can fire
+                if hi is not None:
+                    want = min(want, hi - g)
+                    if want <= 0:
+                        break
                 k = min(s.available(want) for s in streams)
                 if k == 0:
                     break
@@ -461,7 +517,7 @@ class seqFilter:
             while inflight:
                 retire(inflight.popleft())
             extra = 0
-            if not stopped and len(streams) > 1 and streams[0].available(1) > 0:
+            if hi is None and not stopped and len(streams) > 1 and streams[0].available(1) > 0:
                 extra = int(streams[0].take(1).lengths()[0])
             return extra
         finally:

@@ -537,7 +537,7 @@ def run_ours(args):
         ends = {"seq1": "off1", "qual1": "off1", "seq2": "off2", "qual2": "off2"}
         host = {}
         for k in cols:
-            src = wb.t[k][:ne + 9] if k.startswith("off") else wb.t[k][:int(wb.t[ends[k]][ne].item()) + 16]
+            src = wb.t[k][:ne + 9] if k.startswith("off") else wb.t[k][:(int(wb.t[ends[k]][ne].item()) & 0xFFFFFFFF) + 16]
             h = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
             h.copy_(src)
             host[k] = h
@@ -559,8 +559,8 @@ def run_ours(args):
                 b.seq2 = None; b.qual2 = None; b.off2 = None
             return b
 
-        off1 = host["off1"].numpy()
-        off2 = host["off2"].numpy() if cfg["paired"] else None
+        off1 = host["off1"].numpy().view(np.uint32).astype(np.int64)      # uint32 offsets held in int32 tensors (columns up to 4 GiB)
+        off2 = host["off2"].numpy().view(np.uint32).astype(np.int64) if cfg["paired"] else None
         nm = 2 if cfg["paired"] else 1
 
         def col_bytes(lo, hi):
@@ -646,9 +646,10 @@ def run_ours(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    off1d = wb.t["off1"]
-    b1 = int(off1d[n].item() - off1d[0].item())
-    b2 = int(wb.t["off2"][n].item() - wb.t["off2"][0].item()) if cfg["paired"] else 0
+    def span(t):        # uint32 offsets held in an int32 tensor
+        return (int(t[n].item()) & 0xFFFFFFFF) - (int(t[0].item()) & 0xFFFFFFFF)
+    b1 = span(wb.t["off1"])
+    b2 = span(wb.t["off2"]) if cfg["paired"] else 0
     nm = 2 if cfg["paired"] else 1
     lane = args.filter_kernel == "default"
     n_pre = max(0, R.s_hi - R.s_lo) if R.has_window else 0

@@ -204,6 +204,7 @@ typedef struct aqc_ctx aqc_ctx;
 
 /* ---- lifecycle ---- */
 int aqc_abi_version(void);
+int aqc_device_count(void);                        /* CUDA devices visible to the process (directory mode spreads its jobs over them, after.py:168-171) */
 /* device < 0: the current CUDA device. */
 int aqc_create(int device, const aqc_params *params, aqc_ctx **out);
 void aqc_destroy(aqc_ctx *ctx);

@@ -262,6 +262,7 @@ static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, con
 static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline int simt_env_int(const char *name, int dflt) { const char *s = getenv(name); return s ? atoi(s) : dflt; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { memset(p, 0, sizeof *p); p->multiProcessorCount = simt_env_int("AQC_EMU_SMS", 3); return cudaSuccess; }

@@ -174,7 +174,7 @@ def test_emu_empty_mate_reaches_statread(backends):
 
 
 @pytest.mark.parametrize("kernel", ["warp", "lane"])
-@pytest.mark.parametrize("name", ["pe150_default", "pe150_err3_mask_overlap", "pe250_k5_strict", "se100_f0"])
+@pytest.mark.parametrize("name", ["pe150_default", "pe150_err3_mask_overlap", "pe250_k5_strict", "se100_f0", "testdata"])
 def test_emu_pipeline_matches_reference_golden(name, kernel, tmp_path):
     """the whole drop-in pipeline (readers, packed columns, engine calls, writers, JSON) on the emulated engine reproduces
     the reference's golden outputs -- the same check tests/test_gpu_golden.py makes on the GPU"""

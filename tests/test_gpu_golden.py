@@ -48,3 +48,32 @@ def test_directory_mode_on_gpu(tmp_path):
         for rel in ("good/s%s_R1.good.fq.gz" % tag, "good/s%s_R2.good.fq.gz" % tag, "bad/s%s_R1.bad.fq.gz" % tag, "QC/s%s_R1.fq.gz.json" % tag,
                     "QC/s%s_R1.fq.gz.html" % tag):
             assert os.path.exists(str(d / rel)), rel
+
+
+def test_directory_mode_spreads_jobs_over_gpus(tmp_path):
+    """after.py:168-171 starts one process per R1 file; here job i runs on GPU i mod (GPUs of the box) and every job reproduces
+    the single-GPU outputs of its case"""
+    import shutil
+    from afterqc_b200 import cli
+    if cli.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    d = tmp_path / "run"
+    d.mkdir()
+    cases_ = (("a", "pe150_default"), ("b", "pe150_small_head_fallback"), ("c", "testdata"))
+    for tag, case in cases_:
+        src = os.path.join(golden_util.GOLD, case)
+        shutil.copy(os.path.join(src, "x_R1.fq.gz"), str(d / ("s%s_R1.fq.gz" % tag)))
+        shutil.copy(os.path.join(src, "x_R2.fq.gz"), str(d / ("s%s_R2.fq.gz" % tag)))
+    env = dict(os.environ, AQC_TRACE_DEVICE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "after.py"), "-d", str(d), "-g", str(d / "good")],
+                         capture_output=True, text=True, timeout=900, cwd=str(d), env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    used = sorted(set(ln.split()[-1] for ln in out.stdout.splitlines() if ln.startswith("[afterqc_b200] engine on device")))
+    assert len(used) >= 2, out.stdout[-2000:]
+    import json
+    for tag, case in cases_:
+        with open(os.path.join(golden_util.GOLD, case, "expected.json")) as f:
+            exp = json.load(f)
+        for rel, digest in exp["outputs_sha256"].items():
+            p = str(d / rel.replace("x_R", "s%s_R" % tag))
+            assert os.path.exists(p) and golden_util.sha(p) == digest, rel
