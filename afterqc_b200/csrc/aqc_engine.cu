@@ -53,6 +53,7 @@ struct aqc_ctx {
     uint32_t *d_kbits = nullptr;   // stat_kernel: "already stamped" bitmaps of the two mates of a launch (aqc_stat_kernel.cuh)
     Staging stg[2];
     uint32_t chunk_pairs = 1u << 18;
+    uint32_t stat_head = 8192;          // records whose dense k-mers stamp_head_kernel stamps before stat_kernel runs (AQC_STAT_HEAD)
     std::vector<std::array<cudaEvent_t, 4>> ev_pool;    // per timed launch group: start | filter kernel done | list mode done | statistics done
     size_t ev_used = 0;
     uint64_t launches = 0;
@@ -150,8 +151,10 @@ template <bool PAIRED, int NW> void emu_lane_kernel(void **a) { lane_kernel<PAIR
 template <bool PAIRED, int NW, bool POST> void emu_stat_kernel(void **a) { stat_kernel<PAIRED, NW, POST>(*(const SKArgs *)a[0]); }
 void emu_stamp_bits_kernel(void **a) {
     stamp_bits_kernel(*(const unsigned long long **)a[0], *(const unsigned long long **)a[1], *(uint32_t *)a[2], *(unsigned long long *)a[3],
-                      *(uint32_t **)a[4], *(uint32_t **)a[5]);
+                      *(uint32_t **)a[4], *(uint32_t **)a[5], *(uint32_t **)a[6]);
 }
+template <bool PAIRED, bool POST> void emu_stamp_head_kernel(void **a) { stamp_head_kernel<PAIRED, POST>(*(const SKArgs *)a[0]); }
+#define stamp_head_kernel emu_stamp_head_kernel
 #define lane_kernel emu_lane_kernel
 #define stat_kernel emu_stat_kernel
 #endif
@@ -173,9 +176,14 @@ const void *stat_kernel_for(bool paired, int nw, bool post) {
                   : (post ? AQC_KERNEL_HANDLE(stat_kernel<false, 8, true>) : AQC_KERNEL_HANDLE(stat_kernel<false, 8, false>));
 #undef AQC_STAT_ROW
 }
+const void *stamp_head_kernel_for(bool paired, bool post) {
+    return paired ? (post ? AQC_KERNEL_HANDLE(stamp_head_kernel<true, true>) : AQC_KERNEL_HANDLE(stamp_head_kernel<true, false>))
+                  : (post ? AQC_KERNEL_HANDLE(stamp_head_kernel<false, true>) : AQC_KERNEL_HANDLE(stamp_head_kernel<false, false>));
+}
 #ifdef AQC_EMU
 #undef lane_kernel
 #undef stat_kernel
+#undef stamp_head_kernel
 #endif
 
 int alloc_qc(aqc_ctx *ctx, QcHost &q) {
@@ -332,56 +340,54 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
     }
     auto mark = [&](int i) -> int { if (timed) CK(cudaEventRecord(ev[i], stream)); return 0; };
 
-    // statRead over records [lo, hi) of the batch with stat_kernel (aqc_stat_kernel.cuh): the "already stamped" bitmaps of both
-    // mates are rebuilt for the launch's lowest possible stamp; a large range is split into a short head and the rest, so that
-    // the rest finds (nearly) every dense k-mer stamped and never touches the stamp table in HBM.
+    // statRead over records [lo, hi) of the batch with stat_kernel (aqc_stat_kernel.cuh): stamp_head_kernel puts the first-seen
+    // stamps of the first records' dense k-mers into the table, stamp_bits_kernel turns the table into the bitmap "stamped below
+    // every stamp the rest of the range can produce", and stat_kernel walks the whole range with that bitmap in shared memory.
     auto stat_launches = [&](const KArgs &K0, bool post, uint32_t lo, uint32_t hi) -> int {
         if (hi <= lo) return 0;
         const int snw = lane_words_for(maxl);
         const void *sk = stat_kernel_for(pe, snw, post);
-        const size_t ssmem = stat_smem_bytes(ctx->p.qc_kmer, snw);
+        const size_t ssmem = stat_smem_bytes(ctx->p.qc_kmer, snw, STAT_WARPS);
         if (ssmem > ctx->max_dyn_smem) return fail(ctx, AQC_ERR_INVALID, "statistics tables do not fit shared memory");
         const bool both = pe && K0.qc[0].valid && K0.qc[1].valid;
         const uint32_t n_dense = 1u << (2 * ctx->p.qc_kmer), bw = stat_kbit_words(ctx->p.qc_kmer);
-        constexpr uint32_t HEAD = 8192;
-        uint32_t cuts[3] = {lo, hi, hi};
-        int n_parts = 1;
-        if (hi - lo > 4 * HEAD) { cuts[1] = lo + HEAD; n_parts = 2; }
-        for (int part = 0; part < n_parts; part++) {
-            const uint32_t plo = cuts[part], phi = cuts[part + 1];
-            // lowest stamp a record of [plo, phi) can produce: order << 11 (see stat_read)
-            unsigned long long min_order;
-            if (post) min_order = K0.first_index + plo;
-            else {
-                const unsigned long long g = std::max<unsigned long long>(K0.first_index + plo, K0.stat_lo);
-                min_order = K0.order_base + (g - K0.stat_lo);
-            }
-            unsigned long long min_when = min_order << 11;
-            const unsigned long long *f0 = K0.qc[0].valid ? K0.qc[0].kfirst : nullptr, *f1 = (pe && K0.qc[1].valid) ? K0.qc[1].kfirst : nullptr;
-            uint32_t *o0 = ctx->d_kbits, *o1 = ctx->d_kbits + bw;
-            uint32_t nd = n_dense;
-            void *bargs[6] = {(void *)&f0, (void *)&f1, (void *)&nd, (void *)&min_when, (void *)&o0, (void *)&o1};
-#ifndef AQC_EMU
-            const void *bk = (const void *)stamp_bits_kernel;
-#else
-            const void *bk = (const void *)(simt::Entry)emu_stamp_bits_kernel;
-#endif
-            CK(cudaLaunchKernel(bk, dim3(std::max<uint32_t>(1u, std::min<uint32_t>((n_dense + 255) / 256, 64u))), dim3(256), bargs, 0, stream));
-            CK(cudaGetLastError());
-            ctx->launches++;
-            SKArgs SA;
-            memset(&SA, 0, sizeof SA);
-            SA.k = K0;
-            SA.kbits[0] = o0; SA.kbits[1] = o1;
-            SA.lo = plo; SA.hi = phi;
-            const uint32_t per_mate = std::max<uint32_t>(1u, std::min<uint32_t>((phi - plo + STAT_WARPS - 1) / STAT_WARPS,
-                                                                               both ? std::max(1, ctx->sm_count / 2) : ctx->sm_count));
-            const uint32_t sgrid = both ? 2 * per_mate : per_mate;
-            void *sargs[1] = {(void *)&SA};
-            CK(cudaLaunchKernel(sk, dim3(sgrid), dim3(STAT_WARPS * 32), sargs, ssmem, stream));
+        const uint32_t HEAD = ctx->stat_head;
+        SKArgs SA;
+        memset(&SA, 0, sizeof SA);
+        SA.k = K0;
+        uint32_t *o0 = ctx->d_kbits, *o1 = ctx->d_kbits + bw, *nset = ctx->d_kbits + 2 * bw;
+        SA.kbits[0] = o0; SA.kbits[1] = o1; SA.kbits_set = nset;
+        SA.lo = lo; SA.hi = hi; SA.head_hi = std::min<uint64_t>(hi, (uint64_t)lo + HEAD);
+        void *sargs[1] = {(void *)&SA};
+        {
+            const uint32_t units = (SA.head_hi - lo) * (pe ? 2u : 1u);
+            const uint32_t hgrid = std::max<uint32_t>(1u, std::min<uint32_t>((units + 7) / 8, (uint32_t)ctx->sm_count * 8u));
+            CK(cudaLaunchKernel(stamp_head_kernel_for(pe, post), dim3(hgrid), dim3(256), sargs, 0, stream));
             CK(cudaGetLastError());
             ctx->launches++;
         }
+        // lowest stamp a record beyond the head can produce: order << 11 (see stat_read)
+        unsigned long long min_order = post ? K0.first_index + SA.head_hi : K0.order_base + (K0.first_index + SA.head_hi - K0.stat_lo);
+        unsigned long long min_when = min_order << 11;
+        const unsigned long long *f0 = K0.qc[0].valid ? K0.qc[0].kfirst : nullptr, *f1 = (pe && K0.qc[1].valid) ? K0.qc[1].kfirst : nullptr;
+        uint32_t nd = n_dense;
+        CK(cudaMemsetAsync(nset, 0, 2 * sizeof(uint32_t), stream));
+        void *bargs[7] = {(void *)&f0, (void *)&f1, (void *)&nd, (void *)&min_when, (void *)&o0, (void *)&o1, (void *)&nset};
+#ifndef AQC_EMU
+        const void *bk = (const void *)stamp_bits_kernel;
+#else
+        const void *bk = (const void *)(simt::Entry)emu_stamp_bits_kernel;
+#endif
+        CK(cudaLaunchKernel(bk, dim3(std::max<uint32_t>(1u, std::min<uint32_t>((n_dense + 255) / 256, 64u))), dim3(256), bargs, 0, stream));
+        CK(cudaGetLastError());
+        ctx->launches++;
+        const uint32_t tiles = (hi - lo + 31) / 32;
+        const uint32_t per_mate = std::max<uint32_t>(1u, std::min<uint32_t>((tiles + STAT_WARPS - 1) / STAT_WARPS,
+                                                                           both ? std::max(1, ctx->sm_count / 2) : ctx->sm_count));
+        const uint32_t sgrid = both ? 2 * per_mate : per_mate;
+        CK(cudaLaunchKernel(sk, dim3(sgrid), dim3(STAT_WARPS * 32), sargs, ssmem, stream));
+        CK(cudaGetLastError());
+        ctx->launches++;
         return 0;
     };
 
@@ -690,10 +696,14 @@ int aqc_create(int device, const aqc_params *params, aqc_ctx **out) {
             CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
         CK(cudaMalloc(&ctx->d_fb_count, 2 * sizeof(uint32_t)));
-        CK(cudaMalloc(&ctx->d_kbits, 2 * (size_t)stat_kbit_words(ctx->p.qc_kmer) * sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->d_kbits, (2 * (size_t)stat_kbit_words(ctx->p.qc_kmer) + 2) * sizeof(uint32_t)));
         if (const char *cp = getenv("AQC_CHUNK_PAIRS")) {          // host-path chunk size (tests exercise the multi-chunk pipeline with small batches)
             long v = atol(cp);
             if (v >= 4) ctx->chunk_pairs = (uint32_t)std::min<long>(v & ~3L, 1L << 24);
+        }
+        if (const char *sh = getenv("AQC_STAT_HEAD")) {            // tests: a short head leaves k-mers for stat_kernel's own stamp path
+            long v = atol(sh);
+            if (v >= 1) ctx->stat_head = (uint32_t)std::min<long>(v, 1L << 24);
         }
         for (int s = 0; s < AQC_NUM_QC; s++) { int r = alloc_qc(ctx, ctx->qc[s]); if (r) return r; }
         return aqc_reset(ctx);

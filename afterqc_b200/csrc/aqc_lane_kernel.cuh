@@ -30,6 +30,9 @@
 
 namespace aqc {
 
+#ifndef AQC_LANE_MIN_BLOCKS
+#define AQC_LANE_MIN_BLOCKS 5      // CTAs of 4 warps per SM the register allocation aims at for reads <= 160 bases (tuning: profiles/r02_notes.md)
+#endif
 constexpr int LANE_MAX_WARPS = 4;
 
 struct LArgs {
@@ -303,7 +306,7 @@ __host__ __device__ __forceinline__ size_t lane_smem_bytes(int nwarps, int col_c
 }
 
 template <bool PAIRED, int NW>
-__global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : 5)) lane_kernel(const __grid_constant__ LArgs L) {
+__global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : AQC_LANE_MIN_BLOCKS)) lane_kernel(const __grid_constant__ LArgs L) {
     AQC_DYN_SMEM(smem_raw);
     __shared__ __align__(8) uint64_t full_bar[2 * LANE_MAX_WARPS];      // per warp: [0] bases landed, [1] qualities landed
     const KArgs &A = L.k;

@@ -130,6 +130,35 @@ def resolve_side(keys, direct, seed, k):
     return out
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs), so that the page-locked columns it allocates
+    and the threads that fill them are local to that GPU's PCIe root.  Returns a short description; a box with one node (or
+    without the sysfs entries) is left alone."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa node unknown (single node)"
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return "numa node %d has no allowed cpu" % node
+        os.sched_setaffinity(0, allowed)
+        return "numa node %d, %d cpus" % (node, len(allowed))
+    except Exception as e:       # noqa: BLE001
+        return "not bound (%s)" % type(e).__name__
+
+
 def shard_range(n, rank, world):
     return (n * rank) // world, (n * (rank + 1)) // world
 
@@ -157,6 +186,7 @@ def _worker(rank, world, options, port, backend_name, result_q, local_factory=No
     tmo = datetime.timedelta(seconds=int(os.environ.get("AQC_DIST_TIMEOUT", "1800")))
     if backend_name == "nccl":
         torch.cuda.set_device(rank)
+        bind_to_gpu_numa_node(rank)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank), timeout=tmo)
     else:
         dist.init_process_group("gloo", rank=rank, world_size=world, timeout=tmo)

@@ -475,6 +475,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa = None
+    if world > 1:       # page-locked columns and the threads that fill them: local to the GPU's PCIe root
+        from afterqc_b200.multigpu import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(local_rank)
     cfg = args.cfg
     n, QS = args.n, args.qs
     stream = torch.cuda.Stream(device)          # the launching stream of every kernel below (torch events time it)
@@ -719,6 +723,8 @@ def run_ours(args):
             "dtype": "u8", "data": "synthetic", "config": confd, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_python": python_reference_timing(args.config),
         }
+        if numa is not None:
+            line["config"]["numa_rank0"] = numa
         if shard_parity is not None:
             line["shard_parity"] = shard_parity[0]
             line["shard_parity_note"] = shard_parity[1]

@@ -79,6 +79,23 @@ def test_emu_stat_parity(backends):
         orc.close(); eng.close()
 
 
+def test_emu_stat_short_head(backends, monkeypatch):
+    """stat_kernel with a head of 40 records (AQC_STAT_HEAD): most dense k-mers are first met beyond the head and take the
+    kernel's own stamp path (bitmap bit clear -> load, atomicMin); several calls in a row rebuild the bitmap from the table"""
+    monkeypatch.setenv("AQC_STAT_HEAD", "40")
+    for bname, kmer in (("pe150", 8), ("adversarial", 5), ("pe150_jitter", 3)):
+        batch = BATCHES[bname]()
+        p = cases.make_params("default_f0"); p.qc_kmer = kmer; p.qc_sample = batch.n // 2
+        orc, eng = backends(p)
+        third = batch.n // 3
+        for be in (orc, eng):
+            be.stat_reads(batch, _abi.QC_R1_PRE, _abi.QC_R2_PRE, stat_lo=7, stat_hi=third, order_base=0)
+            be.stat_reads(batch, _abi.QC_R1_PRE, _abi.QC_R2_PRE, stat_lo=third, stat_hi=batch.n, order_base=third - 7)
+        compare.assert_records_equal(batch, orc.filter_pairs(batch), eng.filter_pairs(batch), "emu short head %s" % bname)
+        compare.compare_backends(orc, eng, (_abi.QC_R1_PRE, _abi.QC_R2_PRE, _abi.QC_R1_POST, _abi.QC_R2_POST), "emu short head %s k=%d" % (bname, kmer))
+        orc.close(); eng.close()
+
+
 def test_emu_single_end_and_resident(backends):
     batch = cases.synthetic("se100", 3000)
     for pname in ("default_f0", "trim"):
