@@ -154,6 +154,17 @@ __device__ __forceinline__ uint32_t prmt_raw(uint32_t a, uint32_t b, uint32_t se
     return __byte_perm(a, b, sel);
 }
 #endif
+// 16-byte global load that asks the L2 to bring in the whole 128-byte line: lanes that walk their own read 16 bytes at a time
+// come back for the neighbouring sectors a moment later
+__device__ __forceinline__ uint4 ldg_stream16(const uint4 *p) {
+#ifndef AQC_EMU
+    uint4 v;
+    asm volatile("ld.global.L2::128B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) { }
 }

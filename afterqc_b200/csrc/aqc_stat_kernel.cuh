@@ -296,11 +296,11 @@ __global__ void __launch_bounds__(STAT_WARPS * 32, 1) stat_kernel(const __grid_c
         int gc = 0;
 
         uint4 cb = make_uint4(0, 0, 0, 0), cq = make_uint4(0, 0, 0, 0);
-        if (0 < nch) { cb = sp[0]; if (same_lead) cq = qp[0]; }
+        if (0 < nch) { cb = ldg_stream16(sp); if (same_lead) cq = ldg_stream16(qp); }
 #pragma unroll 1
         for (int c = 0; c < maxch; c++) {
             uint4 nb = make_uint4(0, 0, 0, 0), nq = make_uint4(0, 0, 0, 0);
-            if (c + 1 < nch) { nb = sp[c + 1]; if (same_lead) nq = qp[c + 1]; }      // the next piece is on its way while this one is walked
+            if (c + 1 < nch) { nb = ldg_stream16(sp + c + 1); if (same_lead) nq = ldg_stream16(qp + c + 1); }      // the next piece is on its way while this one is walked
             uint32_t bw[4] = {cb.x, cb.y, cb.z, cb.w}, qw[4] = {cq.x, cq.y, cq.z, cq.w};
             if (__builtin_expect(!same_lead, 0)) {            // rare layout: quality bytes one by one
                 if (c < nch) {

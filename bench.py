@@ -429,8 +429,11 @@ def shard_parity_check(args, device, local_rank, stream, world, rank, dist):
     # reduce in place so that rank 0's fetches return the merged blocks
     for v in r.sum_views:
         dist.all_reduce(v, op=dist.ReduceOp.SUM)
+    bias = -(1 << 63)       # stamps are unsigned and "never" is all ones: flip the sign bit so that the signed MIN orders them
     for v in r.min_views:
+        v.bitwise_xor_(bias)
         dist.all_reduce(v, op=dist.ReduceOp.MIN)
+        v.bitwise_xor_(bias)
     torch.cuda.synchronize()
     ok = True
     why = "identical"

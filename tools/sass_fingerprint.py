@@ -7,6 +7,7 @@ version that built them.
 
   python tools/sass_fingerprint.py            compare (exit 1 on a difference in a listed kernel)
   python tools/sass_fingerprint.py --update   rewrite the file for the listed kernels (after re-verifying them on the GPU)
+  python tools/sass_fingerprint.py --relist   list EVERY kernel of the library (after the whole GPU suite passed on this build)
   python tools/sass_fingerprint.py --all      print every kernel's size and hash
 """
 import hashlib
@@ -76,6 +77,14 @@ if __name__ == "__main__":
     if "--all" in sys.argv:
         for k, v in sorted(fingerprints().items()):
             print("%6d %s %s" % (v["instructions"], v["sha1"][:12], demangled(k)))
+    elif "--relist" in sys.argv:
+        got = fingerprints()
+        note = "kernels of libafterqc_b200.so whose parity tests (pytest -m gpu) were green on a B200 with exactly this instruction stream"
+        want = {"note": note, "nvcc": nvcc_version(),
+                "kernels": {k: dict(v, name=demangled(k)) for k, v in sorted(got.items()) if "aqc" in k}}
+        with open(FILE, "w") as f:
+            json.dump(want, f, indent=1, sort_keys=True)
+        print("relisted %d kernels in %s" % (len(want["kernels"]), FILE))
     elif "--update" in sys.argv:
         with open(FILE) as f:
             want = json.load(f)
