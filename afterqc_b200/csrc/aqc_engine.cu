@@ -409,16 +409,17 @@ int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t s
         L.fb_list = ctx->d_fb_list; L.fb_count = ctx->d_fb_count;
         L.lane_col_cap = (32 * maxl + 96 + 15) & ~15;
         const void *lk = lane_kernel_for(pe, nw);
+        // one CTA per SM with as many warps as the kernel is built for and the stage allows, in steps of four (one per scheduler)
         int best_w = 0, best_occ = 0;
-        for (int w = LANE_MAX_WARPS; w >= 1; w--) {           // most resident warps per SM; ties go to the larger CTA
+        for (int w = lane_max_warps(nw, pe); w >= 1 && best_w == 0; w -= (w > 4 ? 4 : 1)) {
             size_t sm = lane_smem_bytes(w, L.lane_col_cap, maxl);
             if (sm > ctx->max_dyn_smem) continue;
             int occ = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lk, w * 32, sm));
-            if (occ * w > best_occ * best_w) { best_w = w; best_occ = occ; }
+            if (occ > 0) { best_w = w; best_occ = occ; }
         }
         if (const char *fw = getenv("AQC_LANE_WARPS")) {        // tuning knob
-            int w = std::max(1, std::min(LANE_MAX_WARPS, atoi(fw)));
+            int w = std::max(1, std::min(lane_max_warps(nw, pe), atoi(fw)));
             size_t sm = lane_smem_bytes(w, L.lane_col_cap, maxl);
             int occ = 0;
             if (sm <= ctx->max_dyn_smem) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lk, w * 32, sm)); if (occ > 0) { best_w = w; best_occ = occ; } }

@@ -30,10 +30,24 @@
 
 namespace aqc {
 
-#ifndef AQC_LANE_MIN_BLOCKS
-#define AQC_LANE_MIN_BLOCKS 5      // CTAs of 4 warps per SM the register allocation aims at for reads <= 160 bases (tuning: profiles/r02_notes.md)
+// ONE CTA per SM, a multiple of four warps (one scheduler each): 16 warps for paired reads <= 160 bases (120 registers, no
+// spills), 12 for paired reads <= 256 bases (161 registers), 24 for single-end reads (72 registers).  Measured on PE150,
+// filter launch for 10 M pairs (profiles/r02_notes.md): five 4-warp CTAs 3.75 ms; one CTA of 16 / 18 / 20 / 22 warps
+// 3.24 / 3.66 / 3.32 / 3.70 ms.
+#ifndef AQC_LANE_WARPS_SHORT
+#define AQC_LANE_WARPS_SHORT 16
 #endif
-constexpr int LANE_MAX_WARPS = 4;
+#ifndef AQC_LANE_WARPS_LONG
+#define AQC_LANE_WARPS_LONG 12
+#endif
+#ifndef AQC_LANE_WARPS_SINGLE
+#define AQC_LANE_WARPS_SINGLE 24
+#endif
+constexpr int LANE_MAX_WARPS = 24;
+__host__ __device__ constexpr int lane_max_warps(int nw, bool paired) {
+    return !paired ? AQC_LANE_WARPS_SINGLE : (nw > 5 ? AQC_LANE_WARPS_LONG : AQC_LANE_WARPS_SHORT);
+}
+static_assert(AQC_LANE_WARPS_SHORT <= LANE_MAX_WARPS && AQC_LANE_WARPS_LONG <= LANE_MAX_WARPS && AQC_LANE_WARPS_SINGLE <= LANE_MAX_WARPS, "barrier array");
 
 struct LArgs {
     KArgs k;                      // batch, parameters, outputs (tile_pairs/col_cap as used by this kernel)
@@ -306,7 +320,7 @@ __host__ __device__ __forceinline__ size_t lane_smem_bytes(int nwarps, int col_c
 }
 
 template <bool PAIRED, int NW>
-__global__ void __launch_bounds__(LANE_MAX_WARPS * 32, (NW > 5 ? 3 : AQC_LANE_MIN_BLOCKS)) lane_kernel(const __grid_constant__ LArgs L) {
+__global__ void __launch_bounds__(lane_max_warps(NW, PAIRED) * 32, 1) lane_kernel(const __grid_constant__ LArgs L) {
     AQC_DYN_SMEM(smem_raw);
     __shared__ __align__(8) uint64_t full_bar[2 * LANE_MAX_WARPS];      // per warp: [0] bases landed, [1] qualities landed
     const KArgs &A = L.k;
