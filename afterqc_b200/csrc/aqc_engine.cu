@@ -12,6 +12,8 @@
 #include "aqc_kernel.cuh"
 #include "aqc_lane_kernel.cuh"
 #include "aqc_stat_kernel.cuh"
+#include "aqc_edit.cuh"
+#include <mutex>
 
 using namespace aqc;
 
@@ -134,6 +136,9 @@ size_t smem_bytes_for(int P, int col_cap, int max_len) {
 #define AQC_KERNEL_HANDLE(...) ((const void *)(__VA_ARGS__))
 #else
 template <int MODE, bool PAIRED> void emu_pair_kernel(void **a) { pair_kernel<MODE, PAIRED>(*(const KArgs *)a[0]); }
+void emu_edit_distance_kernel(void **a) {
+    edit_distance_kernel(*(const uint8_t **)a[0], *(const uint32_t **)a[1], *(const uint8_t **)a[2], *(const uint32_t **)a[3], *(uint32_t *)a[4], *(int32_t **)a[5]);
+}
 void emu_maxlen_kernel(void **a) { maxlen_kernel(*(const uint32_t **)a[0], *(const uint32_t **)a[1], *(uint32_t *)a[2], *(uint32_t **)a[3]); }
 #define pair_kernel emu_pair_kernel
 #define AQC_KERNEL_HANDLE(...) ((const void *)(simt::Entry)(__VA_ARGS__))
@@ -1010,6 +1015,101 @@ int aqc_get_kmer_side_raw(aqc_ctx *ctx, int slot, uint64_t *keys, uint64_t *coun
     for (uint32_t i = 0; i < q.side_cap; i++)
         if (k[i] != AQC_KMER_NEVER) { keys[o] = k[i]; counts[o] = c[i]; first_direct[o] = d[i]; first_seed[o] = sf[i]; o++; }
     return rc;
+}
+
+int aqc_edit_distance_batch(aqc_ctx *ctx, const uint8_t *a, const uint32_t *a_off, const uint8_t *b, const uint32_t *b_off,
+                            uint32_t n, int mem, int32_t *out) {
+    if (!ctx || (n && (!a_off || !b_off || !out))) return AQC_ERR_INVALID;
+    if (mem != AQC_MEM_HOST && mem != AQC_MEM_DEVICE) return fail(ctx, AQC_ERR_INVALID, "bad memory space");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const uint8_t *da = a, *db = b;
+    const uint32_t *dao = a_off, *dbo = b_off;
+    int32_t *dout = out;
+    void *tmp[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    auto release = [&]() { for (void *p : tmp) cudaFree(p); };
+    if (mem == AQC_MEM_HOST) {
+        const size_t na = a_off[n], nb = b_off[n];
+        auto up = [&](int k, const void *src, size_t bytes) -> int {
+            CK(cudaMalloc(&tmp[k], bytes + 16));
+            if (bytes) CK(cudaMemcpyAsync(tmp[k], src, bytes, cudaMemcpyHostToDevice, ctx->compute));
+            return 0;
+        };
+        int rc = up(0, a, na); if (!rc) rc = up(1, b, nb); if (!rc) rc = up(2, a_off, (size_t)(n + 1) * 4); if (!rc) rc = up(3, b_off, (size_t)(n + 1) * 4);
+        if (!rc && cudaMalloc(&tmp[4], (size_t)n * 4) != cudaSuccess) rc = AQC_ERR_NOMEM;
+        if (rc) { release(); return rc; }
+        da = (const uint8_t *)tmp[0]; db = (const uint8_t *)tmp[1]; dao = (const uint32_t *)tmp[2]; dbo = (const uint32_t *)tmp[3]; dout = (int32_t *)tmp[4];
+    }
+    void *args[6] = {(void *)&da, (void *)&dao, (void *)&db, (void *)&dbo, (void *)&n, (void *)&dout};
+#ifndef AQC_EMU
+    const void *kern = (const void *)edit_distance_kernel;
+#else
+    const void *kern = (const void *)(simt::Entry)emu_edit_distance_kernel;
+#endif
+    cudaError_t e = cudaLaunchKernel(kern, dim3(std::max<uint32_t>(1u, std::min<uint32_t>((n + 127) / 128, (uint32_t)ctx->sm_count * 16u))), dim3(128), args, 0, ctx->compute);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    ctx->launches++;
+    if (e == cudaSuccess && mem == AQC_MEM_HOST) {
+        e = cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->compute);
+    }
+    release();
+    if (e != cudaSuccess) { snprintf(ctx->err, sizeof ctx->err, "edit distance launch failed: %s", cudaGetErrorString(e)); return AQC_ERR_CUDA; }
+    return 0;
+}
+
+// ---- libed.so-compatible entry points (editdistance/_editdistance.h:16,23), so that the untouched reference can load this
+// library through its own loader (util.py:15-18 -> ed_ctypes.edit_distance / ed_ctypes.seek_overlap).  One call = one pair:
+// a lazily created context on the current device serves them (a batch entry exists for real work: aqc_edit_distance_batch,
+// aqc_ops_pairs).  seek_overlap has util.overlap_hm's semantics (util.py:158-212: the closed form of the leaked loop variable,
+// constants 3 / 30 / 50 whatever order the caller passes them in -- the reference's own call site swaps two of them), NOT the
+// semantics of the C function of that name, which differs from the Python on ~12 % of pairs.
+namespace {
+aqc_ctx *g_shim_ctx = nullptr;
+std::mutex g_shim_mutex;
+aqc_ctx *shim_ctx() {
+    if (!g_shim_ctx) {
+        aqc_params p;
+        memset(&p, 0, sizeof p);
+        p.paired = 1; p.seq_len_req = 35; p.poly_size_limit = 35; p.allow_mismatch_in_poly = 2; p.qualified_quality_phred = 15;
+        p.unqualified_base_limit = 60; p.n_base_limit = 5; p.qc_sample = 200000; p.qc_kmer = 8;
+        const char *dv = getenv("AQC_DEVICE");
+        if (aqc_create(dv ? atoi(dv) : -1, &p, &g_shim_ctx) != 0) g_shim_ctx = nullptr;
+    }
+    return g_shim_ctx;
+}
+}  // namespace
+
+unsigned int edit_distance(const char *a, const unsigned int asize, const char *b, const unsigned int bsize) {
+    std::lock_guard<std::mutex> lock(g_shim_mutex);
+    aqc_ctx *ctx = shim_ctx();
+    if (!ctx) return 0xFFFFFFFFu;
+    const uint32_t ao[2] = {0, asize}, bo[2] = {0, bsize};
+    int32_t d = -1;
+    if (aqc_edit_distance_batch(ctx, (const uint8_t *)a, ao, (const uint8_t *)b, bo, 1, AQC_MEM_HOST, &d) != 0) return 0xFFFFFFFFu;
+    return (unsigned int)d;
+}
+
+int seek_overlap(const char *r1, const int len1, const char *rc_r2, const int len2, const int limit_distance, const int p5, const int p6) {
+    if (len1 < 0 || len2 < 0 || len1 > AQC_MAX_LEN || len2 > AQC_MAX_LEN) return 0x7FFFFFFF;
+    if (limit_distance != 3 || !((p5 == 30 && p6 == 50) || (p5 == 50 && p6 == 30))) return 0x7FFFFFFF;     // overlap_hm's constants only
+    std::lock_guard<std::mutex> lock(g_shim_mutex);
+    aqc_ctx *ctx = shim_ctx();
+    if (!ctx) return 0x7FFFFFFF;
+    // the caller hands over reverseComplement(r2) (util.py:217); the engine takes r2 itself: complement back (an involution on
+    // util.COMP's alphabet; bytes outside it are 'N' by now and stay 'N')
+    std::vector<uint8_t> s1((size_t)len1 + 16, 0), q1((size_t)len1 + 16, 'I'), s2((size_t)len2 + 16, 0), q2((size_t)len2 + 16, 'I');
+    memcpy(s1.data(), r1, (size_t)len1);
+    Luts L; fill_luts(L);
+    for (int i = 0; i < len2; i++) s2[(size_t)i] = L.lut3[(uint8_t)rc_r2[len2 - 1 - i]];
+    const uint32_t o1[2] = {0, (uint32_t)len1}, o2[2] = {0, (uint32_t)len2};
+    aqc_batch b;
+    memset(&b, 0, sizeof b);
+    b.n = 1; b.seq1 = s1.data(); b.qual1 = q1.data(); b.off1 = o1; b.seq2 = s2.data(); b.qual2 = q2.data(); b.off2 = o2;
+    aqc_ops r;
+    if (aqc_ops_pairs(ctx, &b, AQC_MEM_HOST, &r) != 0) return 0x7FFFFFFF;
+    if (r.ov_len == 0) return 0x7FFFFFFF;                       // overlap_hm's (0, 0, 0): "not matched"
+    return (int)((uint32_t)((int)r.ov_offset << 8) + std::min<uint32_t>(r.ov_diff, 255u));
 }
 
 uint64_t aqc_launch_count(const aqc_ctx *ctx) { return ctx ? ctx->launches : 0; }

@@ -179,6 +179,21 @@ class Engine:
         order = np.argsort(keys, kind="stable")
         return cnt, first, keys[order], sc[order], sf[order]
 
+    def edit_distances(self, pairs):
+        """Levenshtein distance of every (a, b) pair of byte / str strings on the GPU (aqc_edit_distance_batch)"""
+        def col(strs):
+            bs = [x if isinstance(x, (bytes, bytearray)) else x.encode("latin-1") for x in strs]
+            off = np.zeros(len(bs) + 1, dtype=np.uint32)
+            np.cumsum([len(x) for x in bs], out=off[1:])
+            data = np.frombuffer(b"".join(bs) + b"\0" * 16, dtype=np.uint8).copy()
+            return data, off
+        a, ao = col([p[0] for p in pairs])
+        b, bo = col([p[1] for p in pairs])
+        out = np.zeros(len(pairs), dtype=np.int32)
+        if len(pairs):
+            self._check(self._L.aqc_edit_distance_batch(self._h, a.ctypes.data, ao.ctypes.data, b.ctypes.data, bo.ctypes.data, len(pairs), _abi.MEM_HOST, out.ctypes.data))
+        return out
+
     def launch_count(self):
         return int(self._L.aqc_launch_count(self._h))
 

@@ -342,6 +342,21 @@ int aqc_gunzip_buffer_mt(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t o
                          uint64_t stats[3], char *err, uint64_t err_cap);
 void aqc_reader_close(aqc_reader *r);
 
+/* ---- Levenshtein distance of n string pairs, bit-parallel on the GPU (one lane per pair): replaces util.editDistance
+ * (util.py:65-83) -> edit_distance (editdistance/_editdistance.cpp:100-126) for batches.  a / b: byte columns with n + 1
+ * uint32 offsets each; any byte is a valid character; out[i] = -1 when both strings of pair i exceed AQC_MAX_LEN. ---- */
+int aqc_edit_distance_batch(aqc_ctx *ctx, const uint8_t *a, const uint32_t *a_off, const uint8_t *b, const uint32_t *b_off,
+                            uint32_t n, int mem, int32_t *out);
+
+/* ---- the two symbols of the reference's editdistance/libed.so (_editdistance.h:16,23), same signatures, so that the
+ * untouched reference can load this library through util.py:15-18.  edit_distance: as the reference's.  seek_overlap: the
+ * semantics of util.overlap_hm (the Python the reference actually runs), not those of the C function it replaces; returns
+ * (offset << 8) + min(diff, 255), or 0x7FFFFFFF for "not matched" / unsupported constants.  One pair per call, served by a
+ * lazily created context on the current device (AQC_DEVICE overrides). ---- */
+unsigned int edit_distance(const char *a, const unsigned int asize, const char *b, const unsigned int bsize);
+int seek_overlap(const char *r1, const int len1, const char *rc_r2, const int len2, const int limit_distance,
+                 const int complete_compare_require, const int overlap_require);
+
 /* instrumentation for bench.py: kernels launched by this context so far, and the device
  * time in ms of the last filter/stat call's kernels (CUDA events on the launching stream) */
 uint64_t aqc_launch_count(const aqc_ctx *ctx);

@@ -534,3 +534,31 @@ int aqo_reset_filter(aqo_ctx *ctx) { return reset_from(ctx, AQC_QC_R1_POST); }
 #ifdef __cplusplus
 }
 #endif
+
+/* Levenshtein distance, the plain dynamic programme (the number util.editDistance returns, util.py:65-83; the reference
+ * computes it with the editdistance module or editdistance/_editdistance.cpp:100-126, Myers' bit-vector algorithm with a DP
+ * fall-back :64-75 -- all the same function of the two strings).  Checker of aqc_edit_distance_batch; the reference's own C++
+ * is compiled next to it (oracle/Makefile, _ref/libed_ref.so) where /root/reference exists and pins this restatement. */
+int aqo_edit_distance(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb) {
+    if (la == 0) return (int)lb;
+    if (lb == 0) return (int)la;
+    uint32_t *row = (uint32_t *)malloc(((size_t)lb + 1) * sizeof(uint32_t));
+    if (!row) return -1;
+    for (uint32_t j = 0; j <= lb; j++) row[j] = j;
+    for (uint32_t i = 1; i <= la; i++) {
+        uint32_t diag = row[0];
+        row[0] = i;
+        for (uint32_t j = 1; j <= lb; j++) {
+            uint32_t up = row[j];
+            uint32_t v = up + 1;
+            if (row[j - 1] + 1 < v) v = row[j - 1] + 1;
+            if (diag + (a[i - 1] != b[j - 1]) < v) v = diag + (a[i - 1] != b[j - 1]);
+            diag = up;
+            row[j] = v;
+        }
+    }
+    int d = (int)row[lb];
+    free(row);
+    return d;
+}
+

@@ -48,10 +48,30 @@ def lib():
         L.aqo_get_qc.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.aqo_get_kmer_dense.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.aqo_get_kmer_side.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.aqo_edit_distance.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32]
+        L.aqo_edit_distance.restype = C.c_int
         L.aqo_reset.argtypes = [C.c_void_p]
         L.aqo_reset_filter.argtypes = [C.c_void_p]
         _lib = L
     return _lib
+
+
+def edit_distance(a, b):
+    """Levenshtein distance of two byte strings by the oracle's dynamic programme"""
+    a = a if isinstance(a, (bytes, bytearray)) else a.encode("latin-1")
+    b = b if isinstance(b, (bytes, bytearray)) else b.encode("latin-1")
+    return int(lib().aqo_edit_distance(bytes(a), len(a), bytes(b), len(b)))
+
+
+_REF_ED = os.path.join(_HERE, "_ref", "libed_ref.so")
+
+
+def build_ref(reference="/root/reference"):
+    """oracle/_ref/libed_ref.so: the reference's editdistance/_editdistance.cpp compiled where it lies (build container only)"""
+    if not os.path.isfile(os.path.join(reference, "editdistance", "_editdistance.cpp")):
+        return None
+    subprocess.check_call(["make", "-s", "-C", _HERE, "ref", "REFERENCE=" + reference])
+    return _REF_ED
 
 
 class OracleError(RuntimeError):
