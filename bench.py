@@ -90,8 +90,11 @@ def parse_args():
 
 def workload_config(args, world):
     cfg = args.cfg
+    # the same dictionary in the GPU arm and in --impl reference (the driver compares them)
     return {"workload": cfg["workload"], "config": args.config, "units_per_gpu": args.n, "read_len": cfg["L"], "qc_sample": args.qs,
-            "autotrim": cfg["autotrim"], "parallelism": ("read-sharded x%d, NCCL all-reduce of the counter blocks per step" % world) if world > 1 else "1 GPU"}
+            "autotrim": cfg["autotrim"], "filter_kernel": args.filter_kernel,
+            "l2": "inputs (GB per GPU) exceed the 126 MB L2; no explicit flush",
+            "parallelism": ("read-sharded x%d, NCCL all-reduce of the counter blocks per step" % world) if world > 1 else "1 GPU"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -718,16 +721,15 @@ def run_ours(args):
             r = cpu_arm(args, hb, threads)
             cpu = {"value": r["units_per_s"] / 1e6, "unit": cfg["unit"], "cores": r["threads"], "kind": "port", "sample": cpu_sample_text(args, r)}
         confd = workload_config(args, world)
-        confd.update({"filter_kernel": args.filter_kernel, "autotrim_resolved": list(R.trims) if R.trims else None,
-                      "l2": "inputs (%.1f GB/GPU) exceed the 126 MB L2; no explicit flush" % (2 * (b1 + b2) / 1e9)})
         line = {
             "metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "config": confd, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_python": python_reference_timing(args.config),
+            "autotrim_resolved": list(R.trims) if R.trims else None, "input_GB_per_gpu": 2 * (b1 + b2) / 1e9,
         }
         if numa is not None:
-            line["config"]["numa_rank0"] = numa
+            line["numa_rank0"] = numa
         if shard_parity is not None:
             line["shard_parity"] = shard_parity[0]
             line["shard_parity_note"] = shard_parity[1]

@@ -36,7 +36,7 @@ def test_bench_flow_on_emulator(oracle_lib, config, extra):
     assert len(r["phases"]) >= 2
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
     if config == "pe250_full":
-        assert line["config"]["autotrim_resolved"] is not None
+        assert line["autotrim_resolved"] is not None
     if config == "se100":
         assert line["unit"] == "M reads/s"
 
@@ -56,3 +56,7 @@ def test_reference_arm_line(oracle_lib, capsys):
     assert line["impl"] == "reference" and line["steps"] == 2 and line["warmup"] == 1
     assert line["value"] > 0 and line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["config"]["config"] == "pe250_full" and line["cpu_baseline"]["kind"] == "port"
+    # the GPU arm of the same command line carries the same config dictionary
+    import bench_on_emulator
+    ours = bench_on_emulator.run(["--config", "pe250_full", "--pairs", "3000", "--cpu-sample", "600", "--steps", "2", "--warmup", "1"])
+    assert ours["config"] == line["config"]

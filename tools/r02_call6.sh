@@ -13,7 +13,7 @@ import json, sys
 try:
     j = json.load(open(sys.argv[1]))
     print(sys.argv[1].split("/")[-1], "value", round(j["value"], 1), "ms/step", round(j["ms_per_step"], 3), "e2e", j["e2e"] and round(j["e2e"]["value"] or 0, 1),
-          "per-gpu h2d GB/s", j["e2e"] and round(j["e2e"].get("per_gpu_h2d_GBps", 0), 1), "shard_parity", j.get("shard_parity"), j.get("shard_parity_note"), j["config"].get("numa_rank0"))
+          "per-gpu h2d GB/s", j["e2e"] and round(j["e2e"].get("per_gpu_h2d_GBps", 0), 1), "shard_parity", j.get("shard_parity"), j.get("shard_parity_note"), j.get("numa_rank0"))
 except Exception as e:
     print(sys.argv[1], "no line", e)
 PY
