@@ -124,6 +124,22 @@ def adversarial_batch(seed=7, first_index=0):
     return PackedBatch.from_reads([p[0] for p in pairs], [p[1] for p in pairs], first_index=first_index)
 
 
+def homopolymer_batch(n, L=150, seed=3):
+    """reads that pile onto very few k-mers: the first tenth all A (mate 2 all T), then all C / all G, then an ACAC.. repeat,
+    each with a sprinkle of other bases -- a CTA's 16-bit shared-memory counter of one k-mer passes 0x4000 many times, for
+    k-mers in the low and the high half of a counter word, met inside and (C, G, the repeat) beyond the stamped head"""
+    rng = random.Random(seed)
+    r1s, r2s = [], []
+    for i in range(n):
+        base1, base2 = ("A", "T") if i < n // 10 else (("C", "G") if i < (6 * n) // 10 else ("AC", "GT"))
+        s1 = list((base1 * L)[:L]); s2 = list((base2 * L)[:L])
+        for s in (s1, s2):
+            if rng.random() < 0.3:
+                s[rng.randrange(L)] = rng.choice("ACGTN")
+        r1s.append(("".join(s1), _rand_qual(rng, L))); r2s.append(("".join(s2), _rand_qual(rng, L)))
+    return PackedBatch.from_reads(r1s, r2s)
+
+
 def long_read_batch(seed=11, n=300, lo=200, hi=1000):
     rng = random.Random(seed)
     r1s, r2s = [], []

@@ -148,7 +148,12 @@ static inline unsigned __ballot_sync(unsigned m, int pred) {
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
 static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
-static inline void __syncwarp(unsigned m = 0xffffffffu) { simt_check_mask(m); simt::warp_xchg(0, simt::OP_SYNCWARP); }
+// The call site is part of the collective's identity here: hardware would pair __syncwarp()s of different source lines, but in
+// these kernels that is always a bug (lanes that took different decisions about a warp-wide step), and this check finds it.
+static inline void simt_syncwarp_at(int line, unsigned m) { simt_check_mask(m); simt::warp_xchg(0, simt::OP_SYNCWARP + (line << 8)); }
+static inline unsigned simt_mask_or_full() { return 0xffffffffu; }
+static inline unsigned simt_mask_or_full(unsigned m) { return m; }
+#define __syncwarp(...) simt_syncwarp_at(__LINE__, simt_mask_or_full(__VA_ARGS__))
 static inline unsigned __reduce_add_sync(unsigned m, unsigned v) {
     simt_check_mask(m);
     const uint32_t *a = simt::warp_xchg(v, simt::OP_REDUX);

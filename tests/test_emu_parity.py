@@ -96,6 +96,22 @@ def test_emu_stat_short_head(backends, monkeypatch):
         orc.close(); eng.close()
 
 
+def test_emu_stat_counter_spill(backends, monkeypatch):
+    """stat_kernel's 16-bit shared-memory k-mer counters pass 0x4000 (the lane that fills a half moves it to the global table),
+    for unflagged k-mers and for k-mers first met beyond the stamped head (bit 15 of the counter set)"""
+    if backends.kernel != "lane":
+        pytest.skip("stat_kernel only")
+    monkeypatch.setenv("AQC_STAT_HEAD", "40")
+    batch = cases.homopolymer_batch(1200)
+    orc, eng = backends(_abi.Params.defaults(qc_kmer=8))
+    for be in (orc, eng):
+        be.stat_reads(batch, _abi.QC_R1_PRE, _abi.QC_R2_PRE, stat_lo=0, stat_hi=batch.n, order_base=0)
+    compare.compare_backends(orc, eng, (_abi.QC_R1_PRE, _abi.QC_R2_PRE), "emu counter spill")
+    k = eng.kmers(_abi.QC_R1_PRE)
+    assert int(k[0].max()) > 3 * 0x4000          # the case does what it says
+    orc.close(); eng.close()
+
+
 def test_emu_single_end_and_resident(backends):
     batch = cases.synthetic("se100", 3000)
     for pname in ("default_f0", "trim"):

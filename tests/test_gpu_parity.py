@@ -75,6 +75,21 @@ def test_stat_parity(backends, bname):
         orc.close(); eng.close()
 
 
+def test_stat_counter_spill(backends, monkeypatch):
+    """stat_kernel's 16-bit shared-memory k-mer counters pass 0x4000 in every CTA (reads that pile onto a handful of k-mers),
+    for k-mers met in the stamped head and for flagged ones first met beyond it (short head: AQC_STAT_HEAD)"""
+    batch = cases.homopolymer_batch(60000)
+    for head in ("40", None):
+        if head: monkeypatch.setenv("AQC_STAT_HEAD", head)
+        else: monkeypatch.delenv("AQC_STAT_HEAD", raising=False)
+        orc, eng = backends(_abi.Params.defaults(qc_kmer=8))
+        for be in (orc, eng):
+            be.stat_reads(batch, _abi.QC_R1_PRE, _abi.QC_R2_PRE, stat_lo=0, stat_hi=batch.n, order_base=0)
+        compare.compare_backends(orc, eng, (_abi.QC_R1_PRE, _abi.QC_R2_PRE), "counter spill head=%s" % head)
+        assert int(eng.kmers(_abi.QC_R1_PRE)[0].max()) > 148 * 0x4000
+        orc.close(); eng.close()
+
+
 def test_single_end_parity(backends):
     batch = cases.synthetic("se100", 30000)
     for pname in ("default_f0", "trim", "loose"):
