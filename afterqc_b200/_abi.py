@@ -91,6 +91,16 @@ class Columns(C.Structure):
     _fields_ = [("names", C.c_void_p), ("name_off", C.c_void_p), ("seqs", C.c_void_p), ("seq_off", C.c_void_p), ("quals", C.c_void_p)]
 
 
+class Parsed(C.Structure):
+    """aqc_parsed: what aqc_fastq_parse_device leaves in HBM (device pointers owned by the context)"""
+    _fields_ = [
+        ("n_records", C.c_uint64), ("consumed", C.c_uint64), ("bad_record", C.c_uint64), ("seq_bytes", C.c_uint64),
+        ("hit_eof", C.c_int32), ("reserved", C.c_int32),
+        ("seq", C.c_void_p), ("qual", C.c_void_p), ("off", C.c_void_p), ("line_start", C.c_void_p), ("line_len", C.c_void_p),
+        ("text", C.c_void_p),
+    ]
+
+
 HOST_BADBCD1, HOST_BADBCD2 = 16, 17       # host-only pseudo classes of aqc_fastq_emit (barcode pre-pass)
 
 RESULT_DTYPE = np.dtype([

@@ -13,6 +13,7 @@
 #include "aqc_lane_kernel.cuh"
 #include "aqc_stat_kernel.cuh"
 #include "aqc_edit.cuh"
+#include "aqc_parse.cuh"
 #include <mutex>
 
 using namespace aqc;
@@ -53,6 +54,12 @@ struct aqc_ctx {
     uint32_t *d_fb_list = nullptr, *d_fb_count = nullptr;
     size_t fb_cap = 0;
     uint32_t *d_kbits = nullptr;   // stat_kernel: "already stamped" bitmaps of the two mates of a launch (aqc_stat_kernel.cuh)
+    // aqc_fastq_parse_device (aqc_parse.cuh): per slot (one per mate) the device buffers of the last parse, grown on demand
+    struct ParseSlot {
+        uint8_t *text = nullptr, *seq = nullptr, *qual = nullptr;
+        uint32_t *blk = nullptr, *nl = nullptr, *line_start = nullptr, *line_len = nullptr, *rec = nullptr, *part = nullptr, *flags = nullptr;
+        size_t text_cap = 0, col_cap = 0, blk_cap = 0, nl_cap = 0, line_cap = 0, line2_cap = 0, rec_cap = 0, part_cap = 0, flags_cap = 0;
+    } parse[2];
     Staging stg[2];
     uint32_t chunk_pairs = 1u << 18;
     uint32_t stat_head = 8192;          // records whose dense k-mers stamp_head_kernel stamps before stat_kernel runs (AQC_STAT_HEAD)
@@ -139,6 +146,13 @@ template <int MODE, bool PAIRED> void emu_pair_kernel(void **a) { pair_kernel<MO
 void emu_edit_distance_kernel(void **a) {
     edit_distance_kernel(*(const uint8_t **)a[0], *(const uint32_t **)a[1], *(const uint8_t **)a[2], *(const uint32_t **)a[3], *(uint32_t *)a[4], *(int32_t **)a[5]);
 }
+void emu_newline_count_kernel(void **a) { newline_count_kernel(*(const ParseArgs *)a[0]); }
+void emu_newline_write_kernel(void **a) { newline_write_kernel(*(const ParseArgs *)a[0]); }
+void emu_record_kernel(void **a) { record_kernel(*(const ParseArgs *)a[0]); }
+void emu_gather_kernel(void **a) { gather_kernel(*(const ParseArgs *)a[0]); }
+void emu_scan_partial_kernel(void **a) { scan_partial_kernel(*(const ScanArgs *)a[0]); }
+void emu_scan_single_kernel(void **a) { scan_single_kernel(*(const ScanArgs *)a[0]); }
+void emu_scan_final_kernel(void **a) { scan_final_kernel(*(const ScanArgs *)a[0]); }
 void emu_maxlen_kernel(void **a) { maxlen_kernel(*(const uint32_t **)a[0], *(const uint32_t **)a[1], *(uint32_t *)a[2], *(uint32_t **)a[3]); }
 #define pair_kernel emu_pair_kernel
 #define AQC_KERNEL_HANDLE(...) ((const void *)(simt::Entry)(__VA_ARGS__))
@@ -734,6 +748,10 @@ void aqc_destroy(aqc_ctx *ctx) {
     for (auto &ev : ctx->ev_pool) for (auto e : ev) cudaEventDestroy(e);
     cudaFree(ctx->d_counters); cudaFree(ctx->d_luts); cudaFree(ctx->d_error); cudaFree(ctx->d_maxlen);
     cudaFree(ctx->d_fb_list); cudaFree(ctx->d_fb_count); cudaFree(ctx->d_kbits);
+    for (auto &ps : ctx->parse) {
+        cudaFree(ps.text); cudaFree(ps.seq); cudaFree(ps.qual); cudaFree(ps.blk); cudaFree(ps.nl); cudaFree(ps.line_start);
+        cudaFree(ps.line_len); cudaFree(ps.rec); cudaFree(ps.part); cudaFree(ps.flags);
+    }
     if (ctx->own_compute) cudaStreamDestroy(ctx->own_compute);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
@@ -1055,6 +1073,134 @@ int aqc_edit_distance_batch(aqc_ctx *ctx, const uint8_t *a, const uint32_t *a_of
     }
     release();
     if (e != cudaSuccess) { snprintf(ctx->err, sizeof ctx->err, "edit distance launch failed: %s", cudaGetErrorString(e)); return AQC_ERR_CUDA; }
+    return 0;
+}
+
+// ---- FASTQ text -> packed columns in HBM (aqc_parse.cuh) ----
+extern "C++" {
+namespace {
+#ifndef AQC_EMU
+#define PARSE_KERNEL(name) ((const void *)name)
+#else
+#define PARSE_KERNEL(name) ((const void *)(simt::Entry)emu_##name)
+#endif
+template <class T> int grow(aqc_ctx *ctx, T *&p, size_t &cap, size_t want) {
+    if (want <= cap && p) return 0;
+    cudaFree(p); p = nullptr; cap = 0;
+    const size_t n = want + want / 4 + 64;
+    CK(cudaMalloc((void **)&p, n * sizeof(T)));
+    cap = n;
+    return 0;
+}
+int launch1(aqc_ctx *ctx, const void *k, uint32_t grid, const void *arg_struct) {
+    void *args[1] = {const_cast<void *>(arg_struct)};
+    CK(cudaLaunchKernel(k, dim3(std::max<uint32_t>(1u, grid)), dim3(PARSE_BLOCK_THREADS), args, 0, ctx->compute));
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+// exclusive scan of data[0 .. n) in place, data[n] = total
+int device_scan(aqc_ctx *ctx, aqc_ctx::ParseSlot &ps, uint32_t *data, uint32_t n) {
+    ScanArgs S;
+    S.data = data; S.n = n; S.n_part = (n + SCAN_BLOCK_ELEMS - 1) / SCAN_BLOCK_ELEMS;
+    size_t pc = ps.part_cap;
+    int rc = grow(ctx, ps.part, pc, (size_t)S.n_part + 1);
+    ps.part_cap = pc;
+    if (rc) return rc;
+    S.part = ps.part;
+    const uint32_t g = std::min<uint32_t>(std::max<uint32_t>(S.n_part, 1u), (uint32_t)ctx->sm_count * 8u);
+    if ((rc = launch1(ctx, PARSE_KERNEL(scan_partial_kernel), g, &S))) return rc;
+    if ((rc = launch1(ctx, PARSE_KERNEL(scan_single_kernel), 1, &S))) return rc;
+    return launch1(ctx, PARSE_KERNEL(scan_final_kernel), g, &S);
+}
+}  // namespace
+}  // extern "C++"
+
+int aqc_fastq_parse_device(aqc_ctx *ctx, int slot, const uint8_t *text, uint64_t n, int mem, int final, uint64_t max_records,
+                           aqc_parsed *out) {
+    if (!ctx || !out || slot < 0 || slot > 1 || (n && !text)) return AQC_ERR_INVALID;
+    if (mem != AQC_MEM_HOST && mem != AQC_MEM_DEVICE) return fail(ctx, AQC_ERR_INVALID, "bad memory space");
+    if (n > 0xFFFFFF00ull) return fail(ctx, AQC_ERR_INVALID, "a text buffer must stay below 4 GiB (32-bit positions): split it");
+    memset(out, 0, sizeof *out);
+    out->hit_eof = final ? 1 : 0;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    aqc_ctx::ParseSlot &ps = ctx->parse[slot];
+    cudaStream_t st = ctx->compute;
+    int rc;
+    // the text: copied next to a 16-byte boundary of our own (host memory), or used where it lies (device memory) unless its
+    // last line has no newline and this is the end of the file -- the kernels see a '\n' after every line
+    uint8_t last = 0;
+    if (mem == AQC_MEM_HOST) last = text[n - 1];
+    else { CK(cudaMemcpyAsync(&last, text + n - 1, 1, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
+    const bool append = final && last != (uint8_t)'\n';
+    const uint8_t *dtext = text;
+    if (mem == AQC_MEM_HOST || append || ((uintptr_t)text & 15u)) {
+        if ((rc = grow(ctx, ps.text, ps.text_cap, (size_t)n + 32))) return rc;
+        CK(cudaMemcpyAsync(ps.text, text, n, mem == AQC_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+        if (append) CK(cudaMemsetAsync(ps.text + n, '\n', 1, st));
+        dtext = ps.text;
+    }
+    ParseArgs P;
+    memset(&P, 0, sizeof P);
+    P.text = dtext;
+    P.n = (uint32_t)(n + (append ? 1 : 0));
+    P.n_blk = (P.n + PARSE_BLOCK_BYTES - 1) / PARSE_BLOCK_BYTES;
+    if ((rc = grow(ctx, ps.blk, ps.blk_cap, (size_t)P.n_blk + 1))) return rc;
+    if ((rc = grow(ctx, ps.flags, ps.flags_cap, 2))) return rc;
+    P.blk = ps.blk; P.flags = ps.flags;
+    const uint32_t gmax = (uint32_t)ctx->sm_count * 8u;
+    if ((rc = launch1(ctx, PARSE_KERNEL(newline_count_kernel), std::min(P.n_blk, gmax), &P))) return rc;
+    if ((rc = device_scan(ctx, ps, ps.blk, P.n_blk))) return rc;
+    uint32_t n_lines = 0;
+    CK(cudaMemcpyAsync(&n_lines, ps.blk + P.n_blk, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemsetAsync(ps.flags, 0xFF, 8, st));
+    CK(cudaStreamSynchronize(st));
+    const uint32_t n_cand = (uint32_t)std::min<uint64_t>(n_lines / 4u, max_records);
+    if (n_cand == 0) { out->hit_eof = (final && max_records) ? 1 : 0; return 0; }
+    if ((rc = grow(ctx, ps.nl, ps.nl_cap, (size_t)n_lines + 1))) return rc;
+    if ((rc = grow(ctx, ps.line_start, ps.line_cap, (size_t)4 * n_cand))) return rc;
+    if ((rc = grow(ctx, ps.line_len, ps.line2_cap, (size_t)4 * n_cand))) return rc;
+    if ((rc = grow(ctx, ps.rec, ps.rec_cap, (size_t)n_cand + 1))) return rc;
+    P.nl_pos = ps.nl; P.n_rec = n_cand; P.line_start = ps.line_start; P.line_len = ps.line_len; P.rec_len = ps.rec;
+    if ((rc = launch1(ctx, PARSE_KERNEL(newline_write_kernel), std::min(P.n_blk, gmax), &P))) return rc;
+    if ((rc = launch1(ctx, PARSE_KERNEL(record_kernel), std::min((n_cand + PARSE_BLOCK_THREADS - 1) / PARSE_BLOCK_THREADS, gmax), &P))) return rc;
+    uint32_t flags[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+    CK(cudaMemcpyAsync(flags, ps.flags, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // the reference reads record by record: the first empty line ends the file, a bad record before it is an error
+    uint32_t n_keep = n_cand;
+    bool eof = false, bad = false;
+    if (flags[0] < n_keep) { n_keep = flags[0]; eof = true; }
+    if (flags[1] < n_keep) { n_keep = flags[1]; eof = false; bad = true; }
+    P.n_keep = n_keep;
+    uint32_t end_pos = 0, seq_bytes = 0;
+    if (n_keep) {
+        if ((rc = device_scan(ctx, ps, ps.rec, n_keep))) return rc;
+        CK(cudaMemcpyAsync(&seq_bytes, ps.rec + n_keep, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&end_pos, ps.nl + (size_t)4 * n_keep - 1, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (!ps.seq || !ps.qual || ps.col_cap < (size_t)seq_bytes + 32) {
+            cudaFree(ps.seq); cudaFree(ps.qual); ps.seq = ps.qual = nullptr; ps.col_cap = 0;
+            const size_t cap = (size_t)seq_bytes + seq_bytes / 4 + 64;
+            CK(cudaMalloc((void **)&ps.seq, cap));
+            CK(cudaMalloc((void **)&ps.qual, cap));
+            ps.col_cap = cap;
+        }
+        P.seq = ps.seq; P.qual = ps.qual;
+        if ((rc = launch1(ctx, PARSE_KERNEL(gather_kernel), std::min((n_keep + 7) / 8, gmax), &P))) return rc;
+        CK(cudaStreamSynchronize(st));
+    }
+    out->n_records = n_keep;
+    out->consumed = n_keep ? std::min<uint64_t>((uint64_t)end_pos + 1, n) : 0;
+    out->seq_bytes = seq_bytes;
+    out->bad_record = bad ? n_keep : 0;
+    // as aqc_fastq_parse: an empty line ends the file; at the end of the file whatever is left (a partial record) is dropped
+    // (a call that stops at max_records has not looked further: end of file only if the text is used up)
+    out->hit_eof = eof ? 1 : (bad ? 0 : ((uint64_t)n_keep == max_records ? (final && out->consumed >= n) : (final ? 1 : 0)));
+    out->seq = ps.seq; out->qual = ps.qual; out->off = ps.rec; out->line_start = ps.line_start; out->line_len = ps.line_len;
+    out->text = dtext;
+    if (bad) return fail(ctx, AQC_ERR_INVALID, "a quality line is not as long as its sequence line");
     return 0;
 }
 

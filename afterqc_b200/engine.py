@@ -63,6 +63,56 @@ class DeviceBatch:
         self._ptrs = []
 
 
+class ParsedText:
+    """One mate's records parsed on the device (aqc_fastq_parse_device): the packed base / quality columns, the offsets and
+    the line table live in HBM, owned by the engine, until the next parse into the same slot."""
+
+    def __init__(self, engine, st, n_text):
+        self.engine = engine
+        self.n = int(st.n_records)
+        self.consumed = int(st.consumed)
+        self.hit_eof = bool(st.hit_eof)
+        self.seq_bytes = int(st.seq_bytes)
+        self.seq, self.qual, self.off = st.seq, st.qual, st.off
+        self.line_start, self.line_len, self.text = st.line_start, st.line_len, st.text
+        self.n_text = n_text
+
+    def fetch(self):
+        """host copies: dict(seq, qual, off, line_start, line_len)"""
+        e = self.engine
+
+        def down(ptr, count, dtype):
+            a = np.zeros(count, dtype=dtype)
+            if count:
+                e._check(e._L.aqc_memcpy_d2h(e._h, a.ctypes.data, ptr, a.nbytes))
+            return a
+        if self.n == 0:
+            z8, z32 = np.zeros(0, np.uint8), np.zeros(0, np.uint32)
+            return dict(seq=z8, qual=z8, off=np.zeros(1, np.uint32), line_start=z32, line_len=z32)
+        return dict(seq=down(self.seq, self.seq_bytes, np.uint8), qual=down(self.qual, self.seq_bytes, np.uint8),
+                    off=down(self.off, self.n + 1, np.uint32), line_start=down(self.line_start, 4 * self.n, np.uint32),
+                    line_len=down(self.line_len, 4 * self.n, np.uint32))
+
+
+class ParsedDeviceBatch(DeviceBatch):
+    """The columns of one or two ParsedText objects as a resident batch for stat_reads / filter_pairs (no copy)."""
+
+    def __init__(self, engine, mate1, mate2=None, first_index=0):
+        if mate2 is not None and mate2.n != mate1.n:
+            raise ValueError("the two mates hold %d and %d records" % (mate1.n, mate2.n))
+        self.engine = engine
+        self.n = mate1.n
+        self.first_index = first_index
+        self.paired = mate2 is not None
+        self.max_len = 0                          # no hint: the engine reduces the offsets column
+        self._ptrs = []
+        self.seq1, self.qual1, self.off1 = mate1.seq, mate1.qual, mate1.off
+        self.seq2, self.qual2, self.off2 = (mate2.seq, mate2.qual, mate2.off) if mate2 is not None else (None, None, None)
+        self.results = C.c_void_p()
+        engine._check(engine._L.aqc_device_alloc(engine._h, max(1, self.n) * 32, C.byref(self.results)))
+        self._ptrs.append(self.results)
+
+
 class Engine:
     def __init__(self, params, device=-1):
         self._L = _native.lib()
@@ -193,6 +243,24 @@ class Engine:
         if len(pairs):
             self._check(self._L.aqc_edit_distance_batch(self._h, a.ctypes.data, ao.ctypes.data, b.ctypes.data, bo.ctypes.data, len(pairs), _abi.MEM_HOST, out.ctypes.data))
         return out
+
+    def parse_fastq(self, text, slot=0, final=True, max_records=(1 << 62)):
+        """FASTQ text (bytes / uint8 array, host) -> ParsedText in HBM (aqc_fastq_parse_device; csrc/aqc_parse.cuh).
+        Raises ValueError for a record whose quality line is not as long as its sequence line, like the host parser."""
+        buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text, dtype=np.uint8)
+        st = _abi.Parsed()
+        rc = self._L.aqc_fastq_parse_device(self._h, slot, buf.ctypes.data if buf.size else None, buf.size, _abi.MEM_HOST,
+                                            1 if final else 0, max_records, C.byref(st))
+        if rc == _abi.ERR_INVALID and "quality line" in self._L.aqc_last_error(self._h).decode():
+            raise ValueError("FASTQ record %d: quality line length differs from sequence length" % st.bad_record)
+        self._check(rc)
+        return ParsedText(self, st, buf.size)
+
+    def parse_fastq_resident(self, dev_ptr, nbytes, slot=0, final=True, max_records=(1 << 62)):
+        """the same for text that already lies in HBM (16-byte aligned, 16 bytes of slack): no copy unless the last line lacks its newline"""
+        st = _abi.Parsed()
+        self._check(self._L.aqc_fastq_parse_device(self._h, slot, dev_ptr, nbytes, _abi.MEM_DEVICE, 1 if final else 0, max_records, C.byref(st)))
+        return ParsedText(self, st, nbytes)
 
     def launch_count(self):
         return int(self._L.aqc_launch_count(self._h))

@@ -291,6 +291,28 @@ int aqc_fastq_emit(int mate, int which,
                    uint64_t rec_base, const aqc_result *results, uint64_t n,
                    uint8_t *out, uint64_t out_cap, uint64_t *out_len);
 
+/* ---- the same parse on the device (fastq.Reader.nextRead, fastq.py:37-49, for a whole buffer of text): newline index, line
+ * table, validation and the packed base / quality columns of one mate, built in HBM by csrc/aqc_parse.cuh.  Semantics are
+ * aqc_fastq_parse's (rstrip()ped lines, the first empty line ends the file, a trailing partial record stays unconsumed,
+ * AQC_ERR_INVALID + bad_record when a quality line's length differs from its sequence line's; records before it are valid).
+ * text: AQC_MEM_HOST (copied inside) or AQC_MEM_DEVICE; below 4 GiB.  The pointers of *out are DEVICE pointers owned by the
+ * context, valid until the next call with the same slot (0 or 1: the two mates of a pair can be held at once); seq / qual /
+ * off are directly the columns of one mate of an aqc_batch for AQC_MEM_DEVICE calls; line_start / line_len index `text`
+ * (names and '+' lines stay text: only the writers need them). */
+typedef struct aqc_parsed {
+    uint64_t n_records;            /* complete records in the columns */
+    uint64_t consumed;             /* bytes of the text they cover: the next call continues here */
+    uint64_t bad_record;           /* with AQC_ERR_INVALID */
+    uint64_t seq_bytes;            /* bytes in each of seq / qual */
+    int32_t hit_eof, reserved;
+    const uint8_t *seq, *qual;     /* packed, 16-byte aligned, 16 bytes of slack */
+    const uint32_t *off;           /* [n_records + 1] */
+    const uint32_t *line_start, *line_len;   /* [4 * n_records]: name, bases, '+', qualities of every record */
+    const uint8_t *text;           /* the device copy of the text (or the caller's device pointer) the line table refers to */
+} aqc_parsed;
+int aqc_fastq_parse_device(aqc_ctx *ctx, int slot, const uint8_t *text, uint64_t n, int mem, int final, uint64_t max_records,
+                           aqc_parsed *out);
+
 /* ---- barcode (UMI) pre-pass on packed columns (host only; barcodeprocesser.py, preprocesser.py:435-452) ---- */
 #define AQC_HOST_BADBCD1 16   /* host-only pseudo classes for aqc_fastq_emit: pairs rejected before the device loop */
 #define AQC_HOST_BADBCD2 17
