@@ -1188,7 +1188,7 @@ int aqc_fastq_parse_device(aqc_ctx *ctx, int slot, const uint8_t *text, uint64_t
             ps.col_cap = cap;
         }
         P.seq = ps.seq; P.qual = ps.qual;
-        if ((rc = launch1(ctx, PARSE_KERNEL(gather_kernel), std::min((n_keep + 7) / 8, gmax), &P))) return rc;
+        if ((rc = launch1(ctx, PARSE_KERNEL(gather_kernel), std::min((n_keep + 31) / 32, gmax), &P))) return rc;
         CK(cudaStreamSynchronize(st));
     }
     out->n_records = n_keep;

@@ -2,7 +2,7 @@
 //
 // The reference reads a record as four readline()s, rstrip()s each and stops at the first empty line.  Here a buffer of text
 // that is already in HBM is indexed and packed by five small launches; no byte goes back to the host:
-//   newline_count_kernel   16 bytes per thread: SWAR "byte == '\n'" mask, popcount, one count per 4 KB block
+//   newline_count_kernel   64 bytes per thread: SWAR "byte == '\n'" masks, popcount, one count per 16 KB block
 //   (exclusive scan of the block counts: scan_* below)
 //   newline_write_kernel   the same masks again, a block-wide scan of the per-thread counts, positions written in order
 //   record_kernel          one thread per record: its four lines, rstrip()ped; line table (start, length); the first record
@@ -18,13 +18,14 @@
 namespace aqc {
 
 constexpr int PARSE_BLOCK_THREADS = 256;
-constexpr uint32_t PARSE_BLOCK_BYTES = PARSE_BLOCK_THREADS * 16u;
+constexpr uint32_t PARSE_THREAD_BYTES = 64u;       // four 16-byte loads per thread and block step: fewer block-wide scans per byte
+constexpr uint32_t PARSE_BLOCK_BYTES = PARSE_BLOCK_THREADS * PARSE_THREAD_BYTES;
 constexpr uint32_t SCAN_BLOCK_ELEMS = 1024u;      // 256 threads x 4
 
 struct ParseArgs {
     const uint8_t *text;        // 16-byte aligned, readable up to the next multiple of 16 beyond n
     uint32_t n;                 // bytes (including the '\n' the host appended after a last line without one)
-    uint32_t n_blk;             // ceil(n / 4096)
+    uint32_t n_blk;             // ceil(n / PARSE_BLOCK_BYTES)
     uint32_t *blk;              // [n_blk + 1]: newline count per block, scanned in place (exclusive; [n_blk] = total)
     uint32_t *nl_pos;           // [n_lines]: byte position of every '\n', ascending
     uint32_t n_rec;             // records to look at (complete groups of four lines, capped by the caller)
@@ -41,29 +42,35 @@ __device__ __forceinline__ uint32_t newline_bytes(uint32_t w) {
     return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
 }
 
-// the four masks of the thread's 16 bytes, bytes at or beyond n cleared
-__device__ __forceinline__ void newline_masks(const ParseArgs &P, uint32_t byte0, uint32_t m[4]) {
-    m[0] = m[1] = m[2] = m[3] = 0;
-    if (byte0 >= P.n) return;
-    const uint4 v = *reinterpret_cast<const uint4 *>(P.text + byte0);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+// the sixteen masks of the thread's 64 bytes, bytes at or beyond n cleared; returns the number of newlines
+__device__ __forceinline__ uint32_t newline_masks(const ParseArgs &P, uint32_t byte0, uint32_t m[16]) {
+    uint32_t c = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        m[k] = newline_bytes(w[k]);
-        const uint32_t b = byte0 + 4u * (uint32_t)k;
-        if (b + 4u > P.n) {                                  // the word straddles the end: keep bytes b .. n-1
-            const uint32_t valid = P.n > b ? P.n - b : 0u;   // 0..3
-            m[k] &= valid ? (0xFFFFFFFFu >> (8u * (4u - valid))) : 0u;
+    for (int q = 0; q < 4; q++) {
+        const uint32_t q0 = byte0 + 16u * (uint32_t)q;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (q0 < P.n) v = *reinterpret_cast<const uint4 *>(P.text + q0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t mk = q0 < P.n ? newline_bytes(w[k]) : 0u;
+            const uint32_t b = q0 + 4u * (uint32_t)k;
+            if (b + 4u > P.n) {                                  // the word straddles the end: keep bytes b .. n-1
+                const uint32_t valid = P.n > b ? P.n - b : 0u;   // 0..3
+                mk &= valid ? (0xFFFFFFFFu >> (8u * (4u - valid))) : 0u;
+            }
+            m[4 * q + k] = mk;
+            c += (uint32_t)__popc(mk);
         }
     }
+    return c;
 }
 
 __global__ void __launch_bounds__(PARSE_BLOCK_THREADS) newline_count_kernel(const __grid_constant__ ParseArgs P) {
     __shared__ uint32_t wsum[PARSE_BLOCK_THREADS / 32];
     for (uint32_t b = blockIdx.x; b < P.n_blk; b += gridDim.x) {
-        uint32_t m[4];
-        newline_masks(P, b * PARSE_BLOCK_BYTES + threadIdx.x * 16u, m);
-        uint32_t c = (uint32_t)(__popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]));
+        uint32_t m[16];
+        uint32_t c = newline_masks(P, b * PARSE_BLOCK_BYTES + threadIdx.x * PARSE_THREAD_BYTES, m);
         c = __reduce_add_sync(FULL, c);
         if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
         __syncthreads();
@@ -97,14 +104,13 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *w
 __global__ void __launch_bounds__(PARSE_BLOCK_THREADS) newline_write_kernel(const __grid_constant__ ParseArgs P) {
     __shared__ uint32_t wsum[PARSE_BLOCK_THREADS / 32];
     for (uint32_t b = blockIdx.x; b < P.n_blk; b += gridDim.x) {
-        const uint32_t byte0 = b * PARSE_BLOCK_BYTES + threadIdx.x * 16u;
-        uint32_t m[4];
-        newline_masks(P, byte0, m);
-        const uint32_t c = (uint32_t)(__popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]));
+        const uint32_t byte0 = b * PARSE_BLOCK_BYTES + threadIdx.x * PARSE_THREAD_BYTES;
+        uint32_t m[16];
+        const uint32_t c = newline_masks(P, byte0, m);
         uint32_t total;
         uint32_t at = P.blk[b] + block_exclusive_scan(c, wsum, &total);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < 16; k++) {
             uint32_t mk = m[k];
             while (mk) {
                 const int bit = __ffs((int)mk) - 1;          // 7, 15, 23 or 31: byte bit / 8
@@ -199,13 +205,15 @@ __global__ void __launch_bounds__(PARSE_BLOCK_THREADS) record_kernel(const __gri
     }
 }
 
-// dst[0 .. len) = src[0 .. len): aligned 4-byte stores, each fed by two aligned loads and a funnel shift (src may read up to 3
-// bytes past src + len: the text has 16 bytes of slack); the bytes before the first aligned word and after the last one singly
-__device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t lane) {
+// dst[0 .. len) = src[0 .. len) by a group of G lanes: aligned 4-byte stores, each fed by two aligned loads and a funnel shift
+// (src may read up to 3 bytes past src + len: the text has 16 bytes of slack); the bytes before the first aligned word and after
+// the last one singly
+template <uint32_t G>
+__device__ __forceinline__ void group_copy(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t gl) {
     const uint32_t head = min(len, (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
-    if (lane < head) dst[lane] = src[lane];
+    if (gl < head) dst[gl] = src[gl];
     const uint32_t n_words = (len - head) >> 2;
-    for (uint32_t w = lane; w < n_words; w += 32u) {
+    for (uint32_t w = gl; w < n_words; w += G) {
         const uint32_t b = head + 4u * w;
         const uintptr_t a = reinterpret_cast<uintptr_t>(src + b);
         const uint32_t *ap = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
@@ -214,17 +222,18 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint
         *reinterpret_cast<uint32_t *>(dst + b) = __funnelshift_r(lo, hi, sh);
     }
     const uint32_t done = head + 4u * n_words;
-    if (lane < len - done) dst[done + lane] = src[done + lane];
+    if (gl < len - done) dst[done + gl] = src[done + gl];
 }
 
+// eight lanes per record, four records in flight per warp (the kernel waits on memory: two dependent loads, then the copies)
 __global__ void __launch_bounds__(PARSE_BLOCK_THREADS) gather_kernel(const __grid_constant__ ParseArgs P) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t W = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < P.n_keep; r += W) {
+    const uint32_t gl = threadIdx.x & 7u;
+    const uint32_t W = gridDim.x * (blockDim.x >> 3);
+    for (uint32_t r = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); r < P.n_keep; r += W) {
         const uint32_t s1 = P.line_start[4u * r + 1u], s3 = P.line_start[4u * r + 3u];
         const uint32_t dst = P.rec_len[r], len = P.rec_len[r + 1u] - dst;
-        warp_copy(P.seq + dst, P.text + s1, len, lane);
-        warp_copy(P.qual + dst, P.text + s3, len, lane);
+        group_copy<8>(P.seq + dst, P.text + s1, len, gl);
+        group_copy<8>(P.qual + dst, P.text + s3, len, gl);
     }
 }
 
