@@ -304,16 +304,20 @@ bool stat_path(const aqc_ctx *ctx, int max_len) {
     return ctx->p.stat_kernel != 1 && lane_words_for(std::max(max_len, 8)) != 0;
 }
 
-// device-side address of a page-locked host range, or nullptr when the device cannot address all of it
+// device-side address of a page-locked host range, or nullptr when the device cannot address all of it.  The kernels read
+// the column in aligned 16-byte pieces, so the range is widened to 16-byte boundaries first: a registration that ends (or
+// starts) inside such a piece is refused and the caller copies the column as usual.
 const uint8_t *device_view_of_host(const uint8_t *p, size_t first, size_t last) {
     if (!p || last < first) return nullptr;
+    const uintptr_t lo = (reinterpret_cast<uintptr_t>(p) + first) & ~(uintptr_t)15;
+    const uintptr_t hi = ((reinterpret_cast<uintptr_t>(p) + last) | (uintptr_t)15);
     cudaPointerAttributes a0, a1;
-    if (cudaPointerGetAttributes(&a0, p + first) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    if (cudaPointerGetAttributes(&a1, p + last) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaPointerGetAttributes(&a0, reinterpret_cast<const void *>(lo)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaPointerGetAttributes(&a1, reinterpret_cast<const void *>(hi)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost || !a0.devicePointer || !a1.devicePointer) return nullptr;
     const uint8_t *d0 = (const uint8_t *)a0.devicePointer, *d1 = (const uint8_t *)a1.devicePointer;
-    if ((size_t)(d1 - d0) != last - first) return nullptr;          // not one mapping
-    return d0 - first;
+    if ((size_t)(d1 - d0) != (size_t)(hi - lo)) return nullptr;      // not one mapping
+    return d0 + (reinterpret_cast<uintptr_t>(p) + first - lo) - first;        // so that view + first is the device address of p + first
 }
 
 int launch(aqc_ctx *ctx, const DevBatch &b, const LaunchExtra &x, cudaStream_t stream, bool timed) {
