@@ -224,7 +224,9 @@ def run_reference_arm(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled every 50 ms in the background (started before the warm-up: the tool needs a few hundred ms to come up);
+    the samples whose timestamps fall into the timed region are the ones reported"""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
@@ -240,36 +242,53 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def samples(self, t0, t1):
+        """[(sm, sm_max, reasons)] of the samples stamped within [t0, t1] (epoch seconds)"""
+        out = []
+        try:
+            with open(self.path) as f:
+                lines = f.readlines()
+        except OSError:
+            return out
+        for line in lines:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                stamp, frac = p[0].split(".") if "." in p[0] else (p[0], "0")
+                ts = time.mktime(time.strptime(stamp, "%Y/%m/%d %H:%M:%S")) + float("0." + frac)
+                sm, smax = float(p[1]), float(p[2])
+            except ValueError:
+                continue
+            if ts < t0 - 0.03 or ts > t1 + 0.03:
+                continue
+            reasons = [name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9])
+                       if v.lower().startswith("active")]
+            out.append((sm, smax, reasons))
+        return out
+
+    def stop(self, t0, t1, note=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.08)
+        got = self.samples(t0, t1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, smax, reasons = [], [], set()
-        with open(self.path) as f:
-            for line in f:
-                p = [x.strip() for x in line.split(",")]
-                if len(p) < 9:
-                    continue
-                try:
-                    sm.append(float(p[1])); smax.append(float(p[2]))
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
         try:
             os.unlink(self.path)
         except OSError:
             pass
-        if not sm:
+        if not got:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median([g[0] for g in got])), "sm_max_mhz": float(max(g[1] for g in got)),
+               "reasons": sorted({r for g in got for r in g[2]}), "samples": len(got)}
+        if note:
+            out["window"] = note
+        return out
 
 
 class TorchBatch:
@@ -509,23 +528,35 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- resident (kernel-side) number ----------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     warm = max(3, args.warmup)
     for _ in range(warm):
         R.step_resident()
     barrier()
     launches0 = eng.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_wall0 = time.time()
     e0.record(stream)
     for _ in range(args.steps):
         R.step_resident()
     e1.record(stream)
     barrier()
-    clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
+    t_wall1 = time.time()
     launches = eng.launch_count() - launches0
+    clock_note = None
+    if not sampler.samples(t_wall0, t_wall1):
+        # the timed region was shorter than the tool's period: the same steps again, untimed, until it has sampled them twice
+        clock_note = "no sample fell into the %.0f ms timed region; taken over untimed repeats of the same steps right after it" % ((t_wall1 - t_wall0) * 1e3)
+        t_rep = time.time()
+        while time.time() - t_rep < 2.0 and len(sampler.samples(t_wall1, time.time())) < 2:
+            R.step_resident()
+            torch.cuda.synchronize()
+        clocks = sampler.stop(t_wall1, time.time(), clock_note)
+    else:
+        clocks = sampler.stop(t_wall0, t_wall1)
+    ms_total = e0.elapsed_time(e1)
     # durations of the step's launch groups (CUDA events recorded by the engine on the launching stream), three more steps
     phases = []
     for _ in range(3):

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 O=gpurun_out
 nvidia-smi topo -m > $O/topo8.txt 2>&1; nproc; free -g | head -2
-for c in pe250_full pe150_err3; do
+for c in pe150 pe250_full pe150_err3; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29621 bench.py --gpus 8 --config $c --steps 10 --warmup 3 > $O/r02_bench8_$c.json 2> $O/r02_bench8_$c.err; echo "$c exit $?"
   python - $O/r02_bench8_$c.json <<'PY'
 import json, sys
