@@ -30,6 +30,7 @@ slice (`shard_parity`).  `--impl reference` times the CPU arm alone (rank 0 only
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import subprocess
 import sys
@@ -246,9 +247,9 @@ class ClockSampler:
         """[(sm, sm_max, reasons)] of the samples stamped within [t0, t1] (epoch seconds)"""
         out = []
         try:
-            with open(self.path) as f:
+            with open(self.path, errors="replace") as f:
                 lines = f.readlines()
-        except OSError:
+        except Exception:
             return out
         for line in lines:
             p = [x.strip() for x in line.split(",")]
@@ -258,7 +259,7 @@ class ClockSampler:
                 stamp, frac = p[0].split(".") if "." in p[0] else (p[0], "0")
                 ts = time.mktime(time.strptime(stamp, "%Y/%m/%d %H:%M:%S")) + float("0." + frac)
                 sm, smax = float(p[1]), float(p[2])
-            except ValueError:
+            except Exception:
                 continue
             if ts < t0 - 0.03 or ts > t1 + 0.03:
                 continue
@@ -270,17 +271,20 @@ class ClockSampler:
     def stop(self, t0, t1, note=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.08)
-        got = self.samples(t0, t1)
-        self.proc.terminate()
         try:
-            self.proc.wait(timeout=5)
+            time.sleep(0.08)
+            got = self.samples(t0, t1)
         except Exception:
-            self.proc.kill()
-        self.f.close()
+            got = []
         try:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.f.close()
             os.unlink(self.path)
-        except OSError:
+        except Exception:
             pass
         if not got:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
@@ -545,18 +549,24 @@ def run_ours(args):
     barrier()
     t_wall1 = time.time()
     launches = eng.launch_count() - launches0
-    clock_note = None
-    if not sampler.samples(t_wall0, t_wall1):
-        # the timed region was shorter than the tool's period: the same steps again, untimed, until it has sampled them twice
-        clock_note = "no sample fell into the %.0f ms timed region; taken over untimed repeats of the same steps right after it" % ((t_wall1 - t_wall0) * 1e3)
-        t_rep = time.time()
-        while time.time() - t_rep < 2.0 and len(sampler.samples(t_wall1, time.time())) < 2:
+    ms_total = e0.elapsed_time(e1)
+    # Clocks: the samples stamped inside the timed region.  When that region was shorter than the tool's period on ANY rank, every
+    # rank repeats the same steps untimed for ~0.4 s (the same number of steps everywhere: a step holds a collective at N > 1)
+    # and the samples of that stretch are reported instead, with a note.
+    have = torch.tensor([float(len(sampler.samples(t_wall0, t_wall1))), -ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(have, op=dist.ReduceOp.MIN)
+    if have[0].item() < 1:
+        ms_step_max = max(1e-3, -float(have[1].item()) / args.steps)
+        reps = int(min(2000, max(1, math.ceil(400.0 / ms_step_max))))
+        for _ in range(reps):
             R.step_resident()
-            torch.cuda.synchronize()
-        clocks = sampler.stop(t_wall1, time.time(), clock_note)
+        barrier()
+        clocks = sampler.stop(t_wall1, time.time(),
+                              "no sample fell into the %.0f ms timed region (on some rank); taken over %d untimed repeats of the same step right after it"
+                              % ((t_wall1 - t_wall0) * 1e3, reps))
     else:
         clocks = sampler.stop(t_wall0, t_wall1)
-    ms_total = e0.elapsed_time(e1)
     # durations of the step's launch groups (CUDA events recorded by the engine on the launching stream), three more steps
     phases = []
     for _ in range(3):
