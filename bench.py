@@ -295,6 +295,27 @@ class ClockSampler:
         return out
 
 
+def clocks_of_timed_region(sampler, t0, t1, ms_total, steps, world, device, step, barrier):
+    """The clock samples stamped inside the timed region [t0, t1].  When that region was shorter than the tool's period on ANY
+    rank, every rank repeats the same step untimed for ~0.4 s -- the same number of steps everywhere, because a step holds a
+    collective at N > 1 -- and the samples of that stretch are reported instead, with a note."""
+    import torch
+    have = torch.tensor([float(len(sampler.samples(t0, t1))), -float(ms_total)], dtype=torch.float64, device=device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(have, op=dist.ReduceOp.MIN)
+    if have[0].item() >= 1:
+        return sampler.stop(t0, t1)
+    ms_step_max = max(1e-3, -float(have[1].item()) / max(1, steps))
+    reps = int(min(2000, max(1, math.ceil(400.0 / ms_step_max))))
+    for _ in range(reps):
+        step()
+    barrier()
+    return sampler.stop(t1, time.time(),
+                        "no sample fell into the %.0f ms timed region (on some rank); taken over %d untimed repeats of the same step right after it"
+                        % ((t1 - t0) * 1e3, reps))
+
+
 class TorchBatch:
     """HBM-resident batch backed by torch tensors (plumbing only: memory + RNG)."""
 
@@ -550,23 +571,7 @@ def run_ours(args):
     t_wall1 = time.time()
     launches = eng.launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
-    # Clocks: the samples stamped inside the timed region.  When that region was shorter than the tool's period on ANY rank, every
-    # rank repeats the same steps untimed for ~0.4 s (the same number of steps everywhere: a step holds a collective at N > 1)
-    # and the samples of that stretch are reported instead, with a note.
-    have = torch.tensor([float(len(sampler.samples(t_wall0, t_wall1))), -ms_total], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(have, op=dist.ReduceOp.MIN)
-    if have[0].item() < 1:
-        ms_step_max = max(1e-3, -float(have[1].item()) / args.steps)
-        reps = int(min(2000, max(1, math.ceil(400.0 / ms_step_max))))
-        for _ in range(reps):
-            R.step_resident()
-        barrier()
-        clocks = sampler.stop(t_wall1, time.time(),
-                              "no sample fell into the %.0f ms timed region (on some rank); taken over %d untimed repeats of the same step right after it"
-                              % ((t_wall1 - t_wall0) * 1e3, reps))
-    else:
-        clocks = sampler.stop(t_wall0, t_wall1)
+    clocks = clocks_of_timed_region(sampler, t_wall0, t_wall1, ms_total, args.steps, world, device, R.step_resident, barrier)
     # durations of the step's launch groups (CUDA events recorded by the engine on the launching stream), three more steps
     phases = []
     for _ in range(3):
