@@ -13,7 +13,7 @@ SYMBOLS = [
     "aqc_last_error", "aqc_host_alloc", "aqc_host_free", "aqc_device_alloc", "aqc_device_free",
     "aqc_memcpy_h2d", "aqc_memcpy_d2h", "aqc_stat_reads", "aqc_filter_pairs", "aqc_ops_pairs", "aqc_sync",
     "aqc_get_counters", "aqc_add_counters", "aqc_get_qc", "aqc_get_kmer_dense", "aqc_get_kmer_side", "aqc_get_kmer_side_raw", "aqc_last_phase_ms",
-    "aqc_edit_distance_batch", "edit_distance", "seek_overlap", "aqc_launch_count", "aqc_last_kernel_ms", "aqc_set_stream", "aqc_device_ptr", "aqc_fastq_parse", "aqc_fastq_parse_device", "aqc_fastq_emit",
+    "aqc_edit_distance_batch", "edit_distance", "seek_overlap", "aqc_launch_count", "aqc_last_kernel_ms", "aqc_set_stream", "aqc_device_ptr", "aqc_fastq_parse", "aqc_fastq_parse_device", "aqc_fastq_emit", "aqc_fastq_emit_lines",
     "aqc_barcode_pairs", "aqc_gunzip_buffer", "aqc_gunzip_buffer_mt", "aqc_reader_open", "aqc_reader_next", "aqc_reader_release", "aqc_reader_error", "aqc_reader_close",
 ]
 
@@ -80,6 +80,7 @@ def bind(L):
         "aqc_launch_count": (u64, [vp]),
         "aqc_edit_distance_batch": (i32, [vp, vp, vp, vp, vp, u32, i32, vp]),
         "aqc_fastq_parse_device": (i32, [vp, i32, vp, u64, i32, i32, u64, vp]),
+        "aqc_fastq_emit_lines": (i32, [i32, i32, vp, vp, vp, u64, vp, u64, vp, u64, C.POINTER(u64)]),
         "edit_distance": (C.c_uint, [C.c_char_p, C.c_uint, C.c_char_p, C.c_uint]),
         "seek_overlap": (i32, [C.c_char_p, i32, C.c_char_p, i32, i32, i32, i32]),
         "aqc_last_kernel_ms": (C.c_float, [vp]),

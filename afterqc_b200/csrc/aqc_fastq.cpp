@@ -115,31 +115,33 @@ int aqc_fastq_parse(const uint8_t *buf, uint64_t n, int final, uint64_t max_reco
 
 // FASTQ text of the records of one mate selected by `which`: 0 = good, 1 = bad (name becomes "@" FLAG name[1:],
 // preprocesser.py:212-213), 2 = overlapped tails of good pairs (--store_overlap, :615-617).  results[i] belongs to
-// column record rec_base + i.  Slices and edits come from the aqc_result records (see include/afterqc_b200.h).
-int aqc_fastq_emit(int mate, int which,
-                   const uint8_t *names, const uint64_t *name_off, const uint8_t *seqs, const uint64_t *seq_off,
-                   const uint8_t *plus, const uint64_t *plus_off, const uint8_t *quals,
-                   uint64_t rec_base, const aqc_result *results, uint64_t n,
-                   uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
+// record rec_base + i.  Slices and edits come from the aqc_result records (see include/afterqc_b200.h).  `Rec` says where
+// the four lines of a record lie: in packed columns (aqc_fastq_emit) or in the FASTQ text itself (aqc_fastq_emit_lines).
+extern "C++" {
+namespace {
+struct RecLines { const uint8_t *name, *seq, *plus, *qual; uint64_t name_len, seq_len, plus_len; };
+
+template <class Rec>
+int emit_impl(int mate, int which, const Rec &at, uint64_t rec_base, const aqc_result *results, uint64_t n,
+              uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
     if (mate < 0 || mate > 2) return AQC_ERR_INVALID;          // mate 0: index read, passed through whole and unedited
     uint64_t w = 0;
     for (uint64_t i = 0; i < n; i++) {
         const aqc_result &r = results[i];
         const bool good = r.cls == AQC_GOOD;
         if ((which == 1) == good) continue;
-        const uint64_t rec0 = rec_base + i;
+        const RecLines L = at(rec_base + i);
         uint32_t start = mate == 1 ? r.start1 : r.start2, len = mate == 1 ? r.len1 : r.len2;
-        if (mate == 0) { start = 0; len = (uint32_t)(seq_off[rec0 + 1] - seq_off[rec0]); }
+        if (mate == 0) { start = 0; len = (uint32_t)L.seq_len; }
         int corrected = 0;
         for (int e = 0; e < r.n_edits && e < 4; e++) if (AQC_EDIT_KIND(r.edits[e]) < 2) corrected++;
         if (which == 2) {
             if (!(r.ov_len > 30 && (r.ov_diff == 0 || (int)r.ov_diff == corrected))) continue;
             if (mate != 0) { start += len - r.ov_len; len = r.ov_len; }
         }
-        const uint64_t rec = rec_base + i;
-        const uint64_t nl = name_off[rec + 1] - name_off[rec], pl = plus_off[rec + 1] - plus_off[rec];
+        const uint64_t nl = L.name_len, pl = L.plus_len;
         if (w + nl + pl + 2ull * len + 4 + 16 > out_cap) return AQC_ERR_NOMEM;
-        const uint8_t *nm = names + name_off[rec];
+        const uint8_t *nm = L.name;
         if (which == 1) {
             out[w++] = '@';
             const char *f = flag_of(r.cls);
@@ -148,14 +150,13 @@ int aqc_fastq_emit(int mate, int which,
             if (nl > 1) { memcpy(out + w, nm + 1, nl - 1); w += nl - 1; }
         } else { memcpy(out + w, nm, nl); w += nl; }
         out[w++] = '\n';
-        const uint8_t *s = seqs + seq_off[rec], *q = quals + seq_off[rec];
         uint8_t *so = out + w;
-        memcpy(so, s + start, len); w += len;
+        memcpy(so, L.seq + start, len); w += len;
         out[w++] = '\n';
-        memcpy(out + w, plus + plus_off[rec], pl); w += pl;
+        memcpy(out + w, L.plus, pl); w += pl;
         out[w++] = '\n';
         uint8_t *qo = out + w;
-        memcpy(qo, q + start, len); w += len;
+        memcpy(qo, L.qual + start, len); w += len;
         out[w++] = '\n';
         for (int e = 0; mate != 0 && e < r.n_edits && e < 4; e++) {       // apply the correction-walk edits that fall inside the slice
             const uint32_t ed = r.edits[e], kind = AQC_EDIT_KIND(ed);
@@ -171,6 +172,41 @@ int aqc_fastq_emit(int mate, int which,
     }
     *out_len = w;
     return 0;
+}
+}  // namespace
+}  // extern "C++"
+
+int aqc_fastq_emit(int mate, int which,
+                   const uint8_t *names, const uint64_t *name_off, const uint8_t *seqs, const uint64_t *seq_off,
+                   const uint8_t *plus, const uint64_t *plus_off, const uint8_t *quals,
+                   uint64_t rec_base, const aqc_result *results, uint64_t n,
+                   uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
+    auto at = [&](uint64_t rec) {
+        RecLines L;
+        L.name = names + name_off[rec]; L.name_len = name_off[rec + 1] - name_off[rec];
+        L.seq = seqs + seq_off[rec]; L.qual = quals + seq_off[rec]; L.seq_len = seq_off[rec + 1] - seq_off[rec];
+        L.plus = plus + plus_off[rec]; L.plus_len = plus_off[rec + 1] - plus_off[rec];
+        return L;
+    };
+    return emit_impl(mate, which, at, rec_base, results, n, out, out_cap, out_len);
+}
+
+// The same from the FASTQ text and the line table of aqc_fastq_parse_device (line 4r + k of record r: name, bases, '+',
+// qualities; start and length of the rstrip()ped line in `text`).
+int aqc_fastq_emit_lines(int mate, int which, const uint8_t *text, const uint32_t *line_start, const uint32_t *line_len,
+                         uint64_t rec_base, const aqc_result *results, uint64_t n,
+                         uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
+    if (!text || !line_start || !line_len) return AQC_ERR_INVALID;
+    auto at = [&](uint64_t rec) {
+        RecLines L;
+        const uint32_t *s = line_start + 4 * rec, *l = line_len + 4 * rec;
+        L.name = text + s[0]; L.name_len = l[0];
+        L.seq = text + s[1]; L.seq_len = l[1];
+        L.plus = text + s[2]; L.plus_len = l[2];
+        L.qual = text + s[3];
+        return L;
+    };
+    return emit_impl(mate, which, at, rec_base, results, n, out, out_cap, out_len);
 }
 
 // Barcode (UMI) pre-pass of the per-read loop (preprocesser.py:435-452, barcodeprocesser.py): for every pair detect the

@@ -77,6 +77,17 @@ class ParsedText:
         self.line_start, self.line_len, self.text = st.line_start, st.line_len, st.text
         self.n_text = n_text
 
+    def fetch_lines(self):
+        """host copies of the line table only: (line_start, line_len)"""
+        e = self.engine
+        out = []
+        for ptr in (self.line_start, self.line_len):
+            a = np.zeros(4 * self.n, dtype=np.uint32)
+            if self.n:
+                e._check(e._L.aqc_memcpy_d2h(e._h, a.ctypes.data, ptr, a.nbytes))
+            out.append(a)
+        return tuple(out)
+
     def fetch(self):
         """host copies: dict(seq, qual, off, line_start, line_len)"""
         e = self.engine

@@ -384,10 +384,49 @@ def emit(rec, mate, which, rec_base, results):
     return data.tobytes() if len(data) else b""
 
 
+class TextRecords:
+    """Records that were parsed on the device (Engine.parse_fastq): the host keeps the FASTQ text and the line table
+    (start and length of the four rstrip()ped lines of every record); the writers format from those."""
+
+    def __init__(self, text, line_start, line_len, n):
+        self.text = text
+        self.line_start = np.ascontiguousarray(line_start, dtype=np.uint32)
+        self.line_len = np.ascontiguousarray(line_len, dtype=np.uint32)
+        self.n = n
+
+    def lengths(self):
+        return self.line_len[1::4][:self.n].astype(np.int64)
+
+    def done(self):
+        pass
+
+
+def _emit_lines_into(rec, mate, which, rec_base, results, scratch):
+    import ctypes as C
+    from . import _native
+    L = _native.lib()
+    n = len(results)
+    if n == 0:
+        return np.zeros(0, dtype=np.uint8), scratch
+    ll = rec.line_len[4 * rec_base:4 * (rec_base + n)].astype(np.int64)
+    cap = int(ll.sum()) + int(ll[1::4].sum()) + 20 * n + 64
+    if scratch is None or len(scratch) < cap:
+        scratch = np.empty(cap + cap // 8, dtype=np.uint8)
+    olen = C.c_uint64(0)
+    res = np.ascontiguousarray(results)
+    rc = L.aqc_fastq_emit_lines(mate, which, rec.text.ctypes.data, rec.line_start.ctypes.data, rec.line_len.ctypes.data,
+                                rec_base, res.ctypes.data, n, scratch.ctypes.data, cap, C.byref(olen))
+    if rc:
+        raise RuntimeError("aqc_fastq_emit_lines failed (%d)" % rc)
+    return scratch[:olen.value], scratch
+
+
 def emit_into(rec, mate, which, rec_base, results, scratch):
     """emit() into a reusable uint8 scratch array: returns (view of the text, scratch to pass next time)."""
     import ctypes as C
     from . import _native
+    if isinstance(rec, TextRecords):
+        return _emit_lines_into(rec, mate, which, rec_base, results, scratch)
     L = _native.lib()
     n = len(results)
     if n == 0:

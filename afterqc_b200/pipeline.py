@@ -258,7 +258,9 @@ class seqFilter:
         # ---- the per-read loop, in batches (preprocesser.py:411-631) ----
         params = params_from_options(opt, self.paired)
         be.set_params(params)
-        if world == 1:
+        if world == 1 and self._device_parse_applies(be, idx_files):
+            extra = self._filter_stream_device_parse(be, writers)
+        elif world == 1:
             extra = self._filter_stream(be, writers, idx_files)
         else:
             n = self._n_total
@@ -525,6 +527,100 @@ class seqFilter:
                 lane.shutdown()
             for s_ in streams:
                 s_.close()
+
+    # ---- opt-in: FASTQ text parsed on the device (AQC_DEVICE_PARSE=1) ----
+    def _device_parse_applies(self, be, idx_files):
+        """Plain (uncompressed) FASTQ inputs on one GPU, no barcode / index files / --qc_only, an engine that can parse."""
+        opt = self.options
+        if os.environ.get("AQC_DEVICE_PARSE") != "1":
+            return False
+        if idx_files or getattr(opt, "barcode", False) or opt.qc_only or not hasattr(be, "parse_fastq"):
+            return False
+        paths = [opt.read1_file] + ([opt.read2_file] if self.paired else [])
+        return all(not p.endswith((".gz", ".bz2")) for p in paths)
+
+    def _filter_stream_device_parse(self, be, writers, block_bytes=None):
+        """_filter_stream with the parser on the device (csrc/aqc_parse.cuh): the host reads blocks of text, the engine turns
+        them into the packed columns in HBM (Engine.parse_fastq) and filters them where they lie (ParsedDeviceBatch); only
+        the 32-byte records and the line table come back, and the writers format from the text the host already holds.
+        Same loop semantics as _filter_stream: lock step over the mates, the shortest file ends the run, returns the bases
+        of the R1 record the reference reads just before the other file runs out."""
+        from .engine import ParsedDeviceBatch
+        opt = self.options
+        if block_bytes is None:
+            # large enough for the record cap of a step to bind on both mates (then no mate is parsed twice); AQC_DEVICE_PARSE_BLOCK: tests
+            block_bytes = int(os.environ.get("AQC_DEVICE_PARSE_BLOCK", 0)) or max(64 << 20, 512 * self.batch_records)
+        paths = [opt.read1_file] + ([opt.read2_file] if self.paired else [])
+        files = [open(p, "rb") for p in paths]
+        lanes = {name: _OutputLane(w) for name, w in writers.items()}
+        nm = len(files)
+        carry = [np.zeros(0, dtype=np.uint8) for _ in files]        # text not yet consumed
+        ended = [False] * nm                                        # nothing more to read from the file
+        g = 0
+        extra = 0
+        inflight = collections.deque()
+
+        def read_more(m):
+            data = files[m].read(block_bytes)
+            if len(data) < block_bytes:
+                ended[m] = True
+            if len(data):
+                new = np.frombuffer(data, dtype=np.uint8)
+                carry[m] = np.concatenate([carry[m], new]) if len(carry[m]) else new
+
+        def parse(m, cap):
+            try:
+                return be.parse_fastq(carry[m], slot=m, final=ended[m], max_records=cap)
+            except ValueError as e:           # the record number in the message counts from this block
+                raise ValueError(str(e).replace("FASTQ record ", "FASTQ record %d + " % g))
+
+        try:
+            while True:
+                for m in range(nm):
+                    if not ended[m] and len(carry[m]) < block_bytes:
+                        read_more(m)
+                ps = [parse(m, self.batch_records) for m in range(nm)]
+                k = min(p.n for p in ps)
+                if k == 0:
+                    # a mate without a complete record: more text may complete one; otherwise its file is over (end of the
+                    # file or an empty line) and so is the loop, like the reference's at the shortest file
+                    starved = [m for m in range(nm) if ps[m].n == 0 and not ps[m].hit_eof and not ended[m]]
+                    if starved:
+                        for m in starved:
+                            if len(carry[m]) > 16 * block_bytes:
+                                raise ValueError("no complete FASTQ record in %d bytes of %s" % (len(carry[m]), paths[m]))
+                            read_more(m)
+                        continue
+                    if nm > 1 and ps[0].n > 0:
+                        extra = int(ps[0].fetch_lines()[1][1])      # the R1 record read just before the other file ran out
+                    break
+                for m in range(nm):
+                    if ps[m].n > k:
+                        ps[m] = parse(m, k)                         # exactly the records of this step (and their `consumed`)
+                db = ParsedDeviceBatch(be, ps[0], ps[1] if nm > 1 else None, first_index=g)
+                be.filter_pairs(db)
+                res = be.fetch_results(db)
+                db.free()
+                recs = []
+                for m in range(nm):
+                    ls, ll = ps[m].fetch_lines()
+                    recs.append(fastq_io.TextRecords(carry[m], ls, ll, k))      # keeps this block's text alive for the writers
+                inflight.append(self._write_async(lanes, recs[0], recs[1] if nm > 1 else None, res))
+                while len(inflight) > 2:
+                    for f in inflight.popleft():
+                        f.result()
+                for m in range(nm):
+                    carry[m] = carry[m][ps[m].consumed:]
+                g += k
+            while inflight:
+                for f in inflight.popleft():
+                    f.result()
+            return extra
+        finally:
+            for lane in lanes.values():
+                lane.shutdown()
+            for f in files:
+                f.close()
 
     def _barcode_batch(self, be, rec1, rec2, g):
         """Barcode (UMI) files: the pre-pass of preprocesser.py:435-452 on one batch, then the device loop on the pairs

@@ -313,6 +313,12 @@ typedef struct aqc_parsed {
 int aqc_fastq_parse_device(aqc_ctx *ctx, int slot, const uint8_t *text, uint64_t n, int mem, int final, uint64_t max_records,
                            aqc_parsed *out);
 
+/* aqc_fastq_emit for records that were parsed on the device: the four lines of record r are text[line_start[4r + k] ..
+ * + line_len[4r + k]) (host copies of the text and of aqc_parsed's line table). */
+int aqc_fastq_emit_lines(int mate, int which, const uint8_t *text, const uint32_t *line_start, const uint32_t *line_len,
+                         uint64_t rec_base, const aqc_result *results, uint64_t n,
+                         uint8_t *out, uint64_t out_cap, uint64_t *out_len);
+
 /* ---- barcode (UMI) pre-pass on packed columns (host only; barcodeprocesser.py, preprocesser.py:435-452) ---- */
 #define AQC_HOST_BADBCD1 16   /* host-only pseudo classes for aqc_fastq_emit: pairs rejected before the device loop */
 #define AQC_HOST_BADBCD2 17

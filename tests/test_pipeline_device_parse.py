@@ -1,0 +1,67 @@
+"""AQC_DEVICE_PARSE=1: the streaming driver with the FASTQ parser on the device (pipeline._filter_stream_device_parse) writes
+the same files and the same JSON as the default driver (host parser threads).  Emulated engine; small read blocks so that
+records straddle blocks, the mates hold different numbers of records per block and a step is re-parsed with a record cap."""
+import filecmp
+import os
+
+import pytest
+
+import refcmp
+from afterqc_b200 import synth
+
+
+def _run_both(tmp_path, monkeypatch, batch, extra, mutate=None, block="40000"):
+    import emu
+    d = str(tmp_path)
+    refcmp.prepare_case(d, batch, subs=("host", "dev"))
+    if mutate:
+        for sub in ("host", "dev"):
+            mutate(os.path.join(d, sub))
+    paired = batch.paired
+    monkeypatch.delenv("AQC_DEVICE_PARSE", raising=False)
+    refcmp.run_ours(d, "host", paired, extra, lambda p: emu.EmuEngine(p))
+    monkeypatch.setenv("AQC_DEVICE_PARSE", "1")
+    monkeypatch.setenv("AQC_DEVICE_PARSE_BLOCK", block)
+    calls = []
+    from afterqc_b200 import pipeline
+    real = pipeline.seqFilter._filter_stream_device_parse
+
+    def spy(self, be, writers, block_bytes=None):
+        calls.append(1)
+        return real(self, be, writers, block_bytes)
+    monkeypatch.setattr(pipeline.seqFilter, "_filter_stream_device_parse", spy)
+    refcmp.run_ours(d, "dev", paired, extra, lambda p: emu.EmuEngine(p))
+    assert calls, "the device-parse driver did not run"
+    a, b = refcmp.load_json(d, "host"), refcmp.load_json(d, "dev")
+    diffs = [x for x in refcmp.json_diff(a, b) if not x[1].startswith("/command/")]
+    assert not diffs, diffs[:5]
+    for f in refcmp.output_files(paired, extra):
+        assert filecmp.cmp(os.path.join(d, "host", f), os.path.join(d, "dev", f), shallow=False), f
+
+
+@pytest.mark.parametrize("extra", [[], ["-f", "2", "-t", "3", "--qc_sample", "700", "--store_overlap", "on"]])
+def test_device_parse_driver_equals_host_driver(tmp_path, monkeypatch, oracle_lib, extra):
+    _run_both(tmp_path, monkeypatch, synth.generate("pe150", 2600), extra)
+
+
+def test_device_parse_single_end(tmp_path, monkeypatch, oracle_lib):
+    _run_both(tmp_path, monkeypatch, synth.generate("se100", 1800), [])
+
+
+def test_device_parse_shorter_mate_and_empty_line(tmp_path, monkeypatch, oracle_lib):
+    def cut_r2(sub):                        # R2 ends 7 records early: the R1 record read just before that is still counted
+        p = os.path.join(sub, "x_R2.fq")
+        lines = open(p, "rb").read().split(b"\n")
+        open(p, "wb").write(b"\n".join(lines[:4 * (1500 - 7)]) + b"\n")
+    _run_both(tmp_path / "a", monkeypatch, synth.generate("pe150", 1500), [], mutate=cut_r2)
+
+    def blank_r1(sub):                      # an empty line in R1 ends the file there (fastq.py:37-49), CRLF line ends elsewhere
+        p = os.path.join(sub, "x_R1.fq")
+        lines = open(p, "rb").read().split(b"\n")
+        lines = [l + b"\r" for l in lines[:4 * 900]] + [b""] + lines[4 * 900:]
+        open(p, "wb").write(b"\n".join(lines))
+    _run_both(tmp_path / "b", monkeypatch, synth.generate("pe150", 1200), [], mutate=blank_r1)
+
+
+def test_device_parse_one_block(tmp_path, monkeypatch, oracle_lib):
+    _run_both(tmp_path, monkeypatch, synth.generate("pe150", 900), [], block="0")      # the default block: the whole file at once
