@@ -137,6 +137,8 @@ struct aqc_reader {
     size_t map_len = 0;
     int map_fd = -1;
     std::vector<uint8_t> in;
+    bool plain_map = false;                 // uncompressed regular file: parsed straight from the mapping (no read copy, no memmove)
+    const uint8_t *src() const { return plain_map ? (const uint8_t *)map : in.data(); }
     size_t in_pos = 0, in_end = 0;
     bool src_eof = false, file_end = false;
     uint64_t next_index = 0;
@@ -174,6 +176,12 @@ struct aqc_reader {
 
     // more input behind the unparsed tail; returns false on a read error
     bool refill() {
+        if (plain_map) {                                                // the window just grows over the mapping
+            const size_t more = std::min(kReadBlock, map_len - in_end);
+            if (more == 0) src_eof = true;
+            in_end += more;
+            return true;
+        }
         if (in_pos > 0) {
             memmove(in.data(), in.data() + in_pos, in_end - in_pos);
             in_end -= in_pos; in_pos = 0;
@@ -216,7 +224,7 @@ struct aqc_reader {
                 uint64_t *offp[4] = {s.off[0] + s.n, s.off[1] + s.n, s.off[2] + s.n, s.off[3] + s.n};
                 uint64_t nrec = 0, consumed = 0, bad = 0;
                 int hit = 0;
-                int rc = aqc_fastq_parse(in.data() + in_pos, avail, src_eof ? 1 : 0, batch - s.n, s.bytes, offp, &nrec, &consumed, &hit, &bad);
+                int rc = aqc_fastq_parse(src() + in_pos, avail, src_eof ? 1 : 0, batch - s.n, s.bytes, offp, &nrec, &consumed, &hit, &bad);
                 if (rc) {
                     char t[128];
                     snprintf(t, sizeof t, "FASTQ record %llu: quality line length differs from sequence length",
@@ -302,9 +310,22 @@ int aqc_reader_open(const char *path, uint64_t batch_records, uint32_t slots, aq
             if (r->gz) gzbuffer(r->gz, 1u << 20);
         }
     } else {
-        r->fp = fopen(path, "rb");
+        const char *sel = getenv("AQC_READER_MMAP");
+        int fd = (sel && sel[0] == '0') ? -1 : open(path, O_RDONLY);
+        struct stat st;
+        if (fd >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) {
+                madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+                r->map = m; r->map_len = (size_t)st.st_size; r->map_fd = fd; r->plain_map = true;
+            }
+        }
+        if (!r->plain_map) {
+            if (fd >= 0) close(fd);
+            r->fp = fopen(path, "rb");                                  // pipes, empty files, AQC_READER_MMAP=0
+        }
     }
-    if (!r->gz && !r->fp && !r->inf && !r->pinf) { delete r; return AQC_ERR_INVALID; }
+    if (!r->gz && !r->fp && !r->inf && !r->pinf && !r->plain_map) { delete r; return AQC_ERR_INVALID; }
     if (r->gz || r->inf || r->pinf) r->async = new AsyncSource([r](uint8_t *dst, size_t cap) { return r->read_gz(dst, cap); }, kReadBlock, 3);
     r->slots.resize(slots);
     for (uint32_t i = 0; i < slots; i++) {

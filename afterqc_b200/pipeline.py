@@ -176,9 +176,16 @@ class seqFilter:
         self.backend = be
 
         # ---- prefilter QC (preprocesser.py:247-251) ----
-        self._prefilter_stream(be, opt.read1_file, _abi.QC_R1_PRE)
+        # (the reader of mate 2 is opened first: its thread parses the window while mate 1 is being worked on)
+        ahead = fastq_io.open_stream(opt.read2_file, self.batch_records, slots=2) if self.paired else None
+        try:
+            self._prefilter_stream(be, opt.read1_file, _abi.QC_R1_PRE)
+        except BaseException:
+            if ahead is not None:
+                ahead.close()
+            raise
         if self.paired:
-            self._prefilter_stream(be, opt.read2_file, _abi.QC_R2_PRE)
+            self._prefilter_stream(be, opt.read2_file, _abi.QC_R2_PRE, stream=ahead)
         self.r1qc_prefilter = QualityControl(opt.qc_sample, opt.qc_kmer).load(be.qc(_abi.QC_R1_PRE), be.kmers(_abi.QC_R1_PRE))
         self.r1qc_prefilter.qc()
         self.r2qc_prefilter = QualityControl(opt.qc_sample, opt.qc_kmer)
@@ -378,7 +385,7 @@ class seqFilter:
             return n1, 0
         return n_other, extra
 
-    def _prefilter_stream(self, be, path, slot):
+    def _prefilter_stream(self, be, path, slot, stream=None):
         """QualityControl.statFile (qualitycontrol.py:331-357) on a stream: window = records [999, 999+limit) (all when
         limit <= 0); reading stops one record past the window (that is all statFile's counter needs); if fewer than
         1000 records were counted in the window loop the first 999 are stat'd afterwards.  Sharded runs: every rank streams
@@ -395,7 +402,8 @@ class seqFilter:
             m_lo, m_hi = lo + ((w_end - lo) * rank) // world, lo + ((w_end - lo) * (rank + 1)) // world
         else:
             m_lo, m_hi = lo, None
-        stream = fastq_io.open_stream(path, self.batch_records, slots=2)      # the window is short: little read-ahead
+        if stream is None:
+            stream = fastq_io.open_stream(path, self.batch_records, slots=2)  # the window is short: little read-ahead
         g = 0
         head = []
         try:
