@@ -1161,7 +1161,23 @@ int aqc_fastq_parse_device(aqc_ctx *ctx, int slot, const uint8_t *text, uint64_t
     CK(cudaMemsetAsync(ps.flags, 0xFF, 8, st));
     CK(cudaStreamSynchronize(st));
     const uint32_t n_cand = (uint32_t)std::min<uint64_t>(n_lines / 4u, max_records);
-    if (n_cand == 0) { out->hit_eof = (final && max_records) ? 1 : 0; return 0; }
+    if (n_cand == 0) {
+        // fewer than four lines (or no record wanted).  The reference stops at an empty line wherever it is: look at the few
+        // complete lines there are (host text only; a caller with device text sees it with the next, longer buffer)
+        out->hit_eof = (final && max_records) ? 1 : 0;
+        if (!out->hit_eof && max_records && mem == AQC_MEM_HOST) {
+            uint64_t p = 0;
+            for (uint32_t l = 0; l < n_lines && l < 4; l++) {
+                const uint8_t *nl = (const uint8_t *)memchr(text + p, '\n', n - p);
+                if (!nl) break;
+                uint64_t e = (uint64_t)(nl - text);
+                while (e > p && (text[e - 1] == ' ' || text[e - 1] == '\t' || text[e - 1] == '\r' || text[e - 1] == 0x0b || text[e - 1] == 0x0c)) e--;
+                if (e == p) { out->hit_eof = 1; break; }
+                p = (uint64_t)(nl - text) + 1;
+            }
+        }
+        return 0;
+    }
     if ((rc = grow(ctx, ps.nl, ps.nl_cap, (size_t)n_lines + 1))) return rc;
     if ((rc = grow(ctx, ps.line_start, ps.line_cap, (size_t)4 * n_cand))) return rc;
     if ((rc = grow(ctx, ps.line_len, ps.line2_cap, (size_t)4 * n_cand))) return rc;

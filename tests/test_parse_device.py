@@ -76,6 +76,11 @@ def run_cases(make_engine):
     check_same(eng, b"\n".join(lines[:4 * 300] + [b""] + lines[4 * 300:]))      # an empty line ends the file
     check_same(eng, b"\n".join(lines[:4 * 10 + 2] + [b"   "] + lines[4 * 10 + 3:]))   # ... also one of blanks, inside a record
     assert eng.parse_fastq(b"").n == 0
+    for text in (b"\n", b"@x\n\nAC", b"@x\nAC\n  \n"):      # an empty line among fewer than four lines still ends the file
+        p, (rec, consumed, eof) = eng.parse_fastq(text, final=False), host_parse(text, False)
+        assert p.n == 0 and rec is None and p.hit_eof and eof
+    p = eng.parse_fastq(b"@x\nAC\n+", final=False)
+    assert p.n == 0 and not p.hit_eof
     assert eng.parse_fastq(b"@x\nACGT\n", final=True).n == 0
     bad = list(lines)
     bad[4 * 55 + 3] = bad[4 * 55 + 3][:-1]
