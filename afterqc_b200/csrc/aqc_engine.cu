@@ -1218,6 +1218,20 @@ int aqc_fastq_parse_device(aqc_ctx *ctx, int slot, const uint8_t *text, uint64_t
     // as aqc_fastq_parse: an empty line ends the file; at the end of the file whatever is left (a partial record) is dropped
     // (a call that stops at max_records has not looked further: end of file only if the text is used up)
     out->hit_eof = eof ? 1 : (bad ? 0 : ((uint64_t)n_keep == max_records ? (final && out->consumed >= n) : (final ? 1 : 0)));
+    if (!out->hit_eof && !bad && !final && (uint64_t)n_keep < max_records && n_lines > 4u * n_keep && mem == AQC_MEM_HOST) {
+        // the trailing partial record: the reference would still stop at an empty line in it (host text only, see above)
+        uint32_t nlp[5] = {0, 0, 0, 0, 0};
+        const uint32_t first = n_keep ? 4u * n_keep - 1u : 0u, cnt = n_lines - first;          // <= 4 positions
+        CK(cudaMemcpyAsync(nlp, ps.nl + first, (size_t)std::min<uint32_t>(cnt, 5u) * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        uint64_t p = n_keep ? (uint64_t)nlp[0] + 1 : 0;
+        for (uint32_t i = n_keep ? 1u : 0u; i < cnt && i < 5u; i++) {
+            uint64_t e = nlp[i];
+            while (e > p && (text[e - 1] == ' ' || text[e - 1] == '\t' || text[e - 1] == '\r' || text[e - 1] == 0x0b || text[e - 1] == 0x0c)) e--;
+            if (e == p) { out->hit_eof = 1; break; }
+            p = (uint64_t)nlp[i] + 1;
+        }
+    }
     out->seq = ps.seq; out->qual = ps.qual; out->off = ps.rec; out->line_start = ps.line_start; out->line_len = ps.line_len;
     out->text = dtext;
     if (bad) return fail(ctx, AQC_ERR_INVALID, "a quality line is not as long as its sequence line");

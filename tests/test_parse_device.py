@@ -115,3 +115,49 @@ def run_cases(make_engine):
 def test_parse_device_on_emulator():
     import emu
     run_cases(lambda p: emu.EmuEngine(p))
+
+
+def test_parse_device_random_small_texts():
+    """300 random little texts: records of random lengths, stray blanks / CR / tabs at line ends, blank or empty lines, a
+    missing last newline, a bad record here and there; the device parser and the host parser must say the same"""
+    import emu
+    eng = emu.EmuEngine(_abi.Params.defaults())
+    rng = random.Random(11)
+    for case in range(300):
+        lines = []
+        for r in range(rng.randint(0, 12)):
+            L = rng.randint(1, 40)
+            qual_len = L if rng.random() > 0.04 else max(0, L + rng.choice((-1, 1)))
+            rec = [b"@n%d" % r, bytes(rng.choice(b"ACGTN") for _ in range(L)), b"+", bytes(rng.randint(33, 73) for _ in range(qual_len))]
+            for k in range(4):
+                if rng.random() < 0.1:
+                    rec[k] += rng.choice((b" ", b"\t", b"\r", b" \t\r"))
+            if rng.random() < 0.03:
+                rec[rng.randrange(4)] = rng.choice((b"", b" ", b"\t\r"))
+            lines += rec
+        if rng.random() < 0.2 and lines:
+            lines = lines[:rng.randint(1, len(lines))]           # ends inside a record
+        text = b"\n".join(lines) + (b"\n" if rng.random() < 0.6 and lines else b"")
+        for final in (True, False):
+            try:
+                rec, consumed, eof = host_parse(text, final)
+                err = None
+            except ValueError as e:
+                err = str(e)
+            if err is not None:
+                with pytest.raises(ValueError) as ei:
+                    eng.parse_fastq(text, final=final)
+                assert str(ei.value) == err, (case, text)
+                continue
+            p = eng.parse_fastq(text, final=final)
+            n_host = 0 if rec is None else len(rec.seqs.off) - 1
+            assert p.n == n_host and p.consumed == consumed and p.hit_eof == (eof or final), (case, final, text, p.n, n_host, p.consumed, consumed, p.hit_eof, eof)
+            if p.n:
+                d = p.fetch()
+                assert np.array_equal(d["seq"], rec.seqs.data[:int(rec.seqs.off[p.n])]) and np.array_equal(d["qual"], rec.quals.data[:int(rec.seqs.off[p.n])])
+                assert np.array_equal(d["off"].astype(np.int64), rec.seqs.off)
+                t = np.frombuffer(text, dtype=np.uint8)
+                for i in range(p.n):
+                    s, l = int(d["line_start"][4 * i]), int(d["line_len"][4 * i])
+                    assert bytes(t[s:s + l]) == bytes(rec.names.data[rec.names.off[i]:rec.names.off[i + 1]])
+    eng.close()
