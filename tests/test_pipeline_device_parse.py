@@ -65,3 +65,55 @@ def test_device_parse_shorter_mate_and_empty_line(tmp_path, monkeypatch, oracle_
 
 def test_device_parse_one_block(tmp_path, monkeypatch, oracle_lib):
     _run_both(tmp_path, monkeypatch, synth.generate("pe150", 900), [], block="0")      # the default block: the whole file at once
+
+
+def test_device_parse_driver_random_files(tmp_path, monkeypatch, oracle_lib):
+    """random file pairs (ragged lengths, a shorter mate, an empty or blank line somewhere, CRLF) through both drivers with
+    random small read blocks: same outcome -- the same files and JSON, or the same exception type"""
+    import random
+    import emu
+    from afterqc_b200 import pipeline
+    rng = random.Random(23)
+    for case in range(14):
+        n = rng.randint(1200, 2200)
+        batch = synth.generate("pe150", n, len_jitter=rng.choice((0, 40, 90)), seed=100 + case)
+        kind = rng.choice(("plain", "short_r2", "short_r1", "empty_r2", "blank_r1", "crlf"))
+
+        def mutate(sub, kind=kind, n=n, cut=rng.randint(1, 300), at=rng.randint(1001, 1150), inner=rng.randrange(4)):
+            for name, tag in (("x_R1.fq", "r1"), ("x_R2.fq", "r2")):
+                p = os.path.join(sub, name)
+                lines = open(p, "rb").read().split(b"\n")
+                if kind == "short_" + tag:
+                    lines = lines[:4 * (n - cut)] + [b""]
+                elif kind == "empty_" + tag:
+                    lines = lines[:4 * at + inner] + [b""] + lines[4 * at + inner:]
+                elif kind == "blank_" + tag:
+                    lines = lines[:4 * at + inner] + [b" \t"] + lines[4 * at + inner + 1:]
+                elif kind == "crlf":
+                    lines = [l + b"\r" if l else l for l in lines]
+                open(p, "wb").write(b"\n".join(lines))
+        d = str(tmp_path / ("c%d" % case))
+        refcmp.prepare_case(d, batch, subs=("host", "dev"))
+        for sub in ("host", "dev"):
+            mutate(os.path.join(d, sub))
+        extra = rng.choice(([], ["--qc_sample", "500"], ["-f", "1", "-t", "2"]))
+        outcome = []
+        for sub in ("host", "dev"):
+            if sub == "dev":
+                monkeypatch.setenv("AQC_DEVICE_PARSE", "1")
+                monkeypatch.setenv("AQC_DEVICE_PARSE_BLOCK", str(rng.randint(3000, 90000)))
+            else:
+                monkeypatch.delenv("AQC_DEVICE_PARSE", raising=False)
+            try:
+                refcmp.run_ours(d, sub, True, extra, lambda p: emu.EmuEngine(p))
+                outcome.append("ok")
+            except Exception as e:                                   # noqa: BLE001 -- the type is what is compared
+                outcome.append(type(e).__name__)
+        assert outcome[0] == outcome[1], (case, kind, outcome)
+        if outcome[0] != "ok":
+            continue
+        a, b = refcmp.load_json(d, "host"), refcmp.load_json(d, "dev")
+        diffs = [x for x in refcmp.json_diff(a, b) if not x[1].startswith("/command/")]
+        assert not diffs, (case, kind, diffs[:5])
+        for f in refcmp.output_files(True, extra):
+            assert filecmp.cmp(os.path.join(d, "host", f), os.path.join(d, "dev", f), shallow=False), (case, kind, f)
