@@ -14,7 +14,7 @@ SYMBOLS = [
     "aqc_memcpy_h2d", "aqc_memcpy_d2h", "aqc_stat_reads", "aqc_filter_pairs", "aqc_ops_pairs", "aqc_sync",
     "aqc_get_counters", "aqc_add_counters", "aqc_get_qc", "aqc_get_kmer_dense", "aqc_get_kmer_side", "aqc_get_kmer_side_raw", "aqc_last_phase_ms",
     "aqc_edit_distance_batch", "edit_distance", "seek_overlap", "aqc_launch_count", "aqc_last_kernel_ms", "aqc_set_stream", "aqc_device_ptr", "aqc_fastq_parse", "aqc_fastq_parse_device", "aqc_fastq_emit", "aqc_fastq_emit_lines",
-    "aqc_barcode_pairs", "aqc_gunzip_buffer", "aqc_gunzip_buffer_mt", "aqc_reader_open", "aqc_reader_next", "aqc_reader_release", "aqc_reader_error", "aqc_reader_close",
+    "aqc_barcode_pairs", "aqc_gunzip_buffer", "aqc_gunzip_buffer_mt", "aqc_reader_open", "aqc_reader_next", "aqc_reader_release", "aqc_reader_error", "aqc_reader_close", "aqc_text_open", "aqc_text_read",
 ]
 
 _lib = None
@@ -77,6 +77,8 @@ def bind(L):
         "aqc_reader_release": (i32, [vp, u32]),
         "aqc_reader_error": (C.c_char_p, [vp]),
         "aqc_reader_close": (None, [vp]),
+        "aqc_text_open": (i32, [C.c_char_p, C.POINTER(vp)]),
+        "aqc_text_read": (C.c_int64, [vp, vp, u64]),
         "aqc_launch_count": (u64, [vp]),
         "aqc_edit_distance_batch": (i32, [vp, vp, vp, vp, vp, u32, i32, vp]),
         "aqc_fastq_parse_device": (i32, [vp, i32, vp, u64, i32, i32, u64, vp]),

@@ -137,6 +137,7 @@ struct aqc_reader {
     size_t map_len = 0;
     int map_fd = -1;
     std::vector<uint8_t> in;
+    bool raw = false;                       // aqc_text_open: no parser thread, no slots
     bool plain_map = false;                 // uncompressed regular file: parsed straight from the mapping (no read copy, no memmove)
     const uint8_t *src() const { return plain_map ? (const uint8_t *)map : in.data(); }
     size_t in_pos = 0, in_end = 0;
@@ -283,8 +284,39 @@ struct aqc_reader {
 
 extern "C" {
 
+static int reader_open(const char *path, uint64_t batch_records, uint32_t slots, bool raw, aqc_reader **out);
 int aqc_reader_open(const char *path, uint64_t batch_records, uint32_t slots, aqc_reader **out) {
     if (!path || !out || batch_records == 0) return AQC_ERR_INVALID;
+    return reader_open(path, batch_records, slots, false, out);
+}
+// The reader's sources without its parser: decompressed (or plain) text for callers that parse elsewhere (the device parser).
+int aqc_text_open(const char *path, aqc_reader **out) {
+    if (!path || !out) return AQC_ERR_INVALID;
+    return reader_open(path, 1, 2, true, out);
+}
+// up to cap bytes of text (cap >= 4 MiB); 0 at the end of the file, -1 after an error (aqc_reader_error)
+int64_t aqc_text_read(aqc_reader *r, uint8_t *dst, uint64_t cap) {
+    if (!r || !dst || !r->raw) return -1;
+    uint64_t filled = 0;
+    while (!r->src_eof && filled + kReadBlock <= cap) {
+        long got;
+        if (r->plain_map) {
+            got = (long)std::min<size_t>(kReadBlock, r->map_len - r->in_end);
+            memcpy(dst + filled, (const uint8_t *)r->map + r->in_end, (size_t)got);
+            r->in_end += (size_t)got;
+        } else if (r->async) {
+            got = r->async->get(dst + filled);
+        } else {
+            got = (long)fread(dst + filled, 1, kReadBlock, r->fp);
+            if (got == 0 && ferror(r->fp)) { r->msg = "read error"; return -1; }
+        }
+        if (got < 0) return -1;
+        if (got == 0) { r->src_eof = true; break; }
+        filled += (uint64_t)got;
+    }
+    return (int64_t)filled;
+}
+static int reader_open(const char *path, uint64_t batch_records, uint32_t slots, bool raw, aqc_reader **out) {
     if (slots < 2) slots = 2;
     aqc_reader *r = new aqc_reader();
     r->path = path; r->batch = batch_records;
@@ -327,6 +359,8 @@ int aqc_reader_open(const char *path, uint64_t batch_records, uint32_t slots, aq
     }
     if (!r->gz && !r->fp && !r->inf && !r->pinf && !r->plain_map) { delete r; return AQC_ERR_INVALID; }
     if (r->gz || r->inf || r->pinf) r->async = new AsyncSource([r](uint8_t *dst, size_t cap) { return r->read_gz(dst, cap); }, kReadBlock, 3);
+    r->raw = raw;
+    if (raw) { *out = r; return 0; }
     r->slots.resize(slots);
     for (uint32_t i = 0; i < slots; i++) {
         Slot &s = r->slots[i];

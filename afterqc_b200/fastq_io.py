@@ -384,6 +384,66 @@ def emit(rec, mate, which, rec_base, results):
     return data.tobytes() if len(data) else b""
 
 
+class TextSource:
+    """read(n) over the text of a FASTQ file for callers that parse elsewhere (the device parser): plain and .gz files come
+    from the native reader's sources (mapping / multi-threaded gzip decoder, csrc/aqc_stream.cpp) without its parser, .bz2
+    from python's bz2.  read(n) returns n bytes (as a uint8 array) unless the file ends first."""
+
+    BLOCK = 4 << 20
+
+    def __init__(self, path):
+        import ctypes as C
+        self._py = None
+        self._h = None
+        self._keep = np.zeros(0, dtype=np.uint8)
+        self._eof = False
+        if path.endswith(".bz2"):
+            import bz2
+            self._py = bz2.open(path, "rb")
+            return
+        from . import _native
+        self._L = _native.lib()
+        self._h = C.c_void_p()
+        if self._L.aqc_text_open(path.encode(), C.byref(self._h)):
+            self._h = None
+            raise IOError("cannot open %s" % path)
+
+    def read(self, n):
+        if self._py is not None:
+            return np.frombuffer(self._py.read(n), dtype=np.uint8)
+        parts, have = [], 0
+        if len(self._keep):
+            parts.append(self._keep); have = len(self._keep)
+            self._keep = np.zeros(0, dtype=np.uint8)
+        while have < n and not self._eof:
+            cap = max(self.BLOCK, ((n - have + self.BLOCK - 1) // self.BLOCK) * self.BLOCK)
+            buf = np.empty(cap, dtype=np.uint8)
+            got = int(self._L.aqc_text_read(self._h, buf.ctypes.data, cap))
+            if got < 0:
+                raise ValueError(self._L.aqc_reader_error(self._h).decode() or "text source failed")
+            if got == 0:
+                self._eof = True
+                break
+            parts.append(buf[:got]); have += got
+        data = np.concatenate(parts) if len(parts) > 1 else (parts[0] if parts else np.zeros(0, dtype=np.uint8))
+        if len(data) > n:
+            self._keep = data[n:]
+            data = data[:n]
+        return data
+
+    def close(self):
+        if self._py is not None:
+            self._py.close(); self._py = None
+        if self._h is not None:
+            self._L.aqc_reader_close(self._h); self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class TextRecords:
     """Records that were parsed on the device (Engine.parse_fastq): the host keeps the FASTQ text and the line table
     (start and length of the four rstrip()ped lines of every record); the writers format from those."""

@@ -538,14 +538,11 @@ class seqFilter:
 
     # ---- opt-in: FASTQ text parsed on the device (AQC_DEVICE_PARSE=1) ----
     def _device_parse_applies(self, be, idx_files):
-        """Plain (uncompressed) FASTQ inputs on one GPU, no barcode / index files / --qc_only, an engine that can parse."""
+        """FASTQ inputs (plain, .gz, .bz2) on one GPU, no barcode / index files / --qc_only, an engine that can parse."""
         opt = self.options
         if os.environ.get("AQC_DEVICE_PARSE") != "1":
             return False
-        if idx_files or getattr(opt, "barcode", False) or opt.qc_only or not hasattr(be, "parse_fastq"):
-            return False
-        paths = [opt.read1_file] + ([opt.read2_file] if self.paired else [])
-        return all(not p.endswith((".gz", ".bz2")) for p in paths)
+        return not (idx_files or getattr(opt, "barcode", False) or opt.qc_only or not hasattr(be, "parse_fastq"))
 
     def _filter_stream_device_parse(self, be, writers, block_bytes=None):
         """_filter_stream with the parser on the device (csrc/aqc_parse.cuh): the host reads blocks of text, the engine turns
@@ -559,7 +556,7 @@ class seqFilter:
             # large enough for the record cap of a step to bind on both mates (then no mate is parsed twice); AQC_DEVICE_PARSE_BLOCK: tests
             block_bytes = int(os.environ.get("AQC_DEVICE_PARSE_BLOCK", 0)) or max(64 << 20, 512 * self.batch_records)
         paths = [opt.read1_file] + ([opt.read2_file] if self.paired else [])
-        files = [open(p, "rb") for p in paths]
+        files = [fastq_io.TextSource(p) for p in paths]          # text only: inflate threads for .gz, no host parser
         lanes = {name: _OutputLane(w) for name, w in writers.items()}
         nm = len(files)
         carry = [np.zeros(0, dtype=np.uint8) for _ in files]        # text not yet consumed
@@ -569,11 +566,10 @@ class seqFilter:
         inflight = collections.deque()
 
         def read_more(m):
-            data = files[m].read(block_bytes)
-            if len(data) < block_bytes:
+            new = files[m].read(block_bytes)
+            if len(new) < block_bytes:
                 ended[m] = True
-            if len(data):
-                new = np.frombuffer(data, dtype=np.uint8)
+            if len(new):
                 carry[m] = np.concatenate([carry[m], new]) if len(carry[m]) else new
 
         def parse(m, cap):

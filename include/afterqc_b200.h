@@ -369,6 +369,11 @@ int aqc_gunzip_buffer(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_
 int aqc_gunzip_buffer_mt(const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_len, int threads,
                          uint64_t stats[3], char *err, uint64_t err_cap);
 void aqc_reader_close(aqc_reader *r);
+/* The reader's sources without its parser (plain files, .gz through the multi-threaded decoder): text for callers that parse
+ * elsewhere -- the device parser.  aqc_text_read fills up to cap bytes (cap >= 4 MiB; whole 4 MiB blocks): 0 = end of file,
+ * -1 = error (aqc_reader_error).  Close with aqc_reader_close. */
+int aqc_text_open(const char *path, aqc_reader **out);
+int64_t aqc_text_read(aqc_reader *r, uint8_t *dst, uint64_t cap);
 
 /* ---- Levenshtein distance of n string pairs, bit-parallel on the GPU (one lane per pair): replaces util.editDistance
  * (util.py:65-83) -> edit_distance (editdistance/_editdistance.cpp:100-126) for batches.  a / b: byte columns with n + 1

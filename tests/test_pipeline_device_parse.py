@@ -117,3 +117,37 @@ def test_device_parse_driver_random_files(tmp_path, monkeypatch, oracle_lib):
         assert not diffs, (case, kind, diffs[:5])
         for f in refcmp.output_files(True, extra):
             assert filecmp.cmp(os.path.join(d, "host", f), os.path.join(d, "dev", f), shallow=False), (case, kind, f)
+
+
+def test_device_parse_gz_inputs(tmp_path, monkeypatch, oracle_lib):
+    """.gz inputs: the native reader's decoder threads feed text to the device parser (fastq_io.TextSource); outputs are .gz by
+    extension (compared after decompression, quirk Q14)"""
+    import gzip
+    import json
+    import emu
+    from afterqc_b200 import cli
+    from afterqc_b200.pipeline import seqFilter
+    batch = synth.generate("pe150", 2400, len_jitter=30)
+    outs = {}
+    for sub in ("host", "dev"):
+        d = str(tmp_path / sub)
+        os.makedirs(d)
+        synth.write_fastq(batch, os.path.join(d, "p_R1.fq"), os.path.join(d, "p_R2.fq"))
+        for m in ("1", "2"):
+            with open(os.path.join(d, "p_R%s.fq" % m), "rb") as f, gzip.open(os.path.join(d, "x_R%s.fq.gz" % m), "wb", compresslevel=1) as g:
+                g.write(f.read())
+        if sub == "dev":
+            monkeypatch.setenv("AQC_DEVICE_PARSE", "1")
+            monkeypatch.setenv("AQC_DEVICE_PARSE_BLOCK", "70000")
+        else:
+            monkeypatch.delenv("AQC_DEVICE_PARSE", raising=False)
+        opts, _ = cli.parseCommand(["-1", os.path.join(d, "x_R1.fq.gz"), "-2", os.path.join(d, "x_R2.fq.gz"), "-g", os.path.join(d, "good")])
+        cli.normalize_options(opts); opts.barcode = False
+        seqFilter(opts, backend_factory=lambda p: emu.EmuEngine(p)).run()
+        outs[sub] = d
+    a = json.load(open(os.path.join(outs["host"], "QC", "x_R1.fq.gz.json")))
+    b = json.load(open(os.path.join(outs["dev"], "QC", "x_R1.fq.gz.json")))
+    diffs = [x for x in refcmp.json_diff(a, b) if not x[1].startswith("/command/")]
+    assert not diffs, diffs[:5]
+    for f in ("good/x_R1.good.fq.gz", "good/x_R2.good.fq.gz", "bad/x_R1.bad.fq.gz", "bad/x_R2.bad.fq.gz"):
+        assert gzip.open(os.path.join(outs["host"], f)).read() == gzip.open(os.path.join(outs["dev"], f)).read(), f
